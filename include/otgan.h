@@ -1,0 +1,123 @@
+/* otgan.h -- C ABI of libotgan.so: the B200 (sm_100a) implementation of the OT-GAN matching hot path.
+ *
+ * The reference (openai/ot-gan) has no FFI layer: its boundary for this path is the Python signatures of
+ * utils/matching.py (TensorFlow 1.x graph ops).  This header is the C ABI that sits one level below those
+ * signatures; otgan_b200/matching.py is the host-side mirror that binds it with ctypes, and INTEGRATION.md shows the
+ * stub a reference maintainer would add.  Each entry point cites the reference lines it replaces
+ * (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (row-major fp32) unless the name ends in _host;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), launches only this library's own
+ *     kernels, allocates nothing (workspace is sized by otgan_workspace_bytes and passed in) and keeps no global
+ *     mutable state except the thread-local last-error string;
+ *   - return value 0 = OTGAN_OK, negative = error (nothing was launched for OTGAN_EINVAL); otgan_last_error() gives text;
+ *   - results are deterministic (fixed reduction orders, no floating-point atomics): the same inputs give the same bits.
+ */
+#ifndef OTGAN_H
+#define OTGAN_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OTGAN_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define OTGAN_API __attribute__((visibility("default")))
+#else
+#define OTGAN_API
+#endif
+
+enum { OTGAN_OK = 0, OTGAN_EINVAL = -1, OTGAN_ECUDA = -2, OTGAN_ENOSPC = -3, OTGAN_EUNSUPPORTED = -4 };
+
+/* cost kinds (epilogue of the pairwise-dot kernel) */
+enum {
+    OTGAN_COST_COSINE = 0,      /* 1 - x.y                                         utils/matching.py:31-39   */
+    OTGAN_COST_EUCLID_MEAN = 1  /* .5 mean(x^2) + .5 mean(y^2) - x.y / D           toy_example/matching_cpu.py:17-45 */
+};
+
+/* implementation selectors (for A/B parity tests and benchmarking; AUTO picks the fastest valid one) */
+enum { OTGAN_IMPL_AUTO = 0, OTGAN_IMPL_SIMT = 1, OTGAN_IMPL_TCGEN05 = 2 };
+
+#define OTGAN_MAX_BLOCKS 8   /* two-batch matching uses 6 blocks, single-batch 3 */
+#define OTGAN_MAX_TERMS 3
+#define OTGAN_MAX_OUTPUTS 8
+
+OTGAN_API int otgan_abi_version(void);
+OTGAN_API const char* otgan_last_error(void);
+/* number of this library's kernels launched by the calling thread since the last reset (bench.py's gpu_launches) */
+OTGAN_API uint64_t otgan_launch_count(void);
+OTGAN_API void otgan_reset_launch_count(void);
+
+/* ---- cost blocks ------------------------------------------------------------------------------------------------
+ * L[k] = -lam * ( cost(X_k, Y_k) + diag_add[k] * I ),  k < nblk;  X_k: [rows, D] (row stride ldx), Y_k: [cols, D].
+ * Replaces the tf.matmul(..., transpose_b=True) / `1. - ` / concat graph of utils/matching.py:21-43 (two-batch, six
+ * blocks), :101-111 (single batch, +999 on the diagonal) and toy_example/matching_cpu.py:10-49, fused with the
+ * `log_a = -sinkhorn_lambda * distances[i]` scaling of utils/matching.py:50.
+ * X_host / Y_host are HOST arrays of nblk device pointers.  ws: otgan_workspace_bytes_cost(...) bytes. */
+OTGAN_API size_t otgan_workspace_bytes_cost(int nblk, int rows, int cols, int D, int impl);
+OTGAN_API int otgan_cost_blocks_f32(int nblk, int rows, int cols, int D,
+                          const float* const* X_host, const float* const* Y_host, int ldx, int ldy,
+                          int cost_kind, const float* diag_add_host /* [nblk] or NULL */, float lam,
+                          float* L /* [nblk, rows, cols] */, void* ws, size_t ws_bytes, int impl, void* stream);
+
+/* ---- Sinkhorn ---------------------------------------------------------------------------------------------------
+ * For each block k: log_a = L0[k]; T x { log_a -= logsumexp(log_a, axis=1); log_a -= logsumexp(log_a, axis=0) };
+ * P[k] = softmax(log_a, axis=-1); entropy[k] = mean_i( -sum_j P log_softmax(log_a) ); pc[k] = sum_ij P * (-L0/lam).
+ * Replaces utils/matching.py:46-57 (== :113-125, toy_example/matching_cpu.py:51-62).  One persistent kernel: the block
+ * stays in registers/shared memory for all T iterations.  P, entropy, pc may each be NULL.  rows, cols <= 128 in the
+ * single-CTA kernel; larger blocks use the cluster kernel (rows, cols <= 512). */
+OTGAN_API int otgan_sinkhorn_f32(int nblk, int rows, int cols, int T, float lam,
+                       const float* L0 /* [nblk, rows, cols] */, float* P /* [nblk, rows, cols] */,
+                       float* entropy /* [nblk] */, float* pc /* [nblk] */, int impl, void* stream);
+
+/* ---- plan application (matched features / feature gradients) ------------------------------------------------------
+ * out[o] = sum_{t < nterms[o]} coef[o][t] * op(P[blk[o][t]]) * F[src[o][t]],   op = transpose if trans[o][t].
+ * P blocks are [h, h]; F sources are [h, D] (row stride ldf); outputs are [h, D] (row stride ldo).
+ * Replaces the twelve tf.matmul + regroup + 0.5*(f1+f2) of utils/matching.py:63-83 (and :131-134), and with the
+ * fused plan of otgan_grad_features_f32 also train.py:111,125-126. */
+typedef struct {
+    int n_out;
+    int nterms[OTGAN_MAX_OUTPUTS];
+    int blk[OTGAN_MAX_OUTPUTS][OTGAN_MAX_TERMS];
+    int trans[OTGAN_MAX_OUTPUTS][OTGAN_MAX_TERMS];
+    int src[OTGAN_MAX_OUTPUTS][OTGAN_MAX_TERMS];
+    float coef[OTGAN_MAX_OUTPUTS][OTGAN_MAX_TERMS];
+} otgan_plan_t;
+
+OTGAN_API int otgan_plan_apply_f32(const otgan_plan_t* plan_host, int h, int D,
+                         const float* P /* [nblk, h, h] */, const float* const* F_host /* sources */, int ldf,
+                         float* const* out_host /* outputs */, int ldo, int impl, void* stream);
+
+/* Two-batch matched features in the reference's output form: A = [A1;A2], B = [B1;B2] ([2h, D], row stride ld),
+ * P = the six plans in the order [a1a2, b2b1, a1b1, a1b2, a2b1, a2b2]; f_* are [2h, D] (row stride ldo).
+ * utils/matching.py:63-83. */
+OTGAN_API int otgan_matched_two_batch_f32(int h, int D, const float* P, const float* A, const float* B, int ld,
+                                float* f_aa, float* f_bb, float* f_ab, float* f_ba, int ldo, int impl, void* stream);
+/* Fused form: Ga = f_aa - f_ab, Gb = f_bb - f_ba written directly (train.py:111,125-126). */
+OTGAN_API int otgan_grad_features_f32(int h, int D, const float* P, const float* A, const float* B, int ld,
+                            float* Ga, float* Gb, int ldo, int impl, void* stream);
+/* Single-batch matched features: P = [P_aa, P_bb, P_ab] ([n, n] each), A, B: [n, D].  utils/matching.py:131-134. */
+OTGAN_API int otgan_matched_single_batch_f32(int n, int D, const float* P, const float* A, const float* B, int ld,
+                                   float* f_aa, float* f_bb, float* f_ab, float* f_ba, int ldo, int impl, void* stream);
+
+/* ---- distance ---------------------------------------------------------------------------------------------------
+ * out[0] = ( sum(B*f_bb) + sum(A*f_aa) - 2 sum(A*f_ab) ) * scale      utils/matching.py:139-153 (scale = 1/(2 bs G)),
+ * toy_example/matching_cpu.py:155-164 (scale = 1/(2 n D)).  A, B, f_*: [n, D] with row stride ld.
+ * ws: otgan_workspace_bytes_distance(n, D) bytes. */
+OTGAN_API size_t otgan_workspace_bytes_distance(int n, int D);
+OTGAN_API int otgan_calc_distance_f32(int n, int D, const float* A, const float* B, const float* f_aa, const float* f_bb,
+                            const float* f_ab, int ld, float scale, float* out /* [1] */, void* ws, size_t ws_bytes,
+                            void* stream);
+/* out[0] = (pc[2]+pc[3]+pc[4]+pc[5] - 2 pc[0] - 2 pc[1]) / (2 N); out[1] = mean(entropy[0..5]).
+ * The <P,C> form of calc_distance (valid because every plan row sums to one). */
+OTGAN_API int otgan_distance_from_pc_f32(const float* pc /* [6] */, const float* entropy /* [6] */, int n_total,
+                               float* out /* [2] */, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OTGAN_H */

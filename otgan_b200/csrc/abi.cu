@@ -1,0 +1,182 @@
+// abi.cu -- extern "C" entry points of libotgan.so (declared in include/otgan.h): argument validation, implementation
+// selection and the plans that express the reference's matched-feature regrouping.  No torch types, no allocation.
+#include "common.cuh"
+#include <string.h>
+
+namespace otgan {
+
+static thread_local char g_err[512] = "";
+static thread_local uint64_t g_launches = 0;
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches += (uint64_t)n; }
+
+// implemented in the kernel translation units
+size_t cost_simt_workspace_bytes(int nblk, int rows, int cols, int D);
+int cost_simt_launch(int nblk, int rows, int cols, int D, const float* const* X, const float* const* Y, int ldx,
+                     int ldy, int cost_kind, const float* diag, float lam, float* L, void* ws, size_t ws_bytes,
+                     cudaStream_t stream);
+int sinkhorn_reg_launch(int nblk, int rows, int cols, int T, float lam, const float* L0, float* P, float* entropy,
+                        float* pc, cudaStream_t stream);
+int sinkhorn_reg_max_side();
+int distance_from_pc_launch(const float* pc, const float* entropy, int n_total, float* out, cudaStream_t stream);
+int plan_apply_simt_launch(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F, int ldf,
+                           float* const* out, int ldo, cudaStream_t stream);
+size_t distance_workspace_bytes(int n, int D);
+int distance_launch(int n, int D, const float* A, const float* B, const float* f_aa, const float* f_bb,
+                    const float* f_ab, int ld, float scale, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+}  // namespace otgan
+
+using namespace otgan;
+
+extern "C" {
+
+int otgan_abi_version(void) { return OTGAN_ABI_VERSION; }
+const char* otgan_last_error(void) { return g_err; }
+uint64_t otgan_launch_count(void) { return g_launches; }
+void otgan_reset_launch_count(void) { g_launches = 0; }
+
+size_t otgan_workspace_bytes_cost(int nblk, int rows, int cols, int D, int impl)
+{
+    (void)impl;
+    if (nblk < 1 || nblk > OTGAN_MAX_BLOCKS || rows < 1 || cols < 1 || D < 1) return 0;
+    return cost_simt_workspace_bytes(nblk, rows, cols, D);
+}
+
+int otgan_cost_blocks_f32(int nblk, int rows, int cols, int D, const float* const* X_host, const float* const* Y_host,
+                          int ldx, int ldy, int cost_kind, const float* diag_add_host, float lam, float* L, void* ws,
+                          size_t ws_bytes, int impl, void* stream)
+{
+    OTGAN_REQUIRE(nblk >= 1 && nblk <= OTGAN_MAX_BLOCKS, "cost: nblk=%d outside [1,%d]", nblk, OTGAN_MAX_BLOCKS);
+    OTGAN_REQUIRE(rows >= 1 && cols >= 1 && D >= 1, "cost: bad shape rows=%d cols=%d D=%d", rows, cols, D);
+    OTGAN_REQUIRE(ldx >= D && ldy >= D, "cost: row stride smaller than D");
+    OTGAN_REQUIRE(cost_kind == OTGAN_COST_COSINE || cost_kind == OTGAN_COST_EUCLID_MEAN, "cost: unknown cost_kind %d", cost_kind);
+    OTGAN_REQUIRE(X_host && Y_host && L && ws, "cost: null pointer");
+    for (int k = 0; k < nblk; ++k) OTGAN_REQUIRE(X_host[k] && Y_host[k], "cost: null block pointer %d", k);
+    OTGAN_REQUIRE(impl == OTGAN_IMPL_AUTO || impl == OTGAN_IMPL_SIMT, "cost: impl %d not available", impl);
+    return cost_simt_launch(nblk, rows, cols, D, X_host, Y_host, ldx, ldy, cost_kind, diag_add_host, lam, L, ws,
+                            ws_bytes, (cudaStream_t)stream);
+}
+
+int otgan_sinkhorn_f32(int nblk, int rows, int cols, int T, float lam, const float* L0, float* P, float* entropy,
+                       float* pc, int impl, void* stream)
+{
+    OTGAN_REQUIRE(nblk >= 1 && nblk <= 65535, "sinkhorn: nblk=%d", nblk);
+    OTGAN_REQUIRE(rows >= 1 && cols >= 1 && T >= 0, "sinkhorn: bad shape rows=%d cols=%d T=%d", rows, cols, T);
+    OTGAN_REQUIRE(L0 != nullptr, "sinkhorn: null L0");
+    OTGAN_REQUIRE(lam != 0.f || pc == nullptr, "sinkhorn: lam=0 with pc requested");
+    (void)impl;
+    if (rows <= sinkhorn_reg_max_side() && cols <= sinkhorn_reg_max_side())
+        return sinkhorn_reg_launch(nblk, rows, cols, T, lam, L0, P, entropy, pc, (cudaStream_t)stream);
+    set_error("sinkhorn: block %dx%d larger than %d not supported yet", rows, cols, sinkhorn_reg_max_side());
+    return OTGAN_EUNSUPPORTED;
+}
+
+int otgan_plan_apply_f32(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F_host, int ldf,
+                         float* const* out_host, int ldo, int impl, void* stream)
+{
+    OTGAN_REQUIRE(plan && P && F_host && out_host, "plan_apply: null pointer");
+    OTGAN_REQUIRE(plan->n_out >= 1 && plan->n_out <= OTGAN_MAX_OUTPUTS, "plan_apply: n_out=%d", plan->n_out);
+    OTGAN_REQUIRE(h >= 1 && D >= 1 && ldf >= D && ldo >= D, "plan_apply: bad shape h=%d D=%d ldf=%d ldo=%d", h, D, ldf, ldo);
+    for (int o = 0; o < plan->n_out; ++o) {
+        OTGAN_REQUIRE(plan->nterms[o] >= 1 && plan->nterms[o] <= OTGAN_MAX_TERMS, "plan_apply: nterms[%d]=%d", o, plan->nterms[o]);
+        OTGAN_REQUIRE(out_host[o] != nullptr, "plan_apply: null output %d", o);
+        for (int t = 0; t < plan->nterms[o]; ++t) {
+            OTGAN_REQUIRE(plan->blk[o][t] >= 0 && plan->blk[o][t] < OTGAN_MAX_BLOCKS, "plan_apply: blk out of range");
+            OTGAN_REQUIRE(plan->src[o][t] >= 0 && plan->src[o][t] < OTGAN_MAX_OUTPUTS && F_host[plan->src[o][t]],
+                          "plan_apply: bad source");
+        }
+    }
+    OTGAN_REQUIRE(impl == OTGAN_IMPL_AUTO || impl == OTGAN_IMPL_SIMT, "plan_apply: impl %d not available", impl);
+    return plan_apply_simt_launch(plan, h, D, P, F_host, ldf, out_host, ldo, (cudaStream_t)stream);
+}
+
+static void add_term(otgan_plan_t* p, int o, int blk, int trans, int src, float coef)
+{
+    const int t = p->nterms[o]++;
+    p->blk[o][t] = blk; p->trans[o][t] = trans; p->src[o][t] = src; p->coef[o][t] = coef;
+}
+
+// sources: 0 = A1, 1 = A2, 2 = B1, 3 = B2;  plans: 0 = a1a2, 1 = b2b1, 2 = a1b1, 3 = a1b2, 4 = a2b1, 5 = a2b2
+int otgan_matched_two_batch_f32(int h, int D, const float* P, const float* A, const float* B, int ld, float* f_aa,
+                                float* f_bb, float* f_ab, float* f_ba, int ldo, int impl, void* stream)
+{
+    OTGAN_REQUIRE(P && A && B && f_aa && f_bb && f_ab && f_ba, "matched_two_batch: null pointer");
+    OTGAN_REQUIRE(h >= 1 && D >= 1, "matched_two_batch: bad shape");
+    otgan_plan_t p;
+    memset(&p, 0, sizeof(p));
+    p.n_out = 8;
+    add_term(&p, 0, 0, 0, 1, 1.f);                                   // f_aa[A1 rows] = P0 A2          matching.py:64
+    add_term(&p, 1, 0, 1, 0, 1.f);                                   // f_aa[A2 rows] = P0^T A1        :70
+    add_term(&p, 2, 1, 1, 3, 1.f);                                   // f_bb[B1 rows] = P1^T B2        :65
+    add_term(&p, 3, 1, 0, 2, 1.f);                                   // f_bb[B2 rows] = P1 B1          :71
+    add_term(&p, 4, 2, 0, 2, .5f); add_term(&p, 4, 3, 0, 3, .5f);    // f_ab[A1] = .5(P2 B1 + P3 B2)   :66-67,80
+    add_term(&p, 5, 4, 0, 2, .5f); add_term(&p, 5, 5, 0, 3, .5f);    // f_ab[A2] = .5(P4 B1 + P5 B2)   :68-69,80
+    add_term(&p, 6, 2, 1, 0, .5f); add_term(&p, 6, 4, 1, 1, .5f);    // f_ba[B1] = .5(P2^T A1 + P4^T A2) :72,74,82
+    add_term(&p, 7, 3, 1, 0, .5f); add_term(&p, 7, 5, 1, 1, .5f);    // f_ba[B2] = .5(P3^T A1 + P5^T A2) :73,75,82
+    const size_t hl = (size_t)h * ld, ho = (size_t)h * ldo;
+    const float* F[4] = {A, A + hl, B, B + hl};
+    float* out[8] = {f_aa, f_aa + ho, f_bb, f_bb + ho, f_ab, f_ab + ho, f_ba, f_ba + ho};
+    return otgan_plan_apply_f32(&p, h, D, P, F, ld, out, ldo, impl, stream);
+}
+
+int otgan_grad_features_f32(int h, int D, const float* P, const float* A, const float* B, int ld, float* Ga, float* Gb,
+                            int ldo, int impl, void* stream)
+{
+    OTGAN_REQUIRE(P && A && B && Ga && Gb, "grad_features: null pointer");
+    OTGAN_REQUIRE(h >= 1 && D >= 1, "grad_features: bad shape");
+    otgan_plan_t p;
+    memset(&p, 0, sizeof(p));
+    p.n_out = 4;    // grad_ys(fake) = f_aa - f_ab, grad_ys(real) = f_bb - f_ba    (train.py:111,125-126)
+    add_term(&p, 0, 0, 0, 1, 1.f); add_term(&p, 0, 2, 0, 2, -.5f); add_term(&p, 0, 3, 0, 3, -.5f);   // Ga[A1 rows]
+    add_term(&p, 1, 0, 1, 0, 1.f); add_term(&p, 1, 4, 0, 2, -.5f); add_term(&p, 1, 5, 0, 3, -.5f);   // Ga[A2 rows]
+    add_term(&p, 2, 1, 1, 3, 1.f); add_term(&p, 2, 2, 1, 0, -.5f); add_term(&p, 2, 4, 1, 1, -.5f);   // Gb[B1 rows]
+    add_term(&p, 3, 1, 0, 2, 1.f); add_term(&p, 3, 3, 1, 0, -.5f); add_term(&p, 3, 5, 1, 1, -.5f);   // Gb[B2 rows]
+    const size_t hl = (size_t)h * ld, ho = (size_t)h * ldo;
+    const float* F[4] = {A, A + hl, B, B + hl};
+    float* out[4] = {Ga, Ga + ho, Gb, Gb + ho};
+    return otgan_plan_apply_f32(&p, h, D, P, F, ld, out, ldo, impl, stream);
+}
+
+// sources: 0 = A, 1 = B;  plans: 0 = aa, 1 = bb, 2 = ab      (utils/matching.py:131-134)
+int otgan_matched_single_batch_f32(int n, int D, const float* P, const float* A, const float* B, int ld, float* f_aa,
+                                   float* f_bb, float* f_ab, float* f_ba, int ldo, int impl, void* stream)
+{
+    OTGAN_REQUIRE(P && A && B && f_aa && f_bb && f_ab && f_ba, "matched_single_batch: null pointer");
+    OTGAN_REQUIRE(n >= 1 && D >= 1, "matched_single_batch: bad shape");
+    otgan_plan_t p;
+    memset(&p, 0, sizeof(p));
+    p.n_out = 4;
+    add_term(&p, 0, 0, 0, 0, 1.f);
+    add_term(&p, 1, 1, 0, 1, 1.f);
+    add_term(&p, 2, 2, 0, 1, 1.f);
+    add_term(&p, 3, 2, 1, 0, 1.f);
+    const float* F[2] = {A, B};
+    float* out[4] = {f_aa, f_bb, f_ab, f_ba};
+    return otgan_plan_apply_f32(&p, n, D, P, F, ld, out, ldo, impl, stream);
+}
+
+size_t otgan_workspace_bytes_distance(int n, int D) { return distance_workspace_bytes(n, D); }
+
+int otgan_calc_distance_f32(int n, int D, const float* A, const float* B, const float* f_aa, const float* f_bb,
+                            const float* f_ab, int ld, float scale, float* out, void* ws, size_t ws_bytes, void* stream)
+{
+    OTGAN_REQUIRE(n >= 1 && D >= 1 && ld >= D, "calc_distance: bad shape n=%d D=%d ld=%d", n, D, ld);
+    OTGAN_REQUIRE(A && B && f_aa && f_bb && f_ab && out && ws, "calc_distance: null pointer");
+    return distance_launch(n, D, A, B, f_aa, f_bb, f_ab, ld, scale, out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int otgan_distance_from_pc_f32(const float* pc, const float* entropy, int n_total, float* out, void* stream)
+{
+    OTGAN_REQUIRE(pc && entropy && out && n_total > 0, "distance_from_pc: bad arguments");
+    return distance_from_pc_launch(pc, entropy, n_total, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+"""CPU tests of the C-ABI boundary: libotgan.so loads, exports every symbol include/otgan.h declares, the ctypes
+signatures cover them all, and argument validation returns OTGAN_EINVAL before anything touches the GPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "otgan.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"OTGAN_API[^;(]*?\b(otgan_\w+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from otgan_b200 import _lib, build
+    build.build()
+    return _lib.load()
+
+
+def test_header_declares_symbols():
+    names = _declared()
+    assert "otgan_cost_blocks_f32" in names and "otgan_sinkhorn_f32" in names and len(names) >= 14
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from otgan_b200 import _lib
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.SO_PATH]).decode()
+    exported = set(re.findall(r" T (otgan_\w+)", out))
+    missing = [n for n in _declared() if n not in exported]
+    assert not missing, "declared in include/otgan.h but not exported: %s" % missing
+    for n in _declared():
+        assert getattr(lib, n) is not None
+
+
+def test_ctypes_signatures_cover_header(lib):
+    from otgan_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared()
+    assert lib.otgan_abi_version() == 1
+
+
+def test_plan_struct_layout_matches_header():
+    from otgan_b200 import _lib
+    # int n_out + 8 ints + 3 x (8x3 ints) + 8x3 floats
+    assert ctypes.sizeof(_lib.Plan) == 4 * (1 + 8 + 3 * 24 + 24)
+
+
+def test_library_is_sm100a_only():
+    from otgan_b200 import _lib
+    out = subprocess.check_output(["cuobjdump", "-lelf", _lib.SO_PATH]).decode()
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_invalid_arguments_are_rejected_before_launch(lib):
+    from otgan_b200 import _lib
+    null = ctypes.c_void_p(0)
+    one = _lib.ptr_array([16])
+    assert lib.otgan_cost_blocks_f32(0, 4, 4, 4, one, one, 4, 4, 0, None, 1.0, null, null, 0, 0, null) == -1
+    assert b"nblk" in lib.otgan_last_error()
+    assert lib.otgan_cost_blocks_f32(1, 4, 4, 8, one, one, 4, 4, 0, None, 1.0, 16, 16, 0, 0, null) == -1   # ld < D
+    assert lib.otgan_cost_blocks_f32(1, 4, 4, 4, one, one, 4, 4, 7, None, 1.0, 16, 16, 0, 0, null) == -1   # cost kind
+    assert lib.otgan_sinkhorn_f32(1, 0, 4, 1, 1.0, 16, null, null, null, 0, null) == -1
+    assert lib.otgan_sinkhorn_f32(1, 4, 4, -1, 1.0, 16, null, null, null, 0, null) == -1
+    assert lib.otgan_sinkhorn_f32(1, 4, 4, 1, 1.0, null, null, null, null, 0, null) == -1
+    assert lib.otgan_grad_features_f32(4, 4, null, null, null, 4, null, null, 4, 0, null) == -1
+    assert lib.otgan_calc_distance_f32(4, 8, 16, 16, 16, 16, 16, 4, 1.0, 16, 16, 1 << 20, null) == -1     # ld < D
+    assert lib.otgan_distance_from_pc_f32(null, null, 4, null, null) == -1
+    assert lib.otgan_workspace_bytes_cost(6, 128, 128, 32768, 0) > 0
+    assert lib.otgan_workspace_bytes_cost(0, 128, 128, 32768, 0) == 0
+
+
+def test_product_path_has_no_cpu_fallback():
+    """CPU tensors must be rejected, not silently computed elsewhere; and the package must not import the oracle."""
+    import torch
+    from otgan_b200.utils import matching
+    fa = [torch.zeros(2, 4), torch.zeros(2, 4)]
+    with pytest.raises(TypeError):
+        matching.get_matched_features(fa, fa, 1.0, 1)
+    pkg = os.path.join(ROOT, "otgan_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, fn)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, fn
