@@ -74,6 +74,11 @@ OTGAN_API int otgan_sinkhorn_f32(int nblk, int rows, int cols, int T, float lam,
                        const float* L0 /* [nblk, rows, cols] */, float* P /* [nblk, rows, cols] */,
                        float* entropy /* [nblk] */, float* pc /* [nblk] */, int impl, void* stream);
 
+/* Same, additionally reporting per block how many half-steps took the slow (log-domain, max-subtracted) path of the
+ * scaling-form kernel (slow_steps: [nblk] ints or NULL); impl = OTGAN_IMPL_SIMT selects the literal log-domain kernel. */
+OTGAN_API int otgan_sinkhorn_ex_f32(int nblk, int rows, int cols, int T, float lam, const float* L0, float* P,
+                                    float* entropy, float* pc, int* slow_steps, int impl, void* stream);
+
 /* ---- plan application (matched features / feature gradients) ------------------------------------------------------
  * out[o] = sum_{t < nterms[o]} coef[o][t] * op(P[blk[o][t]]) * F[src[o][t]],   op = transpose if trans[o][t].
  * P blocks are [h, h]; F sources are [h, D] (row stride ldf); outputs are [h, D] (row stride ldo).

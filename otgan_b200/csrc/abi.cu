@@ -25,6 +25,8 @@ int cost_simt_launch(int nblk, int rows, int cols, int D, const float* const* X,
 int sinkhorn_reg_launch(int nblk, int rows, int cols, int T, float lam, const float* L0, float* P, float* entropy,
                         float* pc, cudaStream_t stream);
 int sinkhorn_reg_max_side();
+int sinkhorn_fast_launch(int nblk, int rows, int cols, int T, float lam, const float* L0, float* P, float* entropy,
+                         float* pc, int* slow_steps, cudaStream_t stream);
 int distance_from_pc_launch(const float* pc, const float* entropy, int n_total, float* out, cudaStream_t stream);
 int plan_apply_simt_launch(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F, int ldf,
                            float* const* out, int ldo, cudaStream_t stream);
@@ -65,18 +67,27 @@ int otgan_cost_blocks_f32(int nblk, int rows, int cols, int D, const float* cons
                             ws_bytes, (cudaStream_t)stream);
 }
 
-int otgan_sinkhorn_f32(int nblk, int rows, int cols, int T, float lam, const float* L0, float* P, float* entropy,
-                       float* pc, int impl, void* stream)
+int otgan_sinkhorn_ex_f32(int nblk, int rows, int cols, int T, float lam, const float* L0, float* P, float* entropy,
+                          float* pc, int* slow_steps, int impl, void* stream)
 {
     OTGAN_REQUIRE(nblk >= 1 && nblk <= 65535, "sinkhorn: nblk=%d", nblk);
     OTGAN_REQUIRE(rows >= 1 && cols >= 1 && T >= 0, "sinkhorn: bad shape rows=%d cols=%d T=%d", rows, cols, T);
     OTGAN_REQUIRE(L0 != nullptr, "sinkhorn: null L0");
     OTGAN_REQUIRE(lam != 0.f || pc == nullptr, "sinkhorn: lam=0 with pc requested");
-    (void)impl;
-    if (rows <= sinkhorn_reg_max_side() && cols <= sinkhorn_reg_max_side())
-        return sinkhorn_reg_launch(nblk, rows, cols, T, lam, L0, P, entropy, pc, (cudaStream_t)stream);
+    OTGAN_REQUIRE(impl == OTGAN_IMPL_AUTO || impl == OTGAN_IMPL_SIMT, "sinkhorn: impl %d not available", impl);
+    if (rows <= sinkhorn_reg_max_side() && cols <= sinkhorn_reg_max_side()) {
+        if (impl == OTGAN_IMPL_SIMT)   // literal log-domain kernel (every half-step is a max-subtracted LSE)
+            return sinkhorn_reg_launch(nblk, rows, cols, T, lam, L0, P, entropy, pc, (cudaStream_t)stream);
+        return sinkhorn_fast_launch(nblk, rows, cols, T, lam, L0, P, entropy, pc, slow_steps, (cudaStream_t)stream);
+    }
     set_error("sinkhorn: block %dx%d larger than %d not supported yet", rows, cols, sinkhorn_reg_max_side());
     return OTGAN_EUNSUPPORTED;
+}
+
+int otgan_sinkhorn_f32(int nblk, int rows, int cols, int T, float lam, const float* L0, float* P, float* entropy,
+                       float* pc, int impl, void* stream)
+{
+    return otgan_sinkhorn_ex_f32(nblk, rows, cols, T, lam, L0, P, entropy, pc, nullptr, impl, stream);
 }
 
 int otgan_plan_apply_f32(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F_host, int ldf,

@@ -5,7 +5,7 @@
 // reduction, and HBM is touched exactly twice (read L0 = -lambda*C at the start; write P at the end, re-reading L0
 // once for <P,C>).  The reference instead unrolls ~14 TensorFlow ops per iteration per block into the graph.
 //
-// Arithmetic is done in base 2 (log_a * log2(e)) so that every exp/log is a single MUFU ex2/lg2; the reference's
+// exp/log are single MUFU ex2/lg2 ops with log2(e) applied to the (small) max-subtracted differences; the reference's
 // update order is kept literally:   log_a -= LSE(log_a, axis=1);  log_a -= LSE(log_a, axis=0)   (max-subtracted LSE,
 // like tf.reduce_logsumexp), then P = softmax(log_a, -1), entropy = mean_i(-sum_j P log_softmax(log_a)).
 #include "common.cuh"
@@ -69,11 +69,11 @@ sinkhorn_reg_kernel(const float* __restrict__ L0, float* __restrict__ P, float* 
         const int r = r0 + i;
         if (vec && r < rows && c0 < cols) {
             const float4 t = *reinterpret_cast<const float4*>(L0b + (size_t)r * cols + c0);
-            x[i][0] = t.x * LOG2E; x[i][1] = t.y * LOG2E; x[i][2] = t.z * LOG2E; x[i][3] = t.w * LOG2E;
+            x[i][0] = t.x; x[i][1] = t.y; x[i][2] = t.z; x[i][3] = t.w;
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                x[i][j] = (r < rows && c0 + j < cols) ? L0b[(size_t)r * cols + c0 + j] * LOG2E : -INFINITY;
+                x[i][j] = (r < rows && c0 + j < cols) ? L0b[(size_t)r * cols + c0 + j] : -INFINITY;
         }
     }
 
@@ -84,9 +84,10 @@ sinkhorn_reg_kernel(const float* __restrict__ L0, float* __restrict__ P, float* 
             float m = fmaxf(fmaxf(x[i][0], x[i][1]), fmaxf(x[i][2], x[i][3]));
             m = warp_max(m);
             if (m == -INFINITY) m = 0.f;
-            float s = ex2_approx(x[i][0] - m) + ex2_approx(x[i][1] - m) + ex2_approx(x[i][2] - m) + ex2_approx(x[i][3] - m);
+            float s = ex2_approx((x[i][0] - m) * LOG2E) + ex2_approx((x[i][1] - m) * LOG2E) +
+                      ex2_approx((x[i][2] - m) * LOG2E) + ex2_approx((x[i][3] - m) * LOG2E);
             s = warp_sum(s);
-            const float lse = (r0 + i < rows) ? m + lg2_approx(s) : 0.f;
+            const float lse = (r0 + i < rows) ? m + LN2 * lg2_approx(s) : 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) x[i][j] -= lse;
         }
@@ -105,13 +106,13 @@ sinkhorn_reg_kernel(const float* __restrict__ L0, float* __restrict__ P, float* 
             if (cm[j] == -INFINITY) cm[j] = 0.f;
             float s = 0.f;
 #pragma unroll
-            for (int i = 0; i < RPW; ++i) s += ex2_approx(x[i][j] - cm[j]);
+            for (int i = 0; i < RPW; ++i) s += ex2_approx((x[i][j] - cm[j]) * LOG2E);
             cs[j] = s;
         }
         col_allreduce<false>(cs, sc, warp, lane);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float lse = (c0 + j < cols) ? cm[j] + lg2_approx(cs[j]) : 0.f;
+            const float lse = (c0 + j < cols) ? cm[j] + LN2 * lg2_approx(cs[j]) : 0.f;
 #pragma unroll
             for (int i = 0; i < RPW; ++i) x[i][j] -= lse;
         }
@@ -128,9 +129,9 @@ sinkhorn_reg_kernel(const float* __restrict__ L0, float* __restrict__ P, float* 
         float e[4];
         float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { e[j] = ex2_approx(x[i][j] - m); s += e[j]; }
+        for (int j = 0; j < 4; ++j) { e[j] = ex2_approx((x[i][j] - m) * LOG2E); s += e[j]; }
         s = warp_sum(s);
-        const float ls = lg2_approx(s);
+        const float ls = LN2 * lg2_approx(s);
         float p[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -164,7 +165,7 @@ sinkhorn_reg_kernel(const float* __restrict__ L0, float* __restrict__ P, float* 
         float a = 0.f, b = 0.f;
 #pragma unroll
         for (int w = 0; w < NWARPS; ++w) { a += red[0][w]; b += red[1][w]; }
-        if (entropy) entropy[blockIdx.x] = a * LN2 / (float)rows;
+        if (entropy) entropy[blockIdx.x] = a / (float)rows;
         if (pc) pc[blockIdx.x] = -b / lam;       // C = -L0 / lambda
     }
 }

@@ -91,17 +91,24 @@ def cost_blocks(X, Y, lam, cost_kind=_lib.COST_COSINE, diag_add=None, impl=_lib.
     return L
 
 
-def sinkhorn(L, lam, nr_iter, want_plan=True, impl=_lib.IMPL_AUTO):
-    """T Sinkhorn iterations on every block of L = -lam*C -> (P, entropy[nblk], pc[nblk])."""
+def sinkhorn(L, lam, nr_iter, want_plan=True, impl=_lib.IMPL_AUTO, want_stats=False):
+    """T Sinkhorn iterations on every block of L = -lam*C -> (P, entropy[nblk], pc[nblk]) (+ slow_steps[nblk] ints:
+    how many half-steps of the scaling-form kernel fell back to the max-subtracted log-domain path)."""
     lib = _lib.load()
     nblk, rows, cols = L.shape
     assert L.is_cuda and L.dtype == torch.float32 and L.is_contiguous()
     P = _buf("P", (nblk, rows, cols), L.device) if want_plan else None
     ent = _buf("ent", (nblk,), L.device)
     pc = _buf("pc", (nblk,), L.device)
-    rc = lib.otgan_sinkhorn_f32(nblk, rows, cols, int(nr_iter), float(lam), L.data_ptr(),
-                                P.data_ptr() if P is not None else None, ent.data_ptr(), pc.data_ptr(), impl, _stream())
+    slow = _buf("slow", (nblk,), L.device, torch.int32) if want_stats else None
+    if slow is not None:
+        slow.zero_()
+    rc = lib.otgan_sinkhorn_ex_f32(nblk, rows, cols, int(nr_iter), float(lam), L.data_ptr(),
+                                   P.data_ptr() if P is not None else None, ent.data_ptr(), pc.data_ptr(),
+                                   slow.data_ptr() if slow is not None else None, impl, _stream())
     _lib.check(rc, "otgan_sinkhorn_f32")
+    if want_stats:
+        return P, ent, pc, slow
     return P, ent, pc
 
 

@@ -76,22 +76,53 @@ def test_cost_blocks_diag_and_strided_rows(M):
     assert relerr(L[0] / -500.0, C0) < TOL_C and relerr(L[1] / -500.0, C1) < TOL_C
 
 
+@pytest.mark.parametrize("impl", [0, 1])      # 0 = AUTO (scaling-form kernel), 1 = SIMT (literal log-domain kernel)
 @pytest.mark.parametrize("nblk,rows,cols,lam,T", [(6, 128, 128, 500.0, 100), (6, 64, 64, 500.0, 100), (3, 32, 32, 50.0, 10),
-                                                  (2, 17, 23, 100.0, 5), (1, 128, 128, 500.0, 0), (6, 125, 125, 500.0, 30)])
-def test_sinkhorn_kernel(M, nblk, rows, cols, lam, T):
+                                                  (2, 17, 23, 100.0, 5), (1, 128, 128, 500.0, 0), (6, 125, 125, 500.0, 30),
+                                                  (2, 128, 128, 500.0, 1), (2, 100, 128, 2000.0, 50)])
+def test_sinkhorn_kernel(M, nblk, rows, cols, lam, T, impl):
     D = 256
     C = np.stack([mo.cosine_cost(mo.synth_embeddings(rows, D, 30 + k, "clustered", sigma=1.0).astype(np.float64),
                                  mo.synth_embeddings(cols, D, 40 + k, "clustered", sigma=1.0).astype(np.float64))
                   for k in range(nblk)])
     L0 = dev((-lam * C).astype(np.float32))
-    P, ent, pc = M.sinkhorn(L0, lam, T)
+    P, ent, pc = M.sinkhorn(L0, lam, T, True, impl)
     torch.cuda.synchronize()
     C32 = L0.cpu().double().numpy() / -lam        # the oracle sees exactly the fp32 cost the kernel saw
     for k in range(nblk):
         p, e, _ = mo.sinkhorn(C32[k], lam, T, np.float64)
-        assert relerr(P[k], p) < TOL_P
-        assert abs(float(ent[k]) - e) <= TOL_ENT * max(abs(e), 1e-3)
+        scale = max(1.0, lam / 500.0)           # fp32 rounding of -lambda*C grows with lambda
+        assert relerr(P[k], p) < TOL_P * scale
+        assert abs(float(ent[k]) - e) <= TOL_ENT * scale * max(abs(e), 1e-3)
         assert abs(float(pc[k]) - np.sum(p * C32[k])) < 2e-5 * rows
+
+
+def test_sinkhorn_single_batch_diagonal_and_hard_inputs(M):
+    """+999 on the diagonal (-lambda*C = -499500 there), near-duplicate points, and a very peaked problem."""
+    rng = np.random.RandomState(11)
+    X = mo.synth_embeddings(96, 512, 5, "clustered", sigma=0.05).astype(np.float64)     # tight clusters: near-ties
+    C0 = mo.cosine_cost(X, X) + 999.0 * np.eye(96)
+    C1 = rng.rand(96, 96) * 2.0                                                          # spread costs: peaked plans
+    L0 = dev(np.stack([-500.0 * C0, -500.0 * C1]).astype(np.float32))
+    for impl in (0, 1):
+        P, ent, _ = M.sinkhorn(L0, 500.0, 60, True, impl)
+        C32 = L0.cpu().double().numpy() / -500.0
+        for k in range(2):
+            p, e, _ = mo.sinkhorn(C32[k], 500.0, 60, np.float64)
+            assert relerr(P[k], p) < TOL_P
+            assert abs(float(ent[k]) - e) <= 2e-5 * max(abs(e), 1e-3) + 1e-6
+        assert float(torch.diagonal(P[0]).abs().max()) == 0.0
+
+
+def test_sinkhorn_fast_path_is_taken(M):
+    """The scaling-form kernel may fall back to log-domain half-steps only while the potentials are still moving."""
+    C = np.stack([mo.cosine_cost(mo.synth_embeddings(128, 1024, 50 + k, "clustered", sigma=1.0).astype(np.float64),
+                                 mo.synth_embeddings(128, 1024, 60 + k, "clustered", sigma=1.0).astype(np.float64))
+                  for k in range(6)])
+    L0 = dev((-500.0 * C).astype(np.float32))
+    _, _, _, slow = M.sinkhorn(L0, 500.0, 100, True, 0, want_stats=True)
+    slow = slow.cpu().numpy()
+    assert (slow >= 1).all() and (slow <= 40).all(), slow           # 200 half-steps in total
 
 
 def test_sinkhorn_rows_sum_to_one_at_full_size(M):
