@@ -22,6 +22,11 @@ size_t cost_simt_workspace_bytes(int nblk, int rows, int cols, int D);
 int cost_simt_launch(int nblk, int rows, int cols, int D, const float* const* X, const float* const* Y, int ldx,
                      int ldy, int cost_kind, const float* diag, float lam, float* L, void* ws, size_t ws_bytes,
                      cudaStream_t stream);
+bool cost_tc_supported(int nblk, int rows, int cols, int D, const float* const* X, const float* const* Y, int ldx, int ldy);
+size_t cost_tc_workspace_bytes(int nblk, int rows, int cols, int D);
+int cost_tc_launch(int nblk, int rows, int cols, int D, const float* const* X, const float* const* Y, int ldx,
+                   int ldy, int cost_kind, const float* diag, float lam, float* L, void* ws, size_t ws_bytes,
+                   cudaStream_t stream);
 int sinkhorn_reg_launch(int nblk, int rows, int cols, int T, float lam, const float* L0, float* P, float* entropy,
                         float* pc, cudaStream_t stream);
 int sinkhorn_reg_max_side();
@@ -49,7 +54,8 @@ size_t otgan_workspace_bytes_cost(int nblk, int rows, int cols, int D, int impl)
 {
     (void)impl;
     if (nblk < 1 || nblk > OTGAN_MAX_BLOCKS || rows < 1 || cols < 1 || D < 1) return 0;
-    return cost_simt_workspace_bytes(nblk, rows, cols, D);
+    const size_t a = cost_simt_workspace_bytes(nblk, rows, cols, D), b = cost_tc_workspace_bytes(nblk, rows, cols, D);
+    return a > b ? a : b;     // one size fits every implementation the call may select
 }
 
 int otgan_cost_blocks_f32(int nblk, int rows, int cols, int D, const float* const* X_host, const float* const* Y_host,
@@ -62,7 +68,15 @@ int otgan_cost_blocks_f32(int nblk, int rows, int cols, int D, const float* cons
     OTGAN_REQUIRE(cost_kind == OTGAN_COST_COSINE || cost_kind == OTGAN_COST_EUCLID_MEAN, "cost: unknown cost_kind %d", cost_kind);
     OTGAN_REQUIRE(X_host && Y_host && L && ws, "cost: null pointer");
     for (int k = 0; k < nblk; ++k) OTGAN_REQUIRE(X_host[k] && Y_host[k], "cost: null block pointer %d", k);
-    OTGAN_REQUIRE(impl == OTGAN_IMPL_AUTO || impl == OTGAN_IMPL_SIMT, "cost: impl %d not available", impl);
+    OTGAN_REQUIRE(impl == OTGAN_IMPL_AUTO || impl == OTGAN_IMPL_SIMT || impl == OTGAN_IMPL_TCGEN05, "cost: unknown impl %d", impl);
+    const bool tc_ok = cost_tc_supported(nblk, rows, cols, D, X_host, Y_host, ldx, ldy);
+    if (impl == OTGAN_IMPL_TCGEN05 && !tc_ok) {
+        set_error("cost: tcgen05 path needs square blocks <= 128, 16-byte aligned rows (ld %% 4 == 0) and D >= 16");
+        return OTGAN_EUNSUPPORTED;
+    }
+    if (tc_ok && impl != OTGAN_IMPL_SIMT)
+        return cost_tc_launch(nblk, rows, cols, D, X_host, Y_host, ldx, ldy, cost_kind, diag_add_host, lam, L, ws,
+                              ws_bytes, (cudaStream_t)stream);
     return cost_simt_launch(nblk, rows, cols, D, X_host, Y_host, ldx, ldy, cost_kind, diag_add_host, lam, L, ws,
                             ws_bytes, (cudaStream_t)stream);
 }

@@ -185,6 +185,30 @@ Split plan_split(int nblk, int rows, int cols, int D)
 
 }  // namespace
 
+// shared by the SIMT and tcgen05 cost paths: fixed-order split-K reduction + cost epilogue
+int cost_finalize_launch(const float* partial, int S, int nblk, int rows, int cols, int D, int cost_kind,
+                         const float* const* X, const float* const* Y, int ldx, int ldy, const float* diag, float lam,
+                         float* L, float* sq, cudaStream_t stream)
+{
+    CostArgs args;
+    for (int k = 0; k < OTGAN_MAX_BLOCKS; ++k) {
+        args.x[k] = k < nblk ? X[k] : nullptr;
+        args.y[k] = k < nblk ? Y[k] : nullptr;
+        args.diag[k] = (k < nblk && diag) ? diag[k] : 0.f;
+    }
+    if (cost_kind == OTGAN_COST_EUCLID_MEAN) {
+        const int warps = nblk * (rows + cols);
+        row_sqmean_kernel<<<ceil_div(warps * 32, 256), 256, 0, stream>>>(args, nblk, rows, cols, D, ldx, ldy, sq);
+        OTGAN_CHECK_LAUNCH("row_sqmean_kernel");
+    }
+    const size_t total = (size_t)nblk * rows * cols;
+    int fgrid = (int)((total + 255) / 256);
+    fgrid = fgrid > 4 * kNumSMs ? 4 * kNumSMs : fgrid;
+    cost_finalize_kernel<<<fgrid, 256, 0, stream>>>(partial, S, nblk, rows, cols, D, cost_kind, args, sq, lam, L);
+    OTGAN_CHECK_LAUNCH("cost_finalize_kernel");
+    return OTGAN_OK;
+}
+
 size_t cost_simt_workspace_bytes(int nblk, int rows, int cols, int D)
 {
     const Split p = plan_split(nblk, rows, cols, D);
@@ -220,17 +244,7 @@ int cost_simt_launch(int nblk, int rows, int cols, int D, const float* const* X,
     else
         cost_gram_splitk_kernel<false><<<grid, NT, SMEM_BYTES, stream>>>(args, rows, cols, D, ldx, ldy, p.ktiles_per_split, p.tiles_n, partial);
     OTGAN_CHECK_LAUNCH("cost_gram_splitk_kernel");
-    if (cost_kind == OTGAN_COST_EUCLID_MEAN) {
-        const int warps = nblk * (rows + cols);
-        row_sqmean_kernel<<<ceil_div(warps * 32, 256), 256, 0, stream>>>(args, nblk, rows, cols, D, ldx, ldy, sq);
-        OTGAN_CHECK_LAUNCH("row_sqmean_kernel");
-    }
-    const size_t total = (size_t)nblk * rows * cols;
-    int fgrid = (int)((total + 255) / 256);
-    fgrid = fgrid > 4 * kNumSMs ? 4 * kNumSMs : fgrid;
-    cost_finalize_kernel<<<fgrid, 256, 0, stream>>>(partial, p.S, nblk, rows, cols, D, cost_kind, args, sq, lam, L);
-    OTGAN_CHECK_LAUNCH("cost_finalize_kernel");
-    return OTGAN_OK;
+    return cost_finalize_launch(partial, p.S, nblk, rows, cols, D, cost_kind, X, Y, ldx, ldy, diag, lam, L, sq, stream);
 }
 
 }  // namespace otgan
