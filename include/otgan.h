@@ -122,6 +122,19 @@ OTGAN_API int otgan_calc_distance_f32(int n, int D, const float* A, const float*
 OTGAN_API int otgan_distance_from_pc_f32(const float* pc /* [6] */, const float* entropy /* [6] */, int n_total,
                                float* out /* [2] */, void* stream);
 
+/* ---- optimiser / critic head -------------------------------------------------------------------------------------
+ * One fused pass of nn.adam_updates (utils/nn.py:50-73; epsilon inside the root) over a flat parameter buffer, plus the
+ * generator's ExponentialMovingAverage update (train.py:63-64, 223) when ema != NULL:
+ *   v = mom1 v + (1-mom1) g; mg = mom2 mg + (1-mom2) g^2; p -= lr * (v/d1) / sqrt(mg/d2 + 1e-8); ema -= (1-decay)(ema - p)
+ * d1 = 1 - mom1^t, d2 = 1 - mom2^t (t starts at 1).  v may be NULL (mom1 == 0).  n % 4 == 0, 16-byte aligned buffers. */
+OTGAN_API int otgan_adam_ema_f32(size_t n, float* p, const float* g, float* v, float* mg, float* ema, float lr, float mom1,
+                                 float mom2, float d1, float d2, float ema_decay, void* stream);
+/* Critic head (models/dcgan.py:16-19, models/densenet.py:37-42): y = z / ||z||, z = concat(relu(x), relu(-x)) over the
+ * channel axis then flattened; x: [B, HW, C] (NHWC), y: [B, HW*2C], inv_norm: [B].  Backward: dx from dy. */
+OTGAN_API int otgan_crelu_l2norm_fwd_f32(int B, int HW, int C, const float* x, float* y, float* inv_norm, void* stream);
+OTGAN_API int otgan_crelu_l2norm_bwd_f32(int B, int HW, int C, const float* x, const float* y, const float* inv_norm,
+                                         const float* dy, float* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,12 @@ size_t distance_workspace_bytes(int n, int D);
 int distance_launch(int n, int D, const float* A, const float* B, const float* f_aa, const float* f_bb,
                     const float* f_ab, int ld, float scale, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
 
+int adam_ema_launch(size_t n, float* p, const float* g, float* v, float* mg, float* ema, float lr, float mom1, float mom2,
+                    float d1, float d2, float ema_decay, cudaStream_t stream);
+int crelu_l2norm_fwd_launch(int B, int HW, int C, const float* x, float* y, float* inv, cudaStream_t stream);
+int crelu_l2norm_bwd_launch(int B, int HW, int C, const float* x, const float* y, const float* inv, const float* dy,
+                            float* dx, cudaStream_t stream);
+
 }  // namespace otgan
 
 using namespace otgan;
@@ -202,6 +208,30 @@ int otgan_distance_from_pc_f32(const float* pc, const float* entropy, int n_tota
 {
     OTGAN_REQUIRE(pc && entropy && out && n_total > 0, "distance_from_pc: bad arguments");
     return distance_from_pc_launch(pc, entropy, n_total, out, (cudaStream_t)stream);
+}
+
+int otgan_adam_ema_f32(size_t n, float* p, const float* g, float* v, float* mg, float* ema, float lr, float mom1,
+                       float mom2, float d1, float d2, float ema_decay, void* stream)
+{
+    OTGAN_REQUIRE(p && g && mg, "adam_ema: null pointer");
+    OTGAN_REQUIRE(n > 0 && n % 4 == 0, "adam_ema: n=%zu must be a positive multiple of 4 (flat buffers are padded)", n);
+    OTGAN_REQUIRE(aligned16(p) && aligned16(g) && aligned16(mg) && (!v || aligned16(v)) && (!ema || aligned16(ema)),
+                  "adam_ema: buffers must be 16-byte aligned");
+    OTGAN_REQUIRE(d1 != 0.f && d2 != 0.f, "adam_ema: zero bias-correction denominator");
+    return adam_ema_launch(n, p, g, v, mg, ema, lr, mom1, mom2, d1, d2, ema_decay, (cudaStream_t)stream);
+}
+
+int otgan_crelu_l2norm_fwd_f32(int B, int HW, int C, const float* x, float* y, float* inv_norm, void* stream)
+{
+    OTGAN_REQUIRE(B >= 1 && HW >= 1 && C >= 1 && x && y && inv_norm, "crelu_l2norm_fwd: bad arguments");
+    return crelu_l2norm_fwd_launch(B, HW, C, x, y, inv_norm, (cudaStream_t)stream);
+}
+
+int otgan_crelu_l2norm_bwd_f32(int B, int HW, int C, const float* x, const float* y, const float* inv_norm,
+                               const float* dy, float* dx, void* stream)
+{
+    OTGAN_REQUIRE(B >= 1 && HW >= 1 && C >= 1 && x && y && inv_norm && dy && dx, "crelu_l2norm_bwd: bad arguments");
+    return crelu_l2norm_bwd_launch(B, HW, C, x, y, inv_norm, dy, dx, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,133 @@
+// optim_head.cu -- (1) fused Adam + EMA update over a flat parameter buffer (utils/nn.py:50-73 + train.py:63-64):
+//                      one streaming pass instead of ~10 TensorFlow ops per variable; HBM-bound (36 B per parameter).
+//                  (2) critic head: CReLU -> flatten -> L2-normalise (models/dcgan.py:16-19, models/densenet.py:37-42),
+//                      forward and backward, one CTA per image (seven TensorFlow ops fused).
+#include "common.cuh"
+
+namespace otgan {
+
+namespace {
+
+// p, g, v, mg, ema: [n] fp32, n % 4 == 0, 16-byte aligned.  d1 = 1 - mom1^t, d2 = 1 - mom2^t.
+__global__ void __launch_bounds__(256)
+adam_ema_kernel(size_t n4, float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ v,
+                float4* __restrict__ mg, float4* __restrict__ ema, float lr, float mom1, float mom2, float d1, float d2,
+                float ema_decay)
+{
+    auto upd = [&](float& pp, float gg, float& vv, float& mm, float& ee, bool has_v, bool has_e) {
+        float v_hat;
+        if (has_v) {
+            vv = __fadd_rn(__fmul_rn(mom1, vv), __fmul_rn(1.f - mom1, gg));               // v_t           :62
+            v_hat = __fdiv_rn(vv, d1);                                                       // v_hat         :63
+        } else {
+            v_hat = gg;                                                                      //               :66
+        }
+        mm = __fadd_rn(__fmul_rn(mom2, mm), __fmul_rn(1.f - mom2, __fmul_rn(gg, gg)));      // mg_t          :67
+        const float mg_hat = __fdiv_rn(mm, d2);                                              // mg_hat        :68
+        const float g_t = __fdiv_rn(v_hat, __fsqrt_rn(__fadd_rn(mg_hat, 1e-8f)));            // eps inside    :69
+        pp = __fsub_rn(pp, __fmul_rn(lr, g_t));                                              // p_t           :70
+        if (has_e) ee = __fsub_rn(ee, __fmul_rn(1.f - ema_decay, __fsub_rn(ee, pp)));        // TF EMA: shadow -= (1-d)(shadow - var)
+    };
+    const bool has_v = v != nullptr, has_e = ema != nullptr;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 P = p[i], M = mg[i];
+        const float4 G = g[i];
+        float4 V = has_v ? v[i] : make_float4(0, 0, 0, 0), E = has_e ? ema[i] : make_float4(0, 0, 0, 0);
+        upd(P.x, G.x, V.x, M.x, E.x, has_v, has_e);
+        upd(P.y, G.y, V.y, M.y, E.y, has_v, has_e);
+        upd(P.z, G.z, V.z, M.z, E.z, has_v, has_e);
+        upd(P.w, G.w, V.w, M.w, E.w, has_v, has_e);
+        p[i] = P; mg[i] = M;
+        if (has_v) v[i] = V;
+        if (has_e) ema[i] = E;
+    }
+}
+
+__device__ __forceinline__ float block_sum(float s, float* red)
+{
+    s = warp_sum(s);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];     // fixed order
+    __syncthreads();
+    return t;
+}
+
+// x: [B, HW, C] (NHWC) -> y: [B, HW * 2C] = normalise(concat(relu(x), relu(-x)) over channels), inv[b] = 1/||z_b||
+__global__ void __launch_bounds__(256)
+crelu_l2norm_fwd_kernel(int HW, int C, const float* __restrict__ x, float* __restrict__ y, float* __restrict__ inv)
+{
+    __shared__ float red[8];
+    const int b = blockIdx.x, n = HW * C;
+    const float* xb = x + (size_t)b * n;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(xb[i], xb[i], s);      // relu(x)^2 + relu(-x)^2 = x^2
+    const float tot = block_sum(s, red);
+    const float r = 1.0f / sqrtf(tot);                                                // no epsilon (models/dcgan.py:19)
+    if (threadIdx.x == 0) inv[b] = r;
+    float* yb = y + (size_t)b * 2 * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int hw = i / C, c = i - hw * C;
+        const float v = xb[i];
+        yb[(size_t)hw * 2 * C + c] = fmaxf(v, 0.f) * r;
+        yb[(size_t)hw * 2 * C + C + c] = fmaxf(-v, 0.f) * r;
+    }
+}
+
+// dz = (dy - y <y, dy>) * inv ; dx = dz[pos] * [x > 0] - dz[neg] * [x < 0]
+__global__ void __launch_bounds__(256)
+crelu_l2norm_bwd_kernel(int HW, int C, const float* __restrict__ x, const float* __restrict__ y,
+                        const float* __restrict__ inv, const float* __restrict__ dy, float* __restrict__ dx)
+{
+    __shared__ float red[8];
+    const int b = blockIdx.x, n = HW * C;
+    const float* yb = y + (size_t)b * 2 * n;
+    const float* dyb = dy + (size_t)b * 2 * n;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) s = fmaf(yb[i], dyb[i], s);
+    const float dot = block_sum(s, red);
+    const float r = inv[b];
+    const float* xb = x + (size_t)b * n;
+    float* dxb = dx + (size_t)b * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int hw = i / C, c = i - hw * C;
+        const size_t ip = (size_t)hw * 2 * C + c, in_ = ip + C;
+        const float v = xb[i];
+        const float dzp = (dyb[ip] - yb[ip] * dot) * r, dzn = (dyb[in_] - yb[in_] * dot) * r;
+        dxb[i] = (v > 0.f ? dzp : 0.f) - (v < 0.f ? dzn : 0.f);
+    }
+}
+
+}  // namespace
+
+int adam_ema_launch(size_t n, float* p, const float* g, float* v, float* mg, float* ema, float lr, float mom1, float mom2,
+                    float d1, float d2, float ema_decay, cudaStream_t stream)
+{
+    const size_t n4 = n / 4;
+    size_t blocks = (n4 + 255) / 256;
+    if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
+    adam_ema_kernel<<<(unsigned)blocks, 256, 0, stream>>>(n4, reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g),
+                                                          reinterpret_cast<float4*>(v), reinterpret_cast<float4*>(mg),
+                                                          reinterpret_cast<float4*>(ema), lr, mom1, mom2, d1, d2, ema_decay);
+    OTGAN_CHECK_LAUNCH("adam_ema_kernel");
+    return OTGAN_OK;
+}
+
+int crelu_l2norm_fwd_launch(int B, int HW, int C, const float* x, float* y, float* inv, cudaStream_t stream)
+{
+    crelu_l2norm_fwd_kernel<<<B, 256, 0, stream>>>(HW, C, x, y, inv);
+    OTGAN_CHECK_LAUNCH("crelu_l2norm_fwd_kernel");
+    return OTGAN_OK;
+}
+
+int crelu_l2norm_bwd_launch(int B, int HW, int C, const float* x, const float* y, const float* inv, const float* dy,
+                            float* dx, cudaStream_t stream)
+{
+    crelu_l2norm_bwd_kernel<<<B, 256, 0, stream>>>(HW, C, x, y, inv, dy, dx);
+    OTGAN_CHECK_LAUNCH("crelu_l2norm_bwd_kernel");
+    return OTGAN_OK;
+}
+
+}  // namespace otgan

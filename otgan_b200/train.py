@@ -1,0 +1,264 @@
+"""Re-hosted training loop of the reference's train.py (flags, step schedule, hand-built grad_ys, summed tower
+gradients, Adam with the critic ascending, generator EMA, logging) on the B200 path.
+
+    python -m otgan_b200.train --synthetic --nr_gpu 2 --batch_size 128 --nr_sinkhorn_iter 100 --max_steps 20
+    torchrun --nproc-per-node 8 -m otgan_b200.train --synthetic --nr_gpu 8 --batch_size 64 ...
+
+Reference correspondence (train.py line numbers):
+    flags :14-33 (same names and defaults; additions: --synthetic, --max_steps, --log_every)
+    init pass :52-54, parameter split :61-62, EMA :63-64
+    towers :72-85  -> one process per GPU (torch.distributed, NCCL); each rank hosts nr_gpu / world_size towers
+    matching :88-97, distances :101-105, grad_ys :108-130 -> matching.matching_step (fused) or the list API
+    tower-gradient SUM :134-139 -> all_reduce(SUM) of the flat gradient buffer
+    adam_updates with +lr (generator) / -lr (critic) :142-143, EMA on generator steps :223
+    schedule: critic step when step_counter % (nr_gen_per_disc + 1) == 0 :214-226
+The embedding exchange is ONE all-gather of the [2 * bs_local, D] feature slab per step (the reference's tf.concat,
+utils/matching.py:16-19); cost + Sinkhorn are then replicated on every rank (cheap) and each rank back-propagates its
+own rows of grad_ys.  Inception score / PNG tiles are out of scope.
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .data import cifar10_data
+from .utils import matching, nn
+
+
+def build_parser():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--seed', type=int, default=1)
+    parser.add_argument('--batch_size', type=int, default=625)
+    parser.add_argument('--learning_rate_disc', type=float, default=0.0003)
+    parser.add_argument('--learning_rate_gen', type=float, default=0.0003)
+    parser.add_argument('--data_dir', type=str, default='/home/tim/data')
+    parser.add_argument('--save_dir', type=str, default='/local_home/tim/med_gan')
+    parser.add_argument('--optimizer', type=str, default='adam')
+    parser.add_argument('--nonlinearity', type=str, default='crelu')
+    parser.add_argument('--nr_gpu', type=int, default=8, help='How many towers (per-GPU batches) to distribute the training across?')
+    parser.add_argument('--nr_gen_per_disc', type=int, default=5, help='How many times to update the generator for each update of the discriminator?')
+    parser.add_argument('--sinkhorn_lambda', type=float, default=500.)
+    parser.add_argument('--nr_sinkhorn_iter', type=int, default=500)
+    parser.add_argument('--single_batch', dest='single_batch', action='store_true', help='Use simplified batching using a single batch instead of 2')
+    parser.add_argument('--train_disc_against_ema', dest='train_disc_against_ema', action='store_true', help='Should discriminator be trained against samples of EMA generator?')
+    parser.add_argument('--model', type=str, default='dcgan')
+    parser.add_argument('--load_params', dest='load_params', action='store_true')
+    parser.add_argument('--model_name', type=str, default='med_gan_params-2399')
+    parser.add_argument('--no_sinkhorn', dest='no_sinkhorn', action='store_true')
+    # additions (not in the reference)
+    parser.add_argument('--synthetic', action='store_true', help='CIFAR-10-shaped uniform noise instead of the dataset')
+    parser.add_argument('--max_steps', type=int, default=0, help='stop after this many steps (0 = run like the reference)')
+    parser.add_argument('--log_every', type=int, default=0, help='also print a line every N steps')
+    return parser
+
+
+class Trainer:
+    """One data-parallel rank of the OT-GAN step.  `step(x_real_local)` is one sess.run of train.py:214-226."""
+
+    def __init__(self, args, device, rank=0, world=1):
+        assert args.nr_gpu % 2 == 0                                            # train.py:34
+        assert args.nr_gpu % world == 0, "nr_gpu (towers) must be a multiple of the number of ranks"
+        self.args, self.device, self.rank, self.world = args, device, rank, world
+        self.towers_local = args.nr_gpu // world
+        self.bs_local = self.towers_local * args.batch_size
+        if args.model == 'dcgan':
+            from .models.dcgan import generator, discriminator
+        elif args.model == 'densenet':
+            from .models.densenet import generator, discriminator
+        else:
+            raise ValueError(args.model)
+        generator.reset(); discriminator.reset()
+        self.generator, self.discriminator = generator, discriminator
+        self.model_opts = {'batch_size': self.bs_local, 'nonlinearity': args.nonlinearity}      # train.py:45
+        torch.manual_seed(args.seed)                                                            # :48-49
+        # run once for (data dependent) initialization of parameters                              :52-54
+        x_init = torch.zeros((args.batch_size, 32, 32, 3), device=device)
+        with torch.no_grad():
+            f = discriminator(x_init + 0.1, init=True, device=device, **self.model_opts)
+            generator(init=True, device=device, **dict(self.model_opts, batch_size=args.batch_size))
+        self.num_features = f.shape[-1]
+        if world > 1:                                                                            # identical replicas
+            dist.broadcast(discriminator.flat.data, 0)
+            dist.broadcast(generator.flat.data, 0)
+        torch.manual_seed(args.seed + 1000 * rank + 1)          # towers draw independent latents (tf.random_uniform per tower)
+        self.ema = nn.ExponentialMovingAverage(decay=0.999).attach(generator)                   # :63-64
+        opt = {'adam': nn.adam_updates, 'adamax': nn.adamax_updates, 'nesterov': nn.nesterov_updates}.get(args.optimizer)
+        if opt is None:
+            raise ValueError('unsupported optimizer')                                            # :151
+        if args.optimizer == 'adam':
+            self.gen_optimizer = opt(generator, lr=args.learning_rate_gen, mom1=0.5, mom2=0.999, ema=self.ema)
+            self.disc_optimizer = opt(discriminator, lr=-args.learning_rate_disc, mom1=0.5, mom2=0.999)
+        elif args.optimizer == 'adamax':
+            self.gen_optimizer = opt(generator, lr=args.learning_rate_gen, mom1=0.5, mom2=0.999)
+            self.disc_optimizer = opt(discriminator, lr=-args.learning_rate_disc, mom1=0.5, mom2=0.999)
+        else:
+            self.gen_optimizer = opt(generator, lr=args.learning_rate_gen, mom1=0.5)
+            self.disc_optimizer = opt(discriminator, lr=-args.learning_rate_disc, mom1=0.5)
+        self.step_counter = 0
+        self.gather_buf = None
+
+    def _gather_features(self, f_gen, f_dat):
+        return gather_features(f_gen, f_dat, self.world)
+
+    def _match(self, A, B):
+        """A (fake) / B (real): [N, D] features of ALL towers -> (Ga, Gb, [dist, entropy])."""
+        a = self.args
+        G = a.nr_gpu
+        fa, fb = list(torch.chunk(A, G, 0)), list(torch.chunk(B, G, 0))
+        if a.single_batch or a.no_sinkhorn:
+            if a.single_batch:
+                m = matching.get_matched_features_single_batch(fa, fb, a.sinkhorn_lambda, a.nr_sinkhorn_iter)
+            else:
+                m = matching.get_matched_features_random(fa, fb)
+            d = matching.calc_distance(fa, fb, m)
+            Ga = torch.cat([x - y for x, y in zip(m[0], m[2])], 0)                               # train.py:111
+            Gb = torch.cat([x - y for x, y in zip(m[1], m[3])], 0)                               # train.py:126
+            return Ga, Gb, torch.stack([d, m[4].to(d.dtype)])
+        ga, gb, stats = matching.matching_step(fa, fb, a.sinkhorn_lambda, a.nr_sinkhorn_iter)
+        return torch.cat(ga, 0), torch.cat(gb, 0), stats
+
+    def step(self, x_real):
+        """x_real: this rank's [bs_local, 32, 32, 3] real images in [-1, 1].  Returns ('disc'|'gen', stats[2] tensor)."""
+        a = self.args
+        train_disc = self.step_counter % (a.nr_gen_per_disc + 1) == 0                            # :214
+        gen, disc = self.generator, self.discriminator
+        bs = self.bs_local
+        if train_disc:
+            with torch.no_grad():
+                x_gen = gen(ema=self.ema, **self.model_opts) if a.train_disc_against_ema else gen(**self.model_opts)
+            feats = disc(torch.cat([x_gen, x_real], 0), **self.model_opts)                       # fake rows, then real rows
+            f_gen, f_dat = feats[:bs], feats[bs:]
+        else:
+            x_gen = gen(**self.model_opts)
+            with torch.no_grad():
+                f_dat = disc(x_real, **self.model_opts)
+            f_gen = disc(x_gen, **self.model_opts)
+        A, B = self._gather_features(f_gen, f_dat)
+        Ga, Gb, stats = self._match(A.detach(), B.detach())
+        lo, hi = local_rows(self.rank, bs)
+        ga, gb = Ga[lo:hi], Gb[lo:hi]                                                            # this rank's towers
+        if train_disc:
+            (grad,) = torch.autograd.grad([feats], [disc.flat], grad_outputs=[torch.cat([ga, gb], 0)])   # :122-128
+            if self.world > 1:
+                dist.all_reduce(grad, op=dist.ReduceOp.SUM)                                      # :134-139 (sum, not mean)
+            self.disc_optimizer.run(grad, lr=-a.learning_rate_disc)                              # :143,215
+            kind = 'disc'
+        else:
+            (grad,) = torch.autograd.grad([f_gen], [gen.flat], grad_outputs=[ga])                # :111-112
+            if self.world > 1:
+                dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+            self.gen_optimizer.run(grad, lr=a.learning_rate_gen)                                 # :142,222 (+ EMA :223)
+            kind = 'gen'
+        self.step_counter += 1
+        return kind, stats
+
+    def save(self, path):
+        torch.save({'discriminator': {n: p.detach().cpu() for n, p in self.discriminator.named_parameters()},
+                    'generator': {n: p.detach().cpu() for n, p in self.generator.named_parameters()}}, path)
+
+    def load(self, path):
+        ck = torch.load(path, map_location='cpu')
+        with torch.no_grad():
+            for tpl in (self.discriminator, self.generator):
+                for n, p in tpl.named_parameters():
+                    p.copy_(ck[tpl.name][n])
+
+
+def gather_features(f_gen, f_dat, world):
+    """The one collective of the matching path: all-gather of every rank's [2, bs_local, D] feature slab (the
+    reference's tf.concat over towers, utils/matching.py:16-19).  Returns (A, B) = fake / real features of ALL towers,
+    [world * bs_local, D] each, rank-major (rank r hosts towers r*towers_local .. (r+1)*towers_local - 1)."""
+    if world == 1:
+        return f_gen, f_dat
+    local = torch.stack([f_gen.detach(), f_dat.detach()], 0).contiguous()
+    bs, D = local.shape[1], local.shape[2]
+    buf = torch.empty((world * 2, bs, D), device=local.device, dtype=local.dtype)      # concatenated along dim 0
+    dist.all_gather_into_tensor(buf, local)
+    buf = buf.view(world, 2, bs, D)
+    return buf[:, 0].reshape(-1, D), buf[:, 1].reshape(-1, D)
+
+
+def local_rows(rank, bs_local):
+    """Row range of this rank's towers inside the gathered [N, D] feature / grad_ys matrices."""
+    return rank * bs_local, (rank + 1) * bs_local
+
+
+def maybe_flip(x, rng):
+    """train.py:163-170: per-image horizontal flip with probability 0.5 (vectorised)."""
+    flip = rng.rand(x.shape[0]) < 0.5
+    out = x.copy()
+    out[flip] = x[flip][:, :, ::-1, :]
+    return out
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('otgan_b200.train needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    if rank == 0:
+        print(args)
+    trainer = Trainer(args, device, rank, world)
+    if rank == 0:
+        print('model has a hidden representation with %d features' % trainer.num_features)        # train.py:56
+    rng = np.random.RandomState(args.seed + rank)
+    if args.synthetic:
+        trainx = cifar10_data.synthetic(max(args.nr_gpu * args.batch_size * 4, 2048), seed=args.seed)
+    else:
+        trainx, _ = cifar10_data.load(args.data_dir + '/cifar-10-python')
+        trainx = np.transpose(trainx, (0, 2, 3, 1)) / 127.5 - 1.                                  # :158
+        trainx = trainx.astype(np.float32)
+    nr_batches_train_per_gpu = trainx.shape[0] // (args.nr_gpu * args.batch_size)                # :159
+    if args.load_params:
+        trainer.load(os.path.join(args.save_dir, args.model_name))
+    os.makedirs(args.save_dir, exist_ok=True) if rank == 0 and not args.synthetic else None
+    if rank == 0:
+        print('starting training')
+    start_time = time.time()
+    for epoch in range(1000000):
+        begin = time.time()
+        inds = np.random.RandomState(args.seed + epoch).permutation(trainx.shape[0])             # :200 (same on every rank)
+        trainx = trainx[inds]
+        dist_gen, dist_disc, entropy = [], [], []
+        for t in range(nr_batches_train_per_gpu):
+            xs = []
+            for i in range(trainer.towers_local):                                               # :209-211
+                tower = rank * trainer.towers_local + i
+                td = t + tower * nr_batches_train_per_gpu
+                xs.append(maybe_flip(trainx[td * args.batch_size:(td + 1) * args.batch_size], rng))
+            x = torch.from_numpy(np.concatenate(xs, 0)).to(device, non_blocking=True)
+            kind, stats = trainer.step(x)
+            s = stats.tolist()                                                                   # the sess.run fetch
+            (dist_disc if kind == 'disc' else dist_gen).append(s[0])
+            entropy.append(s[1])
+            if rank == 0 and args.log_every and trainer.step_counter % args.log_every == 0:
+                print('step %d (%s): distance %.6f entropy %.6f' % (trainer.step_counter, kind, s[0], s[1]))
+            if args.max_steps and trainer.step_counter >= args.max_steps:
+                break
+        if rank == 0:                                                                            # :231
+            print("Iteration %d, time = %ds, train distance before gen = %.6f, train distance before disc = %.6f, avg matching entropy = %.6f"
+                  % (epoch, time.time() - begin, np.mean(dist_gen) if dist_gen else float('nan'),
+                     np.mean(dist_disc) if dist_disc else float('nan'), np.mean(entropy)))
+            sys.stdout.flush()
+        if (epoch + 1) % 200 == 0 and rank == 0 and not args.synthetic:                          # :275-277
+            trainer.save(os.path.join(args.save_dir, 'med_gan_params-%d' % epoch))
+        if args.max_steps and trainer.step_counter >= args.max_steps:
+            break
+    if rank == 0:
+        print('total updates %d, elapsed %.3f s' % (trainer.step_counter, time.time() - start_time))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,470 @@
+"""Host mirror of the reference's ``utils/nn.py`` (layer library + optimisers) re-hosted on PyTorch for the B200 path.
+
+Same public names and argument meaning as /root/reference/utils/nn.py:
+    conv2d(x, num_filters, pre_activation='celu', filter_size=[3,3], stride=[1,1], pad='SAME', dilate=1, upsample=False,
+           init_scale=1., counters={}, init=False, ema=None, weight_norm=True, use_b=True, use_g=True)      utils/nn.py:328-338
+    dense(x, num_units, pre_activation='celu', init_scale=1., counters={}, init=False, ema=None, ...)      utils/nn.py:315-325
+    get_params / apply_pre_activation / get_name                                                           utils/nn.py:95-206
+    adam_updates / adamax_updates / nesterov_updates                                                       utils/nn.py:29-87
+plus the two TensorFlow mechanisms the reference leans on, restated:
+    make_template(name, spec)  -- tf.make_template: variables are created on the first call and shared afterwards
+    arg_scope([...], **kw)     -- tf.contrib.framework.arg_scope: default keyword arguments for the listed layer functions
+    ExponentialMovingAverage   -- tf.train.ExponentialMovingAverage (train.py:63-64)
+
+Tensors are NHWC at this API exactly like the reference (`[B, H, W, C]`); kernels are stored HWIO (utils/nn.py:123) under
+the TensorFlow variable names (`discriminator/conv2d_0/V`, `.../g`, `.../b`) so reference checkpoints map one-to-one.
+TensorFlow semantics that differ from PyTorch defaults are restated explicitly: `SAME` padding (asymmetric for stride 2),
+`tf.nn.l2_normalize` (x * rsqrt(max(sum x^2, 1e-12))), nearest-neighbour resize (src = dst // 2), CReLU over a LIST of
+inputs interleaved per element ([x0, -x0, x1, -x1, ...], utils/nn.py:198-200).
+
+Convolutions / matmuls currently run on cuDNN / cuBLAS through torch (library rung); the
+optimiser update (adam_updates + EMA) runs in this library's fused CUDA kernel (otgan_adam_ema_f32).
+"""
+import contextlib
+import math
+import threading
+
+import torch
+import torch.nn.functional as F
+
+from .. import _lib
+
+DATA_DEPENDENT_INIT = False   # the reference builds the init assigns but never runs them: default off
+
+_tls = threading.local()
+
+
+# ------------------------------------------------------------------------------------------------ arg_scope
+def _scope_stack():
+    if not hasattr(_tls, "arg_scopes"):
+        _tls.arg_scopes = []
+    return _tls.arg_scopes
+
+
+@contextlib.contextmanager
+def arg_scope(funcs, **kwargs):
+    """tf.contrib.framework.arg_scope restated: default kwargs for the listed layer functions."""
+    _scope_stack().append(({f.__name__ for f in funcs}, kwargs))
+    try:
+        yield
+    finally:
+        _scope_stack().pop()
+
+
+def add_arg_scope(fn):
+    def wrapped(*args, **kwargs):
+        merged = {}
+        for names, kw in _scope_stack():
+            if fn.__name__ in names:
+                merged.update(kw)
+        merged.update(kwargs)
+        return fn(*args, **merged)
+    wrapped.__name__ = fn.__name__
+    wrapped.__doc__ = fn.__doc__
+    return wrapped
+
+
+# ------------------------------------------------------------------------------------------------ variables / templates
+class VariableStore:
+    """All variables of one template, packed into ONE flat fp32 leaf so that gradients come out contiguous and the
+    optimiser is a single fused kernel launch over the flat buffers (utils/nn.py:50-73 does ~10 ops per tensor)."""
+
+    def __init__(self, name, device):
+        self.name, self.device = name, device
+        self.specs = []            # (var_name, shape, offset, numel) in creation order == tf.trainable_variables() order
+        self.index = {}
+        self.pending = {}          # values created during the init pass, before packing
+        self.flat = None           # torch leaf [total], requires_grad
+        self.frozen = False
+
+    def create(self, var_name, shape, init_fn):
+        if var_name in self.index:
+            return
+        if self.frozen:
+            raise RuntimeError("variable %s requested after the template was built" % var_name)
+        numel = int(math.prod(shape))
+        offset = sum(s[3] for s in self.specs)
+        self.specs.append((var_name, tuple(shape), offset, numel))
+        self.index[var_name] = len(self.specs) - 1
+        self.pending[var_name] = init_fn(shape).to(self.device, torch.float32)
+
+    def pack(self):
+        total = sum(s[3] for s in self.specs)
+        pad = (-total) % 4                      # keep the flat buffers float4-sized for the fused optimiser kernel
+        flat = torch.zeros(total + pad, device=self.device, dtype=torch.float32)
+        for name, shape, off, n in self.specs:
+            flat[off:off + n] = self.pending[name].reshape(-1)
+        self.flat = flat.requires_grad_(True)
+        self.pending = {}
+        self.frozen = True
+
+    def get(self, var_name, source=None):
+        """View of one variable; `source` substitutes another flat buffer (the EMA shadow, utils/nn.py:89-93)."""
+        if not self.frozen:
+            return self.pending[var_name]
+        _, shape, off, n = self.specs[self.index[var_name]]
+        buf = self.flat if source is None else source
+        return buf[off:off + n].view(shape)
+
+    def named_parameters(self):
+        return [(n, self.get(n)) for n, _, _, _ in self.specs]
+
+    def num_params(self):
+        return sum(s[3] for s in self.specs)
+
+
+class Template:
+    """tf.make_template(name, spec): first call creates the variables (init pass, train.py:52-54), later calls share them."""
+
+    def __init__(self, name, spec):
+        self.name, self.spec, self.store = name, spec, None
+
+    def __call__(self, *args, **kwargs):
+        device = kwargs.pop("device", None)
+        if self.store is None:
+            if device is None:
+                device = next((a.device for a in args if isinstance(a, torch.Tensor)), None) or torch.device("cuda")
+            self.store = VariableStore(self.name, torch.device(device))
+        prev = getattr(_tls, "store", None)
+        _tls.store = self.store
+        try:
+            out = self.spec(*args, **kwargs)
+        finally:
+            _tls.store = prev
+        if not self.store.frozen:
+            self.store.pack()
+        return out
+
+    # convenience accessors used by the train loop / optimisers / checkpointing
+    @property
+    def flat(self):
+        return self.store.flat
+
+    def named_parameters(self):
+        return self.store.named_parameters()
+
+    def reset(self):
+        self.store = None
+
+
+def make_template(name, spec):
+    return Template(name, spec)
+
+
+class ExponentialMovingAverage:
+    """tf.train.ExponentialMovingAverage(decay) over one template's flat variable buffer (train.py:63-64).
+    `apply` is folded into adam_updates' fused kernel when the optimiser is given `ema=`; `average(store)` is what
+    get_var_maybe_avg (utils/nn.py:89-93) reads."""
+
+    def __init__(self, decay):
+        self.decay = float(decay)
+        self.shadow = None
+
+    def attach(self, template):
+        self.shadow = template.flat.detach().clone()      # TF initialises the shadow to the variable's value
+        return self
+
+    def apply(self, template):
+        if self.shadow is None:
+            self.attach(template)
+        else:
+            self.shadow.mul_(self.decay).add_(template.flat.detach(), alpha=1.0 - self.decay)
+
+
+# ------------------------------------------------------------------------------------------------ helpers (utils/nn.py)
+def int_shape(x):
+    return list(x.shape)
+
+
+def get_name(layer_name, counters):
+    """utils/nn.py:95-100"""
+    if layer_name not in counters:
+        counters[layer_name] = 0
+    name = layer_name + "_" + str(counters[layer_name])
+    counters[layer_name] += 1
+    return name
+
+
+def l2_normalize(v, axes, eps=1e-12):
+    """tf.nn.l2_normalize(v, axes): v * rsqrt(max(sum(v^2, axes), eps))"""
+    sq = torch.sum(v * v, dim=axes, keepdim=True)
+    return v * torch.rsqrt(torch.clamp(sq, min=eps))
+
+
+def _as_list(x):
+    if isinstance(x, tuple):
+        return list(x)
+    if not isinstance(x, list):
+        return [x]
+    return x
+
+
+def apply_pre_activation(x, pre_activation, axis=3):
+    """utils/nn.py:190-206.  For crelu/celu on a list: [x0, -x0, x1, -x1, ...] (interleaved per list element)."""
+    x = _as_list(x)
+    if pre_activation is None:
+        return torch.cat(x, axis) if len(x) > 1 else x[0]
+    if pre_activation == "celu":
+        return F.elu(torch.cat([xs for xi in x for xs in (xi, -xi)], axis))
+    if pre_activation == "crelu":
+        return F.relu(torch.cat([xs for xi in x for xs in (xi, -xi)], axis))
+    if pre_activation == "elu":
+        return F.elu(torch.cat(x, axis))
+    if pre_activation == "relu":
+        return F.relu(torch.cat(x, axis))
+    raise ValueError("unsupported pre-activation")
+
+
+def same_padding(n, k, s):
+    """TensorFlow 'SAME': out = ceil(n/s); total = max((out-1)*s + k - n, 0); before = total // 2, after = the rest."""
+    out = -(-n // s)
+    total = max((out - 1) * s + k - n, 0)
+    return total // 2, total - total // 2
+
+
+def resize_nearest_neighbor(x, size):
+    """tf.image.resize_nearest_neighbor(x, [H, W]) (align_corners=False): src = floor(dst * in / out).  NHWC."""
+    B, H, W, C = x.shape
+    oh, ow = int(size[0]), int(size[1])
+    if oh == H and ow == W:
+        return x
+    if oh % H == 0 and ow % W == 0:
+        return x.repeat_interleave(oh // H, dim=1).repeat_interleave(ow // W, dim=2)
+    ih = torch.div(torch.arange(oh, device=x.device) * H, oh, rounding_mode="floor")
+    iw = torch.div(torch.arange(ow, device=x.device) * W, ow, rounding_mode="floor")
+    return x[:, ih][:, :, iw]
+
+
+def _conv2d_nhwc(x, W, stride, pad):
+    """tf.nn.conv2d(x, W, [1,s,s,1], pad) with NHWC input and HWIO kernel (utils/nn.py:241)."""
+    kh, kw = W.shape[0], W.shape[1]
+    xn = x.permute(0, 3, 1, 2)                                 # NCHW view of channels-last memory: no copy
+    if pad == "SAME":
+        pt, pb = same_padding(x.shape[1], kh, stride[0])
+        pl, pr = same_padding(x.shape[2], kw, stride[1])
+        if pt == pb and pl == pr:
+            y = F.conv2d(xn, W.permute(3, 2, 0, 1), stride=tuple(stride), padding=(pt, pl))
+        else:
+            y = F.conv2d(F.pad(xn, (pl, pr, pt, pb)), W.permute(3, 2, 0, 1), stride=tuple(stride))
+    elif pad == "VALID":
+        y = F.conv2d(xn, W.permute(3, 2, 0, 1), stride=tuple(stride))
+    else:
+        raise ValueError(pad)
+    return y.permute(0, 2, 3, 1)
+
+
+class _CreluL2Norm(torch.autograd.Function):
+    """Critic head on this library's CUDA kernels (otgan_crelu_l2norm_{fwd,bwd}_f32)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        lib = _lib.load()
+        B, H, W, C = x.shape
+        y = torch.empty((B, H * W * 2 * C), device=x.device, dtype=torch.float32)
+        inv = torch.empty((B,), device=x.device, dtype=torch.float32)
+        rc = lib.otgan_crelu_l2norm_fwd_f32(B, H * W, C, x.data_ptr(), y.data_ptr(), inv.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "otgan_crelu_l2norm_fwd_f32")
+        ctx.save_for_backward(x, y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, y, inv = ctx.saved_tensors
+        B, H, W, C = x.shape
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        rc = lib.otgan_crelu_l2norm_bwd_f32(B, H * W, C, x.data_ptr(), y.data_ptr(), inv.data_ptr(), dy.data_ptr(),
+                                            dx.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "otgan_crelu_l2norm_bwd_f32")
+        return dx
+
+
+def crelu_l2norm(x):
+    """The critic head of models/dcgan.py:16-19 / models/densenet.py:37-42:
+        x = concat([relu(x), relu(-x)], 3); x = reshape(x, [B, -1]); x /= sqrt(reduce_sum(square(x), 1, keep_dims))
+    One fused CUDA kernel (forward and backward) on the GPU; the literal op sequence for host-side (CPU tensor) tests."""
+    if x.is_cuda and x.dtype == torch.float32:
+        return _CreluL2Norm.apply(x.contiguous())
+    x = torch.cat([torch.relu(x), torch.relu(-x)], 3)
+    x = x.reshape(x.shape[0], -1)
+    return x / torch.sqrt(torch.sum(torch.square(x), dim=1, keepdim=True))
+
+
+# ------------------------------------------------------------------------------------------------ get_params
+def get_params(layer_name, x=None, init=False, ema=None, use_W=True, use_g=True, use_b=True, f=None, weight_norm=True,
+               init_scale=1.0, filter_size=None, num_units=None, pre_activation=None):
+    """utils/nn.py:103-183: variables V, g, b of one layer (created on the init pass), W = g * V / ||V||."""
+    store = _tls.store
+    scope = store.name + "/" + layer_name
+    ema_src = ema.shadow if ema is not None else None
+    params = {}
+    if init:
+        xl = _as_list(x)
+        nr_in = sum(int(xi.shape[-1]) for xi in xl)
+        if num_units is None:
+            num_units = nr_in
+        if use_W:
+            if pre_activation in ("celu", "crelu"):
+                nr_in *= 2
+            vshape = list(filter_size) + [nr_in, num_units] if filter_size is not None else [nr_in, num_units]
+            store.create(scope + "/V", vshape, lambda s: torch.randn(s) * 0.05)                      # :123-127
+        if use_g:
+            store.create(scope + "/g", [num_units], lambda s: torch.ones(s))                          # :143
+        if use_b:
+            store.create(scope + "/b", [num_units], lambda s: torch.zeros(s))                         # :160
+        if DATA_DEPENDENT_INIT and use_W:
+            V = store.get(scope + "/V")
+            Wn = l2_normalize(V, list(range(V.dim() - 1))) if weight_norm else V
+            x_init = f(x, Wn)
+            red = list(range(x_init.dim() - 1))
+            m_init, v_init = x_init.mean(red), x_init.var(red, unbiased=False)                        # tf.nn.moments :138
+            init_g = init_scale / torch.sqrt(v_init)
+            if use_g:
+                store.get(scope + "/g").copy_(init_g)
+            if use_b:
+                store.get(scope + "/b").copy_(-m_init * init_g)
+    if use_b:
+        params["b"] = store.get(scope + "/b", ema_src)
+    g = store.get(scope + "/g", ema_src) if use_g else None
+    if use_W:
+        V = store.get(scope + "/V", ema_src)
+        W = l2_normalize(V, list(range(V.dim() - 1))) if weight_norm else V                           # :176
+        if use_g:
+            W = W * g.view([1] * (V.dim() - 1) + [V.shape[-1]])                                       # :180
+        params["W"] = W
+    elif use_g:
+        params["g"] = g
+    return params
+
+
+# ------------------------------------------------------------------------------------------------ layers
+def _dense(x, W, pre_activation=None):
+    return apply_pre_activation(x, pre_activation, 1) @ W                                             # :208-209
+
+
+def _conv2d(x, W, stride=(1, 1), pad="SAME", dilate=1, pre_activation=None, upsample=False):
+    """utils/nn.py:234-275 (__list_conv2d): optional NN-upsample of the concatenated list, pre-activation, conv."""
+    xl = _as_list(x)
+    if dilate != 1:
+        raise NotImplementedError("dilated conv is dead code in the reference (SURVEY 2.1 #16)")
+    if upsample:
+        xc = torch.cat(xl, 3) if len(xl) > 1 else xl[0]
+        xl = [resize_nearest_neighbor(xc, [2 * xc.shape[1], 2 * xc.shape[2]])]
+    return _conv2d_nhwc(apply_pre_activation(xl, pre_activation, 3), W, list(stride), pad)
+
+
+@add_arg_scope
+def dense(x, num_units, pre_activation="celu", init_scale=1.0, counters={}, init=False, ema=None, weight_norm=True,
+          use_b=True, use_g=True, **kwargs):
+    """utils/nn.py:315-325"""
+    layer_name = get_name("dense", counters)
+    f = lambda x, W: _dense(x, W, pre_activation)
+    params = get_params(layer_name, x, init, ema, use_W=True, use_g=use_g, use_b=use_b, f=f, weight_norm=weight_norm,
+                        init_scale=init_scale, num_units=num_units, pre_activation=pre_activation)
+    x = f(x, params["W"])
+    if use_b:
+        x = x + params["b"]
+    return x
+
+
+@add_arg_scope
+def conv2d(x, num_filters, pre_activation="celu", filter_size=[3, 3], stride=[1, 1], pad="SAME", dilate=1,
+           upsample=False, init_scale=1.0, counters={}, init=False, ema=None, weight_norm=True, use_b=True, use_g=True,
+           **kwargs):
+    """utils/nn.py:328-338"""
+    layer_name = get_name("conv2d", counters)
+    f = lambda x, W: _conv2d(x, W, stride, pad, dilate, pre_activation, upsample)
+    params = get_params(layer_name, x, init, ema, use_W=True, use_g=use_g, use_b=use_b, f=f, weight_norm=weight_norm,
+                        init_scale=init_scale, filter_size=list(filter_size), num_units=num_filters,
+                        pre_activation=pre_activation)
+    x = f(x, params["W"])
+    if use_b:
+        x = x + params["b"]
+    return x
+
+
+# ------------------------------------------------------------------------------------------------ optimisers
+class _Updates:
+    """What tf.group(*updates) is to sess.run: call .run(grads, lr) to apply one update."""
+
+    def __init__(self, fn):
+        self.run = fn
+
+
+def _flat_of(params):
+    """params: a Template (preferred) or a flat leaf tensor."""
+    return params.flat if isinstance(params, Template) else params
+
+
+def adam_updates(params, cost_or_grads=None, lr=0.001, mom1=0.9, mom2=0.999, ema=None):
+    """utils/nn.py:50-73 on the flat variable buffer, as ONE fused CUDA kernel (otgan_adam_ema_f32):
+        v = mom1 v + (1-mom1) g ; v_hat = v / (1 - mom1^t) ; mg = mom2 mg + (1-mom2) g^2 ; mg_hat = mg / (1 - mom2^t)
+        p = p - lr * v_hat / sqrt(mg_hat + 1e-8)        (epsilon INSIDE the root, t starts at 1)
+    and, when `ema` is given, shadow = decay*shadow + (1-decay)*p in the same pass (train.py:64,223).
+    Returns an object whose .run(grads_flat, lr=None) applies one step (lr may be negative: the critic ascends, train.py:143)."""
+    flat = _flat_of(params)
+    state = {"t": 1, "mg": torch.zeros_like(flat), "v": torch.zeros_like(flat) if mom1 > 0 else None}
+    default_lr = lr
+
+    def run(grads, lr=None):
+        lib = _lib.load()
+        step_lr = default_lr if lr is None else lr
+        g = grads if grads is not None else flat.grad
+        if ema is not None and ema.shadow is None:
+            ema.attach(params)
+        t = state["t"]
+        c1 = (1.0 - mom1 ** t) if mom1 > 0 else 1.0        # bias-correction denominators (utils/nn.py:63,68)
+        c2 = 1.0 - mom2 ** t
+        with torch.no_grad():
+            rc = lib.otgan_adam_ema_f32(flat.numel(), flat.data_ptr(), g.data_ptr(),
+                                        state["v"].data_ptr() if state["v"] is not None else None,
+                                        state["mg"].data_ptr(), ema.shadow.data_ptr() if ema is not None else None,
+                                        float(step_lr), float(mom1), float(mom2), float(c1), float(c2),
+                                        float(ema.decay) if ema is not None else 0.0,
+                                        torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "otgan_adam_ema_f32")
+        state["t"] = t + 1
+
+    u = _Updates(run)
+    u.state = state
+    return u
+
+
+def adamax_updates(params, cost_or_grads=None, lr=0.001, mom1=0.9, mom2=0.999):
+    """utils/nn.py:29-48 (torch ops; not on the benchmarked path)."""
+    flat = _flat_of(params)
+    state = {"mg": torch.zeros_like(flat), "v": torch.zeros_like(flat) if mom1 > 0 else None}
+    default_lr = lr
+
+    def run(grads, lr=None):
+        step_lr = default_lr if lr is None else lr
+        g = grads if grads is not None else flat.grad
+        with torch.no_grad():
+            if mom1 > 0:
+                state["v"].mul_(mom1).add_(g, alpha=1.0 - mom1)
+                v_t = state["v"]
+            else:
+                v_t = g
+            state["mg"] = torch.maximum(mom2 * state["mg"] + 1e-8, g.abs())
+            flat.sub_(step_lr * v_t / state["mg"])
+
+    return _Updates(run)
+
+
+def nesterov_updates(params, cost_or_grads=None, lr=0.01, mom1=0.9):
+    """utils/nn.py:75-87 (torch ops; not on the benchmarked path)."""
+    flat = _flat_of(params)
+    state = {"v": torch.zeros_like(flat)}
+    default_lr = lr
+
+    def run(grads, lr=None):
+        step_lr = default_lr if lr is None else lr
+        g = grads if grads is not None else flat.grad
+        with torch.no_grad():
+            v_new = mom1 * state["v"] - step_lr * g
+            flat.add_(-mom1 * state["v"] + (1.0 + mom1) * v_new)
+            state["v"] = v_new
+
+    return _Updates(run)

@@ -1,0 +1,83 @@
+"""GPU tests (-m gpu) of the optimiser / critic-head kernels and a short run of the re-hosted train loop."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nn_oracle as no
+
+pytestmark = pytest.mark.gpu
+
+
+def test_adam_ema_kernel_vs_oracle():
+    from otgan_b200.utils import nn
+    rng = np.random.RandomState(0)
+    n = 4096 + 8
+    p0 = rng.randn(n).astype(np.float32)
+    flat = torch.from_numpy(p0.copy()).cuda().requires_grad_(True)
+    ema = nn.ExponentialMovingAverage(0.999)
+    ema.shadow = flat.detach().clone()
+    opt = nn.adam_updates(flat, lr=3e-4, mom1=0.5, mom2=0.999, ema=ema)
+    p, v, mg, sh = p0.astype(np.float64), np.zeros(n), np.zeros(n), p0.astype(np.float64)
+    for t in range(1, 6):
+        g = rng.randn(n).astype(np.float32)
+        opt.run(torch.from_numpy(g).cuda(), lr=-3e-4 if t % 2 else 3e-4)
+        p, v, mg = no.adam_step(p, g.astype(np.float64), v, mg, t, -3e-4 if t % 2 else 3e-4, 0.5, 0.999)
+        sh = sh - (1 - 0.999) * (sh - p)
+    np.testing.assert_allclose(flat.detach().cpu().numpy(), p, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(ema.shadow.cpu().numpy(), sh, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(opt.state["mg"].cpu().numpy(), mg, rtol=1e-4, atol=1e-9)    # fp32 state vs fp64 oracle
+
+
+def test_crelu_l2norm_kernel_fwd_bwd():
+    from otgan_b200.utils import nn
+    torch.manual_seed(0)
+    x = torch.randn(5, 4, 4, 96, device="cuda", requires_grad=True)
+    y = nn.crelu_l2norm(x)
+    gy = torch.randn_like(y)
+    (gx,) = torch.autograd.grad([y], [x], [gy])
+    xd = x.detach().double().requires_grad_(True)
+    z = torch.cat([torch.relu(xd), torch.relu(-xd)], 3).reshape(5, -1)
+    yr = z / torch.sqrt(torch.sum(z * z, 1, keepdim=True))
+    (gr,) = torch.autograd.grad([yr], [xd], [gy.double()])
+    assert float((y.double() - yr).abs().max()) < 1e-6 and float((gx.double() - gr).abs().max() / gr.abs().max()) < 1e-5
+    ref = no.head(x.detach().cpu().double().numpy())
+    np.testing.assert_allclose(y.detach().cpu().numpy(), ref, atol=1e-6)
+
+
+def test_dcgan_forward_on_gpu_matches_oracle():
+    from otgan_b200.models import dcgan
+    dcgan.discriminator.reset(); dcgan.generator.reset()
+    torch.manual_seed(0)
+    x = torch.rand(2, 32, 32, 3, device="cuda") * 2 - 1
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dcgan.discriminator(x, init=True)
+    f = dcgan.discriminator(x).detach().cpu().double().numpy()
+    table = {n: p.detach().cpu().double().numpy() for n, p in dcgan.discriminator.named_parameters()}
+    ref = no.dcgan_discriminator(x.cpu().double().numpy(), table)
+    assert np.abs(f - ref).max() / np.abs(ref).max() < 2e-5
+    dcgan.discriminator.reset(); dcgan.generator.reset()
+
+
+@pytest.mark.parametrize("extra", [[], ["--single_batch"], ["--train_disc_against_ema"]])
+def test_train_loop_smoke(extra):
+    """20 steps of the re-hosted loop on synthetic data: finite distance, entropy in (0, ln h], D/G alternation, EMA."""
+    from otgan_b200 import train as T
+    args = T.build_parser().parse_args(["--synthetic", "--nr_gpu", "2", "--batch_size", "32", "--nr_sinkhorn_iter", "50",
+                                        "--nr_gen_per_disc", "2"] + extra)
+    tr = T.Trainer(args, torch.device("cuda", 0))
+    assert tr.num_features == 32768
+    g0, d0 = tr.generator.flat.detach().clone(), tr.discriminator.flat.detach().clone()
+    kinds = []
+    for s in range(9):
+        x = torch.rand(64, 32, 32, 3, device="cuda") * 2 - 1
+        kind, stats = tr.step(x)
+        kinds.append(kind)
+        dist_v, ent = stats.tolist()
+        assert np.isfinite(dist_v) and np.isfinite(ent)
+        h = 64 if "--single_batch" in extra else 32
+        assert 0.0 <= ent <= np.log(h) + 1e-4
+    assert kinds == ["disc", "gen", "gen"] * 3
+    assert not torch.equal(tr.generator.flat.detach(), g0) and not torch.equal(tr.discriminator.flat.detach(), d0)
+    assert not torch.equal(tr.ema.shadow, g0[: tr.ema.shadow.numel()])
+    assert float((tr.ema.shadow - tr.generator.flat.detach()).abs().max()) > 0
