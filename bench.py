@@ -1,18 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- OT-GAN matching hot path on B200: images/sec + Sinkhorn-iters/sec (BASELINE.json metric).
+"""bench.py -- OT-GAN training hot path on B200: images/sec + Sinkhorn-iters/sec (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload headline|cfg2|cfg3|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train|matching]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-One "step" = one pass of the matching hot path over one batch of synthetic critic embeddings:
-cost blocks (utils/matching.py:21-43) -> T Sinkhorn iterations (:46-61) -> feature gradients + distance + entropy
-(:63-83, :139-153, train.py:111,125-126), i.e. everything `train.py` does between the critic forward and backward.
-N real + N fake images are consumed per step, so images/sec = N / step time.
+Workload (same at every N): DCGAN on synthetic CIFAR-10-shaped batches, N = 256 real + 256 generated images
+per step, T = 100 Sinkhorn iterations, lambda = 500, the reference's 1 critic : 5 generator step schedule.  One "step" =
+one `sess.run` of train.py:214-226: generator forward, critic forward on real+fake, the matching hot path (six cosine-cost
+blocks -> Sinkhorn -> feature gradients + distance/entropy), backward, summed tower gradients, Adam (+EMA).
+images/sec = N / step time.  At N GPUs the 256 images are split over the ranks (strong scaling): one all-gather of the
+[2*256/N, D] embedding slab, replicated cost+Sinkhorn, each rank back-propagates its own rows, gradient all-reduce(sum).
 
-Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` goes through the public
-Python API (otgan_b200.utils.matching.matching_step) with pinned HOST buffers, H2D and D2H inside the timed region.
-`--impl reference` times the reference algorithm's CPU restatement (oracle/, C+OpenMP on all host cores; TensorFlow 1.x
-is not installable here) on the same workload; it is the one place besides `cpu_baseline` that executes oracle/.
+`value` feeds the step from device-resident images; `e2e` goes through the public API (otgan_b200.train.Trainer.step)
+with pinned HOST image buffers (H2D inside the timed region) and reads [distance, entropy] back every step.
+`matching` is the matching hot path alone (this library's kernels only) with per-kernel times; `roofline` is its
+dominant kernel against MEASURED_PEAKS.json.  `cpu_baseline` / `--impl reference`: the reference algorithm on the host
+cores -- oracle/ C+OpenMP matching and torch-CPU conv stacks (TensorFlow 1.x is not installable here), on a bounded sample.
 """
 import argparse
 import json
@@ -26,14 +29,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = {
-    # name: (N, D, T, lam)   h = N/2
-    "headline": (256, 32768, 100, 500.0),     # BASELINE.json metric: B=256, 100 iters (DCGAN critic width)
-    "cfg2": (128, 32768, 100, 500.0),
-    "cfg3": (256, 32768, 500, 500.0),
-    "cfg4": (256, 7296, 100, 500.0),          # DenseNet critic width
-}
-N_INPUT_SETS = 4      # rotate 4 x 64 MiB embedding sets (> 126 MB L2) so no step finds its inputs in L2
+N_TOTAL, T_ITERS, LAMBDA, D_FEAT = 256, 100, 500.0, 32768
+N_INPUT_SETS = 4      # matching sub-benchmark: rotate 4 x 64 MiB embedding sets (> 126 MB L2)
 
 
 def peaks():
@@ -92,8 +89,24 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def cpu_reference_time(N, D, T, lam, reps, warmup):
-    """The reference algorithm on the host cores (C+OpenMP restatement, all threads): returns (best seconds, phases, cores)."""
+def workload_config(world, workload):
+    cfg = {"workload": "OT-GAN DCGAN training step (generator + critic fwd/bwd, 6 cosine-cost blocks + %d Sinkhorn iters + "
+                       "feature gradients + distance/entropy, summed tower gradients, Adam+EMA), CIFAR-10-shaped synthetic "
+                       "images: N=%d real + %d generated per step, h=%d, D=%d, lambda=%g, schedule 1 critic : 5 generator"
+                       % (T_ITERS, N_TOTAL, N_TOTAL, N_TOTAL // 2, D_FEAT, LAMBDA),
+           "N": N_TOTAL, "h": N_TOTAL // 2, "D": D_FEAT, "T": T_ITERS, "lambda": LAMBDA, "ranks": world,
+           "images_per_rank": N_TOTAL // world, "towers": 2 * world if world > 1 else 2,
+           "conv_backend": "cuDNN/cuBLAS via torch (library rung; own implicit-GEMM kernels not yet written)",
+           "l2_policy": "per-step working set (activations + 72 M parameters + Adam state, > 1 GB) exceeds the 126 MB L2; the "
+                        "matching sub-benchmark rotates %d input sets (%.0f MiB)" % (N_INPUT_SETS, N_INPUT_SETS * 2 * N_TOTAL * D_FEAT * 4 / 2**20)}
+    if workload == "matching":
+        cfg["workload"] = "matching hot path only (see `matching`): N=%d, h=%d, D=%d, T=%d" % (N_TOTAL, N_TOTAL // 2, D_FEAT, T_ITERS)
+    return cfg
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm (oracle)
+def cpu_matching_time(N, D, T, lam, reps, warmup):
+    """Matching phase on the host cores (C+OpenMP restatement, all threads): (times, best phases, cores)."""
     from oracle import c_oracle as co
     A, B = synth(N, D, 1), synth(N, D, 2)
     cores = co.max_threads()
@@ -109,44 +122,178 @@ def cpu_reference_time(N, D, T, lam, reps, warmup):
     return times, phases, cores
 
 
+class CpuTrainer:
+    """The reference training step on the CPU: torch-CPU conv stacks (the same re-hosted layer library on CPU tensors),
+    oracle/ C matching (utils/matching.py restated), Adam as in utils/nn.py:50-73.  Bounded sample: n_total images."""
+
+    def __init__(self, n_total, T, lam):
+        import torch
+        from otgan_b200.models import dcgan
+        from otgan_b200.utils import nn as onn
+        self.torch, self.n, self.T, self.lam = torch, n_total, T, lam
+        torch.manual_seed(1)
+        dcgan.generator.reset(); dcgan.discriminator.reset()
+        self.gen, self.disc = dcgan.generator, dcgan.discriminator
+        with torch.no_grad():
+            self.disc(torch.zeros(2, 32, 32, 3) + 0.1, init=True, device="cpu")
+            self.gen(2, init=True, device="cpu")
+        self.state = {t.name: {"t": 1, "v": torch.zeros_like(t.flat), "mg": torch.zeros_like(t.flat)} for t in (self.gen, self.disc)}
+        self.step_counter = 0
+
+    def _adam(self, tpl, grad, lr, mom1=0.5, mom2=0.999):
+        torch, st = self.torch, self.state[tpl.name]
+        with torch.no_grad():
+            st["v"].mul_(mom1).add_(grad, alpha=1 - mom1)
+            st["mg"].mul_(mom2).addcmul_(grad, grad, value=1 - mom2)
+            v_hat = st["v"] / (1 - mom1 ** st["t"])
+            mg_hat = st["mg"] / (1 - mom2 ** st["t"])
+            tpl.flat.sub_(lr * v_hat / torch.sqrt(mg_hat + 1e-8))
+            st["t"] += 1
+
+    def step(self, x_real):
+        torch = self.torch
+        from oracle import c_oracle as co
+        n = self.n
+        train_disc = self.step_counter % 6 == 0
+        if train_disc:
+            with torch.no_grad():
+                x_gen = self.gen(n)
+            feats = self.disc(torch.cat([x_gen, x_real], 0))
+            f_gen, f_dat = feats[:n], feats[n:]
+        else:
+            x_gen = self.gen(n)
+            with torch.no_grad():
+                f_dat = self.disc(x_real)
+            f_gen = self.disc(x_gen)
+        r = co.two_batch(f_gen.detach().numpy(), f_dat.detach().numpy(), self.lam, self.T, want_plans=False)
+        ga = torch.from_numpy(r["f_aa"] - r["f_ab"])
+        gb = torch.from_numpy(r["f_bb"] - r["f_ba"])
+        if train_disc:
+            (g,) = torch.autograd.grad([feats], [self.disc.flat], grad_outputs=[torch.cat([ga, gb], 0)])
+            self._adam(self.disc, g, -3e-4)
+        else:
+            (g,) = torch.autograd.grad([f_gen], [self.gen.flat], grad_outputs=[ga])
+            self._adam(self.gen, g, 3e-4)
+        self.step_counter += 1
+        return r["dist"], r["entropy"]
+
+
+def cpu_train_time(n_sample, steps, warmup):
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    tr = CpuTrainer(n_sample, T_ITERS, LAMBDA)
+    x = torch.rand(n_sample, 32, 32, 3) * 2 - 1
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        tr.step(x)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times, torch.get_num_threads()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    N, D, T, lam = WORKLOADS[args.workload]
-    times, phases, cores = cpu_reference_time(N, D, T, lam, args.steps, args.warmup)
+    n_sample = 32                                   # bounded sample of the N=256 step (a CPU step at N=256 is ~10 TFLOP)
+    mt, ph, mcores = cpu_matching_time(N_TOTAL, D_FEAT, T_ITERS, LAMBDA, 3, 1)      # before torch spins up its own pool
+    times, cores = cpu_train_time(n_sample, args.steps, min(args.warmup, 1))
     mean = float(np.mean(times))
-    val = N / mean
+    val = n_sample / mean
     line = {
         "impl": "reference", "metric": "images/sec", "value": val, "unit": "images/sec", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, 1),
-        "sinkhorn_iters_per_sec": T / (phases[1] * 1e-3),
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": mean * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1, args.workload),
+        "sinkhorn_iters_per_sec": T_ITERS / (ph[1] * 1e-3),
         "cpu_baseline": {"value": val, "unit": "images/sec", "cores": cores, "kind": "port",
-                         "sample": "%d full matching steps (cost+Sinkhorn+matched+distance), C+OpenMP restatement of "
-                                   "utils/matching.py; TensorFlow 1.x not installable offline" % args.steps,
-                         "phase_ms": {"cost": phases[0], "sinkhorn": phases[1], "matched_distance": phases[2]}},
+                         "sample": "%d training steps of the same DCGAN step on a bounded batch of %d real + %d generated "
+                                   "images (a CPU step at N=256 is ~10 TFLOP); torch-CPU conv stacks + oracle/ C+OpenMP matching; "
+                                   "TensorFlow 1.x not installable offline" % (args.steps, n_sample, n_sample),
+                         "matching_phase_n256": {"ms": float(np.min(mt)) * 1e3, "images_per_sec": N_TOTAL / float(np.min(mt)),
+                                                 "cores": mcores,
+                                                 "phase_ms": {"cost": ph[0], "sinkhorn": ph[1], "matched_distance": ph[2]}}},
         "e2e": {"value": val, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def workload_config(name, world):
-    N, D, T, lam = WORKLOADS[name]
-    return {"workload": "OT-GAN matching hot path (6 cosine-cost blocks + %d Sinkhorn iters + feature gradients + "
-                        "distance/entropy), %s: N=%d real + %d fake embeddings per step, h=%d, D=%d, lambda=%g, T=%d"
-                        % (T, name, N, N, N // 2, D, lam, T),
-            "N": N, "h": N // 2, "D": D, "T": T, "lambda": lam, "towers": 2, "ranks": world,
-            "l2_policy": "inputs rotate over %d sets of 2x[N,D] fp32 (%.0f MiB total) > 126 MB L2" %
-                         (N_INPUT_SETS, N_INPUT_SETS * 2 * N * D * 4 / 2**20)}
+# ----------------------------------------------------------------------------------------------- our arm
+def matching_benchmark(torch, devv, steps, warmup):
+    """Matching hot path alone (device-resident rotating inputs): step time, per-kernel times, launches."""
+    from otgan_b200 import _lib
+    from otgan_b200.utils import matching as M
+    N, D, T, lam, h = N_TOTAL, D_FEAT, T_ITERS, LAMBDA, N_TOTAL // 2
+    dev_sets = [(torch.from_numpy(synth(N, D, 100 + 2 * s)).to(devv), torch.from_numpy(synth(N, D, 101 + 2 * s)).to(devv))
+                for s in range(N_INPUT_SETS)]
+    stream = torch.cuda.current_stream()
+
+    def step(A, B):
+        return M.matching_step(list(torch.chunk(A, 2, 0)), list(torch.chunk(B, 2, 0)), lam, T)
+
+    for i in range(max(warmup, 3)):
+        step(*dev_sets[i % N_INPUT_SETS])
+    torch.cuda.synchronize()
+    lib = _lib.load()
+    phases = {"cost": [], "sinkhorn": [], "grad": []}
+    for i in range(12):
+        A, B = dev_sets[i % N_INPUT_SETS]
+        a1, a2, b1, b2 = A[:h], A[h:], B[:h], B[h:]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record(stream)
+        L = M.cost_blocks([a1, b2, a1, a1, a2, a2], [a2, b1, b1, b2, b1, b2], lam)
+        ev[1].record(stream)
+        P, ent, pc = M.sinkhorn(L, lam, T)
+        ev[2].record(stream)
+        Ga, Gb = torch.empty_like(A), torch.empty_like(B)
+        ev[3].record(stream)
+        rc = lib.otgan_grad_features_f32(h, D, P.data_ptr(), A.data_ptr(), B.data_ptr(), D, Ga.data_ptr(), Gb.data_ptr(),
+                                         D, 0, stream.cuda_stream)
+        ev[4].record(stream)
+        torch.cuda.synchronize()
+        assert rc == 0
+        if i >= 2:
+            phases["cost"].append(ev[0].elapsed_time(ev[1]))
+            phases["sinkhorn"].append(ev[1].elapsed_time(ev[2]))
+            phases["grad"].append(ev[3].elapsed_time(ev[4]))
+    kernel_ms = {k: float(np.mean(v)) for k, v in phases.items()}
+    _lib.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for i in range(steps):
+        step(*dev_sets[i % N_INPUT_SETS])
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = _lib.launch_count()
+    pk = peaks()
+    alg_bytes = {"cost": 4.0 * 2 * N * D + 24.0 * h * h, "sinkhorn": 48.0 * h * h, "grad": 16.0 * N * D}
+    kernels = {}
+    for k in kernel_ms:
+        gbs = alg_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9
+        kernels[k] = {"ms": kernel_ms[k], "alg_bytes": alg_bytes[k], "achieved_gbs": gbs, "hbm_frac": gbs / pk["hbm_gbs"]}
+    kernels["cost"]["alg_flops"] = 12.0 * h * h * D
+    kernels["grad"]["alg_flops"] = 24.0 * h * h * D
+    kernels["sinkhorn"]["exp_per_sec_log_domain_equiv"] = 12.0 * h * h * T / (kernel_ms["sinkhorn"] * 1e-3)
+    kernels["sinkhorn"]["streaming_form_bytes"] = 96.0 * h * h * T
+    dom = max(kernel_ms, key=kernel_ms.get)
+    roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": kernels[dom]["achieved_gbs"] / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"]}
+    res = {"ms_per_step": ms, "images_per_sec": N / (ms * 1e-3), "sinkhorn_iters_per_sec": T / (kernel_ms["sinkhorn"] * 1e-3),
+           "kernels": kernels, "gpu_launches_per_step": launches / steps}
+    del dev_sets
+    torch.cuda.empty_cache()
+    return res, roof
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from otgan_b200 import _lib
-    from otgan_b200.utils import matching as M
+    from otgan_b200 import train as T
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -157,94 +304,72 @@ def run_ours(args):
     devv = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=devv)
-    N, D, T, lam = WORKLOADS[args.workload]
-    h = N // 2
     _lib.load()
-
-    # ---- inputs resident in HBM (rotating sets) and pinned host copies for the e2e leg
-    host_sets = []
-    for s in range(N_INPUT_SETS):
-        a = torch.from_numpy(synth(N, D, 100 + 2 * s + 1000 * rank)).pin_memory()
-        b = torch.from_numpy(synth(N, D, 101 + 2 * s + 1000 * rank)).pin_memory()
-        host_sets.append((a, b))
-    dev_sets = [(a.to(devv), b.to(devv)) for a, b in host_sets]
-    stream = torch.cuda.current_stream()
-
-    def step(A, B):
-        return M.matching_step(list(torch.chunk(A, 2, 0)), list(torch.chunk(B, 2, 0)), lam, T)
+    assert N_TOTAL % (2 * world) == 0
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        step(*dev_sets[i % N_INPUT_SETS])
+    match_res, roof = (None, None)
+    if rank == 0:
+        match_res, roof = matching_benchmark(torch, devv, 100, 5)
     barrier()
 
-    # ---- per-kernel breakdown (events around each ABI call), used for the roofline object
-    lib = _lib.load()
-    phases = {"cost": [], "sinkhorn": [], "grad": []}
-    for i in range(12):
-        A, B = dev_sets[i % N_INPUT_SETS]
-        a1, a2, b1, b2 = A[:h], A[h:], B[:h], B[h:]
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        ev[0].record(stream)
-        L = M.cost_blocks([a1, b2, a1, a1, a2, a2], [a2, b1, b1, b2, b1, b2], lam)
-        ev[1].record(stream)
-        P, ent, pc = M.sinkhorn(L, lam, T)
-        ev[2].record(stream)
-        Ga = torch.empty_like(A)
-        Gb = torch.empty_like(B)
-        ev[3] = torch.cuda.Event(enable_timing=True)
-        e_start = torch.cuda.Event(enable_timing=True)
-        e_start.record(stream)
-        rc = lib.otgan_grad_features_f32(h, D, P.data_ptr(), A.data_ptr(), B.data_ptr(), D, Ga.data_ptr(), Gb.data_ptr(),
-                                         D, 0, stream.cuda_stream)
-        ev[3].record(stream)
-        torch.cuda.synchronize()
-        assert rc == 0
-        if i >= 2:
-            phases["cost"].append(ev[0].elapsed_time(ev[1]))
-            phases["sinkhorn"].append(ev[1].elapsed_time(ev[2]))
-            phases["grad"].append(e_start.elapsed_time(ev[3]))
-    kernel_ms = {k: float(np.mean(v)) for k, v in phases.items()}
-
-    # ---- timed region 1: device-resident inputs (value)
-    sampler = ClockSampler(local)
-    sampler.start()
-    barrier()
-    _lib.reset_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(args.steps):
-        step(*dev_sets[i % N_INPUT_SETS])
-    e1.record(stream)
-    barrier()
-    launches = _lib.launch_count()
-    ms_total = e0.elapsed_time(e1)
-
-    # ---- timed region 2: end to end through the public API with pinned host buffers (H2D + D2H inside)
-    dA, dB = torch.empty((N, D), device=devv), torch.empty((N, D), device=devv)
-    stats_host = torch.empty(2).pin_memory()
-    for i in range(3):
-        dA.copy_(host_sets[i % N_INPUT_SETS][0], non_blocking=True)
-        dB.copy_(host_sets[i % N_INPUT_SETS][1], non_blocking=True)
-        stats_host.copy_(step(dA, dB)[2], non_blocking=True)
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
-    for i in range(args.steps):
-        ha, hb = host_sets[i % N_INPUT_SETS]
-        dA.copy_(ha, non_blocking=True)
-        dB.copy_(hb, non_blocking=True)
-        stats_host.copy_(step(dA, dB)[2], non_blocking=True)
-        stream.synchronize()          # the host reads the step's (distance, entropy) every step, like sess.run
-    e3.record(stream)
-    barrier()
-    ms_e2e = e2.elapsed_time(e3)
-    sampler.stop_flag = True
-    sampler.join()
+    # ---- the training step (all ranks): towers = 2 per rank, N_TOTAL images in total
+    towers = 2 * world
+    targs = T.build_parser().parse_args(["--synthetic", "--nr_gpu", str(towers), "--batch_size", str(N_TOTAL // towers),
+                                         "--nr_sinkhorn_iter", str(T_ITERS), "--sinkhorn_lambda", str(LAMBDA)])
+    tr = T.Trainer(targs, devv, rank, world)
+    bs = tr.bs_local
+    gen = torch.Generator().manual_seed(1 + rank)
+    host_imgs = [(torch.rand((bs, 32, 32, 3), generator=gen) * 2 - 1).pin_memory() for _ in range(8)]
+    dev_imgs = [h.to(devv) for h in host_imgs]
+    stream = torch.cuda.current_stream()
+    W = max(args.warmup, 3)
+    if args.workload == "train":
+        for i in range(W):
+            tr.step(dev_imgs[i % 8])
+        sampler = ClockSampler(local)
+        sampler.start()
+        barrier()
+        _lib.reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            tr.step(dev_imgs[i % 8])
+        e1.record(stream)
+        barrier()
+        launches = _lib.launch_count()
+        ms_total = e0.elapsed_time(e1)
+        # ---- end to end: pinned host images -> H2D -> step -> D2H of [distance, entropy], every step
+        stats_host = torch.empty(2).pin_memory()
+        x_dev = torch.empty((bs, 32, 32, 3), device=devv)
+        for i in range(2):
+            x_dev.copy_(host_imgs[i % 8], non_blocking=True)
+            stats_host.copy_(tr.step(x_dev)[1], non_blocking=True)
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record(stream)
+        for i in range(args.steps):
+            x_dev.copy_(host_imgs[i % 8], non_blocking=True)
+            stats_host.copy_(tr.step(x_dev)[1], non_blocking=True)
+            stream.synchronize()                       # the host reads (distance, entropy) every step, like sess.run
+        e3.record(stream)
+        barrier()
+        ms_e2e = e2.elapsed_time(e3)
+        sampler.stop_flag = True
+        sampler.join()
+        h2d, d2h = bs * 32 * 32 * 3 * 4 * world, 8
+    else:
+        sampler = ClockSampler(local)
+        sampler.start()
+        res2, _ = matching_benchmark(torch, devv, args.steps, W) if rank == 0 else (None, None)
+        sampler.stop_flag = True
+        sampler.join()
+        ms_total = (res2["ms_per_step"] * args.steps) if rank == 0 else 0.0
+        ms_e2e, launches, h2d, d2h = ms_total, int(match_res["gpu_launches_per_step"] * args.steps) if rank == 0 else 0, 0, 0
 
     t = torch.tensor([ms_total, ms_e2e], device=devv, dtype=torch.float64)
     if world > 1:
@@ -252,44 +377,30 @@ def run_ours(args):
     ms_total, ms_e2e = float(t[0]), float(t[1])
 
     if rank == 0:
-        pk = peaks()
         ms_step = ms_total / args.steps
-        images = N * world                       # every rank processes its own batch (independent matching problems)
-        value = images / (ms_step * 1e-3)
-        e2e_val = images / (ms_e2e / args.steps * 1e-3)
-        alg_bytes = {"cost": 4.0 * 2 * N * D + 24.0 * h * h, "sinkhorn": 48.0 * h * h, "grad": 16.0 * N * D}
-        dom = max(kernel_ms, key=kernel_ms.get)
-        kernels = {}
-        for k in kernel_ms:
-            gbs = alg_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9
-            kernels[k] = {"ms": kernel_ms[k], "alg_bytes": alg_bytes[k], "achieved_gbs": gbs, "hbm_frac": gbs / pk["hbm_gbs"]}
-        kernels["cost"]["alg_flops"] = 12.0 * h * h * D
-        kernels["grad"]["alg_flops"] = 24.0 * h * h * D
-        kernels["sinkhorn"]["exp_per_sec"] = 12.0 * h * h * T / (kernel_ms["sinkhorn"] * 1e-3)
-        kernels["sinkhorn"]["streaming_form_bytes"] = 96.0 * h * h * T
-        ach = kernels[dom]["achieved_gbs"]
+        value = N_TOTAL / (ms_step * 1e-3)
         line = {
             "metric": "images/sec", "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, world),
-            "sinkhorn_iters_per_sec": T / (kernel_ms["sinkhorn"] * 1e-3),
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"]},
-            "kernels": kernels,
-            "e2e": {"value": e2e_val, "unit": "images/sec", "h2d_bytes_per_step": 2 * N * D * 4, "d2h_bytes_per_step": 8,
-                    "ms_per_step": ms_e2e / args.steps},
+            "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world, args.workload),
+            "sinkhorn_iters_per_sec": match_res["sinkhorn_iters_per_sec"],
+            "roofline": roof, "matching": match_res,
+            "e2e": {"value": N_TOTAL / (ms_e2e / args.steps * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": sampler.result(),
         }
         if world == 1 and not args.no_cpu:
-            times, ph, cores = cpu_reference_time(N, D, T, lam, 5, 1)
-            best = float(np.min(times))
-            line["cpu_baseline"] = {"value": N / best, "unit": "images/sec", "cores": cores, "kind": "port",
-                                    "sample": "best of 5 full matching steps of the same workload (C+OpenMP restatement "
-                                              "of utils/matching.py, all host threads)",
-                                    "ms_per_step": best * 1e3,
-                                    "phase_ms": {"cost": ph[0], "sinkhorn": ph[1], "matched_distance": ph[2]},
-                                    "sinkhorn_iters_per_sec": T / (ph[1] * 1e-3)}
+            mt, ph, cores = cpu_matching_time(N_TOTAL, D_FEAT, T_ITERS, LAMBDA, 5, 1)
+            best = float(np.min(mt))
+            tt, tcores = cpu_train_time(32, 2, 1)
+            line["cpu_baseline"] = {"value": 32 / float(np.mean(tt)), "unit": "images/sec", "cores": tcores, "kind": "port",
+                                    "sample": "2 training steps on a bounded batch of 32 real + 32 generated images (torch-CPU "
+                                              "conv stacks + oracle/ C+OpenMP matching; TensorFlow 1.x not installable offline)",
+                                    "ms_per_step": float(np.mean(tt)) * 1e3,
+                                    "matching_phase_n256": {"ms": best * 1e3, "images_per_sec": N_TOTAL / best, "cores": cores,
+                                                            "phase_ms": {"cost": ph[0], "sinkhorn": ph[1], "matched_distance": ph[2]},
+                                                            "sinkhorn_iters_per_sec": T_ITERS / (ph[1] * 1e-3)}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -298,10 +409,10 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="train", choices=["train", "matching"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
