@@ -135,6 +135,16 @@ OTGAN_API int otgan_crelu_l2norm_fwd_f32(int B, int HW, int C, const float* x, f
 OTGAN_API int otgan_crelu_l2norm_bwd_f32(int B, int HW, int C, const float* x, const float* y, const float* inv_norm,
                                          const float* dy, float* dx, void* stream);
 
+/* Weight-norm reparameterisation (utils/nn.py:176-180: W = l2_normalize(V, all-but-last) * g), fused with the layout
+ * change the convolution needs.  V: [K, C] (HWIO kernel flattened, or the [in, out] dense matrix; C = output channels
+ * contiguous), g: [C].  Forward writes Wt: [C, K] (OHWI == channels-last OIHW) and inv_norm: [C].  Backward takes dWt [C, K]
+ * and writes dV [K, C], dg [C].  ws: otgan_workspace_bytes_weightnorm(K, C) bytes. */
+OTGAN_API size_t otgan_workspace_bytes_weightnorm(int K, int C);
+OTGAN_API int otgan_weightnorm_fwd_f32(int K, int C, const float* V, const float* g, float* Wt, float* inv_norm, void* ws,
+                                       size_t ws_bytes, void* stream);
+OTGAN_API int otgan_weightnorm_bwd_f32(int K, int C, const float* V, const float* g, const float* inv_norm,
+                                       const float* dWt, float* dV, float* dg, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

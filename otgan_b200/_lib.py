@@ -45,6 +45,9 @@ SIGNATURES = {
     "otgan_adam_ema_f32": (_i, [_sz, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _vp]),
     "otgan_crelu_l2norm_fwd_f32": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "otgan_crelu_l2norm_bwd_f32": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "otgan_workspace_bytes_weightnorm": (_sz, [_i, _i]),
+    "otgan_weightnorm_fwd_f32": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "otgan_weightnorm_bwd_f32": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

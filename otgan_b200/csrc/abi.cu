@@ -45,6 +45,11 @@ int crelu_l2norm_fwd_launch(int B, int HW, int C, const float* x, float* y, floa
 int crelu_l2norm_bwd_launch(int B, int HW, int C, const float* x, const float* y, const float* inv, const float* dy,
                             float* dx, cudaStream_t stream);
 
+size_t weightnorm_workspace_bytes(int K, int C);
+int weightnorm_fwd_launch(int K, int C, const float* V, const float* g, float* Wt, float* inv, void* ws, cudaStream_t stream);
+int weightnorm_bwd_launch(int K, int C, const float* V, const float* g, const float* inv, const float* dWt, float* dV,
+                          float* dg, void* ws, cudaStream_t stream);
+
 }  // namespace otgan
 
 using namespace otgan;
@@ -232,6 +237,24 @@ int otgan_crelu_l2norm_bwd_f32(int B, int HW, int C, const float* x, const float
 {
     OTGAN_REQUIRE(B >= 1 && HW >= 1 && C >= 1 && x && y && inv_norm && dy && dx, "crelu_l2norm_bwd: bad arguments");
     return crelu_l2norm_bwd_launch(B, HW, C, x, y, inv_norm, dy, dx, (cudaStream_t)stream);
+}
+
+size_t otgan_workspace_bytes_weightnorm(int K, int C) { return (K < 1 || C < 1) ? 0 : weightnorm_workspace_bytes(K, C); }
+
+int otgan_weightnorm_fwd_f32(int K, int C, const float* V, const float* g, float* Wt, float* inv_norm, void* ws,
+                             size_t ws_bytes, void* stream)
+{
+    OTGAN_REQUIRE(K >= 1 && C >= 1 && V && g && Wt && inv_norm && ws, "weightnorm_fwd: bad arguments");
+    OTGAN_REQUIRE(ws_bytes >= weightnorm_workspace_bytes(K, C), "weightnorm_fwd: workspace too small");
+    return weightnorm_fwd_launch(K, C, V, g, Wt, inv_norm, ws, (cudaStream_t)stream);
+}
+
+int otgan_weightnorm_bwd_f32(int K, int C, const float* V, const float* g, const float* inv_norm, const float* dWt,
+                             float* dV, float* dg, void* ws, size_t ws_bytes, void* stream)
+{
+    OTGAN_REQUIRE(K >= 1 && C >= 1 && V && g && inv_norm && dWt && dV && dg && ws, "weightnorm_bwd: bad arguments");
+    OTGAN_REQUIRE(ws_bytes >= weightnorm_workspace_bytes(K, C), "weightnorm_bwd: workspace too small");
+    return weightnorm_bwd_launch(K, C, V, g, inv_norm, dWt, dV, dg, ws, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -98,16 +98,30 @@ class VariableStore:
         self.pending = {}
         self.frozen = True
 
+    def begin_call(self):
+        """One autograd node for ALL variable views of a template call (split_with_sizes: its backward is a single
+        concatenation into the flat gradient; per-variable slices would each materialise a full-size zero gradient)."""
+        if self.frozen:
+            total = self.num_params()
+            self._views = torch.split_with_sizes(self.flat[:total], [s[3] for s in self.specs])
+            self._views_src = {}
+
     def get(self, var_name, source=None):
         """View of one variable; `source` substitutes another flat buffer (the EMA shadow, utils/nn.py:89-93)."""
         if not self.frozen:
             return self.pending[var_name]
-        _, shape, off, n = self.specs[self.index[var_name]]
-        buf = self.flat if source is None else source
-        return buf[off:off + n].view(shape)
+        i = self.index[var_name]
+        _, shape, off, n = self.specs[i]
+        if source is None:
+            if getattr(self, "_views", None) is None:          # outside a template call (inspection): plain slice
+                return self.flat[off:off + n].view(shape)
+            return self._views[i].view(shape)
+        return source[off:off + n].view(shape)
 
     def named_parameters(self):
-        return [(n, self.get(n)) for n, _, _, _ in self.specs]
+        if self.frozen:
+            return [(n, self.flat[off:off + k].view(shape)) for n, shape, off, k in self.specs]
+        return [(n, self.pending[n]) for n, _, _, _ in self.specs]
 
     def num_params(self):
         return sum(s[3] for s in self.specs)
@@ -127,10 +141,12 @@ class Template:
             self.store = VariableStore(self.name, torch.device(device))
         prev = getattr(_tls, "store", None)
         _tls.store = self.store
+        self.store.begin_call()
         try:
             out = self.spec(*args, **kwargs)
         finally:
             _tls.store = prev
+            self.store._views = None
         if not self.store.frozen:
             self.store.pack()
         return out
@@ -237,17 +253,22 @@ def resize_nearest_neighbor(x, size):
 
 def _conv2d_nhwc(x, W, stride, pad):
     """tf.nn.conv2d(x, W, [1,s,s,1], pad) with NHWC input and HWIO kernel (utils/nn.py:241)."""
-    kh, kw = W.shape[0], W.shape[1]
+    if isinstance(W, TransposedWeight):
+        kh, kw = W.vshape[0], W.vshape[1]
+        w_oihw = W.as_oihw()
+    else:
+        kh, kw = W.shape[0], W.shape[1]
+        w_oihw = W.permute(3, 2, 0, 1)
     xn = x.permute(0, 3, 1, 2)                                 # NCHW view of channels-last memory: no copy
     if pad == "SAME":
         pt, pb = same_padding(x.shape[1], kh, stride[0])
         pl, pr = same_padding(x.shape[2], kw, stride[1])
         if pt == pb and pl == pr:
-            y = F.conv2d(xn, W.permute(3, 2, 0, 1), stride=tuple(stride), padding=(pt, pl))
+            y = F.conv2d(xn, w_oihw, stride=tuple(stride), padding=(pt, pl))
         else:
-            y = F.conv2d(F.pad(xn, (pl, pr, pt, pb)), W.permute(3, 2, 0, 1), stride=tuple(stride))
+            y = F.conv2d(F.pad(xn, (pl, pr, pt, pb)), w_oihw, stride=tuple(stride))
     elif pad == "VALID":
-        y = F.conv2d(xn, W.permute(3, 2, 0, 1), stride=tuple(stride))
+        y = F.conv2d(xn, w_oihw, stride=tuple(stride))
     else:
         raise ValueError(pad)
     return y.permute(0, 2, 3, 1)
@@ -292,6 +313,58 @@ def crelu_l2norm(x):
     return x / torch.sqrt(torch.sum(torch.square(x), dim=1, keepdim=True))
 
 
+class TransposedWeight:
+    """W = g * V / ||V|| held output-channel-major ([C, K] == OHWI): what otgan_weightnorm_fwd_f32 writes and what the
+    convolution / F.linear consume without another layout copy."""
+
+    def __init__(self, wt, vshape):
+        self.wt, self.vshape = wt, tuple(vshape)
+
+    def as_oihw(self):
+        kh, kw, ci, co = self.vshape
+        return self.wt.view(co, kh, kw, ci).permute(0, 3, 1, 2)      # logical OIHW, channels-last memory: no copy
+
+
+_wn_ws = {}
+
+
+class _WeightNorm(torch.autograd.Function):
+    """utils/nn.py:176-180 on this library's fused CUDA kernels (otgan_weightnorm_{fwd,bwd}_f32)."""
+
+    @staticmethod
+    def forward(ctx, V, g):
+        lib = _lib.load()
+        C = V.shape[-1]
+        K = V.numel() // C
+        Vc, gc = V.contiguous(), g.contiguous()
+        wt = torch.empty((C, K), device=V.device, dtype=torch.float32)
+        inv = torch.empty((C,), device=V.device, dtype=torch.float32)
+        need = lib.otgan_workspace_bytes_weightnorm(K, C) // 4
+        ws = _wn_ws.get(V.device.index)
+        if ws is None or ws.numel() < need:
+            ws = _wn_ws[V.device.index] = torch.empty((max(need, 64 * 32768),), device=V.device, dtype=torch.float32)
+        rc = lib.otgan_weightnorm_fwd_f32(K, C, Vc.data_ptr(), gc.data_ptr(), wt.data_ptr(), inv.data_ptr(), ws.data_ptr(),
+                                          ws.numel() * 4, torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "otgan_weightnorm_fwd_f32")
+        ctx.save_for_backward(Vc, gc, inv)
+        ctx.vshape = V.shape
+        return wt
+
+    @staticmethod
+    def backward(ctx, dwt):
+        lib = _lib.load()
+        V, g, inv = ctx.saved_tensors
+        C = V.shape[-1]
+        K = V.numel() // C
+        dwt = dwt.contiguous()
+        dV, dg = torch.empty_like(V), torch.empty_like(g)
+        ws = _wn_ws[V.device.index]
+        rc = lib.otgan_weightnorm_bwd_f32(K, C, V.data_ptr(), g.data_ptr(), inv.data_ptr(), dwt.data_ptr(), dV.data_ptr(),
+                                          dg.data_ptr(), ws.data_ptr(), ws.numel() * 4, torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "otgan_weightnorm_bwd_f32")
+        return dV.view(ctx.vshape), dg
+
+
 # ------------------------------------------------------------------------------------------------ get_params
 def get_params(layer_name, x=None, init=False, ema=None, use_W=True, use_g=True, use_b=True, f=None, weight_norm=True,
                init_scale=1.0, filter_size=None, num_units=None, pre_activation=None):
@@ -330,10 +403,13 @@ def get_params(layer_name, x=None, init=False, ema=None, use_W=True, use_g=True,
     g = store.get(scope + "/g", ema_src) if use_g else None
     if use_W:
         V = store.get(scope + "/V", ema_src)
-        W = l2_normalize(V, list(range(V.dim() - 1))) if weight_norm else V                           # :176
-        if use_g:
-            W = W * g.view([1] * (V.dim() - 1) + [V.shape[-1]])                                       # :180
-        params["W"] = W
+        if weight_norm and use_g and V.is_cuda and store.frozen:
+            params["W"] = TransposedWeight(_WeightNorm.apply(V, g), V.shape)                          # :176-180 fused
+        else:
+            W = l2_normalize(V, list(range(V.dim() - 1))) if weight_norm else V                       # :176
+            if use_g:
+                W = W * g.view([1] * (V.dim() - 1) + [V.shape[-1]])                                   # :180
+            params["W"] = W
     elif use_g:
         params["g"] = g
     return params
@@ -341,7 +417,10 @@ def get_params(layer_name, x=None, init=False, ema=None, use_W=True, use_g=True,
 
 # ------------------------------------------------------------------------------------------------ layers
 def _dense(x, W, pre_activation=None):
-    return apply_pre_activation(x, pre_activation, 1) @ W                                             # :208-209
+    x = apply_pre_activation(x, pre_activation, 1)
+    if isinstance(W, TransposedWeight):
+        return F.linear(x, W.wt)
+    return x @ W                                                                                      # :208-209
 
 
 def _conv2d(x, W, stride=(1, 1), pad="SAME", dilate=1, pre_activation=None, upsample=False):

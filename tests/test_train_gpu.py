@@ -44,6 +44,27 @@ def test_crelu_l2norm_kernel_fwd_bwd():
     np.testing.assert_allclose(y.detach().cpu().numpy(), ref, atol=1e-6)
 
 
+@pytest.mark.parametrize("shape", [(5, 5, 6, 40), (3, 3, 64, 16), (100, 200), (5, 5, 256, 96), (1, 1, 7, 3)])
+def test_weightnorm_kernels_vs_torch(shape):
+    """otgan_weightnorm_{fwd,bwd}_f32 against the literal op sequence of utils/nn.py:176-180 (float64 torch ops)."""
+    from otgan_b200.utils import nn
+    torch.manual_seed(len(shape) * 7 + shape[-1])
+    V = (torch.randn(shape, device="cuda") * 0.05).requires_grad_(True)
+    g = (1.0 + 0.3 * torch.rand(shape[-1], device="cuda")).requires_grad_(True)
+    wt = nn._WeightNorm.apply(V, g)
+    C, K = shape[-1], V.numel() // shape[-1]
+    assert wt.shape == (C, K)
+    gw = torch.randn_like(wt)
+    gV, gg = torch.autograd.grad([wt], [V, g], [gw])
+    Vd, gd = V.detach().double().requires_grad_(True), g.detach().double().requires_grad_(True)
+    Wd = nn.l2_normalize(Vd, list(range(Vd.dim() - 1))) * gd
+    wt_ref = Wd.reshape(K, C).t()
+    rV, rg = torch.autograd.grad([wt_ref], [Vd, gd], [gw.double()])
+    assert float((wt.double() - wt_ref).abs().max() / wt_ref.abs().max()) < 2e-6
+    assert float((gV.double() - rV).abs().max() / rV.abs().max()) < 2e-5
+    assert float((gg.double() - rg).abs().max() / rg.abs().max()) < 2e-5
+
+
 def test_dcgan_forward_on_gpu_matches_oracle():
     from otgan_b200.models import dcgan
     dcgan.discriminator.reset(); dcgan.generator.reset()
