@@ -32,6 +32,9 @@ int sinkhorn_reg_launch(int nblk, int rows, int cols, int T, float lam, const fl
 int sinkhorn_reg_max_side();
 int sinkhorn_fast_launch(int nblk, int rows, int cols, int T, float lam, const float* L0, float* P, float* entropy,
                          float* pc, int* slow_steps, cudaStream_t stream);
+int sinkhorn_stream_max_side();
+int sinkhorn_stream_launch(int nblk, int rows, int cols, int T, float lam, const float* L0, float* P, float* entropy,
+                           float* pc, cudaStream_t stream);
 int distance_from_pc_launch(const float* pc, const float* entropy, int n_total, float* out, cudaStream_t stream);
 int plan_apply_simt_launch(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F, int ldf,
                            float* const* out, int ldo, cudaStream_t stream);
@@ -105,7 +108,12 @@ int otgan_sinkhorn_ex_f32(int nblk, int rows, int cols, int T, float lam, const 
             return sinkhorn_reg_launch(nblk, rows, cols, T, lam, L0, P, entropy, pc, (cudaStream_t)stream);
         return sinkhorn_fast_launch(nblk, rows, cols, T, lam, L0, P, entropy, pc, slow_steps, (cudaStream_t)stream);
     }
-    set_error("sinkhorn: block %dx%d larger than %d not supported yet", rows, cols, sinkhorn_reg_max_side());
+    if (rows <= sinkhorn_stream_max_side() && cols <= sinkhorn_stream_max_side()) {
+        OTGAN_REQUIRE(P != nullptr, "sinkhorn: blocks larger than %d need the P buffer as working storage", sinkhorn_reg_max_side());
+        if (slow_steps) OTGAN_CUDA(cudaMemsetAsync(slow_steps, 0, sizeof(int) * nblk, (cudaStream_t)stream));
+        return sinkhorn_stream_launch(nblk, rows, cols, T, lam, L0, P, entropy, pc, (cudaStream_t)stream);
+    }
+    set_error("sinkhorn: block %dx%d larger than %d not supported", rows, cols, sinkhorn_stream_max_side());
     return OTGAN_EUNSUPPORTED;
 }
 

@@ -165,6 +165,49 @@ def test_sinkhorn_fast_path_is_taken(M):
     assert (slow >= 1).all() and (slow <= 40).all(), slow           # 200 half-steps in total
 
 
+@pytest.mark.parametrize("nblk,rows,cols,lam,T", [(3, 256, 256, 500.0, 100), (2, 200, 150, 500.0, 20), (1, 1024, 1024, 500.0, 10),
+                                                  (2, 129, 300, 100.0, 5), (1, 256, 256, 500.0, 0)])
+def test_sinkhorn_large_blocks(M, nblk, rows, cols, lam, T):
+    """Blocks larger than one SM (single-batch N = 256, 64x64-image configs): streaming log-domain kernels."""
+    D = 128
+    C = np.stack([mo.cosine_cost(mo.synth_embeddings(rows, D, 70 + k, "clustered", sigma=1.0).astype(np.float64),
+                                 mo.synth_embeddings(cols, D, 80 + k, "clustered", sigma=1.0).astype(np.float64))
+                  for k in range(nblk)])
+    L0 = dev((-lam * C).astype(np.float32))
+    P, ent, pc = M.sinkhorn(L0, lam, T)
+    torch.cuda.synchronize()
+    C32 = L0.cpu().double().numpy() / -lam
+    for k in range(nblk):
+        p, e, _ = mo.sinkhorn(C32[k], lam, T, np.float64)
+        assert relerr(P[k], p) < TOL_P
+        assert abs(float(ent[k]) - e) <= TOL_ENT * max(abs(e), 1e-3)
+        assert abs(float(pc[k]) - np.sum(p * C32[k])) < 2e-5 * rows
+
+
+def test_single_batch_at_headline_size(M):
+    """utils/matching.py:88-136 at N = 256: three 256 x 256 blocks with +999 on the aa/bb diagonals."""
+    N, D, G = 256, 2048, 4
+    A, B = mo.synth_embeddings(N, D, 1, "clustered", sigma=1.0), mo.synth_embeddings(N, D, 2, "clustered", sigma=1.0)
+    ref = mo.get_matched_features_single_batch(list(np.split(A, G)), list(np.split(B, G)), 500.0, 50)
+    got = M.get_matched_features_single_batch(towers(A, G), towers(B, G), 500.0, 50)
+    for i in range(4):
+        assert relerr(torch.cat(got[i]), np.concatenate(ref[i])) < TOL_F
+    assert abs(float(got[4]) - ref[4]) <= TOL_ENT * abs(ref[4])
+
+
+def test_two_batch_h256(M):
+    """BASELINE config 5 block size (h = 256) through the public API."""
+    N, D, G = 512, 4096, 8
+    A, B = mo.synth_embeddings(N, D, 1, "clustered", sigma=1.0), mo.synth_embeddings(N, D, 2, "clustered", sigma=1.0)
+    fa, fb = list(np.split(A, G)), list(np.split(B, G))
+    ref = mo.get_matched_features(fa, fb, 500.0, 100)
+    ta, tb = towers(A, G), towers(B, G)
+    got = M.get_matched_features(ta, tb, 500.0, 100)
+    for i in range(4):
+        assert relerr(torch.cat(got[i]), np.concatenate(ref[i])) < TOL_F
+    assert abs(float(M.calc_distance(ta, tb, got)) - mo.calc_distance(fa, fb, ref)) < TOL_DIST
+
+
 def test_sinkhorn_rows_sum_to_one_at_full_size(M):
     rng = np.random.RandomState(0)
     L0 = dev((-500.0 * rng.rand(6, 128, 128)).astype(np.float32))
@@ -330,8 +373,6 @@ def test_errors_surface_as_exceptions(M):
     with pytest.raises(TypeError):
         M.get_matched_features([torch.zeros(2, 4, device="cuda", dtype=torch.float64)] * 2,
                                [torch.zeros(2, 4, device="cuda", dtype=torch.float64)] * 2, 1.0, 1)
-    big = torch.zeros(1, 300, 300, device="cuda")
-    try:
+    big = torch.zeros(1, 1100, 1100, device="cuda")
+    with pytest.raises(_lib.OtganError, match="not supported"):
         M.sinkhorn(big, 1.0, 1)
-    except _lib.OtganError as e:
-        assert "not supported" in str(e)
