@@ -94,21 +94,26 @@ typedef struct {
     float coef[OTGAN_MAX_OUTPUTS][OTGAN_MAX_TERMS];
 } otgan_plan_t;
 
+/* ws: otgan_workspace_bytes_plan() bytes (pre-split plan planes of the tensor-core path); may be NULL, which selects
+ * the SIMT kernel. */
+OTGAN_API size_t otgan_workspace_bytes_plan(void);
 OTGAN_API int otgan_plan_apply_f32(const otgan_plan_t* plan_host, int h, int D,
                          const float* P /* [nblk, h, h] */, const float* const* F_host /* sources */, int ldf,
-                         float* const* out_host /* outputs */, int ldo, int impl, void* stream);
+                         float* const* out_host /* outputs */, int ldo, void* ws, size_t ws_bytes, int impl, void* stream);
 
 /* Two-batch matched features in the reference's output form: A = [A1;A2], B = [B1;B2] ([2h, D], row stride ld),
  * P = the six plans in the order [a1a2, b2b1, a1b1, a1b2, a2b1, a2b2]; f_* are [2h, D] (row stride ldo).
  * utils/matching.py:63-83. */
 OTGAN_API int otgan_matched_two_batch_f32(int h, int D, const float* P, const float* A, const float* B, int ld,
-                                float* f_aa, float* f_bb, float* f_ab, float* f_ba, int ldo, int impl, void* stream);
+                                float* f_aa, float* f_bb, float* f_ab, float* f_ba, int ldo, void* ws, size_t ws_bytes,
+                                int impl, void* stream);
 /* Fused form: Ga = f_aa - f_ab, Gb = f_bb - f_ba written directly (train.py:111,125-126). */
 OTGAN_API int otgan_grad_features_f32(int h, int D, const float* P, const float* A, const float* B, int ld,
-                            float* Ga, float* Gb, int ldo, int impl, void* stream);
+                            float* Ga, float* Gb, int ldo, void* ws, size_t ws_bytes, int impl, void* stream);
 /* Single-batch matched features: P = [P_aa, P_bb, P_ab] ([n, n] each), A, B: [n, D].  utils/matching.py:131-134. */
 OTGAN_API int otgan_matched_single_batch_f32(int n, int D, const float* P, const float* A, const float* B, int ld,
-                                   float* f_aa, float* f_bb, float* f_ab, float* f_ba, int ldo, int impl, void* stream);
+                                   float* f_aa, float* f_bb, float* f_ab, float* f_ba, int ldo, void* ws,
+                                   size_t ws_bytes, int impl, void* stream);
 
 /* ---- distance ---------------------------------------------------------------------------------------------------
  * out[0] = ( sum(B*f_bb) + sum(A*f_aa) - 2 sum(A*f_ab) ) * scale      utils/matching.py:139-153 (scale = 1/(2 bs G)),

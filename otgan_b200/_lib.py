@@ -35,10 +35,11 @@ SIGNATURES = {
     "otgan_cost_blocks_f32": (_i, [_i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _f, _vp, _vp, _sz, _i, _vp]),
     "otgan_sinkhorn_f32": (_i, [_i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _i, _vp]),
     "otgan_sinkhorn_ex_f32": (_i, [_i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
-    "otgan_plan_apply_f32": (_i, [ctypes.POINTER(Plan), _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp]),
-    "otgan_matched_two_batch_f32": (_i, [_i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
-    "otgan_grad_features_f32": (_i, [_i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
-    "otgan_matched_single_batch_f32": (_i, [_i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "otgan_workspace_bytes_plan": (_sz, []),
+    "otgan_plan_apply_f32": (_i, [ctypes.POINTER(Plan), _i, _i, _vp, _vp, _i, _vp, _i, _vp, _sz, _i, _vp]),
+    "otgan_matched_two_batch_f32": (_i, [_i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _i, _vp]),
+    "otgan_grad_features_f32": (_i, [_i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _sz, _i, _vp]),
+    "otgan_matched_single_batch_f32": (_i, [_i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _i, _vp]),
     "otgan_workspace_bytes_distance": (_sz, [_i, _i]),
     "otgan_calc_distance_f32": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _sz, _vp]),
     "otgan_distance_from_pc_f32": (_i, [_vp, _vp, _i, _vp, _vp]),

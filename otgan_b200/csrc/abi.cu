@@ -38,6 +38,11 @@ int sinkhorn_stream_launch(int nblk, int rows, int cols, int T, float lam, const
 int distance_from_pc_launch(const float* pc, const float* entropy, int n_total, float* out, cudaStream_t stream);
 int plan_apply_simt_launch(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F, int ldf,
                            float* const* out, int ldo, cudaStream_t stream);
+bool plan_apply_tc_supported(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F, int ldf,
+                             float* const* out, int ldo);
+size_t plan_apply_tc_workspace_bytes(int n_out);
+int plan_apply_tc_launch(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F, int ldf,
+                         float* const* out, int ldo, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t distance_workspace_bytes(int n, int D);
 int distance_launch(int n, int D, const float* A, const float* B, const float* f_aa, const float* f_bb,
                     const float* f_ab, int ld, float scale, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
@@ -123,8 +128,10 @@ int otgan_sinkhorn_f32(int nblk, int rows, int cols, int T, float lam, const flo
     return otgan_sinkhorn_ex_f32(nblk, rows, cols, T, lam, L0, P, entropy, pc, nullptr, impl, stream);
 }
 
+size_t otgan_workspace_bytes_plan(void) { return plan_apply_tc_workspace_bytes(OTGAN_MAX_OUTPUTS); }
+
 int otgan_plan_apply_f32(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F_host, int ldf,
-                         float* const* out_host, int ldo, int impl, void* stream)
+                         float* const* out_host, int ldo, void* ws, size_t ws_bytes, int impl, void* stream)
 {
     OTGAN_REQUIRE(plan && P && F_host && out_host, "plan_apply: null pointer");
     OTGAN_REQUIRE(plan->n_out >= 1 && plan->n_out <= OTGAN_MAX_OUTPUTS, "plan_apply: n_out=%d", plan->n_out);
@@ -138,7 +145,15 @@ int otgan_plan_apply_f32(const otgan_plan_t* plan, int h, int D, const float* P,
                           "plan_apply: bad source");
         }
     }
-    OTGAN_REQUIRE(impl == OTGAN_IMPL_AUTO || impl == OTGAN_IMPL_SIMT, "plan_apply: impl %d not available", impl);
+    OTGAN_REQUIRE(impl == OTGAN_IMPL_AUTO || impl == OTGAN_IMPL_SIMT || impl == OTGAN_IMPL_TCGEN05, "plan_apply: unknown impl %d", impl);
+    const bool tc_ok = ws != nullptr && ws_bytes >= plan_apply_tc_workspace_bytes(plan->n_out) &&
+                       plan_apply_tc_supported(plan, h, D, P, F_host, ldf, out_host, ldo);
+    if (impl == OTGAN_IMPL_TCGEN05 && !tc_ok) {
+        set_error("plan_apply: tcgen05 path needs h <= 128, D >= 32, D/ld %% 4 == 0, 16-byte aligned pointers and a workspace");
+        return OTGAN_EUNSUPPORTED;
+    }
+    if (tc_ok && impl != OTGAN_IMPL_SIMT)
+        return plan_apply_tc_launch(plan, h, D, P, F_host, ldf, out_host, ldo, ws, ws_bytes, (cudaStream_t)stream);
     return plan_apply_simt_launch(plan, h, D, P, F_host, ldf, out_host, ldo, (cudaStream_t)stream);
 }
 
@@ -150,7 +165,7 @@ static void add_term(otgan_plan_t* p, int o, int blk, int trans, int src, float 
 
 // sources: 0 = A1, 1 = A2, 2 = B1, 3 = B2;  plans: 0 = a1a2, 1 = b2b1, 2 = a1b1, 3 = a1b2, 4 = a2b1, 5 = a2b2
 int otgan_matched_two_batch_f32(int h, int D, const float* P, const float* A, const float* B, int ld, float* f_aa,
-                                float* f_bb, float* f_ab, float* f_ba, int ldo, int impl, void* stream)
+                                float* f_bb, float* f_ab, float* f_ba, int ldo, void* ws, size_t ws_bytes, int impl, void* stream)
 {
     OTGAN_REQUIRE(P && A && B && f_aa && f_bb && f_ab && f_ba, "matched_two_batch: null pointer");
     OTGAN_REQUIRE(h >= 1 && D >= 1, "matched_two_batch: bad shape");
@@ -168,11 +183,11 @@ int otgan_matched_two_batch_f32(int h, int D, const float* P, const float* A, co
     const size_t hl = (size_t)h * ld, ho = (size_t)h * ldo;
     const float* F[4] = {A, A + hl, B, B + hl};
     float* out[8] = {f_aa, f_aa + ho, f_bb, f_bb + ho, f_ab, f_ab + ho, f_ba, f_ba + ho};
-    return otgan_plan_apply_f32(&p, h, D, P, F, ld, out, ldo, impl, stream);
+    return otgan_plan_apply_f32(&p, h, D, P, F, ld, out, ldo, ws, ws_bytes, impl, stream);
 }
 
 int otgan_grad_features_f32(int h, int D, const float* P, const float* A, const float* B, int ld, float* Ga, float* Gb,
-                            int ldo, int impl, void* stream)
+                            int ldo, void* ws, size_t ws_bytes, int impl, void* stream)
 {
     OTGAN_REQUIRE(P && A && B && Ga && Gb, "grad_features: null pointer");
     OTGAN_REQUIRE(h >= 1 && D >= 1, "grad_features: bad shape");
@@ -186,12 +201,13 @@ int otgan_grad_features_f32(int h, int D, const float* P, const float* A, const 
     const size_t hl = (size_t)h * ld, ho = (size_t)h * ldo;
     const float* F[4] = {A, A + hl, B, B + hl};
     float* out[4] = {Ga, Ga + ho, Gb, Gb + ho};
-    return otgan_plan_apply_f32(&p, h, D, P, F, ld, out, ldo, impl, stream);
+    return otgan_plan_apply_f32(&p, h, D, P, F, ld, out, ldo, ws, ws_bytes, impl, stream);
 }
 
 // sources: 0 = A, 1 = B;  plans: 0 = aa, 1 = bb, 2 = ab      (utils/matching.py:131-134)
 int otgan_matched_single_batch_f32(int n, int D, const float* P, const float* A, const float* B, int ld, float* f_aa,
-                                   float* f_bb, float* f_ab, float* f_ba, int ldo, int impl, void* stream)
+                                   float* f_bb, float* f_ab, float* f_ba, int ldo, void* ws, size_t ws_bytes, int impl,
+                                   void* stream)
 {
     OTGAN_REQUIRE(P && A && B && f_aa && f_bb && f_ab && f_ba, "matched_single_batch: null pointer");
     OTGAN_REQUIRE(n >= 1 && D >= 1, "matched_single_batch: bad shape");
@@ -204,7 +220,7 @@ int otgan_matched_single_batch_f32(int n, int D, const float* P, const float* A,
     add_term(&p, 3, 2, 1, 0, 1.f);
     const float* F[2] = {A, B};
     float* out[4] = {f_aa, f_bb, f_ab, f_ba};
-    return otgan_plan_apply_f32(&p, n, D, P, F, ld, out, ldo, impl, stream);
+    return otgan_plan_apply_f32(&p, n, D, P, F, ld, out, ldo, ws, ws_bytes, impl, stream);
 }
 
 size_t otgan_workspace_bytes_distance(int n, int D) { return distance_workspace_bytes(n, D); }

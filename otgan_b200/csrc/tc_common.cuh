@@ -33,8 +33,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// Bounded wait: a pipeline-protocol bug must fail loudly (trap -> CUDA error on the stream), never hang the device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) { }
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {          // ~2 s at 2 GHz: orders of magnitude beyond any legitimate wait
+            printf("otgan: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+            __trap();
+        }
+    }
 }
 
 // ---- proxies / fences
@@ -85,6 +93,17 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
     d |= (uint64_t)1 << 16;                               // LBO: unused for swizzled K-major layouts (canonical value 1)
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)swizzle_code << 61;
+    return d;
+}
+// MN-major operand tile (the contiguous dimension is M/N, e.g. a [k][n] row-major matrix used as B): 32-element (128 B)
+// column blocks `lbo_bytes` apart, 8-row K groups `sbo_bytes` apart, SWIZZLE_128B rows of 128 B inside a group.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t swizzle_code) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)swizzle_code << 61;

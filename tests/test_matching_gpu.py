@@ -218,10 +218,14 @@ def test_sinkhorn_rows_sum_to_one_at_full_size(M):
     assert 0.0 <= float(ent.min()) and float(ent.max()) <= np.log(128) + 1e-5
 
 
-@pytest.mark.parametrize("h,D", [(16, 64), (128, 4096), (20, 37), (64, 1000), (128, 32768)])
-def test_plan_apply_kernels(h, D):
+@pytest.mark.parametrize("impl", [1, 2])          # 1 = SIMT (exact fp32), 2 = TMA + tcgen05 3xTF32
+@pytest.mark.parametrize("h,D", [(16, 64), (128, 4096), (20, 37), (64, 1000), (128, 32768), (100, 7296), (4, 32), (128, 160)])
+def test_plan_apply_kernels(M, h, D, impl):
     from otgan_b200 import _lib
     lib = _lib.load()
+    if impl == 2 and D % 4 != 0:
+        pytest.skip("tcgen05 path needs 16-byte aligned rows")
+    ws, ws_bytes = M._plan_ws(torch.device("cuda", 0))
     rng = np.random.RandomState(h * 7 + D)
     P = rng.rand(6, h, h)
     P /= P.sum(axis=2, keepdims=True)
@@ -231,16 +235,20 @@ def test_plan_apply_kernels(h, D):
     outs = [torch.empty(2 * h, D, device="cuda") for _ in range(4)]
     s = torch.cuda.current_stream().cuda_stream
     rc = lib.otgan_matched_two_batch_f32(h, D, Pd.data_ptr(), Ad.data_ptr(), Bd.data_ptr(), D, outs[0].data_ptr(),
-                                         outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(), D, 0, s)
+                                         outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(), D, ws.data_ptr(),
+                                         ws_bytes, impl, s)
     assert rc == 0, lib.otgan_last_error()
+    # SIMT = exact fp32 FMA chains; tcgen05 = 3xTF32 operands (2^-22) + a truncating tensor-core accumulator
+    tol = 3e-6 if impl == 1 else 1e-5
     ref = mo._combine_two_batch(list(P64), A64[:h], A64[h:], B64[:h], B64[h:])
     for o, r in zip(outs, ref):
-        assert relerr(o, r) < 3e-6
+        assert relerr(o, r) < tol
     Ga, Gb = torch.empty(2 * h, D, device="cuda"), torch.empty(2 * h, D, device="cuda")
-    rc = lib.otgan_grad_features_f32(h, D, Pd.data_ptr(), Ad.data_ptr(), Bd.data_ptr(), D, Ga.data_ptr(), Gb.data_ptr(), D, 0, s)
+    rc = lib.otgan_grad_features_f32(h, D, Pd.data_ptr(), Ad.data_ptr(), Bd.data_ptr(), D, Ga.data_ptr(), Gb.data_ptr(), D,
+                                     ws.data_ptr(), ws_bytes, impl, s)
     assert rc == 0, lib.otgan_last_error()
     ra, rb = mo.fused_grad_features(list(P64), A64[:h], A64[h:], B64[:h], B64[h:])
-    assert relerr(Ga, ra) < 3e-6 and relerr(Gb, rb) < 3e-6
+    assert relerr(Ga, ra) < tol and relerr(Gb, rb) < tol
 
 
 # ----------------------------------------------------------------------------------------------- API level
