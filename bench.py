@@ -97,6 +97,8 @@ def workload_config(world, workload):
            "N": N_TOTAL, "h": N_TOTAL // 2, "D": D_FEAT, "T": T_ITERS, "lambda": LAMBDA, "ranks": world,
            "images_per_rank": N_TOTAL // world, "towers": 2 * world if world > 1 else 2,
            "conv_backend": "cuDNN/cuBLAS via torch (library rung; own implicit-GEMM kernels not yet written)",
+           "precision": "fp32 storage everywhere; matching kernels are fp32-exact (3xTF32 operands + fp32 register accumulation); "
+                        "convolutions use cuDNN's default TF32 tensor-core math on fp32 tensors",
            "l2_policy": "per-step working set (activations + 72 M parameters + Adam state, > 1 GB) exceeds the 126 MB L2; the "
                         "matching sub-benchmark rotates %d input sets (%.0f MiB)" % (N_INPUT_SETS, N_INPUT_SETS * 2 * N_TOTAL * D_FEAT * 4 / 2**20)}
     if workload == "matching":
@@ -349,36 +351,49 @@ def run_ours(args):
     if args.workload == "train":
         for i in range(W):
             tr.step(dev_imgs[i % 8])
-        sampler = ClockSampler(local)
-        sampler.start()
-        barrier()
-        _lib.reset_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for i in range(args.steps):
-            tr.step(dev_imgs[i % 8])
-        e1.record(stream)
-        barrier()
-        launches = _lib.launch_count()
-        ms_total = e0.elapsed_time(e1)
-        # ---- end to end: pinned host images -> H2D -> step -> D2H of [distance, entropy], every step
         stats_host = torch.empty(2).pin_memory()
         x_dev = torch.empty((bs, 32, 32, 3), device=devv)
-        for i in range(2):
-            x_dev.copy_(host_imgs[i % 8], non_blocking=True)
-            stats_host.copy_(tr.step(x_dev)[1], non_blocking=True)
-        barrier()
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e2.record(stream)
-        for i in range(args.steps):
-            x_dev.copy_(host_imgs[i % 8], non_blocking=True)
-            stats_host.copy_(tr.step(x_dev)[1], non_blocking=True)
-            stream.synchronize()                       # the host reads (distance, entropy) every step, like sess.run
-        e3.record(stream)
-        barrier()
-        ms_e2e = e2.elapsed_time(e3)
-        sampler.stop_flag = True
-        sampler.join()
+
+        def measure():
+            sampler = ClockSampler(local)
+            sampler.start()
+            barrier()
+            _lib.reset_launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(args.steps):
+                tr.step(dev_imgs[i % 8])
+            e1.record(stream)
+            barrier()
+            n_launch = _lib.launch_count()
+            t_dev = e0.elapsed_time(e1)
+            # ---- end to end: pinned host images -> H2D -> step -> D2H of [distance, entropy], every step
+            for i in range(2):
+                x_dev.copy_(host_imgs[i % 8], non_blocking=True)
+                stats_host.copy_(tr.step(x_dev)[1], non_blocking=True)
+            barrier()
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e2.record(stream)
+            for i in range(args.steps):
+                x_dev.copy_(host_imgs[i % 8], non_blocking=True)
+                stats_host.copy_(tr.step(x_dev)[1], non_blocking=True)
+                stream.synchronize()                   # the host reads (distance, entropy) every step, like sess.run
+            e3.record(stream)
+            barrier()
+            t_e2e = e2.elapsed_time(e3)
+            sampler.stop_flag = True
+            sampler.join()
+            return t_dev, t_e2e, n_launch, sampler
+
+        ms_total, ms_e2e, launches, sampler = measure()
+        bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        remeasured = False
+        flag = torch.tensor([1.0 if bad & set(sampler.result().get("reasons", [])) else 0.0], device=devv)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if flag.item() > 0:                            # thermal / hardware slowdown seen: rejected, measured once more
+            ms_total, ms_e2e, launches, sampler = measure()
+            remeasured = True
         h2d, d2h = bs * 32 * 32 * 3 * 4 * world, 8
     else:
         sampler = ClockSampler(local)
@@ -388,6 +403,7 @@ def run_ours(args):
         sampler.join()
         ms_total = (res2["ms_per_step"] * args.steps) if rank == 0 else 0.0
         ms_e2e, launches, h2d, d2h = ms_total, int(match_res["gpu_launches_per_step"] * args.steps) if rank == 0 else 0, 0, 0
+        remeasured = False
 
     t = torch.tensor([ms_total, ms_e2e], device=devv, dtype=torch.float64)
     if world > 1:
@@ -401,12 +417,12 @@ def run_ours(args):
             "metric": "images/sec", "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
             "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world, args.workload),
-            "sinkhorn_iters_per_sec": match_res["sinkhorn_iters_per_sec"],
+            "sinkhorn_iters_per_sec": match_res["sinkhorn_iters_per_sec"] if match_res else None,
             "roofline": roof, "matching": match_res,
             "e2e": {"value": N_TOTAL / (ms_e2e / args.steps * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            "clocks": sampler.result(),
+            "clocks": dict(sampler.result(), remeasured_after_slowdown=remeasured),
         }
         if world == 1 and not args.no_cpu:
             mt, ph, cores = cpu_matching_time(N_TOTAL, D_FEAT, T_ITERS, LAMBDA, 5, 1)

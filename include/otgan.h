@@ -151,6 +151,18 @@ OTGAN_API int otgan_weightnorm_fwd_f32(int K, int C, const float* V, const float
 OTGAN_API int otgan_weightnorm_bwd_f32(int K, int C, const float* V, const float* g, const float* inv_norm,
                                        const float* dWt, float* dV, float* dg, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- fused activations of the conv stacks (NHWC fp32, C % 4 == 0) ---------------------------------------------------
+ * crelu_pad: z [B, H+pt+pb, W+pl+pr, 2C] = zero-pad( relu(concat([x, -x], channel)) ), x: [B,H,W,C] -- the CReLU
+ *            pre-activation of nn.conv2d (utils/nn.py:198-200) written into the TensorFlow-'SAME'-padded input of the conv.
+ * glu_up   : out [B, up*H, up*W, C] = nearest_upsample_x{1,2}( y[..., :C] * sigmoid(y[..., C:]) ), y: [B,H,W,2C] -- the
+ *            generator's gated linear unit + tf.image.resize_nearest_neighbor (models/dcgan.py:39-48). */
+OTGAN_API int otgan_crelu_pad_fwd_f32(int B, int H, int W, int C, int pad_top, int pad_left, int pad_bottom, int pad_right,
+                                      const float* x, float* z, void* stream);
+OTGAN_API int otgan_crelu_pad_bwd_f32(int B, int H, int W, int C, int pad_top, int pad_left, int pad_bottom, int pad_right,
+                                      const float* x, const float* dz, float* dx, void* stream);
+OTGAN_API int otgan_glu_up_fwd_f32(int B, int H, int W, int C, int up, const float* y, float* out, void* stream);
+OTGAN_API int otgan_glu_up_bwd_f32(int B, int H, int W, int C, int up, const float* y, const float* dout, float* dy, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,10 @@ SIGNATURES = {
     "otgan_workspace_bytes_weightnorm": (_sz, [_i, _i]),
     "otgan_weightnorm_fwd_f32": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "otgan_weightnorm_bwd_f32": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "otgan_crelu_pad_fwd_f32": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "otgan_crelu_pad_bwd_f32": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "otgan_glu_up_fwd_f32": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "otgan_glu_up_bwd_f32": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

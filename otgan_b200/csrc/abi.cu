@@ -58,6 +58,12 @@ int weightnorm_fwd_launch(int K, int C, const float* V, const float* g, float* W
 int weightnorm_bwd_launch(int K, int C, const float* V, const float* g, const float* inv, const float* dWt, float* dV,
                           float* dg, void* ws, cudaStream_t stream);
 
+int crelu_pad_fwd_launch(int B, int H, int W, int C, int pt, int pl, int pb, int pr, const float* x, float* z, cudaStream_t stream);
+int crelu_pad_bwd_launch(int B, int H, int W, int C, int pt, int pl, int pb, int pr, const float* x, const float* dz, float* dx,
+                         cudaStream_t stream);
+int glu_up_fwd_launch(int B, int H, int W, int C, int up, const float* y, float* out, cudaStream_t stream);
+int glu_up_bwd_launch(int B, int H, int W, int C, int up, const float* y, const float* dout, float* dy, cudaStream_t stream);
+
 }  // namespace otgan
 
 using namespace otgan;
@@ -279,6 +285,36 @@ int otgan_weightnorm_bwd_f32(int K, int C, const float* V, const float* g, const
     OTGAN_REQUIRE(K >= 1 && C >= 1 && V && g && inv_norm && dWt && dV && dg && ws, "weightnorm_bwd: bad arguments");
     OTGAN_REQUIRE(ws_bytes >= weightnorm_workspace_bytes(K, C), "weightnorm_bwd: workspace too small");
     return weightnorm_bwd_launch(K, C, V, g, inv_norm, dWt, dV, dg, ws, (cudaStream_t)stream);
+}
+
+int otgan_crelu_pad_fwd_f32(int B, int H, int W, int C, int pad_top, int pad_left, int pad_bottom, int pad_right,
+                            const float* x, float* z, void* stream)
+{
+    OTGAN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 4 && C % 4 == 0 && x && z, "crelu_pad_fwd: bad arguments (C must be a multiple of 4)");
+    OTGAN_REQUIRE(pad_top >= 0 && pad_left >= 0 && pad_bottom >= 0 && pad_right >= 0 && aligned16(x) && aligned16(z), "crelu_pad_fwd: bad padding/alignment");
+    return crelu_pad_fwd_launch(B, H, W, C, pad_top, pad_left, pad_bottom, pad_right, x, z, (cudaStream_t)stream);
+}
+
+int otgan_crelu_pad_bwd_f32(int B, int H, int W, int C, int pad_top, int pad_left, int pad_bottom, int pad_right,
+                            const float* x, const float* dz, float* dx, void* stream)
+{
+    OTGAN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 4 && C % 4 == 0 && x && dz && dx, "crelu_pad_bwd: bad arguments");
+    OTGAN_REQUIRE(aligned16(x) && aligned16(dz) && aligned16(dx), "crelu_pad_bwd: buffers must be 16-byte aligned");
+    return crelu_pad_bwd_launch(B, H, W, C, pad_top, pad_left, pad_bottom, pad_right, x, dz, dx, (cudaStream_t)stream);
+}
+
+int otgan_glu_up_fwd_f32(int B, int H, int W, int C, int up, const float* y, float* out, void* stream)
+{
+    OTGAN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 4 && C % 4 == 0 && (up == 1 || up == 2) && y && out, "glu_up_fwd: bad arguments");
+    OTGAN_REQUIRE(aligned16(y) && aligned16(out), "glu_up_fwd: buffers must be 16-byte aligned");
+    return glu_up_fwd_launch(B, H, W, C, up, y, out, (cudaStream_t)stream);
+}
+
+int otgan_glu_up_bwd_f32(int B, int H, int W, int C, int up, const float* y, const float* dout, float* dy, void* stream)
+{
+    OTGAN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 4 && C % 4 == 0 && (up == 1 || up == 2) && y && dout && dy, "glu_up_bwd: bad arguments");
+    OTGAN_REQUIRE(aligned16(y) && aligned16(dout) && aligned16(dy), "glu_up_bwd: buffers must be 16-byte aligned");
+    return glu_up_bwd_launch(B, H, W, C, up, y, dout, dy, (cudaStream_t)stream);
 }
 
 }  // extern "C"

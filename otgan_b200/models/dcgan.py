@@ -39,16 +39,11 @@ def gen_spec(batch_size, init=False, nonlinearity='crelu', ema=None, u=None, **k
         x = x.reshape(batch_size, 4, 4, 1024)
         x = nn.resize_nearest_neighbor(x, [8, 8])
         x = nn.conv2d(x, 2 * 512, filter_size=[5, 5], pre_activation=None)
-        x, l = torch.chunk(x, 2, 3)
-        x = x * torch.sigmoid(l)
-        x = nn.resize_nearest_neighbor(x, [16, 16])
+        x = nn.glu(x, upsample=True)      # x, l = split(x, 2, 3); x *= sigmoid(l); resize_nearest_neighbor(x, [16, 16])  :39-42
         x = nn.conv2d(x, 2 * 256, filter_size=[5, 5], pre_activation=None)
-        x, l = torch.chunk(x, 2, 3)
-        x = x * torch.sigmoid(l)
-        x = nn.resize_nearest_neighbor(x, [32, 32])
+        x = nn.glu(x, upsample=True)      # ... resize_nearest_neighbor(x, [32, 32])                                        :43-46
         x = nn.conv2d(x, 2 * 128, filter_size=[5, 5], pre_activation=None)
-        x, l = torch.chunk(x, 2, 3)
-        x = x * torch.sigmoid(l)
+        x = nn.glu(x)                     # x, l = split(x, 2, 3); x *= sigmoid(l)                                          :47-48
         x = torch.tanh(nn.conv2d(x, 3, filter_size=[5, 5], pre_activation=None, init_scale=0.1))
         return x
 

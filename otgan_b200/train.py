@@ -121,19 +121,21 @@ class Trainer:
         ga, gb, stats = matching.matching_step(fa, fb, a.sinkhorn_lambda, a.nr_sinkhorn_iter)
         return torch.cat(ga, 0), torch.cat(gb, 0), stats
 
-    def step(self, x_real):
-        """x_real: this rank's [bs_local, 32, 32, 3] real images in [-1, 1].  Returns ('disc'|'gen', stats[2] tensor)."""
+    def step(self, x_real, u=None, apply_update=True):
+        """x_real: this rank's [bs_local, 32, 32, 3] real images in [-1, 1].  Returns ('disc'|'gen', stats[2] tensor).
+        `u` optionally fixes this rank's generator latents (parity tests); `apply_update=False` skips the optimiser and
+        leaves the summed gradient in self.last_grad."""
         a = self.args
         train_disc = self.step_counter % (a.nr_gen_per_disc + 1) == 0                            # :214
         gen, disc = self.generator, self.discriminator
         bs = self.bs_local
         if train_disc:
             with torch.no_grad():
-                x_gen = gen(ema=self.ema, **self.model_opts) if a.train_disc_against_ema else gen(**self.model_opts)
+                x_gen = gen(ema=self.ema, u=u, **self.model_opts) if a.train_disc_against_ema else gen(u=u, **self.model_opts)
             feats = disc(torch.cat([x_gen, x_real], 0), **self.model_opts)                       # fake rows, then real rows
             f_gen, f_dat = feats[:bs], feats[bs:]
         else:
-            x_gen = gen(**self.model_opts)
+            x_gen = gen(u=u, **self.model_opts)
             with torch.no_grad():
                 f_dat = disc(x_real, **self.model_opts)
             f_gen = disc(x_gen, **self.model_opts)
@@ -145,14 +147,17 @@ class Trainer:
             (grad,) = torch.autograd.grad([feats], [disc.flat], grad_outputs=[torch.cat([ga, gb], 0)])   # :122-128
             if self.world > 1:
                 dist.all_reduce(grad, op=dist.ReduceOp.SUM)                                      # :134-139 (sum, not mean)
-            self.disc_optimizer.run(grad, lr=-a.learning_rate_disc)                              # :143,215
+            if apply_update:
+                self.disc_optimizer.run(grad, lr=-a.learning_rate_disc)                          # :143,215
             kind = 'disc'
         else:
             (grad,) = torch.autograd.grad([f_gen], [gen.flat], grad_outputs=[ga])                # :111-112
             if self.world > 1:
                 dist.all_reduce(grad, op=dist.ReduceOp.SUM)
-            self.gen_optimizer.run(grad, lr=a.learning_rate_gen)                                 # :142,222 (+ EMA :223)
+            if apply_update:
+                self.gen_optimizer.run(grad, lr=a.learning_rate_gen)                             # :142,222 (+ EMA :223)
             kind = 'gen'
+        self.last_grad = grad
         self.step_counter += 1
         return kind, stats
 

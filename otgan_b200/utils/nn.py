@@ -251,7 +251,7 @@ def resize_nearest_neighbor(x, size):
     return x[:, ih][:, :, iw]
 
 
-def _conv2d_nhwc(x, W, stride, pad):
+def _conv2d_nhwc(x, W, stride, pad, bias=None):
     """tf.nn.conv2d(x, W, [1,s,s,1], pad) with NHWC input and HWIO kernel (utils/nn.py:241)."""
     if isinstance(W, TransposedWeight):
         kh, kw = W.vshape[0], W.vshape[1]
@@ -264,11 +264,11 @@ def _conv2d_nhwc(x, W, stride, pad):
         pt, pb = same_padding(x.shape[1], kh, stride[0])
         pl, pr = same_padding(x.shape[2], kw, stride[1])
         if pt == pb and pl == pr:
-            y = F.conv2d(xn, w_oihw, stride=tuple(stride), padding=(pt, pl))
+            y = F.conv2d(xn, w_oihw, bias, stride=tuple(stride), padding=(pt, pl))
         else:
-            y = F.conv2d(F.pad(xn, (pl, pr, pt, pb)), w_oihw, stride=tuple(stride))
+            y = F.conv2d(F.pad(xn, (pl, pr, pt, pb)), w_oihw, bias, stride=tuple(stride))
     elif pad == "VALID":
-        y = F.conv2d(xn, w_oihw, stride=tuple(stride))
+        y = F.conv2d(xn, w_oihw, bias, stride=tuple(stride))
     else:
         raise ValueError(pad)
     return y.permute(0, 2, 3, 1)
@@ -311,6 +311,76 @@ def crelu_l2norm(x):
     x = torch.cat([torch.relu(x), torch.relu(-x)], 3)
     x = x.reshape(x.shape[0], -1)
     return x / torch.sqrt(torch.sum(torch.square(x), dim=1, keepdim=True))
+
+
+class _CreluPad(torch.autograd.Function):
+    """relu(concat([x, -x], 3)) written into a zero-padded NHWC buffer (otgan_crelu_pad_{fwd,bwd}_f32)."""
+
+    @staticmethod
+    def forward(ctx, x, pads):
+        lib = _lib.load()
+        B, H, W, C = x.shape
+        pt, pl, pb, pr = pads
+        z = torch.empty((B, H + pt + pb, W + pl + pr, 2 * C), device=x.device, dtype=torch.float32)
+        rc = lib.otgan_crelu_pad_fwd_f32(B, H, W, C, pt, pl, pb, pr, x.data_ptr(), z.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "otgan_crelu_pad_fwd_f32")
+        ctx.save_for_backward(x)
+        ctx.pads = pads
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        lib = _lib.load()
+        (x,) = ctx.saved_tensors
+        B, H, W, C = x.shape
+        pt, pl, pb, pr = ctx.pads
+        dz = dz.contiguous()
+        dx = torch.empty_like(x)
+        rc = lib.otgan_crelu_pad_bwd_f32(B, H, W, C, pt, pl, pb, pr, x.data_ptr(), dz.data_ptr(), dx.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "otgan_crelu_pad_bwd_f32")
+        return dx, None
+
+
+class _GluUp(torch.autograd.Function):
+    """a * sigmoid(l) (+ 2x nearest-neighbour upsample), (a, l) = split(y, 2, 3)  (otgan_glu_up_{fwd,bwd}_f32)."""
+
+    @staticmethod
+    def forward(ctx, y, up):
+        lib = _lib.load()
+        B, H, W, C2 = y.shape
+        C = C2 // 2
+        out = torch.empty((B, up * H, up * W, C), device=y.device, dtype=torch.float32)
+        rc = lib.otgan_glu_up_fwd_f32(B, H, W, C, up, y.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "otgan_glu_up_fwd_f32")
+        ctx.save_for_backward(y)
+        ctx.up = up
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        (y,) = ctx.saved_tensors
+        B, H, W, C2 = y.shape
+        dout = dout.contiguous()
+        dy = torch.empty_like(y)
+        rc = lib.otgan_glu_up_bwd_f32(B, H, W, C2 // 2, ctx.up, y.data_ptr(), dout.data_ptr(), dy.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "otgan_glu_up_bwd_f32")
+        return dy, None
+
+
+def glu(y, upsample=False):
+    """x, l = tf.split(y, 2, 3); x *= tf.nn.sigmoid(l)  [; x = resize_nearest_neighbor(x, 2x)]   (models/dcgan.py:39-48).
+    One fused CUDA kernel on the GPU; the literal ops for CPU tensors."""
+    if y.is_cuda and y.dtype == torch.float32 and y.dim() == 4 and (y.shape[3] // 2) % 4 == 0:
+        return _GluUp.apply(y.contiguous(), 2 if upsample else 1)
+    x, l = torch.chunk(y, 2, 3)
+    x = x * torch.sigmoid(l)
+    if upsample:
+        x = resize_nearest_neighbor(x, [2 * x.shape[1], 2 * x.shape[2]])
+    return x
 
 
 class TransposedWeight:
@@ -423,7 +493,7 @@ def _dense(x, W, pre_activation=None):
     return x @ W                                                                                      # :208-209
 
 
-def _conv2d(x, W, stride=(1, 1), pad="SAME", dilate=1, pre_activation=None, upsample=False):
+def _conv2d(x, W, stride=(1, 1), pad="SAME", dilate=1, pre_activation=None, upsample=False, bias=None):
     """utils/nn.py:234-275 (__list_conv2d): optional NN-upsample of the concatenated list, pre-activation, conv."""
     xl = _as_list(x)
     if dilate != 1:
@@ -431,7 +501,15 @@ def _conv2d(x, W, stride=(1, 1), pad="SAME", dilate=1, pre_activation=None, upsa
     if upsample:
         xc = torch.cat(xl, 3) if len(xl) > 1 else xl[0]
         xl = [resize_nearest_neighbor(xc, [2 * xc.shape[1], 2 * xc.shape[2]])]
-    return _conv2d_nhwc(apply_pre_activation(xl, pre_activation, 3), W, list(stride), pad)
+    if (pre_activation == "crelu" and len(xl) == 1 and pad == "SAME" and xl[0].is_cuda and xl[0].dtype == torch.float32
+            and xl[0].shape[3] % 4 == 0):
+        # CReLU written straight into the TensorFlow-'SAME'-padded input of the convolution (one fused kernel)
+        kh, kw = (W.vshape[0], W.vshape[1]) if isinstance(W, TransposedWeight) else (W.shape[0], W.shape[1])
+        pt, pb = same_padding(xl[0].shape[1], kh, stride[0])
+        pl, pr = same_padding(xl[0].shape[2], kw, stride[1])
+        z = _CreluPad.apply(xl[0].contiguous(), (pt, pl, pb, pr))
+        return _conv2d_nhwc(z, W, list(stride), "VALID", bias)
+    return _conv2d_nhwc(apply_pre_activation(xl, pre_activation, 3), W, list(stride), pad, bias)
 
 
 @add_arg_scope
@@ -458,10 +536,8 @@ def conv2d(x, num_filters, pre_activation="celu", filter_size=[3, 3], stride=[1,
     params = get_params(layer_name, x, init, ema, use_W=True, use_g=use_g, use_b=use_b, f=f, weight_norm=weight_norm,
                         init_scale=init_scale, filter_size=list(filter_size), num_units=num_filters,
                         pre_activation=pre_activation)
-    x = f(x, params["W"])
-    if use_b:
-        x = x + params["b"]
-    return x
+    # tf.nn.bias_add (:337) rides in the convolution's epilogue instead of a separate pass over the activations
+    return _conv2d(x, params["W"], stride, pad, dilate, pre_activation, upsample, bias=params["b"] if use_b else None)
 
 
 # ------------------------------------------------------------------------------------------------ optimisers

@@ -1,0 +1,59 @@
+"""Multi-GPU parity script (run under torchrun on G GPUs): the summed tower gradient, distance and entropy of one critic
+step and one generator step computed by G ranks (all-gather + own-row backward + all-reduce) must equal the same step
+computed by a single rank on the full batch with identical images, latents and parameters.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port P tests/mgpu_parity.py
+Prints "MGPU PARITY OK" on rank 0 (exit code 0) or the first mismatch (exit code 1).  Not bitwise: per-rank batches change
+cuDNN's reduction order in wgrad, so the gate is 1e-4 relative on gradients, 1e-6 absolute on the distance.
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from otgan_b200 import train as T  # noqa: E402
+
+
+def main():
+    world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False          # fp32 convolutions: keeps the comparison at fp32 noise
+    N, towers = 64, 2 * world
+    argv = ["--synthetic", "--nr_gpu", str(towers), "--batch_size", str(N // towers), "--nr_sinkhorn_iter", "50"]
+    g = torch.Generator().manual_seed(1234)
+    x_all = (torch.rand((N, 32, 32, 3), generator=g) * 2 - 1).to(dev)
+    u_all = (torch.rand((N, 100), generator=g) * 2 - 1).to(dev)
+    ok, msgs = True, []
+    for step_kind in ("disc", "gen"):
+        res = {}
+        for mode in ("multi", "single"):
+            w, r = (world, rank) if mode == "multi" else (1, 0)
+            tr = T.Trainer(T.build_parser().parse_args(argv), dev, r, w)          # same seed -> identical parameters
+            tr.step_counter = 0 if step_kind == "disc" else 1
+            bs = tr.bs_local
+            lo = r * bs
+            kind, stats = tr.step(x_all[lo:lo + bs], u=u_all[lo:lo + bs], apply_update=False)
+            assert kind == step_kind
+            res[mode] = (tr.last_grad.clone(), stats.clone())
+        gm, sm = res["multi"]
+        gs, ss = res["single"]
+        rel = float((gm - gs).abs().max() / gs.abs().max())
+        dd, de = abs(float(sm[0] - ss[0])), abs(float(sm[1] - ss[1]))
+        if rank == 0:
+            msgs.append("%s step: grad rel err %.2e, |d distance| %.2e, |d entropy| %.2e" % (step_kind, rel, dd, de))
+        ok = ok and rel < 1e-4 and dd < 1e-6 and de < 1e-5
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("\n".join(msgs))
+        print("MGPU PARITY OK (world %d)" % world if flag.item() == 1.0 else "MGPU PARITY FAILED")
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -65,6 +65,34 @@ def test_weightnorm_kernels_vs_torch(shape):
     assert float((gg.double() - rg).abs().max() / rg.abs().max()) < 2e-5
 
 
+def test_fused_activation_kernels_vs_torch():
+    """otgan_crelu_pad_* and otgan_glu_up_* against the literal op sequences (float64 torch ops), forward and backward."""
+    from otgan_b200.utils import nn
+    torch.manual_seed(3)
+    x = torch.randn(3, 6, 6, 8, device="cuda", requires_grad=True)
+    for pads in ((1, 1, 2, 2), (2, 2, 2, 2), (0, 0, 1, 1), (0, 0, 0, 0)):
+        z = nn._CreluPad.apply(x, pads)
+        gz = torch.randn_like(z)
+        (gx,) = torch.autograd.grad([z], [x], [gz])
+        xd = x.detach().double().requires_grad_(True)
+        zr = torch.nn.functional.pad(torch.relu(torch.cat([xd, -xd], 3)).permute(0, 3, 1, 2),
+                                     (pads[1], pads[3], pads[0], pads[2])).permute(0, 2, 3, 1)
+        (gr,) = torch.autograd.grad([zr], [xd], [gz.double()])
+        assert torch.equal(z.double(), zr) and float((gx.double() - gr).abs().max()) == 0.0
+    y = torch.randn(2, 5, 5, 16, device="cuda", requires_grad=True)
+    for up in (False, True):
+        o = nn.glu(y, upsample=up)
+        go = torch.randn_like(o)
+        (gy,) = torch.autograd.grad([o], [y], [go])
+        yd = y.detach().double().requires_grad_(True)
+        a, l = torch.chunk(yd, 2, 3)
+        orf = a * torch.sigmoid(l)
+        if up:
+            orf = orf.repeat_interleave(2, 1).repeat_interleave(2, 2)
+        (gr,) = torch.autograd.grad([orf], [yd], [go.double()])
+        assert float((o.double() - orf).abs().max()) < 1e-6 and float((gy.double() - gr).abs().max()) < 1e-5
+
+
 def test_dcgan_forward_on_gpu_matches_oracle():
     from otgan_b200.models import dcgan
     dcgan.discriminator.reset(); dcgan.generator.reset()
@@ -102,3 +130,17 @@ def test_train_loop_smoke(extra):
     assert not torch.equal(tr.generator.flat.detach(), g0) and not torch.equal(tr.discriminator.flat.detach(), d0)
     assert not torch.equal(tr.ema.shadow, g0[: tr.ema.shadow.numel()])
     assert float((tr.ema.shadow - tr.generator.flat.detach()).abs().max()) > 0
+
+
+def test_multi_gpu_parity_two_ranks():
+    """G-rank step == 1-rank step on identical data (tests/mgpu_parity.py under torchrun); needs >= 2 visible GPUs."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    script = os.path.join(os.path.dirname(__file__), "mgpu_parity.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29577", script],
+                         capture_output=True, text=True, timeout=280)
+    assert out.returncode == 0 and "MGPU PARITY OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
