@@ -163,6 +163,30 @@ OTGAN_API int otgan_crelu_pad_bwd_f32(int B, int H, int W, int C, int pad_top, i
 OTGAN_API int otgan_glu_up_fwd_f32(int B, int H, int W, int C, int up, const float* y, float* out, void* stream);
 OTGAN_API int otgan_glu_up_bwd_f32(int B, int H, int W, int C, int up, const float* y, const float* dout, float* dy, void* stream);
 
+/* ---- convolutions (utils/nn.py:234-241, 328-338: tf.nn.conv2d(x, W, [1,s,s,1], 'SAME') + tf.nn.bias_add, NHWC fp32) ------
+ * im2col-free implicit GEMM on the tensor cores (TMA boxes of the NHWC tensors, tcgen05 kind::tf32, fp32 accumulation).
+ * Geometry: x [B,H,W,Cin], y / dy [B,H/stride,W/stride,Cout], filter kh x kw, stride 1 or 2, pad_top / pad_left = the
+ * TensorFlow 'SAME' leading padding (5x5/s1: 2, 5x5/s2: 1, 3x3/s1: 1, 3x3/s2: 0); the trailing padding is implied.
+ * Weights: w_ohwi [Cout, kh*kw*Cin] (what otgan_weightnorm_fwd_f32 writes), w_ihwo [Cin, kh*kw*Cout] (otgan_ohwi_to_ihwo_f32).
+ * Shapes the tensor-core kernels do not tile (channels not a multiple of 32/128, extents not powers of two) return
+ * OTGAN_EUNSUPPORTED.  Pointers 16-byte aligned.
+ *   fprop : y  = conv(x, w) + bias                       (bias may be NULL)
+ *   dgrad : dx = d conv / d x  applied to dy             (what tf.gradients emits as Conv2DBackpropInput)
+ *   wgrad : dw_ohwi = d conv / d w applied to dy         (Conv2DBackpropFilter); ws: otgan_workspace_bytes_conv_wgrad
+ *   colsum: out[C] = column sums of x [P, C]              (BiasAddGrad); ws: otgan_workspace_bytes_colsum */
+OTGAN_API int otgan_conv2d_fprop_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top,
+                                      int pad_left, const float* x, const float* w_ohwi, const float* bias, float* y,
+                                      void* stream);
+OTGAN_API int otgan_conv2d_dgrad_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top,
+                                      int pad_left, const float* dy, const float* w_ihwo, float* dx, void* stream);
+OTGAN_API size_t otgan_workspace_bytes_conv_wgrad(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride);
+OTGAN_API int otgan_conv2d_wgrad_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top,
+                                      int pad_left, const float* dy, const float* x, float* dw_ohwi, void* ws,
+                                      size_t ws_bytes, void* stream);
+OTGAN_API int otgan_ohwi_to_ihwo_f32(int Cout, int taps, int Cin, const float* w_ohwi, float* w_ihwo, void* stream);
+OTGAN_API size_t otgan_workspace_bytes_colsum(int P, int C);
+OTGAN_API int otgan_colsum_f32(int P, int C, const float* x, float* out, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

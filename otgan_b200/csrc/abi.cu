@@ -63,6 +63,16 @@ int crelu_pad_bwd_launch(int B, int H, int W, int C, int pt, int pl, int pb, int
                          cudaStream_t stream);
 int glu_up_fwd_launch(int B, int H, int W, int C, int up, const float* y, float* out, cudaStream_t stream);
 int glu_up_bwd_launch(int B, int H, int W, int C, int up, const float* y, const float* dout, float* dy, cudaStream_t stream);
+int conv_fprop_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo,
+                      const float* x, const float* w, const float* bias, float* y, cudaStream_t stream);
+int conv_dgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo,
+                      const float* dy, const float* wt, float* dx, cudaStream_t stream);
+size_t conv_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int kh, int kw);
+int conv_wgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo,
+                      const float* dy, const float* x, float* dw, void* ws, size_t ws_bytes, cudaStream_t stream);
+int ohwi_to_ihwo_launch(int Cout, int T, int Cin, const float* w, float* wt, cudaStream_t stream);
+size_t colsum_workspace_bytes(int P, int C);
+int colsum_launch(int P, int C, const float* x, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 }  // namespace otgan
 
@@ -315,6 +325,57 @@ int otgan_glu_up_bwd_f32(int B, int H, int W, int C, int up, const float* y, con
     OTGAN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 4 && C % 4 == 0 && (up == 1 || up == 2) && y && dout && dy, "glu_up_bwd: bad arguments");
     OTGAN_REQUIRE(aligned16(y) && aligned16(dout) && aligned16(dy), "glu_up_bwd: buffers must be 16-byte aligned");
     return glu_up_bwd_launch(B, H, W, C, up, y, dout, dy, (cudaStream_t)stream);
+}
+
+int otgan_conv2d_fprop_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top, int pad_left,
+                            const float* x, const float* w_ohwi, const float* bias, float* y, void* stream)
+{
+    OTGAN_REQUIRE(x && w_ohwi && y, "conv2d_fprop: null pointer");
+    OTGAN_REQUIRE(stride == 1 || stride == 2, "conv2d_fprop: stride %d not in {1, 2}", stride);
+    OTGAN_REQUIRE(aligned16(x) && aligned16(w_ohwi) && aligned16(y) && (!bias || aligned16(bias)), "conv2d_fprop: buffers must be 16-byte aligned");
+    return conv_fprop_launch(B, H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, H / stride, W / stride, x, w_ohwi, bias, y,
+                             (cudaStream_t)stream);
+}
+
+int otgan_conv2d_dgrad_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top, int pad_left,
+                            const float* dy, const float* w_ihwo, float* dx, void* stream)
+{
+    OTGAN_REQUIRE(dy && w_ihwo && dx, "conv2d_dgrad: null pointer");
+    OTGAN_REQUIRE(stride == 1 || stride == 2, "conv2d_dgrad: stride %d not in {1, 2}", stride);
+    OTGAN_REQUIRE(aligned16(dy) && aligned16(w_ihwo) && aligned16(dx), "conv2d_dgrad: buffers must be 16-byte aligned");
+    return conv_dgrad_launch(B, H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, H / stride, W / stride, dy, w_ihwo, dx,
+                             (cudaStream_t)stream);
+}
+
+size_t otgan_workspace_bytes_conv_wgrad(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride)
+{
+    if (B < 1 || H < 1 || W < 1 || Cin < 1 || Cout < 1 || kh < 1 || kw < 1 || (stride != 1 && stride != 2)) return 0;
+    return conv_wgrad_workspace_bytes(B, H / stride, W / stride, Cin, Cout, kh, kw);
+}
+
+int otgan_conv2d_wgrad_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top, int pad_left,
+                            const float* dy, const float* x, float* dw_ohwi, void* ws, size_t ws_bytes, void* stream)
+{
+    OTGAN_REQUIRE(dy && x && dw_ohwi, "conv2d_wgrad: null pointer");
+    OTGAN_REQUIRE(stride == 1 || stride == 2, "conv2d_wgrad: stride %d not in {1, 2}", stride);
+    OTGAN_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dw_ohwi) && (!ws || aligned16(ws)), "conv2d_wgrad: buffers must be 16-byte aligned");
+    return conv_wgrad_launch(B, H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, H / stride, W / stride, dy, x, dw_ohwi, ws,
+                             ws_bytes, (cudaStream_t)stream);
+}
+
+int otgan_ohwi_to_ihwo_f32(int Cout, int taps, int Cin, const float* w_ohwi, float* w_ihwo, void* stream)
+{
+    OTGAN_REQUIRE(Cout >= 1 && taps >= 1 && taps <= 65535 && Cin >= 1 && w_ohwi && w_ihwo, "ohwi_to_ihwo: bad arguments");
+    return ohwi_to_ihwo_launch(Cout, taps, Cin, w_ohwi, w_ihwo, (cudaStream_t)stream);
+}
+
+size_t otgan_workspace_bytes_colsum(int P, int C) { return (P < 1 || C < 1) ? 0 : colsum_workspace_bytes(P, C); }
+
+int otgan_colsum_f32(int P, int C, const float* x, float* out, void* ws, size_t ws_bytes, void* stream)
+{
+    OTGAN_REQUIRE(P >= 1 && C >= 4 && C % 4 == 0 && x && out && ws, "colsum: bad arguments (C must be a multiple of 4)");
+    OTGAN_REQUIRE(aligned16(x) && aligned16(out) && aligned16(ws), "colsum: buffers must be 16-byte aligned");
+    return colsum_launch(P, C, x, out, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,654 @@
+// conv_tc.cu -- im2col-free implicit-GEMM convolutions on the 5th-gen tensor cores (TMA -> smem -> tcgen05.mma kind::tf32
+// -> TMEM -> registers -> global) for the conv stacks of models/dcgan.py (utils/nn.py:234-241 -> tf.nn.conv2d NHWC, 'SAME').
+//
+// All three passes are sums over the filter taps of small GEMMs whose operand tiles are plain TMA boxes of the NHWC
+// tensors -- no im2col buffer, no padded copy:
+//   fprop  y[n,oh,ow,co]  = sum_{kh,kw,ci} x[n, s*oh+kh-pt, s*ow+kw-pl, ci] * W[co,kh,kw,ci]
+//          A = a [bw x bh x bn] = 128-pixel box of x shifted by the tap (K-major: the 32 channels of a K-chunk are the
+//          contiguous 128-byte rows), B = 256 (or 128) rows of the OHWI weight matrix [Cout, kh*kw*Cin].
+//   dgrad  dx[n,ih,iw,ci] = sum_{kh,kw,co} dy[n, (ih+pt-kh)/s, (iw+pl-kw)/s, co] * W[co,kh,kw,ci]
+//          the same kernel on dy with the IHWO weight matrix [Cin, kh*kw*Cout]; for stride 2 the output pixels are
+//          split into the s*s parity classes (each class sees only the taps with kh = ih+pt mod s: 2x2, 2x3, 3x2, 3x3
+//          of the 5x5 filter), so no zero-insertion FLOPs are spent.
+//   wgrad  dW[co,kh,kw,ci] = sum_{n,oh,ow} dy[n,oh,ow,co] * x[n, s*oh+kh-pt, s*ow+kw-pl, ci]
+//          K = pixels: both operands are MN-major (channels contiguous), staged as [32 pixel x 32 channel] boxes in the
+//          SWIZZLE_128B / 32-byte-atom layout (the layout plan_apply_tc.cu established for MN-major 32-bit operands).
+// Padding: TMA zero-fills the part of a box that lies outside the tensor (coordinates are signed), which is exactly
+// TensorFlow's 'SAME' zero padding, including the asymmetric stride-2 case (5x5/s2: 1 before, 2 after).  Stride 2 is
+// expressed with four parity views of x (base offset (ph*W+pw)*C, dims [C, W/2, H/2, B]) so every tap is a dense box.
+//
+// Precision: operands are the fp32 tensors read as TF32 by the tensor core (10-bit mantissa, the same math class as the
+// cuDNN TF32 kernels this replaces), fp32 accumulation in TMEM.
+//
+// Kernel shape (both kernels): 192 threads = warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 2-5 epilogue
+// (TMEM lane quadrant = warp & 3).  Persistent CTAs (one per SM) walk the tile list; 4-6 smem stages of BK = 32;
+// accumulator 128 x TN fp32 in TMEM, double buffered so the epilogue of one tile overlaps the MMAs of the next.
+#include "tc_common.cuh"
+#include <string.h>
+
+namespace otgan {
+
+namespace {
+
+using namespace tc;
+
+constexpr int BK = 32;                        // K-chunk: 32 fp32 = 128-byte rows == swizzle span
+constexpr int TM = 128;
+constexpr int A_TILE = TM * BK * 4;           // 16 KB
+constexpr int BOX32 = 32 * 32 * 4;            // 4 KB: one [32 x 32] fp32 box of the MN-major layout
+constexpr int MAX_TAPS = 32;
+constexpr int NUM_EPI_THREADS = 128, NUM_THREADS = 64 + NUM_EPI_THREADS;
+constexpr uint32_t SW128 = 2, SW128_BASE32B = 1;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+template <int TN> struct Cfg {
+    static constexpr int B_TILE = TN * BK * 4;
+    static constexpr int STAGE_BYTES = A_TILE + B_TILE;
+    static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;          // TN = 256: 4 stages of 48 KB; TN = 128: 6 of 32 KB
+    static constexpr int TMEM_COLS = 2 * TN;
+    static constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256;
+};
+
+struct Tap { int map, dw, dh, wcol; };
+
+// ---------------------------------------------------------------------------------------------- fprop / dgrad
+struct GemmParams {
+    CUtensorMap amap[4];                      // activation views (stride 2 fprop: the four parity views)
+    CUtensorMap bmap;                         // weight matrix [N rows, Ktot] K-major
+    Tap taps[MAX_TAPS];
+    int cls_tap_begin[5];                     // class c sums taps [begin[c], begin[c+1])
+    long long cls_out_off[4];                 // output offset of the class (floats)
+    int n_cls, m_tiles, n_tiles, n_items;
+    int bw, bh, bn, tiles_w, tiles_h;         // pixel box (bw*bh*bn = 128) and tile grid of one class
+    int kchunks;                              // 32-channel chunks per tap
+    long long osW, osH, osN;                  // output pixel strides (floats)
+    float* out;
+    const float* bias;                        // [N] or null
+};
+
+template <int TN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
+{
+    using C = Cfg<TN>;
+    constexpr int STAGES = C::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bars = smem_base + STAGES * C::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int b) { return bars + 8u * (2 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return bars + 8u * (2 * STAGES + 2 + b); };
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * C::STAGE_BYTES + 8 * (2 * STAGES + 4));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.amap[i]);
+        tma_prefetch_desc(&p.bmap);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), NUM_EPI_THREADS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int c = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int mt = item % p.m_tiles, rest = item / p.m_tiles;
+                const int nt = rest % p.n_tiles, cls = rest / p.n_tiles;
+                const int w0 = (mt % p.tiles_w) * p.bw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
+                const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
+                for (int t = p.cls_tap_begin[cls]; t < p.cls_tap_begin[cls + 1]; ++t) {
+                    const Tap tap = p.taps[t];
+                    const CUtensorMap* am = &p.amap[tap.map];
+                    for (int kc = 0; kc < p.kchunks; ++kc, ++c) {
+                        const int s = c % STAGES;
+                        mbar_wait(empty_bar(s), (((uint32_t)(c / STAGES)) & 1u) ^ 1u);
+                        mbar_arrive_expect_tx(full_bar(s), (uint32_t)C::STAGE_BYTES);
+                        const uint32_t dst = smem_base + s * C::STAGE_BYTES;
+                        tma_load_4d(dst, am, full_bar(s), kc * BK, w0 + tap.dw, h0 + tap.dh, n0);
+                        tma_load_2d(dst + A_TILE, &p.bmap, full_bar(s), tap.wcol + kc * BK, nt * TN);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(TM, TN);
+            int c = 0, n = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
+                const int cls = (item / p.m_tiles) / p.n_tiles, b = n & 1;
+                mbar_wait(tempty_bar(b), (((uint32_t)(n >> 1)) & 1u) ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(b * TN);
+                const int nst = (p.cls_tap_begin[cls + 1] - p.cls_tap_begin[cls]) * p.kchunks;
+                for (int st = 0; st < nst; ++st, ++c) {
+                    const int s = c % STAGES;
+                    mbar_wait(full_bar(s), ((uint32_t)(c / STAGES)) & 1u);
+                    tcgen05_fence_after();
+                    const uint32_t a0 = smem_base + s * C::STAGE_BYTES, b0 = a0 + A_TILE;
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {          // tf32 MMA K = 8 elements = 32 bytes inside the swizzled row
+                        const uint64_t ad = umma_desc_kmajor(a0 + k * 32, 1024, SW128);
+                        const uint64_t bd = umma_desc_kmajor(b0 + k * 32, 1024, SW128);
+                        umma_tf32(d, ad, bd, idesc, (st > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(tfull_bar(b));
+            }
+        }
+    } else {
+        // ===================================================== epilogue warps: TMEM -> (+bias) -> global
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;                          // tile row = pixel index inside the box (w fastest)
+        const int rw = r % p.bw, rh = (r / p.bw) % p.bh, rn = r / (p.bw * p.bh);
+        int n = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
+            const int mt = item % p.m_tiles, rest = item / p.m_tiles;
+            const int nt = rest % p.n_tiles, cls = rest / p.n_tiles, b = n & 1;
+            const int w0 = (mt % p.tiles_w) * p.bw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
+            const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
+            float* out = p.out + p.cls_out_off[cls] + (long long)(n0 + rn) * p.osN + (long long)(h0 + rh) * p.osH +
+                         (long long)(w0 + rw) * p.osW + nt * TN;
+            const float* bias = p.bias ? p.bias + nt * TN : nullptr;
+            mbar_wait(tfull_bar(b), ((uint32_t)(n >> 1)) & 1u);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < TN / 32; ++cc) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TN + cc * 32), v);
+                tmem_ld_wait();
+                if (bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + j));
+                        v[j] = __float_as_uint(__uint_as_float(v[j]) + bb.x);
+                        v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + bb.y);
+                        v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + bb.z);
+                        v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + bb.w);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<uint4*>(out + cc * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            tcgen05_fence_before();
+            mbar_arrive(tempty_bar(b));
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- wgrad
+struct WgradParams {
+    CUtensorMap dymap;                        // dy as [P pixels, Cout], box [32 px x 32 co]
+    CUtensorMap xmap[4];                      // x views (parity views for stride 2), box [32 ci] x [bw x bh x bn = 32 px]
+    Tap taps[MAX_TAPS];                       // map, dw, dh, wcol = tap * Cin
+    int ntaps, co_tiles, ci_tiles, splits, n_items;
+    int bw, bh, bn, tiles_w, tiles_h;         // 32-pixel chunk box and the chunk grid over the OUTPUT pixels
+    int nchunks, chunks_per_split;
+    int ldw;                                  // row stride of dW (= ntaps * Cin)
+    long long split_stride;                   // floats between split partials
+    float* out;
+};
+
+template <int TN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ WgradParams p)
+{
+    using C = Cfg<TN>;
+    constexpr int STAGES = C::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bars = smem_base + STAGES * C::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int b) { return bars + 8u * (2 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return bars + 8u * (2 * STAGES + 2 + b); };
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * C::STAGE_BYTES + 8 * (2 * STAGES + 4));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.dymap);
+        for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.xmap[i]);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), NUM_EPI_THREADS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    // item -> (split, tap, ci tile, co tile); co fastest so neighbouring CTAs share the x boxes, all CTAs walk the
+    // pixel range in step so dy / x are read from HBM once and then hit in L2
+    auto decode = [&](int item, int& cot, int& cit, int& t, int& sp) {
+        cot = item % p.co_tiles; item /= p.co_tiles;
+        cit = item % p.ci_tiles; item /= p.ci_tiles;
+        t = item % p.ntaps;
+        sp = item / p.ntaps;
+    };
+    auto chunk_range = [&](int sp, int& c0, int& c1) {
+        c0 = sp * p.chunks_per_split;
+        c1 = c0 + p.chunks_per_split;
+        c1 = c1 > p.nchunks ? p.nchunks : c1;
+    };
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int c = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                int cot, cit, t, sp, c0, c1;
+                decode(item, cot, cit, t, sp);
+                chunk_range(sp, c0, c1);
+                const Tap tap = p.taps[t];
+                const CUtensorMap* xm = &p.xmap[tap.map];
+                for (int ch = c0; ch < c1; ++ch, ++c) {
+                    const int s = c % STAGES;
+                    mbar_wait(empty_bar(s), (((uint32_t)(c / STAGES)) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(full_bar(s), (uint32_t)C::STAGE_BYTES);
+                    const uint32_t dst = smem_base + s * C::STAGE_BYTES;
+                    const int w0 = (ch % p.tiles_w) * p.bw, h0 = ((ch / p.tiles_w) % p.tiles_h) * p.bh;
+                    const int n0 = (ch / (p.tiles_w * p.tiles_h)) * p.bn;
+#pragma unroll
+                    for (int j = 0; j < TM / 32; ++j)
+                        tma_load_2d(dst + j * BOX32, &p.dymap, full_bar(s), cot * TM + 32 * j, ch * 32);
+#pragma unroll
+                    for (int j = 0; j < TN / 32; ++j)
+                        tma_load_4d(dst + A_TILE + j * BOX32, xm, full_bar(s), cit * TN + 32 * j, w0 + tap.dw, h0 + tap.dh, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(TM, TN, /*a_mn_major=*/1, /*b_mn_major=*/1);
+            int c = 0, n = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
+                int cot, cit, t, sp, c0, c1;
+                decode(item, cot, cit, t, sp);
+                chunk_range(sp, c0, c1);
+                const int b = n & 1;
+                mbar_wait(tempty_bar(b), (((uint32_t)(n >> 1)) & 1u) ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(b * TN);
+                for (int ch = c0; ch < c1; ++ch, ++c) {
+                    const int s = c % STAGES;
+                    mbar_wait(full_bar(s), ((uint32_t)(c / STAGES)) & 1u);
+                    tcgen05_fence_after();
+                    const uint32_t a0 = smem_base + s * C::STAGE_BYTES, b0 = a0 + A_TILE;
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        // MN-major, SWIZZLE_128B with 32-byte atoms: 32-channel blocks LBO = 4096 B apart, 4-pixel K groups
+                        // SBO = 512 B apart; one K = 8 MMA spans two groups; K-step = 8 pixel rows = +1024 B
+                        const uint64_t ad = umma_desc_mnmajor(a0 + k * 1024, BOX32, 512, SW128_BASE32B);
+                        const uint64_t bd = umma_desc_mnmajor(b0 + k * 1024, BOX32, 512, SW128_BASE32B);
+                        umma_tf32(d, ad, bd, idesc, (ch > c0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(tfull_bar(b));
+            }
+        }
+    } else {
+        // ===================================================== epilogue warps: TMEM -> dW (or the split partial)
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;                          // output channel inside the tile
+        int n = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
+            int cot, cit, t, sp;
+            decode(item, cot, cit, t, sp);
+            const int b = n & 1;
+            float* out = p.out + (long long)sp * p.split_stride + (long long)(cot * TM + r) * p.ldw + p.taps[t].wcol + cit * TN;
+            mbar_wait(tfull_bar(b), ((uint32_t)(n >> 1)) & 1u);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < TN / 32; ++cc) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TN + cc * 32), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<uint4*>(out + cc * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            tcgen05_fence_before();
+            mbar_arrive(tempty_bar(b));
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// out[i] = sum_s partial[s][i]  (fixed order: deterministic split-K)
+__global__ void __launch_bounds__(256)
+split_reduce_kernel(size_t n4, int S, size_t stride4, const float4* __restrict__ partial, float4* __restrict__ out)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 a = partial[i];
+        for (int s = 1; s < S; ++s) {
+            const float4 b = partial[i + s * stride4];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        out[i] = a;
+    }
+}
+
+// Wt[ci][t][co] = W[co][t][ci]   (OHWI -> IHWO, the weight matrix of dgrad); one (co, ci) 32x32 tile per block, per tap
+__global__ void __launch_bounds__(256)
+ohwi_to_ihwo_kernel(int Cout, int T, int Cin, const float* __restrict__ w, float* __restrict__ wt)
+{
+    __shared__ float tile[32][33];
+    const int t = blockIdx.z, ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int co = co0 + i, ci = ci0 + tx;
+        tile[i][tx] = (co < Cout && ci < Cin) ? w[((size_t)co * T + t) * Cin + ci] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int ci = ci0 + i, co = co0 + tx;
+        if (ci < Cin && co < Cout) wt[((size_t)ci * T + t) * Cout + co] = tile[tx][i];
+    }
+}
+
+// column sums of a [P, C] matrix (the bias gradient, tf.nn.bias_add backward): partial[slab][C] then a fixed-order reduce
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(int P, int C, int rows_per_slab, const float* __restrict__ x, float* __restrict__ partial)
+{
+    __shared__ float4 red[8][32];
+    const int c4 = blockIdx.x * 32 + (threadIdx.x & 31);         // float4 column
+    const int ry = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * rows_per_slab;
+    int r1 = r0 + rows_per_slab;
+    r1 = r1 > P ? P : r1;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 * 4 < C)
+        for (int r = r0 + ry; r < r1; r += 8) {
+            const float4 v = *reinterpret_cast<const float4*>(x + (size_t)r * C + c4 * 4);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+    red[ry][threadIdx.x & 31] = a;
+    __syncthreads();
+    if (ry == 0 && c4 * 4 < C) {
+        for (int i = 1; i < 8; ++i) {
+            const float4 v = red[i][threadIdx.x];
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        *reinterpret_cast<float4*>(partial + (size_t)blockIdx.y * C + c4 * 4) = a;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host helpers
+inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// pixel box with `npix` pixels over a [Wt, Ht, Bt] grid (w fastest): bw*bh*bn == npix, each dividing its extent
+bool pixel_box(int npix, int Wt, int Ht, int Bt, int* bw, int* bh, int* bn)
+{
+    if (!is_pow2(Wt) || !is_pow2(Ht)) return false;
+    *bw = Wt < npix ? Wt : npix;
+    const int rem = npix / *bw;
+    *bh = Ht < rem ? Ht : rem;
+    *bn = rem / *bh;
+    return (*bw) * (*bh) * (*bn) == npix && Bt % *bn == 0 && *bn <= 256;
+}
+
+// 4-D view of an NHWC tensor [B, H, W, C] sub-sampled by `s` starting at pixel (ph, pw): dims [C, W/s, H/s, B]
+bool make_view_map(CUtensorMap* map, const float* base, int B, int H, int W, int C, int s, int ph, int pw,
+                   const unsigned box[4], CUtensorMapSwizzle swz)
+{
+    const unsigned long long dims[4] = {(unsigned long long)C, (unsigned long long)(W / s), (unsigned long long)(H / s), (unsigned long long)B};
+    const unsigned long long str[3] = {(unsigned long long)s * C * 4, (unsigned long long)s * W * C * 4, (unsigned long long)H * W * C * 4};
+    return make_tensor_map_nd(map, base + ((size_t)ph * W + pw) * C, 4, dims, str, box, swz);
+}
+
+template <int TN>
+int launch_gemm(const GemmParams& p, cudaStream_t stream)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        OTGAN_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<TN>::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
+    conv_gemm_tc_kernel<TN><<<grid, NUM_THREADS, Cfg<TN>::SMEM_BYTES, stream>>>(p);
+    OTGAN_CHECK_LAUNCH("conv_gemm_tc_kernel");
+    return OTGAN_OK;
+}
+
+template <int TN>
+int launch_wgrad(const WgradParams& p, cudaStream_t stream)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        OTGAN_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<TN>::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
+    conv_wgrad_tc_kernel<TN><<<grid, NUM_THREADS, Cfg<TN>::SMEM_BYTES, stream>>>(p);
+    OTGAN_CHECK_LAUNCH("conv_wgrad_tc_kernel");
+    return OTGAN_OK;
+}
+
+bool conv_dims_ok(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo)
+{
+    if (B < 1 || H < 1 || W < 1 || Cin < 1 || Cout < 1 || kh < 1 || kw < 1 || kh * kw > MAX_TAPS) return false;
+    if (s != 1 && s != 2) return false;
+    if (pt < 0 || pl < 0 || pt >= kh || pl >= kw) return false;
+    if (H % s || W % s || Ho != H / s || Wo != W / s) return false;      // TensorFlow 'SAME' on even extents
+    return true;
+}
+
+int wgrad_splits(int items, int nchunks)
+{
+    int S = 1;
+    if (items < 2 * kNumSMs) S = (2 * kNumSMs + items - 1) / items;      // at least two waves of work items
+    S = S > 16 ? 16 : S;
+    S = S > nchunks ? nchunks : S;
+    return S < 1 ? 1 : S;
+}
+
+}  // namespace
+
+// y[B,Ho,Wo,Cout] = conv(x[B,H,W,Cin], w[Cout, kh*kw*Cin]) + bias
+int conv_fprop_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo,
+                      const float* x, const float* w, const float* bias, float* y, cudaStream_t stream)
+{
+    OTGAN_REQUIRE(conv_dims_ok(B, H, W, Cin, Cout, kh, kw, s, pt, pl, Ho, Wo), "conv_fprop: unsupported geometry");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    if (Cin % BK || Cout % 128 || !pixel_box(TM, Wo, Ho, B, &p.bw, &p.bh, &p.bn)) {
+        set_error("conv_fprop(tcgen05): needs Cin %% 32 == 0, Cout %% 128 == 0, power-of-two output extent tiling into 128-pixel boxes "
+                  "(B=%d H=%d W=%d Cin=%d Cout=%d)", B, H, W, Cin, Cout);
+        return OTGAN_EUNSUPPORTED;
+    }
+    const int TN = (Cout % 256 == 0) ? 256 : 128;
+    const unsigned box[4] = {(unsigned)BK, (unsigned)p.bw, (unsigned)p.bh, (unsigned)p.bn};
+    for (int ph = 0; ph < s; ++ph)
+        for (int pw = 0; pw < s; ++pw)
+            if (!make_view_map(&p.amap[ph * s + pw], x, B, H, W, Cin, s, ph, pw, box, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
+    for (int i = s * s; i < 4; ++i) p.amap[i] = p.amap[0];
+    if (!make_tensor_map_2d(&p.bmap, w, Cout, kh * kw * Cin, kh * kw * Cin, TN, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
+    int nt = 0;
+    for (int a = 0; a < kh; ++a)
+        for (int b = 0; b < kw; ++b) {
+            const int oh = a - pt, ow = b - pl;                  // input offset relative to s*oh, s*ow
+            const int ph = oh & (s - 1), pw = ow & (s - 1);      // parity (two's complement: -1 & 1 == 1)
+            p.taps[nt++] = Tap{ph * s + pw, (ow - pw) / s, (oh - ph) / s, (a * kw + b) * Cin};
+        }
+    p.n_cls = 1;
+    p.cls_tap_begin[0] = 0; p.cls_tap_begin[1] = nt;
+    p.cls_out_off[0] = 0;
+    p.tiles_w = Wo / p.bw; p.tiles_h = Ho / p.bh;
+    p.m_tiles = p.tiles_w * p.tiles_h * (B / p.bn);
+    p.n_tiles = Cout / TN;
+    p.n_items = p.m_tiles * p.n_tiles;
+    p.kchunks = Cin / BK;
+    p.osW = Cout; p.osH = (long long)Wo * Cout; p.osN = (long long)Ho * Wo * Cout;
+    p.out = y; p.bias = bias;
+    return TN == 256 ? launch_gemm<256>(p, stream) : launch_gemm<128>(p, stream);
+}
+
+// dx[B,H,W,Cin] = conv_transpose(dy[B,Ho,Wo,Cout], wt[Cin, kh*kw*Cout])
+int conv_dgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo,
+                      const float* dy, const float* wt, float* dx, cudaStream_t stream)
+{
+    OTGAN_REQUIRE(conv_dims_ok(B, H, W, Cin, Cout, kh, kw, s, pt, pl, Ho, Wo), "conv_dgrad: unsupported geometry");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    if (Cout % BK || Cin % 128 || !pixel_box(TM, W / s, H / s, B, &p.bw, &p.bh, &p.bn)) {
+        set_error("conv_dgrad(tcgen05): needs Cout %% 32 == 0, Cin %% 128 == 0, power-of-two extents tiling into 128-pixel boxes "
+                  "(B=%d H=%d W=%d Cin=%d Cout=%d)", B, H, W, Cin, Cout);
+        return OTGAN_EUNSUPPORTED;
+    }
+    const int TN = (Cin % 256 == 0) ? 256 : 128;
+    const unsigned box[4] = {(unsigned)BK, (unsigned)p.bw, (unsigned)p.bh, (unsigned)p.bn};
+    if (!make_view_map(&p.amap[0], dy, B, Ho, Wo, Cout, 1, 0, 0, box, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
+    for (int i = 1; i < 4; ++i) p.amap[i] = p.amap[0];
+    if (!make_tensor_map_2d(&p.bmap, wt, Cin, kh * kw * Cout, kh * kw * Cout, TN, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
+    // parity classes of the input pixel (ih, iw): ih = s*j + ph gets the taps with (ph + pt - a) % s == 0, from output row
+    // oh = j + (ph + pt - a) / s
+    int nt = 0;
+    p.n_cls = s * s;
+    for (int ph = 0; ph < s; ++ph)
+        for (int pw = 0; pw < s; ++pw) {
+            const int cls = ph * s + pw;
+            p.cls_tap_begin[cls] = nt;
+            p.cls_out_off[cls] = ((long long)ph * W + pw) * Cin;
+            for (int a = 0; a < kh; ++a) {
+                if ((ph + pt - a) % s) continue;
+                for (int b = 0; b < kw; ++b) {
+                    if ((pw + pl - b) % s) continue;
+                    p.taps[nt++] = Tap{0, (pw + pl - b) / s, (ph + pt - a) / s, (a * kw + b) * Cout};
+                }
+            }
+            if (nt == p.cls_tap_begin[cls]) { set_error("conv_dgrad: a parity class has no filter tap (k < stride)"); return OTGAN_EUNSUPPORTED; }
+        }
+    p.cls_tap_begin[p.n_cls] = nt;
+    p.tiles_w = (W / s) / p.bw; p.tiles_h = (H / s) / p.bh;
+    p.m_tiles = p.tiles_w * p.tiles_h * (B / p.bn);
+    p.n_tiles = Cin / TN;
+    p.n_items = p.m_tiles * p.n_tiles * p.n_cls;
+    p.kchunks = Cout / BK;
+    p.osW = (long long)s * Cin; p.osH = (long long)s * W * Cin; p.osN = (long long)H * W * Cin;
+    p.out = dx; p.bias = nullptr;
+    return TN == 256 ? launch_gemm<256>(p, stream) : launch_gemm<128>(p, stream);
+}
+
+size_t conv_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int kh, int kw)
+{
+    const int TN = (Cin % 256 == 0) ? 256 : 128;
+    const int items = (Cout / TM) * (Cin / TN) * kh * kw;
+    const long long P = (long long)B * Ho * Wo;
+    const int S = wgrad_splits(items < 1 ? 1 : items, (int)(P / 32 < 1 ? 1 : P / 32));
+    return S > 1 ? (size_t)S * Cout * kh * kw * Cin * sizeof(float) + 256 : 256;
+}
+
+// dw[Cout, kh*kw*Cin] = sum over pixels dy (x) x
+int conv_wgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo,
+                      const float* dy, const float* x, float* dw, void* ws, size_t ws_bytes, cudaStream_t stream)
+{
+    OTGAN_REQUIRE(conv_dims_ok(B, H, W, Cin, Cout, kh, kw, s, pt, pl, Ho, Wo), "conv_wgrad: unsupported geometry");
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    const long long P = (long long)B * Ho * Wo;
+    if (Cin % 128 || Cout % TM || Wo > 32 || !pixel_box(32, Wo, Ho, B, &p.bw, &p.bh, &p.bn)) {
+        set_error("conv_wgrad(tcgen05): needs Cin %% 128 == 0, Cout %% 128 == 0, power-of-two output extent <= 32 wide "
+                  "(B=%d H=%d W=%d Cin=%d Cout=%d)", B, H, W, Cin, Cout);
+        return OTGAN_EUNSUPPORTED;
+    }
+    const int TN = (Cin % 256 == 0) ? 256 : 128;
+    if (!make_tensor_map_2d(&p.dymap, dy, (int)P, Cout, Cout, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return OTGAN_EUNSUPPORTED;
+    const unsigned box[4] = {32u, (unsigned)p.bw, (unsigned)p.bh, (unsigned)p.bn};
+    for (int ph = 0; ph < s; ++ph)
+        for (int pw = 0; pw < s; ++pw)
+            if (!make_view_map(&p.xmap[ph * s + pw], x, B, H, W, Cin, s, ph, pw, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return OTGAN_EUNSUPPORTED;
+    for (int i = s * s; i < 4; ++i) p.xmap[i] = p.xmap[0];
+    int nt = 0;
+    for (int a = 0; a < kh; ++a)
+        for (int b = 0; b < kw; ++b) {
+            const int oh = a - pt, ow = b - pl;
+            const int ph = oh & (s - 1), pw = ow & (s - 1);
+            p.taps[nt++] = Tap{ph * s + pw, (ow - pw) / s, (oh - ph) / s, (a * kw + b) * Cin};
+        }
+    p.ntaps = nt;
+    p.co_tiles = Cout / TM; p.ci_tiles = Cin / TN;
+    p.tiles_w = Wo / p.bw; p.tiles_h = Ho / p.bh;
+    p.nchunks = (int)(P / 32);
+    const int items = p.co_tiles * p.ci_tiles * nt;
+    p.splits = wgrad_splits(items, p.nchunks);
+    p.chunks_per_split = ceil_div(p.nchunks, p.splits);
+    p.splits = ceil_div(p.nchunks, p.chunks_per_split);
+    p.n_items = items * p.splits;
+    p.ldw = nt * Cin;
+    p.split_stride = (long long)Cout * p.ldw;
+    if (p.splits > 1) {
+        OTGAN_REQUIRE(ws && ws_bytes >= (size_t)p.splits * p.split_stride * sizeof(float), "conv_wgrad: workspace too small");
+        p.out = reinterpret_cast<float*>(ws);
+    } else {
+        p.out = dw;
+    }
+    const int rc = TN == 256 ? launch_wgrad<256>(p, stream) : launch_wgrad<128>(p, stream);
+    if (rc != OTGAN_OK || p.splits == 1) return rc;
+    const size_t n4 = (size_t)p.split_stride / 4;
+    const int grid = (int)((n4 + 255) / 256 < (size_t)(8 * kNumSMs) ? (n4 + 255) / 256 : (size_t)(8 * kNumSMs));
+    split_reduce_kernel<<<grid, 256, 0, stream>>>(n4, p.splits, n4, reinterpret_cast<const float4*>(p.out), reinterpret_cast<float4*>(dw));
+    OTGAN_CHECK_LAUNCH("split_reduce_kernel");
+    return OTGAN_OK;
+}
+
+int ohwi_to_ihwo_launch(int Cout, int T, int Cin, const float* w, float* wt, cudaStream_t stream)
+{
+    dim3 grid(ceil_div(Cin, 32), ceil_div(Cout, 32), T);
+    ohwi_to_ihwo_kernel<<<grid, 256, 0, stream>>>(Cout, T, Cin, w, wt);
+    OTGAN_CHECK_LAUNCH("ohwi_to_ihwo_kernel");
+    return OTGAN_OK;
+}
+
+size_t colsum_workspace_bytes(int P, int C)
+{
+    (void)P;
+    return (size_t)64 * C * sizeof(float) + 256;
+}
+
+int colsum_launch(int P, int C, const float* x, float* out, void* ws, size_t ws_bytes, cudaStream_t stream)
+{
+    OTGAN_REQUIRE(ws && ws_bytes >= colsum_workspace_bytes(P, C), "colsum: workspace too small");
+    int slabs = ceil_div(P, 256);
+    slabs = slabs > 64 ? 64 : slabs;
+    const int rows_per_slab = ceil_div(P, slabs);
+    slabs = ceil_div(P, rows_per_slab);
+    float* partial = reinterpret_cast<float*>(ws);
+    colsum_partial_kernel<<<dim3(ceil_div(C, 128), slabs), 256, 0, stream>>>(P, C, rows_per_slab, x, partial);
+    OTGAN_CHECK_LAUNCH("colsum_partial_kernel");
+    const size_t n4 = (size_t)C / 4;
+    split_reduce_kernel<<<(int)((n4 + 255) / 256), 256, 0, stream>>>(n4, slabs, n4, reinterpret_cast<const float4*>(partial), reinterpret_cast<float4*>(out));
+    OTGAN_CHECK_LAUNCH("split_reduce_kernel");
+    return OTGAN_OK;
+}
+
+}  // namespace otgan

@@ -37,5 +37,22 @@ bool make_tensor_map_2d(CUtensorMap* map, const float* base, int rows, int cols,
     return true;
 }
 
+bool make_tensor_map_nd(CUtensorMap* map, const float* base, int rank, const unsigned long long* dims,
+                        const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swizzle)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return false; }
+    if (rank < 1 || rank > 5) { set_error("tensor map rank %d not in 1..5", rank); return false; }
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], estr[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr, bx, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (rank %d) failed with CUresult %d", rank, (int)r); return false; }
+    return true;
+}
+
 }  // namespace tc
 }  // namespace otgan

@@ -56,6 +56,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// 4-D tiled load (innermost coordinate first).  Coordinates are signed: elements of the box that fall outside the tensor
+// (negative or past the end) are ZERO-FILLED and still counted in the mbarrier's transaction bytes -- this is what makes the
+// convolution padding free (conv_tc.cu).
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -140,6 +148,10 @@ __device__ __forceinline__ uint32_t cvt_rna_tf32(float x) {
 // swizzle: CU_TENSOR_MAP_SWIZZLE_64B / _128B.  Returns false (and sets the error string) on failure.
 bool make_tensor_map_2d(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows, int box_cols,
                         CUtensorMapSwizzle swizzle);
+
+// General form: `rank` dimensions (innermost first), byte strides of dimensions 1..rank-1 (multiples of 16), box extents.
+bool make_tensor_map_nd(CUtensorMap* map, const float* base, int rank, const unsigned long long* dims,
+                        const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swizzle);
 
 }  // namespace tc
 }  // namespace otgan

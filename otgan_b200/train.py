@@ -138,7 +138,8 @@ class Trainer:
             x_gen = gen(u=u, **self.model_opts)
             with torch.no_grad():
                 f_dat = disc(x_real, **self.model_opts)
-            f_gen = disc(x_gen, **self.model_opts)
+            with nn.frozen_params():                      # tf.gradients(xs=gen_params): no critic filter gradients
+                f_gen = disc(x_gen, **self.model_opts)
         A, B = self._gather_features(f_gen, f_dat)
         Ga, Gb, stats = self._match(A.detach(), B.detach())
         lo, hi = local_rows(self.rank, bs)

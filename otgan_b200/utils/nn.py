@@ -100,10 +100,13 @@ class VariableStore:
 
     def begin_call(self):
         """One autograd node for ALL variable views of a template call (split_with_sizes: its backward is a single
-        concatenation into the flat gradient; per-variable slices would each materialise a full-size zero gradient)."""
+        concatenation into the flat gradient; per-variable slices would each materialise a full-size zero gradient).
+        Under `frozen_params()` the views are detached: the call back-propagates to its INPUT only (the critic inside a
+        generator step, train.py:111-112 -- tf.gradients(xs=gen_params) never builds the critic's filter gradients)."""
         if self.frozen:
             total = self.num_params()
-            self._views = torch.split_with_sizes(self.flat[:total], [s[3] for s in self.specs])
+            src = self.flat.detach() if getattr(_tls, "freeze_params", False) else self.flat
+            self._views = torch.split_with_sizes(src[:total], [s[3] for s in self.specs])
             self._views_src = {}
 
     def get(self, var_name, source=None):
@@ -165,6 +168,17 @@ class Template:
 
 def make_template(name, spec):
     return Template(name, spec)
+
+
+@contextlib.contextmanager
+def frozen_params():
+    """Template calls inside this context treat their variables as constants (no parameter gradients are built)."""
+    prev = getattr(_tls, "freeze_params", False)
+    _tls.freeze_params = True
+    try:
+        yield
+    finally:
+        _tls.freeze_params = prev
 
 
 class ExponentialMovingAverage:
@@ -272,6 +286,91 @@ def _conv2d_nhwc(x, W, stride, pad, bias=None):
     else:
         raise ValueError(pad)
     return y.permute(0, 2, 3, 1)
+
+
+CONV_BACKEND = "tcgen05"      # "tcgen05": this library's implicit-GEMM kernels where they tile the shape; "cudnn": library rung only
+_conv_ws = {}
+
+
+def _workspace(device, nbytes):
+    """Grow-only per-device scratch buffer for the convolution kernels (split-K partials, bias-gradient partials)."""
+    ws = _conv_ws.get(device.index)
+    if ws is None or ws.numel() * 4 < nbytes:
+        ws = _conv_ws[device.index] = torch.empty((max(nbytes // 4 + 64, 1 << 20),), device=device, dtype=torch.float32)
+    return ws
+
+
+def _pow2(v):
+    return v > 0 and (v & (v - 1)) == 0
+
+
+def conv_tc_supported(xshape, cout, kh, kw, stride, pad):
+    """Shapes the tcgen05 implicit-GEMM kernels tile (fprop, dgrad and wgrad alike): channels in multiples of 128,
+    power-of-two extents, and a batch that fills whole 128-pixel (fprop/dgrad) and 32-pixel (wgrad) boxes."""
+    B, H, W, cin = xshape
+    if pad != "SAME" or stride[0] != stride[1] or stride[0] not in (1, 2) or kh * kw > 32:
+        return False
+    s = stride[0]
+    if cin % 128 or cout % 128 or H % s or W % s:
+        return False
+    ho, wo = H // s, W // s
+    if not (_pow2(ho) and _pow2(wo)) or wo > 32:
+        return False
+    img = ho * wo
+    return (img >= 128 or (B * img) % 128 == 0) and (img >= 32 or (B * img) % 32 == 0)
+
+
+class _ConvTC(torch.autograd.Function):
+    """tf.nn.conv2d(x, W, [1,s,s,1], 'SAME') + bias_add on this library's tcgen05 implicit-GEMM kernels
+    (otgan_conv2d_{fprop,dgrad,wgrad}_tf32, otgan_colsum_f32).  x: NHWC, wt: OHWI [Cout, kh*kw*Cin]."""
+
+    @staticmethod
+    def forward(ctx, x, wt, bias, geom):
+        lib = _lib.load()
+        kh, kw, s, pt, pl = geom
+        B, H, W, cin = x.shape
+        cout = wt.shape[0]
+        x, wt = x.contiguous(), wt.contiguous()
+        if bias is not None and bias.data_ptr() % 16:
+            bias = bias.clone()
+        y = torch.empty((B, H // s, W // s, cout), device=x.device, dtype=torch.float32)
+        rc = lib.otgan_conv2d_fprop_tf32(B, H, W, cin, cout, kh, kw, s, pt, pl, x.data_ptr(), wt.data_ptr(),
+                                         bias.data_ptr() if bias is not None else None, y.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "otgan_conv2d_fprop_tf32")
+        ctx.save_for_backward(x, wt)
+        ctx.geom, ctx.has_bias = geom, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, wt = ctx.saved_tensors
+        kh, kw, s, pt, pl = ctx.geom
+        B, H, W, cin = x.shape
+        cout = wt.shape[0]
+        dy = dy.contiguous()
+        stream = torch.cuda.current_stream().cuda_stream
+        dx = dwt = db = None
+        if ctx.needs_input_grad[0]:
+            wt_t = torch.empty((cin, kh * kw * cout), device=x.device, dtype=torch.float32)
+            _lib.check(lib.otgan_ohwi_to_ihwo_f32(cout, kh * kw, cin, wt.data_ptr(), wt_t.data_ptr(), stream), "otgan_ohwi_to_ihwo_f32")
+            dx = torch.empty_like(x)
+            rc = lib.otgan_conv2d_dgrad_tf32(B, H, W, cin, cout, kh, kw, s, pt, pl, dy.data_ptr(), wt_t.data_ptr(), dx.data_ptr(), stream)
+            _lib.check(rc, "otgan_conv2d_dgrad_tf32")
+        if ctx.needs_input_grad[1]:
+            need = lib.otgan_workspace_bytes_conv_wgrad(B, H, W, cin, cout, kh, kw, s)
+            ws = _workspace(x.device, need)
+            dwt = torch.empty_like(wt)
+            rc = lib.otgan_conv2d_wgrad_tf32(B, H, W, cin, cout, kh, kw, s, pt, pl, dy.data_ptr(), x.data_ptr(), dwt.data_ptr(),
+                                             ws.data_ptr(), ws.numel() * 4, stream)
+            _lib.check(rc, "otgan_conv2d_wgrad_tf32")
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            P = dy.numel() // cout
+            ws = _workspace(x.device, lib.otgan_workspace_bytes_colsum(P, cout))
+            db = torch.empty((cout,), device=x.device, dtype=torch.float32)
+            _lib.check(lib.otgan_colsum_f32(P, cout, dy.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream), "otgan_colsum_f32")
+        return dx, dwt, db, None
 
 
 class _CreluL2Norm(torch.autograd.Function):
@@ -501,6 +600,15 @@ def _conv2d(x, W, stride=(1, 1), pad="SAME", dilate=1, pre_activation=None, upsa
     if upsample:
         xc = torch.cat(xl, 3) if len(xl) > 1 else xl[0]
         xl = [resize_nearest_neighbor(xc, [2 * xc.shape[1], 2 * xc.shape[2]])]
+    on_gpu = len(xl) == 1 and xl[0].is_cuda and xl[0].dtype == torch.float32 and xl[0].dim() == 4
+    if on_gpu and CONV_BACKEND == "tcgen05" and isinstance(W, TransposedWeight) and pre_activation in (None, "crelu"):
+        kh, kw, cin, cout = W.vshape
+        B, H, Wd, C = xl[0].shape
+        if conv_tc_supported((B, H, Wd, cin), cout, kh, kw, stride, pad):
+            # TensorFlow 'SAME' zero padding costs nothing here: the kernels' TMA boxes are zero-filled outside the tensor
+            z = xl[0].contiguous() if pre_activation is None else _CreluPad.apply(xl[0].contiguous(), (0, 0, 0, 0))
+            geom = (kh, kw, stride[0], same_padding(H, kh, stride[0])[0], same_padding(Wd, kw, stride[1])[0])
+            return _ConvTC.apply(z, W.wt, bias, geom)
     if (pre_activation == "crelu" and len(xl) == 1 and pad == "SAME" and xl[0].is_cuda and xl[0].dtype == torch.float32
             and xl[0].shape[3] % 4 == 0):
         # CReLU written straight into the TensorFlow-'SAME'-padded input of the convolution (one fused kernel)

@@ -1,0 +1,161 @@
+"""GPU tests (-m gpu) of the tcgen05 implicit-GEMM convolution kernels (otgan_conv2d_{fprop,dgrad,wgrad}_tf32) through the
+C ABI, against a float64 restatement of tf.nn.conv2d(x, W, [1,s,s,1], 'SAME') (utils/nn.py:241) and its two gradients.
+
+Two kinds of check:
+  * exact: inputs are small integers (exactly representable in TF32, sums < 2^24) so the tensor-core result must equal
+    the float64 reference BIT FOR BIT -- any tile / tap / padding / layout mistake shows up as a hard mismatch;
+  * tolerance: N(0,1) inputs, error bounded by the TF32 operand rounding (2^-11 relative per operand, random-sign sum):
+    max-abs-err <= 4e-3 * max-abs-value, written next to each assert.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# (B, H, W, Cin, Cout, k, stride): every DCGAN layer class at reduced batch, plus 3x3 (DenseNet-style) taps
+SHAPES = [
+    (8, 8, 8, 128, 128, 5, 1),
+    (8, 8, 8, 128, 128, 5, 2),
+    (2, 32, 32, 128, 256, 5, 1),
+    (2, 32, 32, 256, 256, 5, 2),
+    (4, 16, 16, 256, 128, 5, 2),
+    (8, 8, 8, 256, 512, 5, 2),
+    (4, 16, 16, 128, 256, 3, 1),
+    (4, 16, 16, 128, 128, 3, 2),
+]
+
+
+def _same_pad(n, k, s):
+    out = -(-n // s)
+    total = max((out - 1) * s + k - n, 0)
+    return total // 2, total - total // 2
+
+
+def _ref_conv(x, w_ohwi, bias, k, s):
+    """float64 reference: x NHWC, w [Cout, k, k, Cin] -> y NHWC (TensorFlow 'SAME')."""
+    B, H, W, C = x.shape
+    pt, pb = _same_pad(H, k, s)
+    pl, pr = _same_pad(W, k, s)
+    xn = F.pad(x.permute(0, 3, 1, 2), (pl, pr, pt, pb))
+    y = F.conv2d(xn, w_ohwi.permute(0, 3, 1, 2), bias, stride=s)
+    return y.permute(0, 2, 3, 1)
+
+
+def _make(shape, exact, seed):
+    B, H, W, Cin, Cout, k, s = shape
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    if exact:
+        x = torch.randint(-2, 3, (B, H, W, Cin), device="cuda", generator=g).float()
+        w = torch.randint(-2, 3, (Cout, k, k, Cin), device="cuda", generator=g).float()
+        b = torch.randint(-4, 5, (Cout,), device="cuda", generator=g).float()
+        dy = torch.randint(-2, 3, (B, H // s, W // s, Cout), device="cuda", generator=g).float()
+    else:
+        x = torch.randn((B, H, W, Cin), device="cuda", generator=g)
+        w = torch.randn((Cout, k, k, Cin), device="cuda", generator=g) * 0.05
+        b = torch.randn((Cout,), device="cuda", generator=g)
+        dy = torch.randn((B, H // s, W // s, Cout), device="cuda", generator=g)
+    return x, w, b, dy
+
+
+def _run_ours(shape, x, w, b, dy):
+    from otgan_b200.utils import nn
+    B, H, W, Cin, Cout, k, s = shape
+    assert nn.conv_tc_supported((B, H, W, Cin), Cout, k, k, [s, s], "SAME")
+    xr = x.clone().requires_grad_(True)
+    wr = w.reshape(Cout, -1).clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    geom = (k, k, s, _same_pad(H, k, s)[0], _same_pad(W, k, s)[0])
+    y = nn._ConvTC.apply(xr, wr, br, geom)
+    dx, dw, db = torch.autograd.grad([y], [xr, wr, br], [dy])
+    return y.detach(), dx, dw.view(Cout, k, k, Cin), db
+
+
+def _run_ref(shape, x, w, b, dy):
+    B, H, W, Cin, Cout, k, s = shape
+    xd, wd, bd = (t.double().requires_grad_(True) for t in (x, w, b))
+    y = _ref_conv(xd, wd, bd, k, s)
+    dx, dw, db = torch.autograd.grad([y], [xd, wd, bd], [dy.double()])
+    return y.detach(), dx, dw, db
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_conv_kernels_exact_on_integer_inputs(shape):
+    x, w, b, dy = _make(shape, True, 1)
+    ours = _run_ours(shape, x, w, b, dy)
+    ref = _run_ref(shape, x, w, b, dy)
+    for name, o, r in zip(("fprop", "dgrad", "wgrad", "bias-grad"), ours, ref):
+        diff = (o.double() - r).abs()
+        assert float(diff.max()) == 0.0, "%s %s: %d / %d elements differ, max |diff| %g" % (
+            name, shape, int((diff > 0).sum()), diff.numel(), float(diff.max()))
+
+
+@pytest.mark.parametrize("shape", SHAPES[:6])
+def test_conv_kernels_tf32_tolerance(shape):
+    x, w, b, dy = _make(shape, False, 2)
+    ours = _run_ours(shape, x, w, b, dy)
+    ref = _run_ref(shape, x, w, b, dy)
+    for name, o, r in zip(("fprop", "dgrad", "wgrad", "bias-grad"), ours, ref):
+        err = float((o.double() - r).abs().max() / r.abs().max())
+        assert err <= 4e-3, (name, shape, err)          # TF32 operands (10-bit mantissa), fp32 accumulation
+
+
+def test_wgrad_split_k_is_deterministic():
+    shape = (2, 32, 32, 256, 256, 5, 2)
+    x, w, b, dy = _make(shape, False, 3)
+    a = _run_ours(shape, x, w, b, dy)
+    c = _run_ours(shape, x, w, b, dy)
+    for o1, o2 in zip(a, c):
+        assert torch.equal(o1, o2)
+
+
+def test_unsupported_shapes_are_rejected_not_miscomputed():
+    from otgan_b200 import _lib
+    lib = _lib.load()
+    x = torch.zeros(2 * 32 * 32 * 3, device="cuda")
+    w = torch.zeros(128 * 75, device="cuda")
+    y = torch.zeros(2 * 32 * 32 * 128, device="cuda")
+    rc = lib.otgan_conv2d_fprop_tf32(2, 32, 32, 3, 128, 5, 5, 1, 2, 2, x.data_ptr(), w.data_ptr(), None, y.data_ptr(), None)
+    assert rc == -4 and b"Cin" in lib.otgan_last_error()
+
+
+def test_dcgan_networks_match_library_convolutions():
+    """Critic and generator forward + backward with this library's convolution kernels vs the cuDNN rung (fp32, TF32
+    off) on the same parameters, inputs and output gradients (no Sinkhorn in between: lambda = 500 would amplify the
+    TF32 rounding of the features): features / images and flat parameter gradients agree to TF32 accuracy."""
+    from otgan_b200.models.dcgan import discriminator, generator
+    from otgan_b200.utils import nn
+    dev = torch.device("cuda", 0)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    res = {}
+    try:
+        discriminator.reset(); generator.reset()
+        torch.manual_seed(3)
+        with torch.no_grad():
+            discriminator(torch.zeros(16, 32, 32, 3, device=dev), init=True, device=dev)
+            generator(init=True, device=dev, batch_size=16)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        x = torch.rand(16, 32, 32, 3, device=dev, generator=g) * 2 - 1
+        u = torch.rand(16, 100, device=dev, generator=g) * 2 - 1
+        gy = torch.randn(16, 32768, device=dev, generator=g)
+        _lib_count = {}
+        for backend in ("tcgen05", "cudnn"):
+            nn.CONV_BACKEND = backend
+            xr = x.clone().requires_grad_(True)
+            f = discriminator(xr)
+            gd, gx = torch.autograd.grad([f], [discriminator.flat, xr], [gy])
+            img = generator(batch_size=16, u=u)
+            with nn.frozen_params():
+                f2 = discriminator(img)
+            (gg,) = torch.autograd.grad([f2], [generator.flat], [gy])
+            res[backend] = (f.detach(), gd, gx, img.detach(), gg)
+    finally:
+        nn.CONV_BACKEND = "tcgen05"
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    names = ("critic features", "critic parameter gradient", "critic input gradient", "generator images", "generator parameter gradient")
+    for name, a, c in zip(names, res["tcgen05"], res["cudnn"]):
+        err = float((a - c).abs().max() / c.abs().max())
+        assert err <= 1e-2, (name, err)              # TF32 operand rounding through up to 8 convolution layers
