@@ -135,6 +135,10 @@ OTGAN_API int otgan_distance_from_pc_f32(const float* pc /* [6] */, const float*
  * d1 = 1 - mom1^t, d2 = 1 - mom2^t (t starts at 1).  v may be NULL (mom1 == 0).  n % 4 == 0, 16-byte aligned buffers. */
 OTGAN_API int otgan_adam_ema_f32(size_t n, float* p, const float* g, float* v, float* mg, float* ema, float lr, float mom1,
                                  float mom2, float d1, float d2, float ema_decay, void* stream);
+/* Same update with the step-dependent scalars read from DEVICE memory: hyper_dev = [lr, d1, d2].  The launch arguments are
+ * then identical every step, so a training step captured in a CUDA graph can be replayed (the host refreshes hyper_dev). */
+OTGAN_API int otgan_adam_ema_dev_f32(size_t n, float* p, const float* g, float* v, float* mg, float* ema,
+                                     const float* hyper_dev, float mom1, float mom2, float ema_decay, void* stream);
 /* Critic head (models/dcgan.py:16-19, models/densenet.py:37-42): y = z / ||z||, z = concat(relu(x), relu(-x)) over the
  * channel axis then flattened; x: [B, HW, C] (NHWC), y: [B, HW*2C], inv_norm: [B].  Backward: dx from dy. */
 OTGAN_API int otgan_crelu_l2norm_fwd_f32(int B, int HW, int C, const float* x, float* y, float* inv_norm, void* stream);

@@ -44,6 +44,7 @@ SIGNATURES = {
     "otgan_calc_distance_f32": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _sz, _vp]),
     "otgan_distance_from_pc_f32": (_i, [_vp, _vp, _i, _vp, _vp]),
     "otgan_adam_ema_f32": (_i, [_sz, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _vp]),
+    "otgan_adam_ema_dev_f32": (_i, [_sz, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _vp]),
     "otgan_crelu_l2norm_fwd_f32": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "otgan_crelu_l2norm_bwd_f32": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "otgan_workspace_bytes_weightnorm": (_sz, [_i, _i]),

@@ -48,7 +48,7 @@ int distance_launch(int n, int D, const float* A, const float* B, const float* f
                     const float* f_ab, int ld, float scale, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 int adam_ema_launch(size_t n, float* p, const float* g, float* v, float* mg, float* ema, float lr, float mom1, float mom2,
-                    float d1, float d2, float ema_decay, cudaStream_t stream);
+                    float d1, float d2, float ema_decay, const float* hyper, cudaStream_t stream);
 int crelu_l2norm_fwd_launch(int B, int HW, int C, const float* x, float* y, float* inv, cudaStream_t stream);
 int crelu_l2norm_bwd_launch(int B, int HW, int C, const float* x, const float* y, const float* inv, const float* dy,
                             float* dx, cudaStream_t stream);
@@ -263,7 +263,17 @@ int otgan_adam_ema_f32(size_t n, float* p, const float* g, float* v, float* mg, 
     OTGAN_REQUIRE(aligned16(p) && aligned16(g) && aligned16(mg) && (!v || aligned16(v)) && (!ema || aligned16(ema)),
                   "adam_ema: buffers must be 16-byte aligned");
     OTGAN_REQUIRE(d1 != 0.f && d2 != 0.f, "adam_ema: zero bias-correction denominator");
-    return adam_ema_launch(n, p, g, v, mg, ema, lr, mom1, mom2, d1, d2, ema_decay, (cudaStream_t)stream);
+    return adam_ema_launch(n, p, g, v, mg, ema, lr, mom1, mom2, d1, d2, ema_decay, nullptr, (cudaStream_t)stream);
+}
+
+int otgan_adam_ema_dev_f32(size_t n, float* p, const float* g, float* v, float* mg, float* ema, const float* hyper_dev,
+                           float mom1, float mom2, float ema_decay, void* stream)
+{
+    OTGAN_REQUIRE(p && g && mg && hyper_dev, "adam_ema_dev: null pointer");
+    OTGAN_REQUIRE(n > 0 && n % 4 == 0, "adam_ema_dev: n=%zu must be a positive multiple of 4 (flat buffers are padded)", n);
+    OTGAN_REQUIRE(aligned16(p) && aligned16(g) && aligned16(mg) && (!v || aligned16(v)) && (!ema || aligned16(ema)),
+                  "adam_ema_dev: buffers must be 16-byte aligned");
+    return adam_ema_launch(n, p, g, v, mg, ema, 0.f, mom1, mom2, 1.f, 1.f, ema_decay, hyper_dev, (cudaStream_t)stream);
 }
 
 int otgan_crelu_l2norm_fwd_f32(int B, int HW, int C, const float* x, float* y, float* inv_norm, void* stream)

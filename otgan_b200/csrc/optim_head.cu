@@ -12,8 +12,9 @@ namespace {
 __global__ void __launch_bounds__(256)
 adam_ema_kernel(size_t n4, float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ v,
                 float4* __restrict__ mg, float4* __restrict__ ema, float lr, float mom1, float mom2, float d1, float d2,
-                float ema_decay)
+                float ema_decay, const float* __restrict__ hyper)
 {
+    if (hyper) { lr = hyper[0]; d1 = hyper[1]; d2 = hyper[2]; }   // step-dependent scalars from device memory (CUDA-graph replay)
     auto upd = [&](float& pp, float gg, float& vv, float& mm, float& ee, bool has_v, bool has_e) {
         float v_hat;
         if (has_v) {
@@ -103,14 +104,14 @@ crelu_l2norm_bwd_kernel(int HW, int C, const float* __restrict__ x, const float*
 }  // namespace
 
 int adam_ema_launch(size_t n, float* p, const float* g, float* v, float* mg, float* ema, float lr, float mom1, float mom2,
-                    float d1, float d2, float ema_decay, cudaStream_t stream)
+                    float d1, float d2, float ema_decay, const float* hyper, cudaStream_t stream)
 {
     const size_t n4 = n / 4;
     size_t blocks = (n4 + 255) / 256;
     if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
     adam_ema_kernel<<<(unsigned)blocks, 256, 0, stream>>>(n4, reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g),
                                                           reinterpret_cast<float4*>(v), reinterpret_cast<float4*>(mg),
-                                                          reinterpret_cast<float4*>(ema), lr, mom1, mom2, d1, d2, ema_decay);
+                                                          reinterpret_cast<float4*>(ema), lr, mom1, mom2, d1, d2, ema_decay, hyper);
     OTGAN_CHECK_LAUNCH("adam_ema_kernel");
     return OTGAN_OK;
 }

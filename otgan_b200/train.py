@@ -53,6 +53,7 @@ def build_parser():
     parser.add_argument('--synthetic', action='store_true', help='CIFAR-10-shaped uniform noise instead of the dataset')
     parser.add_argument('--max_steps', type=int, default=0, help='stop after this many steps (0 = run like the reference)')
     parser.add_argument('--log_every', type=int, default=0, help='also print a line every N steps')
+    parser.add_argument('--cuda_graphs', action='store_true', help='replay each step from a captured CUDA graph')
     return parser
 
 
@@ -100,6 +101,8 @@ class Trainer:
             self.disc_optimizer = opt(discriminator, lr=-args.learning_rate_disc, mom1=0.5)
         self.step_counter = 0
         self.gather_buf = None
+        self.graphs = None                                 # set by enable_cuda_graphs()
+        self.replayed_launches = 0                         # libotgan kernels executed through graph replays
 
     def _gather_features(self, f_gen, f_dat):
         return gather_features(f_gen, f_dat, self.world)
@@ -124,9 +127,21 @@ class Trainer:
     def step(self, x_real, u=None, apply_update=True):
         """x_real: this rank's [bs_local, 32, 32, 3] real images in [-1, 1].  Returns ('disc'|'gen', stats[2] tensor).
         `u` optionally fixes this rank's generator latents (parity tests); `apply_update=False` skips the optimiser and
-        leaves the summed gradient in self.last_grad."""
+        leaves the summed gradient in self.last_grad.  After enable_cuda_graphs() the step is one graph replay."""
         a = self.args
         train_disc = self.step_counter % (a.nr_gen_per_disc + 1) == 0                            # :214
+        kind = 'disc' if train_disc else 'gen'
+        if self.graphs is not None and apply_update:
+            return kind, self._replay(kind, x_real, u)
+        stats = self._step_body(kind, x_real, u, apply_update)
+        self.step_counter += 1
+        return kind, stats
+
+    def _step_body(self, kind, x_real, u, apply_update=True, hyper_dev=None):
+        """One sess.run of train.py:214-226 as a pure stream of kernel launches (no host synchronisation): this is also
+        exactly what enable_cuda_graphs() captures."""
+        a = self.args
+        train_disc = kind == 'disc'
         gen, disc = self.generator, self.discriminator
         bs = self.bs_local
         if train_disc:
@@ -149,18 +164,91 @@ class Trainer:
             if self.world > 1:
                 dist.all_reduce(grad, op=dist.ReduceOp.SUM)                                      # :134-139 (sum, not mean)
             if apply_update:
-                self.disc_optimizer.run(grad, lr=-a.learning_rate_disc)                          # :143,215
-            kind = 'disc'
+                self.disc_optimizer.run(grad, lr=-a.learning_rate_disc, hyper_dev=hyper_dev)     # :143,215
         else:
             (grad,) = torch.autograd.grad([f_gen], [gen.flat], grad_outputs=[ga])                # :111-112
             if self.world > 1:
                 dist.all_reduce(grad, op=dist.ReduceOp.SUM)
             if apply_update:
-                self.gen_optimizer.run(grad, lr=a.learning_rate_gen)                             # :142,222 (+ EMA :223)
-            kind = 'gen'
+                self.gen_optimizer.run(grad, lr=a.learning_rate_gen, hyper_dev=hyper_dev)        # :142,222 (+ EMA :223)
         self.last_grad = grad
+        return stats
+
+    # ---- CUDA graphs: one captured critic step and one captured generator step, replayed with refreshed inputs ----------
+    def enable_cuda_graphs(self, warmup=3):
+        """Capture the critic step and the generator step (forward, all-gather, matching, backward, all-reduce, Adam+EMA:
+        ~150 kernel launches each) into two CUDA graphs.  A step then costs three small host-to-device copies (images,
+        latents, [lr, d1, d2]) and one graph launch, which removes the Python / launch latency that dominates once the
+        per-rank batch is small (8 GPUs: 32 images per rank).  Training state is snapshotted around the warm-up runs, so
+        enabling graphs does not change the trajectory.  Only the adam optimiser has a replayable update."""
+        if self.graphs is not None:
+            return
+        a = self.args
+        assert a.optimizer == 'adam', "CUDA-graph replay needs the fused Adam kernel (device-resident step scalars)"
+        dev = self.device
+        bs = self.bs_local
+        self.g_x = torch.zeros((bs, 32, 32, 3), device=dev)
+        self.g_u = torch.zeros((bs, 100), device=dev)
+        self.g_hyper = {k: torch.zeros(3, device=dev) for k in ('disc', 'gen')}
+        self.g_hyper_host = {k: torch.zeros(3).pin_memory() for k in ('disc', 'gen')}
+        opts = {'disc': self.disc_optimizer, 'gen': self.gen_optimizer}
+        # snapshot everything a training step mutates
+        snap = [t.detach().clone() for t in self._mutable_state()]
+        snap_t = {k: o.state["t"] for k, o in opts.items()}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for k in ('disc', 'gen'):
+                lr = -a.learning_rate_disc if k == 'disc' else a.learning_rate_gen
+                self.g_hyper[k].copy_(torch.tensor([lr, 0.5, 0.001]))
+            for _ in range(warmup):                       # allocator / workspace / cudaFuncSetAttribute warm-up, eager
+                for k in ('disc', 'gen'):
+                    self._step_body(k, self.g_x, self.g_u, True, hyper_dev=self.g_hyper[k])
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(dev)
+        if self.world > 1:
+            dist.barrier()
+        from . import _lib
+        graphs, outs, self.g_launches = {}, {}, {}
+        pool = None
+        for k in ('disc', 'gen'):
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
+                outs[k] = self._step_body(k, self.g_x, self.g_u, True, hyper_dev=self.g_hyper[k])
+            self.g_launches[k] = _lib.launch_count() - n0      # this library's kernels inside one replay of the graph
+            pool = g.pool()
+            graphs[k] = g
+        torch.cuda.synchronize(dev)
+        with torch.no_grad():                             # restore the pre-warm-up training state
+            for t, s0 in zip(self._mutable_state(), snap):
+                t.copy_(s0)
+        for k, o in opts.items():
+            o.state["t"] = snap_t[k]
+        self.graphs, self.g_stats = graphs, outs
+
+    def _mutable_state(self):
+        out = [self.generator.flat, self.discriminator.flat, self.ema.shadow]
+        for o in (self.gen_optimizer, self.disc_optimizer):
+            out += [o.state["mg"]] + ([o.state["v"]] if o.state.get("v") is not None else [])
+        return out
+
+    def _replay(self, kind, x_real, u):
+        a = self.args
+        opt = self.disc_optimizer if kind == 'disc' else self.gen_optimizer
+        lr, d1, d2 = opt.hyper(-a.learning_rate_disc if kind == 'disc' else a.learning_rate_gen)
+        hh = self.g_hyper_host[kind]
+        hh[0], hh[1], hh[2] = lr, d1, d2
+        self.g_hyper[kind].copy_(hh, non_blocking=True)
+        self.g_x.copy_(x_real, non_blocking=True)
+        if u is None:
+            self.g_u.uniform_(-1.0, 1.0)                                                         # tf.random_uniform  dcgan.py:30
+        else:
+            self.g_u.copy_(u, non_blocking=True)
+        self.graphs[kind].replay()
+        self.replayed_launches += self.g_launches[kind]
         self.step_counter += 1
-        return kind, stats
+        return self.g_stats[kind]
 
     def save(self, path):
         torch.save({'discriminator': {n: p.detach().cpu() for n, p in self.discriminator.named_parameters()},
@@ -227,6 +315,8 @@ def main(argv=None):
     nr_batches_train_per_gpu = trainx.shape[0] // (args.nr_gpu * args.batch_size)                # :159
     if args.load_params:
         trainer.load(os.path.join(args.save_dir, args.model_name))
+    if args.cuda_graphs:
+        trainer.enable_cuda_graphs()
     os.makedirs(args.save_dir, exist_ok=True) if rank == 0 and not args.synthetic else None
     if rank == 0:
         print('starting training')

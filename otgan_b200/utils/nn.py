@@ -671,27 +671,41 @@ def adam_updates(params, cost_or_grads=None, lr=0.001, mom1=0.9, mom2=0.999, ema
     state = {"t": 1, "mg": torch.zeros_like(flat), "v": torch.zeros_like(flat) if mom1 > 0 else None}
     default_lr = lr
 
-    def run(grads, lr=None):
+    def hyper(lr=None):
+        """(lr, d1, d2) of the NEXT update -- the step-dependent scalars of utils/nn.py:63,68 -- and advance t.  Used with
+        run(..., hyper_dev=...) when the update is replayed from a CUDA graph."""
+        t = state["t"]
+        state["t"] = t + 1
+        return (float(default_lr if lr is None else lr), (1.0 - mom1 ** t) if mom1 > 0 else 1.0, 1.0 - mom2 ** t)
+
+    def run(grads, lr=None, hyper_dev=None):
         lib = _lib.load()
         step_lr = default_lr if lr is None else lr
         g = grads if grads is not None else flat.grad
         if ema is not None and ema.shadow is None:
             ema.attach(params)
+        stream = torch.cuda.current_stream().cuda_stream
+        v_ptr = state["v"].data_ptr() if state["v"] is not None else None
+        e_ptr = ema.shadow.data_ptr() if ema is not None else None
+        decay = float(ema.decay) if ema is not None else 0.0
+        if hyper_dev is not None:                           # scalars come from device memory; t is advanced by hyper()
+            with torch.no_grad():
+                rc = lib.otgan_adam_ema_dev_f32(flat.numel(), flat.data_ptr(), g.data_ptr(), v_ptr, state["mg"].data_ptr(), e_ptr,
+                                                hyper_dev.data_ptr(), float(mom1), float(mom2), decay, stream)
+            _lib.check(rc, "otgan_adam_ema_dev_f32")
+            return
         t = state["t"]
         c1 = (1.0 - mom1 ** t) if mom1 > 0 else 1.0        # bias-correction denominators (utils/nn.py:63,68)
         c2 = 1.0 - mom2 ** t
         with torch.no_grad():
-            rc = lib.otgan_adam_ema_f32(flat.numel(), flat.data_ptr(), g.data_ptr(),
-                                        state["v"].data_ptr() if state["v"] is not None else None,
-                                        state["mg"].data_ptr(), ema.shadow.data_ptr() if ema is not None else None,
-                                        float(step_lr), float(mom1), float(mom2), float(c1), float(c2),
-                                        float(ema.decay) if ema is not None else 0.0,
-                                        torch.cuda.current_stream().cuda_stream)
+            rc = lib.otgan_adam_ema_f32(flat.numel(), flat.data_ptr(), g.data_ptr(), v_ptr, state["mg"].data_ptr(), e_ptr,
+                                        float(step_lr), float(mom1), float(mom2), float(c1), float(c2), decay, stream)
         _lib.check(rc, "otgan_adam_ema_f32")
         state["t"] = t + 1
 
     u = _Updates(run)
     u.state = state
+    u.hyper = hyper
     return u
 
 

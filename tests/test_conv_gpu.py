@@ -24,6 +24,10 @@ SHAPES = [
     (8, 8, 8, 256, 512, 5, 2),
     (4, 16, 16, 128, 256, 3, 1),
     (4, 16, 16, 128, 128, 3, 2),
+    (16, 8, 8, 1024, 1024, 5, 2),        # DCGAN critic layers at batch 16 (several N / channel tiles per launch)
+    (16, 16, 16, 512, 512, 5, 2),
+    (16, 8, 8, 1024, 1024, 5, 1),        # DCGAN generator layers
+    (16, 16, 16, 512, 512, 5, 1),
 ]
 
 
@@ -120,10 +124,76 @@ def test_unsupported_shapes_are_rejected_not_miscomputed():
     assert rc == -4 and b"Cin" in lib.otgan_last_error()
 
 
-def test_dcgan_networks_match_library_convolutions():
-    """Critic and generator forward + backward with this library's convolution kernels vs the cuDNN rung (fp32, TF32
-    off) on the same parameters, inputs and output gradients (no Sinkhorn in between: lambda = 500 would amplify the
-    TF32 rounding of the features): features / images and flat parameter gradients agree to TF32 accuracy."""
+def test_dcgan_networks_every_conv_call_checked_against_float64():
+    """Run the DCGAN critic + generator forward and backward on the tcgen05 kernels and check EVERY convolution call the
+    networks make (forward output, input gradient, filter gradient, bias gradient) against a float64 convolution of the
+    very tensors that call received.  (Comparing whole-network gradients against an fp32 run is not a usable gate: a
+    TF32-sized perturbation flips the sign of a few near-zero CReLU pre-activations, which moves individual bias-gradient
+    sums by ~10%; see test_dcgan_networks_agree_with_library_convolutions for that loose end-to-end bound.)"""
+    from otgan_b200.models.dcgan import discriminator, generator
+    from otgan_b200.utils import nn
+    dev = torch.device("cuda", 0)
+    calls = []
+    orig_fwd, orig_bwd = nn._ConvTC.forward, nn._ConvTC.backward
+
+    def fwd(ctx, x, wt, bias, geom):
+        y = orig_fwd(ctx, x, wt, bias, geom)
+        ctx._rec = {"x": x.detach().clone(), "wt": wt.detach().clone(), "b": None if bias is None else bias.detach().clone(),
+                    "geom": geom, "y": y.detach().clone()}
+        calls.append(ctx._rec)
+        return y
+
+    def bwd(ctx, dy):
+        res = orig_bwd(ctx, dy)
+        ctx._rec.update(dy=dy.detach().clone(), dx=res[0], dw=res[1], db=res[2])
+        return res
+
+    nn._ConvTC.forward, nn._ConvTC.backward = staticmethod(fwd), staticmethod(bwd)
+    try:
+        discriminator.reset(); generator.reset()
+        torch.manual_seed(3)
+        with torch.no_grad():
+            discriminator(torch.zeros(16, 32, 32, 3, device=dev), init=True, device=dev)
+            generator(init=True, device=dev, batch_size=16)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        x = torch.rand(16, 32, 32, 3, device=dev, generator=g) * 2 - 1
+        u = torch.rand(16, 100, device=dev, generator=g) * 2 - 1
+        gy = torch.randn(16, 32768, device=dev, generator=g)
+        f = discriminator(x)
+        torch.autograd.grad([f], [discriminator.flat], [gy])
+        img = generator(batch_size=16, u=u)
+        with nn.frozen_params():
+            f2 = discriminator(img)
+        torch.autograd.grad([f2], [generator.flat], [gy])
+    finally:
+        nn._ConvTC.forward, nn._ConvTC.backward = staticmethod(orig_fwd), staticmethod(orig_bwd)
+    assert len(calls) == 3 + 3 + 3                     # critic c1-c3, generator g1-g3, critic c1-c3 on the generated images
+    n_dx = n_dw = 0
+    for rec in calls:
+        kh, kw, s, pt, pl = rec["geom"]
+        cout = rec["wt"].shape[0]
+        cin = rec["x"].shape[3]
+        xd = rec["x"].double().requires_grad_(True)
+        wd = rec["wt"].double().view(cout, kh, kw, cin).requires_grad_(True)
+        bd = rec["b"].double().requires_grad_(True)
+        yr = _ref_conv(xd, wd, bd, kh, s)
+        dxr, dwr, dbr = torch.autograd.grad([yr], [xd, wd, bd], [rec["dy"].double()])
+        tag = (tuple(rec["x"].shape), cout, s)
+        assert float((rec["y"].double() - yr).abs().max() / yr.abs().max()) <= 4e-3, ("fprop", tag)
+        if rec["dx"] is not None:
+            n_dx += 1
+            assert float((rec["dx"].double() - dxr).abs().max() / dxr.abs().max()) <= 4e-3, ("dgrad", tag)
+        if rec["dw"] is not None:
+            n_dw += 1
+            assert float((rec["dw"].double().view_as(dwr) - dwr).abs().max() / dwr.abs().max()) <= 4e-3, ("wgrad", tag)
+            assert float((rec["db"].double() - dbr).abs().max() / dbr.abs().max()) <= 4e-3, ("bias-grad", tag)
+    assert n_dx == 9 and n_dw == 6                     # the critic inside the generator step builds no filter gradients
+
+
+def test_dcgan_networks_agree_with_library_convolutions():
+    """Loose end-to-end bound: critic and generator forward + backward with this library's convolution kernels vs the cuDNN
+    rung (fp32, TF32 off) on the same parameters, inputs and output gradients.  Outputs agree to TF32 accuracy; gradients
+    are compared in the L2 norm / by direction (CReLU sign flips of near-zero pre-activations, see above)."""
     from otgan_b200.models.dcgan import discriminator, generator
     from otgan_b200.utils import nn
     dev = torch.device("cuda", 0)
@@ -141,7 +211,6 @@ def test_dcgan_networks_match_library_convolutions():
         x = torch.rand(16, 32, 32, 3, device=dev, generator=g) * 2 - 1
         u = torch.rand(16, 100, device=dev, generator=g) * 2 - 1
         gy = torch.randn(16, 32768, device=dev, generator=g)
-        _lib_count = {}
         for backend in ("tcgen05", "cudnn"):
             nn.CONV_BACKEND = backend
             xr = x.clone().requires_grad_(True)
@@ -151,11 +220,15 @@ def test_dcgan_networks_match_library_convolutions():
             with nn.frozen_params():
                 f2 = discriminator(img)
             (gg,) = torch.autograd.grad([f2], [generator.flat], [gy])
-            res[backend] = (f.detach(), gd, gx, img.detach(), gg)
+            res[backend] = (f.detach(), img.detach(), gd, gx, gg)
     finally:
         nn.CONV_BACKEND = "tcgen05"
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
-    names = ("critic features", "critic parameter gradient", "critic input gradient", "generator images", "generator parameter gradient")
-    for name, a, c in zip(names, res["tcgen05"], res["cudnn"]):
-        err = float((a - c).abs().max() / c.abs().max())
-        assert err <= 1e-2, (name, err)              # TF32 operand rounding through up to 8 convolution layers
+    names = ("critic features", "generator images", "critic parameter gradient", "critic input gradient", "generator parameter gradient")
+    for i, (name, a, c) in enumerate(zip(names, res["tcgen05"], res["cudnn"])):
+        if i < 2:
+            assert float((a - c).abs().max() / c.abs().max()) <= 5e-3, name          # TF32 operand rounding, 4 layers deep
+        else:
+            rel_l2 = float((a - c).norm() / c.norm())
+            cos = float(torch.dot(a.flatten(), c.flatten()) / (a.norm() * c.norm()))
+            assert rel_l2 <= 0.1 and cos >= 0.995, (name, rel_l2, cos)

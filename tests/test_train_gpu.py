@@ -144,3 +144,33 @@ def test_multi_gpu_parity_two_ranks():
                           "--master-addr", "127.0.0.1", "--master-port", "29577", script],
                          capture_output=True, text=True, timeout=280)
     assert out.returncode == 0 and "MGPU PARITY OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_cuda_graph_replay_matches_eager_steps():
+    """enable_cuda_graphs(): six replayed steps (1 critic + 5 generator) leave the same parameters, EMA shadow and
+    [distance, entropy] as six eagerly launched steps from the same state (same images, same latents)."""
+    from otgan_b200 import train as T
+    args = T.build_parser().parse_args(["--synthetic", "--nr_gpu", "2", "--batch_size", "8", "--nr_sinkhorn_iter", "20"])
+    g = torch.Generator(device="cuda").manual_seed(11)
+    xs = [torch.rand(16, 32, 32, 3, device="cuda", generator=g) * 2 - 1 for _ in range(7)]
+    us = [torch.rand(16, 100, device="cuda", generator=g) * 2 - 1 for _ in range(7)]
+    out = {}
+    for mode in ("eager", "graph"):
+        tr = T.Trainer(args, torch.device("cuda", 0))
+        if mode == "graph":
+            tr.enable_cuda_graphs()
+            assert tr.step_counter == 0 and tr.gen_optimizer.state["t"] == 1
+        stats = []
+        for x, u in zip(xs, us):
+            kind, s = tr.step(x, u=u)
+            stats.append(s.clone())
+        torch.cuda.synchronize()
+        out[mode] = (tr.generator.flat.detach().clone(), tr.discriminator.flat.detach().clone(), tr.ema.shadow.clone(),
+                     torch.stack(stats))
+        if mode == "graph":
+            assert tr.replayed_launches > 7 * 20 and tr.step_counter == 7
+    errs = {name: float((a - c).abs().max()) / float(c.abs().max())
+            for name, a, c in zip(("generator", "critic", "ema", "stats"), out["eager"], out["graph"])}
+    print(errs)
+    # same kernels in the same order; the only run-to-run freedom is cuDNN's algorithm choice for the two 3-channel layers
+    assert all(e <= 1e-3 for e in errs.values()), errs

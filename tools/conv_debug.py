@@ -19,6 +19,12 @@ SHAPES = [
     (2, 32, 32, 256, 256, 5, 2),
     (4, 16, 16, 256, 128, 5, 2),
     (8, 4, 4, 128, 128, 3, 1),
+    (16, 8, 8, 1024, 1024, 5, 2),        # the DCGAN layers at batch 16: several N tiles / channel tiles per launch
+    (16, 16, 16, 512, 512, 5, 2),
+    (16, 32, 32, 256, 256, 5, 2),
+    (16, 8, 8, 1024, 1024, 5, 1),
+    (16, 16, 16, 512, 512, 5, 1),
+    (16, 32, 32, 256, 256, 5, 1),
 ]
 OPS = ("fprop", "dgrad", "wgrad")
 
