@@ -208,8 +208,14 @@ struct WgradParams {
     float* out;
 };
 
+// wgrad thread layout: warp 0 = producer of the dy boxes (+ expect_tx), warp 1 = MMA issuer, warps 2-5 = epilogue,
+// warps 6-7 = producers of the x boxes.  Measured with one producer thread: 12 small TMA copies per stage cost ~1200 issue
+// cycles (address arithmetic + the uniform-register hand-off around every UTMALDG) against 512 cycles of MMA, tensor pipe
+// 48% busy; three producer threads with incremental coordinates (no division in the loop) keep the pipe fed.
+constexpr int WGRAD_THREADS = 256;
+
 template <int TN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(WGRAD_THREADS, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ WgradParams p)
 {
     using C = Cfg<TN>;
@@ -253,30 +259,39 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradParams p)
         c1 = c1 > p.nchunks ? p.nchunks : c1;
     };
 
-    if (warp == 0) {
-        // ===================================================== TMA producer (one thread; issuing the 12 boxes of a stage from 12
-        // lanes at once was measured SLOWER: 370 vs 450 TFLOP/s)
+    if (warp == 0 || warp >= 6) {
+        // ===================================================== TMA producers: warp 0 -> the TM/32 dy boxes, warps 6, 7 -> half of
+        // the TN/32 x boxes each.  All three walk the same (item, chunk) sequence and wait on the same empty barrier.
         if (lane == 0) {
-            int c = 0;
+            constexpr int XB = TN / 64;                       // x boxes per x-producer warp
+            const int role = warp == 0 ? 0 : warp - 5;        // 0: dy, 1 / 2: x halves
+            int s = 0;
+            uint32_t ph = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 int cot, cit, t, sp, c0, c1;
                 decode(item, cot, cit, t, sp);
                 chunk_range(sp, c0, c1);
                 const Tap tap = p.taps[t];
                 const CUtensorMap* xm = &p.xmap[tap.map];
-                for (int ch = c0; ch < c1; ++ch, ++c) {
-                    const int s = c % STAGES;
-                    mbar_wait(empty_bar(s), (((uint32_t)(c / STAGES)) & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(full_bar(s), (uint32_t)C::STAGE_BYTES);
+                int tw = c0 % p.tiles_w, th = (c0 / p.tiles_w) % p.tiles_h, tn = c0 / (p.tiles_w * p.tiles_h);
+                const int co0 = cot * TM, ci0 = cit * TN + (role == 2 ? 32 * XB : 0);
+                for (int ch = c0; ch < c1; ++ch) {
+                    mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t dst = smem_base + s * C::STAGE_BYTES;
-                    const int w0 = (ch % p.tiles_w) * p.bw, h0 = ((ch / p.tiles_w) % p.tiles_h) * p.bh;
-                    const int n0 = (ch / (p.tiles_w * p.tiles_h)) * p.bn;
+                    if (role == 0) {
+                        mbar_arrive_expect_tx(full_bar(s), (uint32_t)C::STAGE_BYTES);
 #pragma unroll
-                    for (int j = 0; j < TM / 32; ++j)
-                        tma_load_2d(dst + j * BOX32, &p.dymap, full_bar(s), cot * TM + 32 * j, ch * 32);
+                        for (int j = 0; j < TM / 32; ++j)
+                            tma_load_2d(dst + j * BOX32, &p.dymap, full_bar(s), co0 + 32 * j, ch * 32);
+                    } else {
+                        const uint32_t dstx = dst + A_TILE + (role == 2 ? XB * BOX32 : 0);
+                        const int cw = tw * p.bw + tap.dw, chh = th * p.bh + tap.dh, cn = tn * p.bn;
 #pragma unroll
-                    for (int j = 0; j < TN / 32; ++j)
-                        tma_load_4d(dst + A_TILE + j * BOX32, xm, full_bar(s), cit * TN + 32 * j, w0 + tap.dw, h0 + tap.dh, n0);
+                        for (int j = 0; j < XB; ++j)
+                            tma_load_4d(dstx + j * BOX32, xm, full_bar(s), ci0 + 32 * j, cw, chh, cn);
+                    }
+                    if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -450,7 +465,7 @@ int launch_wgrad(const WgradParams& p, cudaStream_t stream)
         attr_set = true;
     }
     const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
-    conv_wgrad_tc_kernel<TN><<<grid, NUM_THREADS, Cfg<TN>::SMEM_BYTES, stream>>>(p);
+    conv_wgrad_tc_kernel<TN><<<grid, WGRAD_THREADS, Cfg<TN>::SMEM_BYTES, stream>>>(p);
     OTGAN_CHECK_LAUNCH("conv_wgrad_tc_kernel");
     return OTGAN_OK;
 }

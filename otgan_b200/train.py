@@ -190,7 +190,6 @@ class Trainer:
         self.g_x = torch.zeros((bs, 32, 32, 3), device=dev)
         self.g_u = torch.zeros((bs, 100), device=dev)
         self.g_hyper = {k: torch.zeros(3, device=dev) for k in ('disc', 'gen')}
-        self.g_hyper_host = {k: torch.zeros(3).pin_memory() for k in ('disc', 'gen')}
         opts = {'disc': self.disc_optimizer, 'gen': self.gen_optimizer}
         # snapshot everything a training step mutates
         snap = [t.detach().clone() for t in self._mutable_state()]
@@ -237,9 +236,10 @@ class Trainer:
         a = self.args
         opt = self.disc_optimizer if kind == 'disc' else self.gen_optimizer
         lr, d1, d2 = opt.hyper(-a.learning_rate_disc if kind == 'disc' else a.learning_rate_gen)
-        hh = self.g_hyper_host[kind]
-        hh[0], hh[1], hh[2] = lr, d1, d2
-        self.g_hyper[kind].copy_(hh, non_blocking=True)
+        # the step scalars travel as kernel ARGUMENTS of three fill launches (an async copy from a reused pinned buffer
+        # would race with the next step's host write)
+        hd = self.g_hyper[kind]
+        hd[0:1].fill_(lr); hd[1:2].fill_(d1); hd[2:3].fill_(d2)
         self.g_x.copy_(x_real, non_blocking=True)
         if u is None:
             self.g_u.uniform_(-1.0, 1.0)                                                         # tf.random_uniform  dcgan.py:30
