@@ -311,6 +311,80 @@ def matching_benchmark(torch, devv, steps, warmup):
     return res, roof
 
 
+CONV_LAYERS = {  # DCGAN layers on the tcgen05 kernels at the N=256 step: (B, H, W, Cin, Cout, k, stride)   SURVEY App. B.1
+    "critic conv2d_1": (2 * N_TOTAL, 32, 32, 256, 256, 5, 2), "critic conv2d_2": (2 * N_TOTAL, 16, 16, 512, 512, 5, 2),
+    "critic conv2d_3": (2 * N_TOTAL, 8, 8, 1024, 1024, 5, 2), "generator conv2d_0": (N_TOTAL, 8, 8, 1024, 1024, 5, 1),
+    "generator conv2d_1": (N_TOTAL, 16, 16, 512, 512, 5, 1), "generator conv2d_2": (N_TOTAL, 32, 32, 256, 256, 5, 1)}
+# dram__bytes_read.sum + dram__bytes_write.sum of the profiled launch (profiles/r01_h_conv_fprop_ncu_full.txt)
+CONV_ROOFLINE_LAUNCH, CONV_ROOFLINE_TRAFFIC = "critic conv2d_3", 743.63e6 + 23.21e6
+
+
+def conv_benchmark(torch, iters=5):
+    """Live per-launch times (CUDA events on the launching stream, 2 warm-up + `iters` launches, tensors >> L2 per layer
+    sweep) of this library's convolution kernels on every DCGAN layer of the N=256 step.  Algorithmic FLOPs per launch =
+    2 * B*Ho*Wo * Cout * k*k*Cin."""
+    from otgan_b200 import _lib
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    out = {}
+    for name, (B, H, W, Cin, Cout, k, s) in CONV_LAYERS.items():
+        Ho, Wo = H // s, W // s
+        flops = 2.0 * B * Ho * Wo * Cout * k * k * Cin
+        pad = (max((Ho - 1) * s + k - H, 0)) // 2
+        x = torch.randn(B, H, W, Cin, device="cuda")
+        w = torch.randn(Cout, k * k * Cin, device="cuda") * 0.02
+        b = torch.randn(Cout, device="cuda")
+        dy = torch.randn(B, Ho, Wo, Cout, device="cuda")
+        y, dx, dw = torch.empty_like(dy), torch.empty_like(x), torch.empty_like(w)
+        wt = torch.empty(Cin, k * k * Cout, device="cuda")
+        ws = torch.empty(lib.otgan_workspace_bytes_conv_wgrad(B, H, W, Cin, Cout, k, k, s) // 4 + 64, device="cuda")
+        _lib.check(lib.otgan_ohwi_to_ihwo_f32(Cout, k * k, Cin, w.data_ptr(), wt.data_ptr(), st), "ohwi_to_ihwo")
+        ops = {
+            "fprop": lambda: lib.otgan_conv2d_fprop_tf32(B, H, W, Cin, Cout, k, k, s, pad, pad, x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), None, 0, st),
+            "dgrad": lambda: lib.otgan_conv2d_dgrad_tf32(B, H, W, Cin, Cout, k, k, s, pad, pad, dy.data_ptr(), wt.data_ptr(), dx.data_ptr(), None, 0, st),
+            "wgrad": lambda: lib.otgan_conv2d_wgrad_tf32(B, H, W, Cin, Cout, k, k, s, pad, pad, dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel() * 4, st),
+        }
+        row = {"shape": [B, H, W, Cin, Cout, k, s], "gflop": flops / 1e9}
+        for op, fn in ops.items():
+            for _ in range(2):
+                _lib.check(fn(), op)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            row[op] = {"ms": ms, "tflops": flops / ms / 1e9}
+        out[name] = row
+        del x, w, b, dy, y, dx, dw, wt, ws
+        torch.cuda.empty_cache()
+    return out
+
+
+def conv_roofline(conv):
+    """Roofline object of the step's dominant kernel, conv_gemm_tc_kernel<256> (fprop / dgrad; 41% of the step in the ncu
+    launch list), on the launch that was also captured with ncu --set full: critic conv2d_3 fprop."""
+    pk = peaks()
+    full = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    r = conv[CONV_ROOFLINE_LAUNCH]["fprop"]
+    gemm = [conv[n][op] for n in conv for op in ("fprop", "dgrad")]
+    flops = [conv[n]["gflop"] for n in conv for _ in ("fprop", "dgrad")]
+    mean_tf = sum(flops) / sum(g["ms"] for g in gemm)                        # GFLOP / ms = TFLOP/s
+    return {"bound": "tensor", "kernel": "conv_gemm_tc_kernel<256> (%s fprop, 429.5 GFLOP per launch)" % CONV_ROOFLINE_LAUNCH,
+            "achieved": r["tflops"], "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": r["tflops"] / pk["bf16_tflops"],
+            "traffic": CONV_ROOFLINE_TRAFFIC,
+            "frac_of_tf32_ceiling": r["tflops"] / (pk["bf16_tflops"] / 2.0),
+            "achieved_all_fprop_dgrad_launches": mean_tf,
+            "frac_of_tf32_ceiling_all_fprop_dgrad_launches": mean_tf / (pk["bf16_tflops"] / 2.0),
+            "bf16_tflops_sustained": full.get("bf16_tflops_sustained"),
+            "peak_source": pk["source"],
+            "note": "operands are fp32 tensors consumed as TF32 (kind::tf32): the tensor pipe runs TF32 at half the bf16 rate, so "
+                    "the ceiling of this kernel is peak/2; `frac` is against the measured dense bf16 burst peak as the contract "
+                    "asks, frac_of_tf32_ceiling against half of it.  ncu: tensor pipe 84.5% active, DRAM 15% (traffic field)."}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -334,9 +408,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    match_res, roof = (None, None)
+    match_res, roof, conv_res = (None, None, None)
     if rank == 0:
-        match_res, roof = matching_benchmark(torch, devv, 100, 5)
+        match_res, match_roof = matching_benchmark(torch, devv, 100, 5)
+        if args.n_total:                           # diagnostics run at another N: keep the matching roofline only
+            roof = match_roof
+        else:
+            conv_res = conv_benchmark(torch)
+            roof = conv_roofline(conv_res)
+            match_res["roofline_matching"] = match_roof
     barrier()
 
     # ---- the training step (all ranks): towers = 2 per rank, N_TOTAL images in total
@@ -344,8 +424,19 @@ def run_ours(args):
     targs = T.build_parser().parse_args(["--synthetic", "--nr_gpu", str(towers), "--batch_size", str(N_TOTAL // towers),
                                          "--nr_sinkhorn_iter", str(T_ITERS), "--sinkhorn_lambda", str(LAMBDA)])
     tr = T.Trainer(targs, devv, rank, world)
+    graphs_on = False
     if args.cuda_graphs:
-        tr.enable_cuda_graphs()
+        try:
+            tr.enable_cuda_graphs()
+            graphs_on = True
+        except Exception as e:                     # never lose the measurement to a capture problem: launch eagerly instead
+            sys.stderr.write("bench.py: CUDA-graph capture failed (%r); falling back to eager launches\n" % (e,))
+            tr.graphs = None
+        flag = torch.tensor([1.0 if graphs_on else 0.0], device=devv)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)       # all ranks replay, or none does
+        if flag.item() < 1.0:
+            tr.graphs, graphs_on = None, False
     bs = tr.bs_local
     gen = torch.Generator().manual_seed(1 + rank)
     host_imgs = [(torch.rand((bs, 32, 32, 3), generator=gen) * 2 - 1).pin_memory() for _ in range(8)]
@@ -423,10 +514,10 @@ def run_ours(args):
             "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world, args.workload),
             "sinkhorn_iters_per_sec": match_res["sinkhorn_iters_per_sec"] if match_res else None,
-            "roofline": roof, "matching": match_res,
+            "roofline": roof, "conv_layers": conv_res, "matching": match_res,
             "e2e": {"value": N_TOTAL / (ms_e2e / args.steps * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "cuda_graphs": graphs_on,
             "clocks": dict(sampler.result(), remeasured_after_slowdown=remeasured),
         }
         if world == 1 and not args.no_cpu:

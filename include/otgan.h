@@ -176,13 +176,18 @@ OTGAN_API int otgan_glu_up_bwd_f32(int B, int H, int W, int C, int up, const flo
  * OTGAN_EUNSUPPORTED.  Pointers 16-byte aligned.
  *   fprop : y  = conv(x, w) + bias                       (bias may be NULL)
  *   dgrad : dx = d conv / d x  applied to dy             (what tf.gradients emits as Conv2DBackpropInput)
+ *           fprop / dgrad take an optional workspace of otgan_workspace_bytes_conv_gemm(dims of the OUTPUT tensor) bytes:
+ *           with it, launches that have fewer output tiles than SMs (small per-GPU batches) split the filter taps over
+ *           more CTAs and sum the partials in a fixed order; ws = NULL runs unsplit.
  *   wgrad : dw_ohwi = d conv / d w applied to dy         (Conv2DBackpropFilter); ws: otgan_workspace_bytes_conv_wgrad
  *   colsum: out[C] = column sums of x [P, C]              (BiasAddGrad); ws: otgan_workspace_bytes_colsum */
+OTGAN_API size_t otgan_workspace_bytes_conv_gemm(int B, int H, int W, int C);
 OTGAN_API int otgan_conv2d_fprop_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top,
                                       int pad_left, const float* x, const float* w_ohwi, const float* bias, float* y,
-                                      void* stream);
+                                      void* ws, size_t ws_bytes, void* stream);
 OTGAN_API int otgan_conv2d_dgrad_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top,
-                                      int pad_left, const float* dy, const float* w_ihwo, float* dx, void* stream);
+                                      int pad_left, const float* dy, const float* w_ihwo, float* dx, void* ws,
+                                      size_t ws_bytes, void* stream);
 OTGAN_API size_t otgan_workspace_bytes_conv_wgrad(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride);
 OTGAN_API int otgan_conv2d_wgrad_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top,
                                       int pad_left, const float* dy, const float* x, float* dw_ohwi, void* ws,

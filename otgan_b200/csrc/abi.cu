@@ -63,10 +63,11 @@ int crelu_pad_bwd_launch(int B, int H, int W, int C, int pt, int pl, int pb, int
                          cudaStream_t stream);
 int glu_up_fwd_launch(int B, int H, int W, int C, int up, const float* y, float* out, cudaStream_t stream);
 int glu_up_bwd_launch(int B, int H, int W, int C, int up, const float* y, const float* dout, float* dy, cudaStream_t stream);
+size_t conv_gemm_workspace_bytes(int B, int H, int W, int C);
 int conv_fprop_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo,
-                      const float* x, const float* w, const float* bias, float* y, cudaStream_t stream);
+                      const float* x, const float* w, const float* bias, float* y, void* ws, size_t ws_bytes, cudaStream_t stream);
 int conv_dgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo,
-                      const float* dy, const float* wt, float* dx, cudaStream_t stream);
+                      const float* dy, const float* wt, float* dx, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t conv_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int kh, int kw);
 int conv_wgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo,
                       const float* dy, const float* x, float* dw, void* ws, size_t ws_bytes, cudaStream_t stream);
@@ -337,24 +338,32 @@ int otgan_glu_up_bwd_f32(int B, int H, int W, int C, int up, const float* y, con
     return glu_up_bwd_launch(B, H, W, C, up, y, dout, dy, (cudaStream_t)stream);
 }
 
+size_t otgan_workspace_bytes_conv_gemm(int B, int H, int W, int C)
+{
+    if (B < 1 || H < 1 || W < 1 || C < 1) return 0;
+    return conv_gemm_workspace_bytes(B, H, W, C);
+}
+
 int otgan_conv2d_fprop_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top, int pad_left,
-                            const float* x, const float* w_ohwi, const float* bias, float* y, void* stream)
+                            const float* x, const float* w_ohwi, const float* bias, float* y, void* ws, size_t ws_bytes,
+                            void* stream)
 {
     OTGAN_REQUIRE(x && w_ohwi && y, "conv2d_fprop: null pointer");
     OTGAN_REQUIRE(stride == 1 || stride == 2, "conv2d_fprop: stride %d not in {1, 2}", stride);
-    OTGAN_REQUIRE(aligned16(x) && aligned16(w_ohwi) && aligned16(y) && (!bias || aligned16(bias)), "conv2d_fprop: buffers must be 16-byte aligned");
+    OTGAN_REQUIRE(aligned16(x) && aligned16(w_ohwi) && aligned16(y) && (!bias || aligned16(bias)) && (!ws || aligned16(ws)),
+                  "conv2d_fprop: buffers must be 16-byte aligned");
     return conv_fprop_launch(B, H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, H / stride, W / stride, x, w_ohwi, bias, y,
-                             (cudaStream_t)stream);
+                             ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int otgan_conv2d_dgrad_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top, int pad_left,
-                            const float* dy, const float* w_ihwo, float* dx, void* stream)
+                            const float* dy, const float* w_ihwo, float* dx, void* ws, size_t ws_bytes, void* stream)
 {
     OTGAN_REQUIRE(dy && w_ihwo && dx, "conv2d_dgrad: null pointer");
     OTGAN_REQUIRE(stride == 1 || stride == 2, "conv2d_dgrad: stride %d not in {1, 2}", stride);
-    OTGAN_REQUIRE(aligned16(dy) && aligned16(w_ihwo) && aligned16(dx), "conv2d_dgrad: buffers must be 16-byte aligned");
+    OTGAN_REQUIRE(aligned16(dy) && aligned16(w_ihwo) && aligned16(dx) && (!ws || aligned16(ws)), "conv2d_dgrad: buffers must be 16-byte aligned");
     return conv_dgrad_launch(B, H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, H / stride, W / stride, dy, w_ihwo, dx,
-                             (cudaStream_t)stream);
+                             ws, ws_bytes, (cudaStream_t)stream);
 }
 
 size_t otgan_workspace_bytes_conv_wgrad(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride)

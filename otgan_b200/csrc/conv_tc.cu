@@ -59,6 +59,8 @@ struct GemmParams {
     int cls_tap_begin[5];                     // class c sums taps [begin[c], begin[c+1])
     long long cls_out_off[4];                 // output offset of the class (floats)
     int n_cls, m_tiles, n_tiles, n_items;
+    int splits;                               // split-K over the taps of a class (small-M launches); partials split_stride apart
+    long long split_stride;
     int bw, bh, bn, tiles_w, tiles_h;         // pixel box (bw*bh*bn = 128) and tile grid of one class
     int kchunks;                              // 32-channel chunks per tap
     long long osW, osH, osN;                  // output pixel strides (floats)
@@ -97,16 +99,27 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
+    // item -> (split, class, N tile, M tile); a split sums a contiguous share of the class's taps
+    auto decode = [&](int item, int& mt, int& nt, int& cls, int& sp, int& t0, int& t1) {
+        mt = item % p.m_tiles; item /= p.m_tiles;
+        nt = item % p.n_tiles; item /= p.n_tiles;
+        cls = item % p.n_cls;
+        sp = item / p.n_cls;
+        const int tb = p.cls_tap_begin[cls], T = p.cls_tap_begin[cls + 1] - tb;
+        t0 = tb + (T * sp) / p.splits;
+        t1 = tb + (T * (sp + 1)) / p.splits;
+    };
+
     if (warp == 0) {
         // ===================================================== TMA producer
         if (lane == 0) {
             int c = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const int mt = item % p.m_tiles, rest = item / p.m_tiles;
-                const int nt = rest % p.n_tiles, cls = rest / p.n_tiles;
+                int mt, nt, cls, sp, t0, t1;
+                decode(item, mt, nt, cls, sp, t0, t1);
                 const int w0 = (mt % p.tiles_w) * p.bw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
                 const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
-                for (int t = p.cls_tap_begin[cls]; t < p.cls_tap_begin[cls + 1]; ++t) {
+                for (int t = t0; t < t1; ++t) {
                     const Tap tap = p.taps[t];
                     const CUtensorMap* am = &p.amap[tap.map];
                     for (int kc = 0; kc < p.kchunks; ++kc, ++c) {
@@ -126,11 +139,13 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
             const uint32_t idesc = umma_idesc_tf32(TM, TN);
             int c = 0, n = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
-                const int cls = (item / p.m_tiles) / p.n_tiles, b = n & 1;
+                int mt, nt, cls, sp, t0, t1;
+                decode(item, mt, nt, cls, sp, t0, t1);
+                const int b = n & 1;
                 mbar_wait(tempty_bar(b), (((uint32_t)(n >> 1)) & 1u) ^ 1u);
                 tcgen05_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(b * TN);
-                const int nst = (p.cls_tap_begin[cls + 1] - p.cls_tap_begin[cls]) * p.kchunks;
+                const int nst = (t1 - t0) * p.kchunks;
                 for (int st = 0; st < nst; ++st, ++c) {
                     const int s = c % STAGES;
                     mbar_wait(full_bar(s), ((uint32_t)(c / STAGES)) & 1u);
@@ -154,13 +169,14 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
         const int rw = r % p.bw, rh = (r / p.bw) % p.bh, rn = r / (p.bw * p.bh);
         int n = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
-            const int mt = item % p.m_tiles, rest = item / p.m_tiles;
-            const int nt = rest % p.n_tiles, cls = rest / p.n_tiles, b = n & 1;
+            int mt, nt, cls, sp, t0, t1;
+            decode(item, mt, nt, cls, sp, t0, t1);
+            const int b = n & 1;
             const int w0 = (mt % p.tiles_w) * p.bw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
             const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
-            float* out = p.out + p.cls_out_off[cls] + (long long)(n0 + rn) * p.osN + (long long)(h0 + rh) * p.osH +
-                         (long long)(w0 + rw) * p.osW + nt * TN;
-            const float* bias = p.bias ? p.bias + nt * TN : nullptr;
+            float* out = p.out + sp * p.split_stride + p.cls_out_off[cls] + (long long)(n0 + rn) * p.osN +
+                         (long long)(h0 + rh) * p.osH + (long long)(w0 + rw) * p.osW + nt * TN;
+            const float* bias = (p.bias && sp == 0) ? p.bias + nt * TN : nullptr;     // the first partial carries the bias
             mbar_wait(tfull_bar(b), ((uint32_t)(n >> 1)) & 1u);
             tcgen05_fence_after();
 #pragma unroll 1
@@ -442,6 +458,44 @@ bool make_view_map(CUtensorMap* map, const float* base, int B, int H, int W, int
     return make_tensor_map_nd(map, base + ((size_t)ph * W + pw) * C, 4, dims, str, box, swz);
 }
 
+// Split-K of fprop / dgrad: when a launch has fewer tiles than SMs (small batch per GPU), the taps of each class are
+// shared out over up to 148 / tiles CTAs that write partial outputs, summed in fixed order afterwards.
+int gemm_splits(int tiles, int min_taps)
+{
+    if (tiles >= (kNumSMs * 3) / 4) return 1;
+    int S = kNumSMs / tiles;
+    S = S > min_taps ? min_taps : S;
+    S = S > 8 ? 8 : S;
+    return S < 1 ? 1 : S;
+}
+
+// finish a fprop / dgrad launch: pick the split, point the kernel at the workspace, launch, reduce
+template <int TN>
+int launch_gemm(const GemmParams& p, cudaStream_t stream);
+
+int run_gemm(GemmParams& p, int TN, size_t out_numel, float* out, void* ws, size_t ws_bytes, cudaStream_t stream)
+{
+    int min_taps = MAX_TAPS;
+    for (int c = 0; c < p.n_cls; ++c) {
+        const int T = p.cls_tap_begin[c + 1] - p.cls_tap_begin[c];
+        min_taps = T < min_taps ? T : min_taps;
+    }
+    const int tiles = p.m_tiles * p.n_tiles * p.n_cls;
+    p.splits = gemm_splits(tiles, min_taps);
+    if (p.splits > 1 && (!ws || ws_bytes < (size_t)p.splits * out_numel * sizeof(float))) p.splits = 1;   // no room: unsplit
+    p.split_stride = (long long)out_numel;
+    p.n_items = tiles * p.splits;
+    p.out = p.splits > 1 ? reinterpret_cast<float*>(ws) : out;
+    const int rc = TN == 256 ? launch_gemm<256>(p, stream) : launch_gemm<128>(p, stream);
+    if (rc != OTGAN_OK || p.splits == 1) return rc;
+    const size_t n4 = out_numel / 4;
+    const size_t blocks = (n4 + 255) / 256;
+    const int grid = (int)(blocks < (size_t)(8 * kNumSMs) ? blocks : (size_t)(8 * kNumSMs));
+    split_reduce_kernel<<<grid, 256, 0, stream>>>(n4, p.splits, n4, reinterpret_cast<const float4*>(p.out), reinterpret_cast<float4*>(out));
+    OTGAN_CHECK_LAUNCH("split_reduce_kernel");
+    return OTGAN_OK;
+}
+
 template <int TN>
 int launch_gemm(const GemmParams& p, cudaStream_t stream)
 {
@@ -501,8 +555,20 @@ int wgrad_splits(int items, int nchunks, double flops, double dw_bytes)
 }  // namespace
 
 // y[B,Ho,Wo,Cout] = conv(x[B,H,W,Cin], w[Cout, kh*kw*Cin]) + bias
+// workspace of a fprop / dgrad launch whose OUTPUT is [B, H, W, C]: room for the split-K partials (0 when the launch already
+// has enough tiles to fill the SMs)
+size_t conv_gemm_workspace_bytes(int B, int H, int W, int C)
+{
+    const long long pix = (long long)B * H * W;
+    const int TN = (C % 256 == 0) ? 256 : 128;
+    const long long tiles = (pix / TM) * (C / TN);
+    if (tiles < 1 || tiles >= kNumSMs) return 256;
+    const int S = gemm_splits((int)tiles, 8);
+    return S > 1 ? (size_t)S * pix * C * sizeof(float) + 256 : 256;
+}
+
 int conv_fprop_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo,
-                      const float* x, const float* w, const float* bias, float* y, cudaStream_t stream)
+                      const float* x, const float* w, const float* bias, float* y, void* ws, size_t ws_bytes, cudaStream_t stream)
 {
     OTGAN_REQUIRE(conv_dims_ok(B, H, W, Cin, Cout, kh, kw, s, pt, pl, Ho, Wo), "conv_fprop: unsupported geometry");
     GemmParams p;
@@ -532,16 +598,15 @@ int conv_fprop_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
     p.tiles_w = Wo / p.bw; p.tiles_h = Ho / p.bh;
     p.m_tiles = p.tiles_w * p.tiles_h * (B / p.bn);
     p.n_tiles = Cout / TN;
-    p.n_items = p.m_tiles * p.n_tiles;
     p.kchunks = Cin / BK;
     p.osW = Cout; p.osH = (long long)Wo * Cout; p.osN = (long long)Ho * Wo * Cout;
-    p.out = y; p.bias = bias;
-    return TN == 256 ? launch_gemm<256>(p, stream) : launch_gemm<128>(p, stream);
+    p.bias = bias;
+    return run_gemm(p, TN, (size_t)B * Ho * Wo * Cout, y, ws, ws_bytes, stream);
 }
 
 // dx[B,H,W,Cin] = conv_transpose(dy[B,Ho,Wo,Cout], wt[Cin, kh*kw*Cout])
 int conv_dgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo,
-                      const float* dy, const float* wt, float* dx, cudaStream_t stream)
+                      const float* dy, const float* wt, float* dx, void* ws, size_t ws_bytes, cudaStream_t stream)
 {
     OTGAN_REQUIRE(conv_dims_ok(B, H, W, Cin, Cout, kh, kw, s, pt, pl, Ho, Wo), "conv_dgrad: unsupported geometry");
     GemmParams p;
@@ -578,11 +643,10 @@ int conv_dgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
     p.tiles_w = (W / s) / p.bw; p.tiles_h = (H / s) / p.bh;
     p.m_tiles = p.tiles_w * p.tiles_h * (B / p.bn);
     p.n_tiles = Cin / TN;
-    p.n_items = p.m_tiles * p.n_tiles * p.n_cls;
     p.kchunks = Cout / BK;
     p.osW = (long long)s * Cin; p.osH = (long long)s * W * Cin; p.osN = (long long)H * W * Cin;
-    p.out = dx; p.bias = nullptr;
-    return TN == 256 ? launch_gemm<256>(p, stream) : launch_gemm<128>(p, stream);
+    p.bias = nullptr;
+    return run_gemm(p, TN, (size_t)B * H * W * Cin, dx, ws, ws_bytes, stream);
 }
 
 size_t conv_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int kh, int kw)

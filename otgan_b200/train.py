@@ -165,6 +165,8 @@ class Trainer:
                 dist.all_reduce(grad, op=dist.ReduceOp.SUM)                                      # :134-139 (sum, not mean)
             if apply_update:
                 self.disc_optimizer.run(grad, lr=-a.learning_rate_disc, hyper_dev=hyper_dev)     # :143,215
+                if a.optimizer == 'adam':
+                    disc.store.refresh_weight_cache()      # W of the updated critic, reused by the generator steps that follow
         else:
             (grad,) = torch.autograd.grad([f_gen], [gen.flat], grad_outputs=[ga])                # :111-112
             if self.world > 1:
@@ -224,6 +226,7 @@ class Trainer:
                 t.copy_(s0)
         for k, o in opts.items():
             o.state["t"] = snap_t[k]
+        self.discriminator.store.refresh_weight_cache()   # ... including the cached critic weights (same buffers)
         self.graphs, self.g_stats = graphs, outs
 
     def _mutable_state(self):
@@ -260,6 +263,7 @@ class Trainer:
             for tpl in (self.discriminator, self.generator):
                 for n, p in tpl.named_parameters():
                     p.copy_(ck[tpl.name][n])
+                tpl.store.version += 1                     # cached weights are stale
 
 
 def gather_features(f_gen, f_dat, world):

@@ -76,6 +76,9 @@ class VariableStore:
         self.pending = {}          # values created during the init pass, before packing
         self.flat = None           # torch leaf [total], requires_grad
         self.frozen = False
+        self.version = 0           # bumped by every optimiser update of this store's variables
+        self.cache_version = -1    # version the weight cache below was computed from (-1: never)
+        self.wcache = {}           # scope -> (wt [C,K], inv [C], wt_ihwo or None): W = g V/||V|| for gradient-free calls
 
     def create(self, var_name, shape, init_fn):
         if var_name in self.index:
@@ -120,6 +123,56 @@ class VariableStore:
                 return self.flat[off:off + n].view(shape)
             return self._views[i].view(shape)
         return source[off:off + n].view(shape)
+
+    def refresh_weight_cache(self):
+        """Recompute W = g * V / ||V|| of every weight-normalised layer (and the IHWO copy the dgrad kernel reads) into
+        persistent buffers.  Calls that build no parameter gradients (torch.no_grad() / frozen_params(): the critic inside
+        the five generator steps that follow a critic update, train.py:214-226) then reuse them instead of re-running the
+        weight-norm and transpose kernels over all 34 M critic parameters twice per step.  The buffers keep their
+        addresses, so a captured CUDA graph can both refresh and read them."""
+        lib = _lib.load()
+        stream = torch.cuda.current_stream().cuda_stream
+        with torch.no_grad():
+            for name, shape, off, n in self.specs:
+                if not name.endswith("/V"):
+                    continue
+                scope = name[:-2]
+                if scope + "/g" not in self.index:
+                    continue
+                C = shape[-1]
+                K = n // C
+                V = self.flat[off:off + n]
+                _, _, goff, gn = self.specs[self.index[scope + "/g"]]
+                g = self.flat[goff:goff + gn]
+                ent = self.wcache.get(scope)
+                if ent is None:
+                    wt = torch.empty((C, K), device=self.device, dtype=torch.float32)
+                    inv = torch.empty((C,), device=self.device, dtype=torch.float32)
+                    wt_t = None
+                    if len(shape) == 4 and shape[2] % 32 == 0 and (C % 32 == 0):
+                        wt_t = torch.empty((shape[2], shape[0] * shape[1] * C), device=self.device, dtype=torch.float32)
+                    ent = self.wcache[scope] = (wt, inv, wt_t)
+                wt, inv, wt_t = ent
+                need = lib.otgan_workspace_bytes_weightnorm(K, C) // 4
+                ws = _wn_ws.get(self.device.index)
+                if ws is None or ws.numel() < need:
+                    ws = _wn_ws[self.device.index] = torch.empty((max(need, 64 * 32768),), device=self.device, dtype=torch.float32)
+                rc = lib.otgan_weightnorm_fwd_f32(K, C, V.data_ptr(), g.data_ptr(), wt.data_ptr(), inv.data_ptr(), ws.data_ptr(),
+                                                  ws.numel() * 4, stream)
+                _lib.check(rc, "otgan_weightnorm_fwd_f32")
+                if wt_t is not None:
+                    rc = lib.otgan_ohwi_to_ihwo_f32(C, shape[0] * shape[1], shape[2], wt.data_ptr(), wt_t.data_ptr(), stream)
+                    _lib.check(rc, "otgan_ohwi_to_ihwo_f32")
+        self.cache_version = self.version
+
+    def cached_weight(self, scope):
+        """(wt, wt_ihwo) if the cache is current and this call builds no parameter gradients, else None."""
+        if self.cache_version != self.version or scope not in self.wcache:
+            return None
+        if torch.is_grad_enabled() and not getattr(_tls, "freeze_params", False):
+            return None
+        wt, _, wt_t = self.wcache[scope]
+        return wt, wt_t
 
     def named_parameters(self):
         if self.frozen:
@@ -325,18 +378,20 @@ class _ConvTC(torch.autograd.Function):
     (otgan_conv2d_{fprop,dgrad,wgrad}_tf32, otgan_colsum_f32).  x: NHWC, wt: OHWI [Cout, kh*kw*Cin]."""
 
     @staticmethod
-    def forward(ctx, x, wt, bias, geom):
+    def forward(ctx, x, wt, bias, geom, wt_ihwo=None):
         lib = _lib.load()
         kh, kw, s, pt, pl = geom
+        ctx.wt_ihwo = wt_ihwo
         B, H, W, cin = x.shape
         cout = wt.shape[0]
         x, wt = x.contiguous(), wt.contiguous()
         if bias is not None and bias.data_ptr() % 16:
             bias = bias.clone()
         y = torch.empty((B, H // s, W // s, cout), device=x.device, dtype=torch.float32)
+        ws = _workspace(x.device, lib.otgan_workspace_bytes_conv_gemm(B, H // s, W // s, cout))
         rc = lib.otgan_conv2d_fprop_tf32(B, H, W, cin, cout, kh, kw, s, pt, pl, x.data_ptr(), wt.data_ptr(),
                                          bias.data_ptr() if bias is not None else None, y.data_ptr(),
-                                         torch.cuda.current_stream().cuda_stream)
+                                         ws.data_ptr(), ws.numel() * 4, torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "otgan_conv2d_fprop_tf32")
         ctx.save_for_backward(x, wt)
         ctx.geom, ctx.has_bias = geom, bias is not None
@@ -353,10 +408,14 @@ class _ConvTC(torch.autograd.Function):
         stream = torch.cuda.current_stream().cuda_stream
         dx = dwt = db = None
         if ctx.needs_input_grad[0]:
-            wt_t = torch.empty((cin, kh * kw * cout), device=x.device, dtype=torch.float32)
-            _lib.check(lib.otgan_ohwi_to_ihwo_f32(cout, kh * kw, cin, wt.data_ptr(), wt_t.data_ptr(), stream), "otgan_ohwi_to_ihwo_f32")
+            wt_t = ctx.wt_ihwo
+            if wt_t is None:
+                wt_t = torch.empty((cin, kh * kw * cout), device=x.device, dtype=torch.float32)
+                _lib.check(lib.otgan_ohwi_to_ihwo_f32(cout, kh * kw, cin, wt.data_ptr(), wt_t.data_ptr(), stream), "otgan_ohwi_to_ihwo_f32")
             dx = torch.empty_like(x)
-            rc = lib.otgan_conv2d_dgrad_tf32(B, H, W, cin, cout, kh, kw, s, pt, pl, dy.data_ptr(), wt_t.data_ptr(), dx.data_ptr(), stream)
+            ws = _workspace(x.device, lib.otgan_workspace_bytes_conv_gemm(B, H, W, cin))
+            rc = lib.otgan_conv2d_dgrad_tf32(B, H, W, cin, cout, kh, kw, s, pt, pl, dy.data_ptr(), wt_t.data_ptr(), dx.data_ptr(),
+                                             ws.data_ptr(), ws.numel() * 4, stream)
             _lib.check(rc, "otgan_conv2d_dgrad_tf32")
         if ctx.needs_input_grad[1]:
             need = lib.otgan_workspace_bytes_conv_wgrad(B, H, W, cin, cout, kh, kw, s)
@@ -370,7 +429,7 @@ class _ConvTC(torch.autograd.Function):
             ws = _workspace(x.device, lib.otgan_workspace_bytes_colsum(P, cout))
             db = torch.empty((cout,), device=x.device, dtype=torch.float32)
             _lib.check(lib.otgan_colsum_f32(P, cout, dy.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream), "otgan_colsum_f32")
-        return dx, dwt, db, None
+        return dx, dwt, db, None, None
 
 
 class _CreluL2Norm(torch.autograd.Function):
@@ -486,8 +545,8 @@ class TransposedWeight:
     """W = g * V / ||V|| held output-channel-major ([C, K] == OHWI): what otgan_weightnorm_fwd_f32 writes and what the
     convolution / F.linear consume without another layout copy."""
 
-    def __init__(self, wt, vshape):
-        self.wt, self.vshape = wt, tuple(vshape)
+    def __init__(self, wt, vshape, wt_ihwo=None):
+        self.wt, self.vshape, self.wt_ihwo = wt, tuple(vshape), wt_ihwo       # wt_ihwo: cached [Cin, kh*kw*Cout] copy (dgrad)
 
     def as_oihw(self):
         kh, kw, ci, co = self.vshape
@@ -572,7 +631,10 @@ def get_params(layer_name, x=None, init=False, ema=None, use_W=True, use_g=True,
     g = store.get(scope + "/g", ema_src) if use_g else None
     if use_W:
         V = store.get(scope + "/V", ema_src)
-        if weight_norm and use_g and V.is_cuda and store.frozen:
+        cached = store.cached_weight(scope) if (weight_norm and use_g and ema is None and store.frozen) else None
+        if cached is not None:
+            params["W"] = TransposedWeight(cached[0], V.shape, cached[1])                             # reuse (no param grads)
+        elif weight_norm and use_g and V.is_cuda and store.frozen:
             params["W"] = TransposedWeight(_WeightNorm.apply(V, g), V.shape)                          # :176-180 fused
         else:
             W = l2_normalize(V, list(range(V.dim() - 1))) if weight_norm else V                       # :176
@@ -608,7 +670,7 @@ def _conv2d(x, W, stride=(1, 1), pad="SAME", dilate=1, pre_activation=None, upsa
             # TensorFlow 'SAME' zero padding costs nothing here: the kernels' TMA boxes are zero-filled outside the tensor
             z = xl[0].contiguous() if pre_activation is None else _CreluPad.apply(xl[0].contiguous(), (0, 0, 0, 0))
             geom = (kh, kw, stride[0], same_padding(H, kh, stride[0])[0], same_padding(Wd, kw, stride[1])[0])
-            return _ConvTC.apply(z, W.wt, bias, geom)
+            return _ConvTC.apply(z, W.wt, bias, geom, W.wt_ihwo)
     if (pre_activation == "crelu" and len(xl) == 1 and pad == "SAME" and xl[0].is_cuda and xl[0].dtype == torch.float32
             and xl[0].shape[3] % 4 == 0):
         # CReLU written straight into the TensorFlow-'SAME'-padded input of the convolution (one fused kernel)
@@ -682,6 +744,8 @@ def adam_updates(params, cost_or_grads=None, lr=0.001, mom1=0.9, mom2=0.999, ema
         lib = _lib.load()
         step_lr = default_lr if lr is None else lr
         g = grads if grads is not None else flat.grad
+        if isinstance(params, Template):
+            params.store.version += 1                       # cached W = g V/||V|| of this template is stale from here on
         if ema is not None and ema.shadow is None:
             ema.attach(params)
         stream = torch.cuda.current_stream().cuda_stream
@@ -718,6 +782,8 @@ def adamax_updates(params, cost_or_grads=None, lr=0.001, mom1=0.9, mom2=0.999):
     def run(grads, lr=None):
         step_lr = default_lr if lr is None else lr
         g = grads if grads is not None else flat.grad
+        if isinstance(params, Template):
+            params.store.version += 1
         with torch.no_grad():
             if mom1 > 0:
                 state["v"].mul_(mom1).add_(g, alpha=1.0 - mom1)
@@ -739,6 +805,8 @@ def nesterov_updates(params, cost_or_grads=None, lr=0.01, mom1=0.9):
     def run(grads, lr=None):
         step_lr = default_lr if lr is None else lr
         g = grads if grads is not None else flat.grad
+        if isinstance(params, Template):
+            params.store.version += 1
         with torch.no_grad():
             v_new = mom1 * state["v"] - step_lr * g
             flat.add_(-mom1 * state["v"] + (1.0 + mom1) * v_new)

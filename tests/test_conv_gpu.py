@@ -120,7 +120,7 @@ def test_unsupported_shapes_are_rejected_not_miscomputed():
     x = torch.zeros(2 * 32 * 32 * 3, device="cuda")
     w = torch.zeros(128 * 75, device="cuda")
     y = torch.zeros(2 * 32 * 32 * 128, device="cuda")
-    rc = lib.otgan_conv2d_fprop_tf32(2, 32, 32, 3, 128, 5, 5, 1, 2, 2, x.data_ptr(), w.data_ptr(), None, y.data_ptr(), None)
+    rc = lib.otgan_conv2d_fprop_tf32(2, 32, 32, 3, 128, 5, 5, 1, 2, 2, x.data_ptr(), w.data_ptr(), None, y.data_ptr(), None, 0, None)
     assert rc == -4 and b"Cin" in lib.otgan_last_error()
 
 
@@ -136,8 +136,8 @@ def test_dcgan_networks_every_conv_call_checked_against_float64():
     calls = []
     orig_fwd, orig_bwd = nn._ConvTC.forward, nn._ConvTC.backward
 
-    def fwd(ctx, x, wt, bias, geom):
-        y = orig_fwd(ctx, x, wt, bias, geom)
+    def fwd(ctx, x, wt, bias, geom, wt_ihwo=None):
+        y = orig_fwd(ctx, x, wt, bias, geom, wt_ihwo)
         ctx._rec = {"x": x.detach().clone(), "wt": wt.detach().clone(), "b": None if bias is None else bias.detach().clone(),
                     "geom": geom, "y": y.detach().clone()}
         calls.append(ctx._rec)

@@ -184,3 +184,37 @@ def test_cuda_graph_replay_matches_eager_steps():
     print(errs)
     # same kernels in the same order; the only run-to-run freedom is cuDNN's algorithm choice for the two 3-channel layers
     assert all(e <= 1e-3 for e in errs.values()), errs
+
+
+def test_critic_weight_cache_matches_recomputed_weights():
+    """Generator steps reuse the critic's W = g V/||V|| (and its IHWO copy) computed once after the critic update: the
+    features / input gradient through the cached weights equal those through freshly normalised weights, and an
+    optimiser update invalidates the cache."""
+    from otgan_b200.models.dcgan import discriminator, generator
+    from otgan_b200.utils import nn
+    dev = torch.device("cuda", 0)
+    discriminator.reset(); generator.reset()
+    torch.manual_seed(7)
+    with torch.no_grad():
+        discriminator(torch.zeros(8, 32, 32, 3, device=dev), init=True, device=dev)
+    st = discriminator.store
+    x = (torch.rand(8, 32, 32, 3, device=dev) * 2 - 1).requires_grad_(True)
+    gy = torch.randn(8, 32768, device=dev)
+    assert st.cache_version != st.version
+    with nn.frozen_params():
+        f0 = discriminator(x)
+    (g0,) = torch.autograd.grad([f0], [x], [gy])
+    st.refresh_weight_cache()
+    assert st.cache_version == st.version and st.cached_weight("discriminator/conv2d_1") is None      # grad mode: not used
+    with nn.frozen_params():
+        assert st.cached_weight("discriminator/conv2d_1") is not None
+        f1 = discriminator(x)
+    (g1,) = torch.autograd.grad([f1], [x], [gy])
+    assert torch.equal(f0, f1) and torch.equal(g0, g1)
+    opt = nn.adam_updates(discriminator, lr=1e-3, mom1=0.5, mom2=0.999)
+    opt.run(torch.randn_like(discriminator.flat))
+    with nn.frozen_params():
+        assert st.cached_weight("discriminator/conv2d_1") is None                                     # stale after the update
+        f2 = discriminator(x)
+    assert not torch.equal(f1, f2)
+    discriminator.reset(); generator.reset()

@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--layers", type=str, default=",".join(LAYERS))
     ap.add_argument("--no-cudnn", action="store_true")
+    ap.add_argument("--batch-div", type=int, default=1, help="divide the batch (8 = the per-rank batch of an 8-GPU run)")
     args = ap.parse_args()
     lib = _lib.load()
     st = torch.cuda.current_stream().cuda_stream
@@ -57,6 +58,7 @@ def main():
     rows = []
     for name in args.layers.split(","):
         B, H, W, Cin, Cout, k, s = LAYERS[name]
+        B = max(B // args.batch_div, 8)
         Ho, Wo = H // s, W // s
         flops = 2.0 * B * Ho * Wo * Cout * k * k * Cin
         x = torch.randn(B, H, W, Cin, device="cuda")
@@ -71,18 +73,20 @@ def main():
         pl, pr = same_pad(W, k, s)
         need = lib.otgan_workspace_bytes_conv_wgrad(B, H, W, Cin, Cout, k, k, s)
         ws = torch.empty(need // 4 + 64, device="cuda")
+        gneed = max(lib.otgan_workspace_bytes_conv_gemm(B, Ho, Wo, Cout), lib.otgan_workspace_bytes_conv_gemm(B, H, W, Cin))
+        gws = torch.empty(gneed // 4 + 64, device="cuda")
 
         def fprop():
-            _lib.check(lib.otgan_conv2d_fprop_tf32(B, H, W, Cin, Cout, k, k, s, pt, pl, x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), st), "fprop")
+            _lib.check(lib.otgan_conv2d_fprop_tf32(B, H, W, Cin, Cout, k, k, s, pt, pl, x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), gws.data_ptr(), gws.numel() * 4, st), "fprop")
 
         def dgrad():
             _lib.check(lib.otgan_ohwi_to_ihwo_f32(Cout, k * k, Cin, w.data_ptr(), wt.data_ptr(), st), "transpose")
-            _lib.check(lib.otgan_conv2d_dgrad_tf32(B, H, W, Cin, Cout, k, k, s, pt, pl, dy.data_ptr(), wt.data_ptr(), dx.data_ptr(), st), "dgrad")
+            _lib.check(lib.otgan_conv2d_dgrad_tf32(B, H, W, Cin, Cout, k, k, s, pt, pl, dy.data_ptr(), wt.data_ptr(), dx.data_ptr(), gws.data_ptr(), gws.numel() * 4, st), "dgrad")
 
         def wgrad():
             _lib.check(lib.otgan_conv2d_wgrad_tf32(B, H, W, Cin, Cout, k, k, s, pt, pl, dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel() * 4, st), "wgrad")
 
-        row = {"layer": name, "shape": LAYERS[name], "gflop": flops / 1e9}
+        row = {"layer": name, "shape": (B,) + LAYERS[name][1:], "gflop": flops / 1e9}
         for op, fn in (("fprop", fprop), ("dgrad", dgrad), ("wgrad", wgrad)):
             ms = timeit(fn, args.iters)
             row[op + "_ms"] = ms
@@ -104,10 +108,10 @@ def main():
         print(json.dumps(row))
         sys.stdout.flush()
         rows.append(row)
-        del x, w, dy, y, dx, dw, wt, ws
+        del x, w, dy, y, dx, dw, wt, ws, gws
         torch.cuda.empty_cache()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "conv_bench.json"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", "conv_bench%s.json" % ("" if args.batch_div == 1 else "_div%d" % args.batch_div)), "w") as f:
         json.dump(rows, f, indent=1)
 
 

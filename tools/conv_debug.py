@@ -78,11 +78,13 @@ def run_case(op, si):
     y = F.conv2d(F.pad(xd.permute(0, 3, 1, 2), (pl, pr, pt, pb)), wd.permute(0, 3, 1, 2), bd, stride=s).permute(0, 2, 3, 1)
     dxr, dwr, dbr = torch.autograd.grad([y], [xd, wd, bd], [dy.double()])
     st = torch.cuda.current_stream().cuda_stream
-    print("case %s shape %s (pad %d/%d)" % (op, SHAPES[si], pt, pb))
+    gneed = max(lib.otgan_workspace_bytes_conv_gemm(B, H // s, W // s, Cout), lib.otgan_workspace_bytes_conv_gemm(B, H, W, Cin))
+    gws = torch.empty((gneed // 4 + 64,), device="cuda")
+    print("case %s shape %s (pad %d/%d), split-K workspace %d bytes" % (op, SHAPES[si], pt, pb, gneed))
     ok = True
     if op == "fprop":
         out = torch.full((B, H // s, W // s, Cout), float("nan"), device="cuda")
-        rc = lib.otgan_conv2d_fprop_tf32(B, H, W, Cin, Cout, k, k, s, pt, pl, x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), st)
+        rc = lib.otgan_conv2d_fprop_tf32(B, H, W, Cin, Cout, k, k, s, pt, pl, x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), gws.data_ptr(), gws.numel() * 4, st)
         _lib.check(rc, "fprop")
         torch.cuda.synchronize()
         ok = describe("y", out, y.detach(), ["n", "oh", "ow", "co"])
@@ -93,7 +95,7 @@ def run_case(op, si):
         wt_ref = w.view(Cout, k * k, Cin).permute(2, 1, 0).reshape(Cin, -1)
         ok = describe("w_ihwo", wt, wt_ref.double(), ["ci", "tap*co"])
         out = torch.full((B, H, W, Cin), float("nan"), device="cuda")
-        rc = lib.otgan_conv2d_dgrad_tf32(B, H, W, Cin, Cout, k, k, s, pt, pl, dy.data_ptr(), wt.data_ptr(), out.data_ptr(), st)
+        rc = lib.otgan_conv2d_dgrad_tf32(B, H, W, Cin, Cout, k, k, s, pt, pl, dy.data_ptr(), wt.data_ptr(), out.data_ptr(), gws.data_ptr(), gws.numel() * 4, st)
         _lib.check(rc, "dgrad")
         torch.cuda.synchronize()
         ok = describe("dx", out, dxr, ["n", "ih", "iw", "ci"]) and ok
