@@ -532,8 +532,19 @@ def run_ours(args):
                                                             "phase_ms": {"cost": ph[0], "sinkhorn": ph[1], "matched_distance": ph[2]},
                                                             "sinkhorn_iters_per_sec": T_ITERS / (ph[1] * 1e-3)}}
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down: captured graphs hold NCCL kernels; destroying the process group under them was observed to hang
+        # (2-GPU run, after the JSON line was printed).  Drop the graphs, drain the device, meet once more, and leave
+        # without the collective destructor -- every rank exits 0 on its own.
+        tr.graphs = tr.g_stats = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -44,8 +44,9 @@ constexpr int SMEM_BUDGET = 200 * 1024;
 template <int TN> struct Cfg {
     static constexpr int B_TILE = TN * BK * 4;
     static constexpr int STAGE_BYTES = A_TILE + B_TILE;
-    static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;          // TN = 256: 4 stages of 48 KB; TN = 128: 6 of 32 KB
-    static constexpr int TMEM_COLS = 2 * TN;
+    static constexpr int STAGES_ = SMEM_BUDGET / STAGE_BYTES;         // TN = 256: 4 stages of 48 KB; TN = 128: 6 of 32 KB
+    static constexpr int STAGES = STAGES_ > 8 ? 8 : STAGES_;          // TN = 16 (18 KB stages): 8 is plenty
+    static constexpr int TMEM_COLS = 2 * TN < 32 ? 32 : 2 * TN;
     static constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256;
 };
 
@@ -63,6 +64,8 @@ struct GemmParams {
     long long split_stride;
     int bw, bh, bn, tiles_w, tiles_h;         // pixel box (bw*bh*bn = 128) and tile grid of one class
     int kchunks;                              // 32-channel chunks per tap
+    int n_valid;                              // real output channels (TN = 16 variant: N <= 16, rest of the tile is ignored)
+    int b_box_bytes;                          // bytes of one weight box (rows actually present in the weight matrix)
     long long osW, osH, osN;                  // output pixel strides (floats)
     float* out;
     const float* bias;                        // [N] or null
@@ -125,7 +128,7 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
                     for (int kc = 0; kc < p.kchunks; ++kc, ++c) {
                         const int s = c % STAGES;
                         mbar_wait(empty_bar(s), (((uint32_t)(c / STAGES)) & 1u) ^ 1u);
-                        mbar_arrive_expect_tx(full_bar(s), (uint32_t)C::STAGE_BYTES);
+                        mbar_arrive_expect_tx(full_bar(s), (uint32_t)(A_TILE + p.b_box_bytes));
                         const uint32_t dst = smem_base + s * C::STAGE_BYTES;
                         tma_load_4d(dst, am, full_bar(s), kc * BK, w0 + tap.dw, h0 + tap.dh, n0);
                         tma_load_2d(dst + A_TILE, &p.bmap, full_bar(s), tap.wcol + kc * BK, nt * TN);
@@ -179,6 +182,16 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
             const float* bias = (p.bias && sp == 0) ? p.bias + nt * TN : nullptr;     // the first partial carries the bias
             mbar_wait(tfull_bar(b), ((uint32_t)(n >> 1)) & 1u);
             tcgen05_fence_after();
+            if constexpr (TN == 16) {
+                // narrow outputs (the generator's 3-channel image, the critic's image gradient): only n_valid columns exist;
+                // the weight box has n_valid rows, the other accumulator columns hold garbage and are never stored
+                uint32_t v[16];
+                tmem_ld_32x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TN), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j < p.n_valid) out[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + j) : 0.f);
+            } else {
 #pragma unroll 1
             for (int cc = 0; cc < TN / 32; ++cc) {
                 uint32_t v[32];
@@ -197,6 +210,7 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<uint4*>(out + cc * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
             }
             tcgen05_fence_before();
             mbar_arrive(tempty_bar(b));
@@ -481,12 +495,12 @@ int run_gemm(GemmParams& p, int TN, size_t out_numel, float* out, void* ws, size
         min_taps = T < min_taps ? T : min_taps;
     }
     const int tiles = p.m_tiles * p.n_tiles * p.n_cls;
-    p.splits = gemm_splits(tiles, min_taps);
+    p.splits = (out_numel % 4) ? 1 : gemm_splits(tiles, min_taps);
     if (p.splits > 1 && (!ws || ws_bytes < (size_t)p.splits * out_numel * sizeof(float))) p.splits = 1;   // no room: unsplit
     p.split_stride = (long long)out_numel;
     p.n_items = tiles * p.splits;
     p.out = p.splits > 1 ? reinterpret_cast<float*>(ws) : out;
-    const int rc = TN == 256 ? launch_gemm<256>(p, stream) : launch_gemm<128>(p, stream);
+    const int rc = TN == 256 ? launch_gemm<256>(p, stream) : TN == 128 ? launch_gemm<128>(p, stream) : launch_gemm<16>(p, stream);
     if (rc != OTGAN_OK || p.splits == 1) return rc;
     const size_t n4 = out_numel / 4;
     const size_t blocks = (n4 + 255) / 256;
@@ -560,6 +574,7 @@ int wgrad_splits(int items, int nchunks, double flops, double dw_bytes)
 size_t conv_gemm_workspace_bytes(int B, int H, int W, int C)
 {
     const long long pix = (long long)B * H * W;
+    if (C % 128) return 256;                                          // narrow (TN = 16) outputs are never split
     const int TN = (C % 256 == 0) ? 256 : 128;
     const long long tiles = (pix / TM) * (C / TN);
     if (tiles < 1 || tiles >= kNumSMs) return 256;
@@ -573,18 +588,20 @@ int conv_fprop_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
     OTGAN_REQUIRE(conv_dims_ok(B, H, W, Cin, Cout, kh, kw, s, pt, pl, Ho, Wo), "conv_fprop: unsupported geometry");
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    if (Cin % BK || Cout % 128 || !pixel_box(TM, Wo, Ho, B, &p.bw, &p.bh, &p.bn)) {
-        set_error("conv_fprop(tcgen05): needs Cin %% 32 == 0, Cout %% 128 == 0, power-of-two output extent tiling into 128-pixel boxes "
-                  "(B=%d H=%d W=%d Cin=%d Cout=%d)", B, H, W, Cin, Cout);
+    if (Cin % BK || (Cout % 128 && Cout > 16) || !pixel_box(TM, Wo, Ho, B, &p.bw, &p.bh, &p.bn)) {
+        set_error("conv_fprop(tcgen05): needs Cin %% 32 == 0, Cout %% 128 == 0 or Cout <= 16, power-of-two output extent tiling into "
+                  "128-pixel boxes (B=%d H=%d W=%d Cin=%d Cout=%d)", B, H, W, Cin, Cout);
         return OTGAN_EUNSUPPORTED;
     }
-    const int TN = (Cout % 256 == 0) ? 256 : 128;
+    const int TN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : 16;
+    const int brows = Cout < TN ? Cout : TN;
+    p.n_valid = Cout; p.b_box_bytes = brows * BK * 4;
     const unsigned box[4] = {(unsigned)BK, (unsigned)p.bw, (unsigned)p.bh, (unsigned)p.bn};
     for (int ph = 0; ph < s; ++ph)
         for (int pw = 0; pw < s; ++pw)
             if (!make_view_map(&p.amap[ph * s + pw], x, B, H, W, Cin, s, ph, pw, box, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
     for (int i = s * s; i < 4; ++i) p.amap[i] = p.amap[0];
-    if (!make_tensor_map_2d(&p.bmap, w, Cout, kh * kw * Cin, kh * kw * Cin, TN, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
+    if (!make_tensor_map_2d(&p.bmap, w, Cout, kh * kw * Cin, kh * kw * Cin, brows, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
     int nt = 0;
     for (int a = 0; a < kh; ++a)
         for (int b = 0; b < kw; ++b) {
@@ -597,7 +614,7 @@ int conv_fprop_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
     p.cls_out_off[0] = 0;
     p.tiles_w = Wo / p.bw; p.tiles_h = Ho / p.bh;
     p.m_tiles = p.tiles_w * p.tiles_h * (B / p.bn);
-    p.n_tiles = Cout / TN;
+    p.n_tiles = Cout < TN ? 1 : Cout / TN;
     p.kchunks = Cin / BK;
     p.osW = Cout; p.osH = (long long)Wo * Cout; p.osN = (long long)Ho * Wo * Cout;
     p.bias = bias;
@@ -611,16 +628,18 @@ int conv_dgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
     OTGAN_REQUIRE(conv_dims_ok(B, H, W, Cin, Cout, kh, kw, s, pt, pl, Ho, Wo), "conv_dgrad: unsupported geometry");
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    if (Cout % BK || Cin % 128 || !pixel_box(TM, W / s, H / s, B, &p.bw, &p.bh, &p.bn)) {
-        set_error("conv_dgrad(tcgen05): needs Cout %% 32 == 0, Cin %% 128 == 0, power-of-two extents tiling into 128-pixel boxes "
-                  "(B=%d H=%d W=%d Cin=%d Cout=%d)", B, H, W, Cin, Cout);
+    if (Cout % BK || (Cin % 128 && Cin > 16) || !pixel_box(TM, W / s, H / s, B, &p.bw, &p.bh, &p.bn)) {
+        set_error("conv_dgrad(tcgen05): needs Cout %% 32 == 0, Cin %% 128 == 0 or Cin <= 16, power-of-two extents tiling into "
+                  "128-pixel boxes (B=%d H=%d W=%d Cin=%d Cout=%d)", B, H, W, Cin, Cout);
         return OTGAN_EUNSUPPORTED;
     }
-    const int TN = (Cin % 256 == 0) ? 256 : 128;
+    const int TN = (Cin % 256 == 0) ? 256 : (Cin % 128 == 0) ? 128 : 16;
+    const int brows = Cin < TN ? Cin : TN;
+    p.n_valid = Cin; p.b_box_bytes = brows * BK * 4;
     const unsigned box[4] = {(unsigned)BK, (unsigned)p.bw, (unsigned)p.bh, (unsigned)p.bn};
     if (!make_view_map(&p.amap[0], dy, B, Ho, Wo, Cout, 1, 0, 0, box, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
     for (int i = 1; i < 4; ++i) p.amap[i] = p.amap[0];
-    if (!make_tensor_map_2d(&p.bmap, wt, Cin, kh * kw * Cout, kh * kw * Cout, TN, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
+    if (!make_tensor_map_2d(&p.bmap, wt, Cin, kh * kw * Cout, kh * kw * Cout, brows, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
     // parity classes of the input pixel (ih, iw): ih = s*j + ph gets the taps with (ph + pt - a) % s == 0, from output row
     // oh = j + (ph + pt - a) / s
     int nt = 0;
@@ -642,7 +661,7 @@ int conv_dgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
     p.cls_tap_begin[p.n_cls] = nt;
     p.tiles_w = (W / s) / p.bw; p.tiles_h = (H / s) / p.bh;
     p.m_tiles = p.tiles_w * p.tiles_h * (B / p.bn);
-    p.n_tiles = Cin / TN;
+    p.n_tiles = Cin < TN ? 1 : Cin / TN;
     p.kchunks = Cout / BK;
     p.osW = (long long)s * Cin; p.osH = (long long)s * W * Cin; p.osN = (long long)H * W * Cin;
     p.bias = nullptr;

@@ -357,6 +357,13 @@ def main(argv=None):
     if rank == 0:
         print('total updates %d, elapsed %.3f s' % (trainer.step_counter, time.time() - start_time))
     if world > 1:
+        if trainer.graphs is not None:                      # see bench.py: no collective destructor under captured NCCL graphs
+            trainer.graphs = trainer.g_stats = None
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 

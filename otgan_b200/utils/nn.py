@@ -342,6 +342,7 @@ def _conv2d_nhwc(x, W, stride, pad, bias=None):
 
 
 CONV_BACKEND = "tcgen05"      # "tcgen05": this library's implicit-GEMM kernels where they tile the shape; "cudnn": library rung only
+CONV_NARROW = True            # route the two 3-channel layers through _ConvNarrow (False: cuDNN, for A/B timing)
 _conv_ws = {}
 
 
@@ -430,6 +431,99 @@ class _ConvTC(torch.autograd.Function):
             db = torch.empty((cout,), device=x.device, dtype=torch.float32)
             _lib.check(lib.otgan_colsum_f32(P, cout, dy.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream), "otgan_colsum_f32")
         return dx, dwt, db, None, None
+
+
+def conv_narrow_supported(xshape, cout, kh, kw, stride, pad):
+    """The two 3-channel layers of DCGAN (critic conv2d_0: 3 -> 128, generator conv2d_3: 128 -> 3): stride 1, one side of
+    the layer has <= 16 channels, the other a multiple of 128."""
+    B, H, W, cin = xshape
+    if pad != "SAME" or tuple(stride) != (1, 1) or kh * kw > 32 or kh % 2 == 0 or kw % 2 == 0:
+        return False
+    if not ((cin <= 16 and cout % 128 == 0) or (cin % 128 == 0 and cout <= 16)):
+        return False
+    if not (_pow2(H) and _pow2(W)) or W > 32:
+        return False
+    return H * W >= 128 or (B * H * W) % 128 == 0
+
+
+def _pad_channels(t, c):
+    """Zero-pad the last (channel) axis to c entries."""
+    return t if t.shape[-1] == c else F.pad(t, (0, c - t.shape[-1]))
+
+
+class _ConvNarrow(torch.autograd.Function):
+    """The 3-channel convolutions on the tcgen05 kernels where they apply:
+        few INPUT channels (critic conv2d_0):  fprop = the GEMM kernel on the image / filter zero-padded to 32 channels,
+                                               dgrad = the narrow-output (N <= 16) variant of the GEMM kernel;
+        few OUTPUT channels (generator conv2d_3): fprop = the narrow-output variant, dgrad = the GEMM kernel on dy / filter
+                                               zero-padded to 32 channels.
+    The filter gradient of these two layers (0.4% of the step's FLOPs, a [128 x 75] reduction over all pixels) is the one
+    convolution pass still computed by cuDNN."""
+
+    @staticmethod
+    def forward(ctx, x, wt, bias, geom):
+        lib = _lib.load()
+        kh, kw, s, pt, pl = geom
+        B, H, W, cin = x.shape
+        cout = wt.shape[0]
+        x, wt = x.contiguous(), wt.contiguous()
+        if bias is not None and bias.data_ptr() % 16:
+            bias = bias.clone()
+        stream = torch.cuda.current_stream().cuda_stream
+        if cin <= 16:
+            xk = _pad_channels(x, 32)
+            wk = _pad_channels(wt.view(cout, kh * kw, cin), 32).reshape(cout, -1)
+            ck = 32
+        else:
+            xk, wk, ck = x, wt, cin
+        y = torch.empty((B, H, W, cout), device=x.device, dtype=torch.float32)
+        ws = _workspace(x.device, lib.otgan_workspace_bytes_conv_gemm(B, H, W, cout))
+        rc = lib.otgan_conv2d_fprop_tf32(B, H, W, ck, cout, kh, kw, 1, pt, pl, xk.data_ptr(), wk.data_ptr(),
+                                         bias.data_ptr() if bias is not None else None, y.data_ptr(), ws.data_ptr(),
+                                         ws.numel() * 4, stream)
+        _lib.check(rc, "otgan_conv2d_fprop_tf32")
+        ctx.save_for_backward(x, wt)
+        ctx.geom, ctx.has_bias = geom, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, wt = ctx.saved_tensors
+        kh, kw, s, pt, pl = ctx.geom
+        B, H, W, cin = x.shape
+        cout = wt.shape[0]
+        dy = dy.contiguous()
+        stream = torch.cuda.current_stream().cuda_stream
+        dx = dwt = db = None
+        if ctx.needs_input_grad[0]:
+            if cout <= 16:                                 # few output channels: pad dy and the IHWO filter to 32
+                dyk = _pad_channels(dy, 32)
+                wt_t = _pad_channels(wt.view(cout, kh * kw, cin).permute(2, 1, 0), 32).reshape(cin, -1)
+                ck = 32
+            else:
+                dyk, ck = dy, cout
+                wt_t = torch.empty((cin, kh * kw * cout), device=x.device, dtype=torch.float32)
+                _lib.check(lib.otgan_ohwi_to_ihwo_f32(cout, kh * kw, cin, wt.data_ptr(), wt_t.data_ptr(), stream), "otgan_ohwi_to_ihwo_f32")
+            dx = torch.empty_like(x)
+            ws = _workspace(x.device, lib.otgan_workspace_bytes_conv_gemm(B, H, W, cin))
+            rc = lib.otgan_conv2d_dgrad_tf32(B, H, W, cin, ck, kh, kw, 1, pt, pl, dyk.data_ptr(), wt_t.contiguous().data_ptr(),
+                                             dx.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream)
+            _lib.check(rc, "otgan_conv2d_dgrad_tf32")
+        if ctx.needs_input_grad[1]:
+            w_oihw = wt.view(cout, kh, kw, cin).permute(0, 3, 1, 2)
+            _, dw, _ = torch.ops.aten.convolution_backward(dy.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), w_oihw, None, [1, 1],
+                                                           [pt, pl], [1, 1], False, [0, 0], 1, [False, True, False])
+            dwt = dw.permute(0, 2, 3, 1).reshape(cout, -1)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            if cout % 4 == 0:
+                P = dy.numel() // cout
+                ws = _workspace(x.device, lib.otgan_workspace_bytes_colsum(P, cout))
+                db = torch.empty((cout,), device=x.device, dtype=torch.float32)
+                _lib.check(lib.otgan_colsum_f32(P, cout, dy.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream), "otgan_colsum_f32")
+            else:
+                db = dy.reshape(-1, cout).sum(0)
+        return dx, dwt, db, None
 
 
 class _CreluL2Norm(torch.autograd.Function):
@@ -671,6 +765,9 @@ def _conv2d(x, W, stride=(1, 1), pad="SAME", dilate=1, pre_activation=None, upsa
             z = xl[0].contiguous() if pre_activation is None else _CreluPad.apply(xl[0].contiguous(), (0, 0, 0, 0))
             geom = (kh, kw, stride[0], same_padding(H, kh, stride[0])[0], same_padding(Wd, kw, stride[1])[0])
             return _ConvTC.apply(z, W.wt, bias, geom, W.wt_ihwo)
+        if pre_activation is None and CONV_NARROW and conv_narrow_supported((B, H, Wd, cin), cout, kh, kw, stride, pad):
+            geom = (kh, kw, 1, same_padding(H, kh, 1)[0], same_padding(Wd, kw, 1)[0])
+            return _ConvNarrow.apply(xl[0].contiguous(), W.wt, bias, geom)
     if (pre_activation == "crelu" and len(xl) == 1 and pad == "SAME" and xl[0].is_cuda and xl[0].dtype == torch.float32
             and xl[0].shape[3] % 4 == 0):
         # CReLU written straight into the TensorFlow-'SAME'-padded input of the convolution (one fused kernel)

@@ -4,9 +4,13 @@ computed by a single rank on the full batch with identical images, latents and p
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port P tests/mgpu_parity.py
 Prints "MGPU PARITY OK" on rank 0 (exit code 0) or the first mismatch (exit code 1).  Not bitwise: per-rank batch sizes
-change cuDNN's algorithms / reduction order (1e-7-class feature differences), and lambda = 500 amplifies those into 1e-3 on
-grad_ys (measured), so the script checks the distributed LOGIC at lambda = 10 where fp32 noise stays small (measured 7e-5 ..
-2e-4; an indexing or reduction bug would be O(1)): gate 1e-3 relative on the summed gradients, 1e-6 absolute on the distance.
+change the tile / split-K configuration of the convolution kernels, i.e. the fp32 accumulation order (1e-7-class feature
+differences), and lambda = 500 amplifies those into 1e-3 on grad_ys (measured), so the script checks the distributed LOGIC
+at lambda = 10 where that noise stays small (an indexing or reduction bug would be O(1)).  Two passes:
+  * library rung (cuDNN, strict fp32):  gate 1e-3 relative on the summed gradients (measured 7e-5 .. 2e-4);
+  * tcgen05 convolution kernels (TF32 operands): gate 5e-3 -- an fp32-sized input difference occasionally moves an
+    activation across a TF32 truncation boundary (measured 4e-4 .. 1.6e-3);
+1e-6 absolute on the distance and 1e-5 on the entropy in both.
 """
 import os
 import sys
@@ -29,25 +33,29 @@ def main():
     g = torch.Generator().manual_seed(1234)
     x_all = (torch.rand((N, 32, 32, 3), generator=g) * 2 - 1).to(dev)
     u_all = (torch.rand((N, 100), generator=g) * 2 - 1).to(dev)
+    from otgan_b200.utils import nn
     ok, msgs = True, []
-    for step_kind in ("disc", "gen"):
-        res = {}
-        for mode in ("multi", "single"):
-            w, r = (world, rank) if mode == "multi" else (1, 0)
-            tr = T.Trainer(T.build_parser().parse_args(argv), dev, r, w)          # same seed -> identical parameters
-            tr.step_counter = 0 if step_kind == "disc" else 1
-            bs = tr.bs_local
-            lo = r * bs
-            kind, stats = tr.step(x_all[lo:lo + bs], u=u_all[lo:lo + bs], apply_update=False)
-            assert kind == step_kind
-            res[mode] = (tr.last_grad.clone(), stats.clone())
-        gm, sm = res["multi"]
-        gs, ss = res["single"]
-        rel = float((gm - gs).abs().max() / gs.abs().max())
-        dd, de = abs(float(sm[0] - ss[0])), abs(float(sm[1] - ss[1]))
-        if rank == 0:
-            msgs.append("%s step: grad rel err %.2e, |d distance| %.2e, |d entropy| %.2e" % (step_kind, rel, dd, de))
-        ok = ok and rel < 1e-3 and dd < 1e-6 and de < 1e-5
+    for backend, gate in (("cudnn", 1e-3), ("tcgen05", 5e-3)):
+      nn.CONV_BACKEND = backend
+      for step_kind in ("disc", "gen"):
+          res = {}
+          for mode in ("multi", "single"):
+              w, r = (world, rank) if mode == "multi" else (1, 0)
+              tr = T.Trainer(T.build_parser().parse_args(argv), dev, r, w)          # same seed -> identical parameters
+              tr.step_counter = 0 if step_kind == "disc" else 1
+              bs = tr.bs_local
+              lo = r * bs
+              kind, stats = tr.step(x_all[lo:lo + bs], u=u_all[lo:lo + bs], apply_update=False)
+              assert kind == step_kind
+              res[mode] = (tr.last_grad.clone(), stats.clone())
+          gm, sm = res["multi"]
+          gs, ss = res["single"]
+          rel = float((gm - gs).abs().max() / gs.abs().max())
+          dd, de = abs(float(sm[0] - ss[0])), abs(float(sm[1] - ss[1]))
+          if rank == 0:
+              msgs.append("%s / %s step: grad rel err %.2e, |d distance| %.2e, |d entropy| %.2e" % (backend, step_kind, rel, dd, de))
+          ok = ok and rel < gate and dd < 1e-6 and de < 1e-5
+    nn.CONV_BACKEND = "tcgen05"
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -232,3 +232,28 @@ def test_dcgan_networks_agree_with_library_convolutions():
             rel_l2 = float((a - c).norm() / c.norm())
             cos = float(torch.dot(a.flatten(), c.flatten()) / (a.norm() * c.norm()))
             assert rel_l2 <= 0.1 and cos >= 0.995, (name, rel_l2, cos)
+
+
+@pytest.mark.parametrize("shape", [(8, 32, 32, 3, 128, 5, 1), (8, 32, 32, 128, 3, 5, 1), (4, 16, 16, 3, 128, 3, 1), (4, 16, 16, 256, 3, 3, 1)])
+@pytest.mark.parametrize("exact", [True, False])
+def test_narrow_channel_convolutions(shape, exact):
+    """The 3-channel layers (critic conv2d_0, generator conv2d_3) through _ConvNarrow: channel-padded GEMM kernel, the
+    narrow-output (N <= 16) variant, cuDNN filter gradient.  Integer inputs: fprop / dgrad exact; N(0,1): 4e-3 (TF32)."""
+    from otgan_b200.utils import nn
+    B, H, W, Cin, Cout, k, s = shape
+    assert nn.conv_narrow_supported((B, H, W, Cin), Cout, k, k, [1, 1], "SAME")
+    x, w, b, dy = _make(shape, exact, 4)
+    xr = x.clone().requires_grad_(True)
+    wr = w.reshape(Cout, -1).clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    geom = (k, k, 1, _same_pad(H, k, 1)[0], _same_pad(W, k, 1)[0])
+    y = nn._ConvNarrow.apply(xr, wr, br, geom)
+    dx, dw, db = torch.autograd.grad([y], [xr, wr, br], [dy])
+    ours = (y.detach(), dx, dw.view(Cout, k, k, Cin), db)
+    ref = _run_ref(shape, x, w, b, dy)
+    for name, o, r in zip(("fprop", "dgrad", "wgrad", "bias-grad"), ours, ref):
+        err = float((o.double() - r).abs().max() / r.abs().max())
+        if exact and name in ("fprop", "dgrad", "bias-grad"):
+            assert err == 0.0, (name, shape, err)
+        else:
+            assert err <= 4e-3, (name, shape, err)
