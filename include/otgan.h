@@ -193,6 +193,14 @@ OTGAN_API int otgan_conv2d_wgrad_tf32(int B, int H, int W, int Cin, int Cout, in
                                       int pad_left, const float* dy, const float* x, float* dw_ohwi, void* ws,
                                       size_t ws_bytes, void* stream);
 OTGAN_API int otgan_ohwi_to_ihwo_f32(int Cout, int taps, int Cin, const float* w_ohwi, float* w_ihwo, void* stream);
+/* Narrow (<= 16 channel) side of the 3-channel layers, computed as one GEMM over all (tap, channel) columns + a shift
+ * (conv_narrow.cu).  off_t = (kh - pad_top, kw - pad_left), negated when flip != 0 (gradient orientation).
+ *   im2col: col[px][t*C + c] = x[px + off_t][c] (0 outside the image), columns kh*kw*C .. ldc-1 zero; x: [B,H,W,C]
+ *   col2im: y[px][c] = bias[c] + sum_t z[px + off_t][t*C + c] (rows outside the image contribute 0); z: [B*H*W, ldz] */
+OTGAN_API int otgan_im2col_narrow_f32(int B, int H, int W, int C, int kh, int kw, int pad_top, int pad_left, int flip,
+                                      const float* x, float* col, int ldc, void* stream);
+OTGAN_API int otgan_col2im_narrow_f32(int B, int H, int W, int C, int kh, int kw, int pad_top, int pad_left, int flip,
+                                      const float* z, int ldz, const float* bias, float* y, void* stream);
 OTGAN_API size_t otgan_workspace_bytes_colsum(int P, int C);
 OTGAN_API int otgan_colsum_f32(int P, int C, const float* x, float* out, void* ws, size_t ws_bytes, void* stream);
 

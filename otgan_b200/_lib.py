@@ -60,6 +60,8 @@ SIGNATURES = {
     "otgan_workspace_bytes_conv_wgrad": (_sz, [_i] * 8),
     "otgan_conv2d_wgrad_tf32": (_i, [_i] * 10 + [_vp, _vp, _vp, _vp, _sz, _vp]),
     "otgan_ohwi_to_ihwo_f32": (_i, [_i, _i, _i, _vp, _vp, _vp]),
+    "otgan_im2col_narrow_f32": (_i, [_i] * 9 + [_vp, _vp, _i, _vp]),
+    "otgan_col2im_narrow_f32": (_i, [_i] * 9 + [_vp, _i, _vp, _vp, _vp]),
     "otgan_workspace_bytes_colsum": (_sz, [_i, _i]),
     "otgan_colsum_f32": (_i, [_i, _i, _vp, _vp, _vp, _sz, _vp]),
 }

@@ -73,6 +73,10 @@ int conv_wgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
                       const float* dy, const float* x, float* dw, void* ws, size_t ws_bytes, cudaStream_t stream);
 int ohwi_to_ihwo_launch(int Cout, int T, int Cin, const float* w, float* wt, cudaStream_t stream);
 size_t colsum_workspace_bytes(int P, int C);
+int im2col_narrow_launch(int B, int H, int W, int C, int kh, int kw, int pt, int pl, int flip, const float* x, float* col,
+                         int ldc, cudaStream_t stream);
+int col2im_narrow_launch(int B, int H, int W, int C, int kh, int kw, int pt, int pl, int flip, const float* z, int ldz,
+                         const float* bias, float* y, cudaStream_t stream);
 int colsum_launch(int P, int C, const float* x, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 }  // namespace otgan
@@ -395,6 +399,22 @@ int otgan_colsum_f32(int P, int C, const float* x, float* out, void* ws, size_t 
     OTGAN_REQUIRE(P >= 1 && C >= 4 && C % 4 == 0 && x && out && ws, "colsum: bad arguments (C must be a multiple of 4)");
     OTGAN_REQUIRE(aligned16(x) && aligned16(out) && aligned16(ws), "colsum: buffers must be 16-byte aligned");
     return colsum_launch(P, C, x, out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int otgan_im2col_narrow_f32(int B, int H, int W, int C, int kh, int kw, int pad_top, int pad_left, int flip, const float* x,
+                            float* col, int ldc, void* stream)
+{
+    OTGAN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 1 && C <= 16 && kh >= 1 && kw >= 1 && x && col, "im2col_narrow: bad arguments");
+    OTGAN_REQUIRE(ldc >= kh * kw * C && ldc % 4 == 0 && aligned16(col), "im2col_narrow: ldc must be a multiple of 4 and >= kh*kw*C, col 16-byte aligned");
+    return im2col_narrow_launch(B, H, W, C, kh, kw, pad_top, pad_left, flip ? 1 : 0, x, col, ldc, (cudaStream_t)stream);
+}
+
+int otgan_col2im_narrow_f32(int B, int H, int W, int C, int kh, int kw, int pad_top, int pad_left, int flip, const float* z,
+                            int ldz, const float* bias, float* y, void* stream)
+{
+    OTGAN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 1 && C <= 16 && kh >= 1 && kw >= 1 && z && y, "col2im_narrow: bad arguments");
+    OTGAN_REQUIRE(ldz >= kh * kw * C, "col2im_narrow: ldz must be >= kh*kw*C");
+    return col2im_narrow_launch(B, H, W, C, kh, kw, pad_top, pad_left, flip ? 1 : 0, z, ldz, bias, y, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -548,12 +548,12 @@ bool conv_dims_ok(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s,
 }
 
 // Split-K factor of wgrad.  CTAs are persistent and take items round-robin, so the launch lasts ceil(n / 148) item times:
-// pick S (<= 16, >= 16 chunks per split) minimising  compute / wave-efficiency + the partial write / reduce traffic.
+// pick S (<= 148, >= 16 chunks per split) minimising  compute / wave-efficiency + the partial write / reduce traffic.
 int wgrad_splits(int items, int nchunks, double flops, double dw_bytes)
 {
     int best = 1;
     double best_t = 1e30;
-    for (int S = 1; S <= 16; ++S) {
+    for (int S = 1; S <= kNumSMs; ++S) {
         if (S > 1 && nchunks / S < 16) break;
         const int cps = (nchunks + S - 1) / S;
         const int Se = (nchunks + cps - 1) / cps;

@@ -439,7 +439,7 @@ def conv_narrow_supported(xshape, cout, kh, kw, stride, pad):
     B, H, W, cin = xshape
     if pad != "SAME" or tuple(stride) != (1, 1) or kh * kw > 32 or kh % 2 == 0 or kw % 2 == 0:
         return False
-    if not ((cin <= 16 and cout % 128 == 0) or (cin % 128 == 0 and cout <= 16)):
+    if not ((cin <= 16 and cout == 128) or (cin == 128 and cout <= 16)) or kh * kw * min(cin, cout) > 128:
         return False
     if not (_pow2(H) and _pow2(W)) or W > 32:
         return False
@@ -452,13 +452,35 @@ def _pad_channels(t, c):
 
 
 class _ConvNarrow(torch.autograd.Function):
-    """The 3-channel convolutions on the tcgen05 kernels where they apply:
-        few INPUT channels (critic conv2d_0):  fprop = the GEMM kernel on the image / filter zero-padded to 32 channels,
-                                               dgrad = the narrow-output (N <= 16) variant of the GEMM kernel;
-        few OUTPUT channels (generator conv2d_3): fprop = the narrow-output variant, dgrad = the GEMM kernel on dy / filter
-                                               zero-padded to 32 channels.
-    The filter gradient of these two layers (0.4% of the step's FLOPs, a [128 x 75] reduction over all pixels) is the one
-    convolution pass still computed by cuDNN."""
+    """The 3-channel convolutions (critic conv2d_0: 3 -> 128, generator conv2d_3: 128 -> 3) on this library's kernels.
+    With 3 channels on one side a per-tap implicit GEMM re-reads the wide tensor 25 times with no reuse, so:
+        narrow OUTPUT (generator fprop, critic dgrad): one 1x1 GEMM  z[px][t*C + c] = wide[px] . w2[t*C + c]  on the tcgen05
+            kernel (the wide tensor is read once), then otgan_col2im_narrow_f32 shifts and sums the 25 taps;
+        narrow INPUT of a filter gradient (both layers): otgan_im2col_narrow_f32 expands the 3-channel tensor to
+            [pixels, 128] columns, then ONE 1x1 wgrad GEMM on the tcgen05 kernel (split over all SMs along the pixels);
+        the remaining two passes (critic fprop, generator dgrad) run the GEMM kernel on the 3-channel tensor / filter
+            zero-padded to 32 channels."""
+
+    @staticmethod
+    def _gemm1x1(lib, x, w2, B, H, W, stream):
+        """z [B,H,W,128] = x [B,H,W,K] . w2[128, K]^T  (conv_gemm_tc_kernel as a 1x1 convolution)."""
+        z = torch.empty((B, H, W, w2.shape[0]), device=x.device, dtype=torch.float32)
+        rc = lib.otgan_conv2d_fprop_tf32(B, H, W, x.shape[3], w2.shape[0], 1, 1, 1, 0, 0, x.data_ptr(), w2.data_ptr(), None,
+                                         z.data_ptr(), None, 0, stream)
+        _lib.check(rc, "otgan_conv2d_fprop_tf32 (1x1)")
+        return z
+
+    @staticmethod
+    def _wgrad1x1(lib, wide, col, B, H, W, stream):
+        """out [Cw, 128] = sum_px wide[px][:]^T col[px][:]   (conv_wgrad_tc_kernel as a 1x1 convolution)."""
+        cw = wide.shape[-1]
+        need = lib.otgan_workspace_bytes_conv_wgrad(B, H, W, 128, cw, 1, 1, 1)
+        ws = _workspace(wide.device, need)
+        out = torch.empty((cw, 128), device=wide.device, dtype=torch.float32)
+        rc = lib.otgan_conv2d_wgrad_tf32(B, H, W, 128, cw, 1, 1, 1, 0, 0, wide.data_ptr(), col.data_ptr(), out.data_ptr(),
+                                         ws.data_ptr(), ws.numel() * 4, stream)
+        _lib.check(rc, "otgan_conv2d_wgrad_tf32 (1x1)")
+        return out
 
     @staticmethod
     def forward(ctx, x, wt, bias, geom):
@@ -466,22 +488,27 @@ class _ConvNarrow(torch.autograd.Function):
         kh, kw, s, pt, pl = geom
         B, H, W, cin = x.shape
         cout = wt.shape[0]
+        taps = kh * kw
         x, wt = x.contiguous(), wt.contiguous()
         if bias is not None and bias.data_ptr() % 16:
             bias = bias.clone()
         stream = torch.cuda.current_stream().cuda_stream
-        if cin <= 16:
-            xk = _pad_channels(x, 32)
-            wk = _pad_channels(wt.view(cout, kh * kw, cin), 32).reshape(cout, -1)
-            ck = 32
-        else:
-            xk, wk, ck = x, wt, cin
         y = torch.empty((B, H, W, cout), device=x.device, dtype=torch.float32)
-        ws = _workspace(x.device, lib.otgan_workspace_bytes_conv_gemm(B, H, W, cout))
-        rc = lib.otgan_conv2d_fprop_tf32(B, H, W, ck, cout, kh, kw, 1, pt, pl, xk.data_ptr(), wk.data_ptr(),
-                                         bias.data_ptr() if bias is not None else None, y.data_ptr(), ws.data_ptr(),
-                                         ws.numel() * 4, stream)
-        _lib.check(rc, "otgan_conv2d_fprop_tf32")
+        if cin <= 16:                                      # critic conv2d_0: image and filter zero-padded to 32 channels
+            xk = _pad_channels(x, 32)
+            wk = _pad_channels(wt.view(cout, taps, cin), 32).reshape(cout, -1)
+            ws = _workspace(x.device, lib.otgan_workspace_bytes_conv_gemm(B, H, W, cout))
+            rc = lib.otgan_conv2d_fprop_tf32(B, H, W, 32, cout, kh, kw, 1, pt, pl, xk.data_ptr(), wk.data_ptr(),
+                                             bias.data_ptr() if bias is not None else None, y.data_ptr(), ws.data_ptr(),
+                                             ws.numel() * 4, stream)
+            _lib.check(rc, "otgan_conv2d_fprop_tf32")
+        else:                                              # generator conv2d_3: 1x1 GEMM over the 75 (tap, co) columns + shift
+            w2 = torch.zeros((128, cin), device=x.device, dtype=torch.float32)
+            w2[:taps * cout] = wt.view(cout, taps, cin).permute(1, 0, 2).reshape(taps * cout, cin)
+            z = _ConvNarrow._gemm1x1(lib, x, w2, B, H, W, stream)
+            rc = lib.otgan_col2im_narrow_f32(B, H, W, cout, kh, kw, pt, pl, 0, z.data_ptr(), 128,
+                                             bias.data_ptr() if bias is not None else None, y.data_ptr(), stream)
+            _lib.check(rc, "otgan_col2im_narrow_f32")
         ctx.save_for_backward(x, wt)
         ctx.geom, ctx.has_bias = geom, bias is not None
         return y
@@ -493,28 +520,37 @@ class _ConvNarrow(torch.autograd.Function):
         kh, kw, s, pt, pl = ctx.geom
         B, H, W, cin = x.shape
         cout = wt.shape[0]
+        taps = kh * kw
         dy = dy.contiguous()
         stream = torch.cuda.current_stream().cuda_stream
         dx = dwt = db = None
         if ctx.needs_input_grad[0]:
-            if cout <= 16:                                 # few output channels: pad dy and the IHWO filter to 32
-                dyk = _pad_channels(dy, 32)
-                wt_t = _pad_channels(wt.view(cout, kh * kw, cin).permute(2, 1, 0), 32).reshape(cin, -1)
-                ck = 32
-            else:
-                dyk, ck = dy, cout
-                wt_t = torch.empty((cin, kh * kw * cout), device=x.device, dtype=torch.float32)
-                _lib.check(lib.otgan_ohwi_to_ihwo_f32(cout, kh * kw, cin, wt.data_ptr(), wt_t.data_ptr(), stream), "otgan_ohwi_to_ihwo_f32")
             dx = torch.empty_like(x)
-            ws = _workspace(x.device, lib.otgan_workspace_bytes_conv_gemm(B, H, W, cin))
-            rc = lib.otgan_conv2d_dgrad_tf32(B, H, W, cin, ck, kh, kw, 1, pt, pl, dyk.data_ptr(), wt_t.contiguous().data_ptr(),
-                                             dx.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream)
-            _lib.check(rc, "otgan_conv2d_dgrad_tf32")
+            if cin <= 16:                                  # critic conv2d_0: z[px][t*cin + ci] = dy[px] . W[:, t, ci], then shift
+                w2 = torch.zeros((128, cout), device=x.device, dtype=torch.float32)
+                w2[:taps * cin] = wt.t()
+                z = _ConvNarrow._gemm1x1(lib, dy, w2, B, H, W, stream)
+                _lib.check(lib.otgan_col2im_narrow_f32(B, H, W, cin, kh, kw, pt, pl, 1, z.data_ptr(), 128, None, dx.data_ptr(), stream),
+                           "otgan_col2im_narrow_f32")
+            else:                                          # generator conv2d_3: dy and the IHWO filter zero-padded to 32 channels
+                dyk = _pad_channels(dy, 32)
+                wt_t = _pad_channels(wt.view(cout, taps, cin).permute(2, 1, 0), 32).reshape(cin, -1).contiguous()
+                ws = _workspace(x.device, lib.otgan_workspace_bytes_conv_gemm(B, H, W, cin))
+                rc = lib.otgan_conv2d_dgrad_tf32(B, H, W, cin, 32, kh, kw, 1, pt, pl, dyk.data_ptr(), wt_t.data_ptr(), dx.data_ptr(),
+                                                 ws.data_ptr(), ws.numel() * 4, stream)
+                _lib.check(rc, "otgan_conv2d_dgrad_tf32")
         if ctx.needs_input_grad[1]:
-            w_oihw = wt.view(cout, kh, kw, cin).permute(0, 3, 1, 2)
-            _, dw, _ = torch.ops.aten.convolution_backward(dy.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), w_oihw, None, [1, 1],
-                                                           [pt, pl], [1, 1], False, [0, 0], 1, [False, True, False])
-            dwt = dw.permute(0, 2, 3, 1).reshape(cout, -1)
+            col = torch.empty((B, H, W, 128), device=x.device, dtype=torch.float32)
+            if cin <= 16:                                  # dW[co][t*cin + ci] = sum_px dy[px][co] x[px + off_t][ci]
+                _lib.check(lib.otgan_im2col_narrow_f32(B, H, W, cin, kh, kw, pt, pl, 0, x.data_ptr(), col.data_ptr(), 128, stream),
+                           "otgan_im2col_narrow_f32")
+                out = _ConvNarrow._wgrad1x1(lib, dy, col, B, H, W, stream)
+                dwt = out[:, :taps * cin].contiguous()
+            else:                                          # dW[co][t][ci] = sum_px x[px][ci] dy[px - off_t][co]
+                _lib.check(lib.otgan_im2col_narrow_f32(B, H, W, cout, kh, kw, pt, pl, 1, dy.data_ptr(), col.data_ptr(), 128, stream),
+                           "otgan_im2col_narrow_f32")
+                out = _ConvNarrow._wgrad1x1(lib, x, col, B, H, W, stream)          # [cin][t*cout + co]
+                dwt = out[:, :taps * cout].reshape(cin, taps, cout).permute(2, 1, 0).reshape(cout, taps * cin)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             if cout % 4 == 0:
                 P = dy.numel() // cout

@@ -234,11 +234,12 @@ def test_dcgan_networks_agree_with_library_convolutions():
             assert rel_l2 <= 0.1 and cos >= 0.995, (name, rel_l2, cos)
 
 
-@pytest.mark.parametrize("shape", [(8, 32, 32, 3, 128, 5, 1), (8, 32, 32, 128, 3, 5, 1), (4, 16, 16, 3, 128, 3, 1), (4, 16, 16, 256, 3, 3, 1)])
+@pytest.mark.parametrize("shape", [(8, 32, 32, 3, 128, 5, 1), (8, 32, 32, 128, 3, 5, 1), (4, 16, 16, 3, 128, 3, 1), (4, 16, 16, 128, 3, 3, 1)])
 @pytest.mark.parametrize("exact", [True, False])
 def test_narrow_channel_convolutions(shape, exact):
-    """The 3-channel layers (critic conv2d_0, generator conv2d_3) through _ConvNarrow: channel-padded GEMM kernel, the
-    narrow-output (N <= 16) variant, cuDNN filter gradient.  Integer inputs: fprop / dgrad exact; N(0,1): 4e-3 (TF32)."""
+    """The 3-channel layers (critic conv2d_0, generator conv2d_3) through _ConvNarrow: 1x1 GEMM + col2im shift for the
+    narrow-output passes, im2col + 1x1 wgrad GEMM for the filter gradients, channel-padded GEMM kernel for the other two.
+    Integer inputs: every pass exact; N(0,1): 4e-3 (TF32 operands)."""
     from otgan_b200.utils import nn
     B, H, W, Cin, Cout, k, s = shape
     assert nn.conv_narrow_supported((B, H, W, Cin), Cout, k, k, [1, 1], "SAME")
@@ -253,7 +254,7 @@ def test_narrow_channel_convolutions(shape, exact):
     ref = _run_ref(shape, x, w, b, dy)
     for name, o, r in zip(("fprop", "dgrad", "wgrad", "bias-grad"), ours, ref):
         err = float((o.double() - r).abs().max() / r.abs().max())
-        if exact and name in ("fprop", "dgrad", "bias-grad"):
+        if exact:
             assert err == 0.0, (name, shape, err)
         else:
             assert err <= 4e-3, (name, shape, err)
