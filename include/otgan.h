@@ -193,6 +193,32 @@ OTGAN_API int otgan_conv2d_wgrad_tf32(int B, int H, int W, int Cin, int Cout, in
                                       int pad_left, const float* dy, const float* x, float* dw_ohwi, void* ws,
                                       size_t ws_bytes, void* stream);
 OTGAN_API int otgan_ohwi_to_ihwo_f32(int Cout, int taps, int Cin, const float* w_ohwi, float* w_ihwo, void* stream);
+/* ---- fused 2x nearest-neighbour upsample + convolution (models/dcgan.py:37-46: resize_nearest_neighbor -> nn.conv2d) -----------
+ * y [B, 2Hl, 2Wl, Cout] = conv(upsample2x(x_low [B, Hl, Wl, Cin]), W, stride 1, 'SAME') + bias without materialising the
+ * upsampled tensor: output pixel (2i+a, 2j+b) reads x_low rows i + floor((a + kh - pad)/2), so the kh taps of the filter
+ * collapse onto n1 = otgan_up2_subtaps(k, pad) low-resolution rows (5x5: 3, 3x3: 2) and each of the 4 output parity classes
+ * (a, b) is an n1 x n1 convolution of x_low with a pre-summed sub-filter: 9 taps instead of 25 for the generator's layers.
+ *   w_sub      [4][Cout][n1*n1*Cin]   = otgan_up2_weight_presum_f32(w_ohwi)             (class index 2a + b)
+ *   w_sub_ihwo [4][Cin][n1*n1*Cout]   = otgan_ohwi_to_ihwo_f32 of each class of w_sub   (dgrad)
+ *   dw_ohwi = otgan_up2_weight_unsum_f32(dw_sub): the chain rule of the pre-sum          (after wgrad)
+ * Exact algebra of the reference's two ops; only the floating-point summation order differs. */
+OTGAN_API int otgan_up2_subtaps(int k, int pad);
+OTGAN_API int otgan_up2_weight_presum_f32(int Cout, int kh, int kw, int Cin, int pad_top, int pad_left, const float* w_ohwi,
+                                          float* w_sub, void* stream);
+OTGAN_API int otgan_up2_weight_unsum_f32(int Cout, int kh, int kw, int Cin, int pad_top, int pad_left, const float* dw_sub,
+                                         float* dw_ohwi, void* stream);
+OTGAN_API int otgan_conv2d_up2_fprop_tf32(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pad_top, int pad_left,
+                                          const float* x_low, const float* w_sub, const float* bias, float* y, void* ws,
+                                          size_t ws_bytes, void* stream);
+OTGAN_API int otgan_conv2d_up2_dgrad_tf32(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pad_top, int pad_left,
+                                          const float* dy, const float* w_sub_ihwo, float* dx_low, void* ws, size_t ws_bytes,
+                                          void* stream);
+OTGAN_API size_t otgan_workspace_bytes_conv_up2_wgrad(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pad_top,
+                                                      int pad_left);
+OTGAN_API int otgan_conv2d_up2_wgrad_tf32(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pad_top, int pad_left,
+                                          const float* dy, const float* x_low, float* dw_sub, void* ws, size_t ws_bytes,
+                                          void* stream);
+
 /* Narrow (<= 16 channel) side of the 3-channel layers, computed as one GEMM over all (tap, channel) columns + a shift
  * (conv_narrow.cu).  off_t = (kh - pad_top, kw - pad_left), negated when flip != 0 (gradient orientation).
  *   im2col: col[px][t*C + c] = x[px + off_t][c] (0 outside the image), columns kh*kw*C .. ldc-1 zero; x: [B,H,W,C]

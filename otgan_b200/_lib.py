@@ -60,6 +60,13 @@ SIGNATURES = {
     "otgan_workspace_bytes_conv_wgrad": (_sz, [_i] * 8),
     "otgan_conv2d_wgrad_tf32": (_i, [_i] * 10 + [_vp, _vp, _vp, _vp, _sz, _vp]),
     "otgan_ohwi_to_ihwo_f32": (_i, [_i, _i, _i, _vp, _vp, _vp]),
+    "otgan_up2_subtaps": (_i, [_i, _i]),
+    "otgan_up2_weight_presum_f32": (_i, [_i] * 6 + [_vp, _vp, _vp]),
+    "otgan_up2_weight_unsum_f32": (_i, [_i] * 6 + [_vp, _vp, _vp]),
+    "otgan_conv2d_up2_fprop_tf32": (_i, [_i] * 9 + [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "otgan_conv2d_up2_dgrad_tf32": (_i, [_i] * 9 + [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "otgan_workspace_bytes_conv_up2_wgrad": (_sz, [_i] * 9),
+    "otgan_conv2d_up2_wgrad_tf32": (_i, [_i] * 9 + [_vp, _vp, _vp, _vp, _sz, _vp]),
     "otgan_im2col_narrow_f32": (_i, [_i] * 9 + [_vp, _vp, _i, _vp]),
     "otgan_col2im_narrow_f32": (_i, [_i] * 9 + [_vp, _i, _vp, _vp, _vp]),
     "otgan_workspace_bytes_colsum": (_sz, [_i, _i]),

@@ -73,6 +73,16 @@ int conv_wgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
                       const float* dy, const float* x, float* dw, void* ws, size_t ws_bytes, cudaStream_t stream);
 int ohwi_to_ihwo_launch(int Cout, int T, int Cin, const float* w, float* wt, cudaStream_t stream);
 size_t colsum_workspace_bytes(int P, int C);
+int up2_subtaps(int k, int pad);
+int up2_presum_launch(int Cout, int kh, int kw, int Cin, int pt, int pl, const float* w, float* w_sub, cudaStream_t stream);
+int up2_unsum_launch(int Cout, int kh, int kw, int Cin, int pt, int pl, const float* dw_sub, float* dw, cudaStream_t stream);
+int conv_up2_fprop_launch(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pt, int pl, const float* x_low,
+                          const float* w_sub, const float* bias, float* y, void* ws, size_t ws_bytes, cudaStream_t stream);
+int conv_up2_dgrad_launch(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pt, int pl, const float* dy,
+                          const float* w_sub_t, float* dx_low, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t conv_up2_wgrad_workspace_bytes(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pt, int pl);
+int conv_up2_wgrad_launch(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pt, int pl, const float* dy,
+                          const float* x_low, float* dw_sub, void* ws, size_t ws_bytes, cudaStream_t stream);
 int im2col_narrow_launch(int B, int H, int W, int C, int kh, int kw, int pt, int pl, int flip, const float* x, float* col,
                          int ldc, cudaStream_t stream);
 int col2im_narrow_launch(int B, int H, int W, int C, int kh, int kw, int pt, int pl, int flip, const float* z, int ldz,
@@ -415,6 +425,56 @@ int otgan_col2im_narrow_f32(int B, int H, int W, int C, int kh, int kw, int pad_
     OTGAN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 1 && C <= 16 && kh >= 1 && kw >= 1 && z && y, "col2im_narrow: bad arguments");
     OTGAN_REQUIRE(ldz >= kh * kw * C, "col2im_narrow: ldz must be >= kh*kw*C");
     return col2im_narrow_launch(B, H, W, C, kh, kw, pad_top, pad_left, flip ? 1 : 0, z, ldz, bias, y, (cudaStream_t)stream);
+}
+
+int otgan_up2_subtaps(int k, int pad) { return (k < 1 || pad < 0 || pad >= k) ? 0 : up2_subtaps(k, pad); }
+
+int otgan_up2_weight_presum_f32(int Cout, int kh, int kw, int Cin, int pad_top, int pad_left, const float* w_ohwi, float* w_sub,
+                                void* stream)
+{
+    OTGAN_REQUIRE(Cout >= 1 && Cin >= 1 && kh >= 1 && kw >= 1 && pad_top >= 0 && pad_left >= 0 && pad_top < kh && pad_left < kw && w_ohwi && w_sub,
+                  "up2_weight_presum: bad arguments");
+    return up2_presum_launch(Cout, kh, kw, Cin, pad_top, pad_left, w_ohwi, w_sub, (cudaStream_t)stream);
+}
+
+int otgan_up2_weight_unsum_f32(int Cout, int kh, int kw, int Cin, int pad_top, int pad_left, const float* dw_sub, float* dw_ohwi,
+                               void* stream)
+{
+    OTGAN_REQUIRE(Cout >= 1 && Cin >= 1 && kh >= 1 && kw >= 1 && pad_top >= 0 && pad_left >= 0 && pad_top < kh && pad_left < kw && dw_sub && dw_ohwi,
+                  "up2_weight_unsum: bad arguments");
+    return up2_unsum_launch(Cout, kh, kw, Cin, pad_top, pad_left, dw_sub, dw_ohwi, (cudaStream_t)stream);
+}
+
+int otgan_conv2d_up2_fprop_tf32(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pad_top, int pad_left,
+                                const float* x_low, const float* w_sub, const float* bias, float* y, void* ws, size_t ws_bytes,
+                                void* stream)
+{
+    OTGAN_REQUIRE(x_low && w_sub && y, "conv2d_up2_fprop: null pointer");
+    OTGAN_REQUIRE(aligned16(x_low) && aligned16(w_sub) && aligned16(y) && (!bias || aligned16(bias)) && (!ws || aligned16(ws)),
+                  "conv2d_up2_fprop: buffers must be 16-byte aligned");
+    return conv_up2_fprop_launch(B, Hl, Wl, Cin, Cout, kh, kw, pad_top, pad_left, x_low, w_sub, bias, y, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int otgan_conv2d_up2_dgrad_tf32(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pad_top, int pad_left,
+                                const float* dy, const float* w_sub_ihwo, float* dx_low, void* ws, size_t ws_bytes, void* stream)
+{
+    OTGAN_REQUIRE(dy && w_sub_ihwo && dx_low, "conv2d_up2_dgrad: null pointer");
+    OTGAN_REQUIRE(aligned16(dy) && aligned16(w_sub_ihwo) && aligned16(dx_low) && (!ws || aligned16(ws)), "conv2d_up2_dgrad: buffers must be 16-byte aligned");
+    return conv_up2_dgrad_launch(B, Hl, Wl, Cin, Cout, kh, kw, pad_top, pad_left, dy, w_sub_ihwo, dx_low, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+size_t otgan_workspace_bytes_conv_up2_wgrad(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pad_top, int pad_left)
+{
+    if (B < 1 || Hl < 1 || Wl < 1 || Cin < 1 || Cout < 1 || kh < 1 || kw < 1) return 0;
+    return conv_up2_wgrad_workspace_bytes(B, Hl, Wl, Cin, Cout, kh, kw, pad_top, pad_left);
+}
+
+int otgan_conv2d_up2_wgrad_tf32(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pad_top, int pad_left,
+                                const float* dy, const float* x_low, float* dw_sub, void* ws, size_t ws_bytes, void* stream)
+{
+    OTGAN_REQUIRE(dy && x_low && dw_sub, "conv2d_up2_wgrad: null pointer");
+    OTGAN_REQUIRE(aligned16(dy) && aligned16(x_low) && aligned16(dw_sub) && (!ws || aligned16(ws)), "conv2d_up2_wgrad: buffers must be 16-byte aligned");
+    return conv_up2_wgrad_launch(B, Hl, Wl, Cin, Cout, kh, kw, pad_top, pad_left, dy, x_low, dw_sub, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

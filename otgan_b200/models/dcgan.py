@@ -37,7 +37,7 @@ def gen_spec(batch_size, init=False, nonlinearity='crelu', ema=None, u=None, **k
         x, l = torch.chunk(x, 2, 1)
         x = x * torch.sigmoid(l)                                                # gated linear unit  :35-36
         x = x.reshape(batch_size, 4, 4, 1024)
-        x = nn.resize_nearest_neighbor(x, [8, 8])
+        x = nn.upsample2x(x)              # tf.image.resize_nearest_neighbor(x, [8, 8])  :37-38 (fused into the next conv2d)
         x = nn.conv2d(x, 2 * 512, filter_size=[5, 5], pre_activation=None)
         x = nn.glu(x, upsample=True)      # x, l = split(x, 2, 3); x *= sigmoid(l); resize_nearest_neighbor(x, [16, 16])  :39-42
         x = nn.conv2d(x, 2 * 256, filter_size=[5, 5], pre_activation=None)

@@ -342,6 +342,7 @@ def _conv2d_nhwc(x, W, stride, pad, bias=None):
 
 
 CONV_BACKEND = "tcgen05"      # "tcgen05": this library's implicit-GEMM kernels where they tile the shape; "cudnn": library rung only
+UPSAMPLE_FUSION = True        # nn.upsample2x / nn.glu(upsample=True) hand the following conv2d an un-materialised Upsampled2x
 CONV_NARROW = True            # route the two 3-channel layers through _ConvNarrow (False: cuDNN, for A/B timing)
 _conv_ws = {}
 
@@ -562,6 +563,122 @@ class _ConvNarrow(torch.autograd.Function):
         return dx, dwt, db, None
 
 
+class Upsampled2x:
+    """A 2x nearest-neighbour upsampled NHWC tensor that has NOT been materialised: `low` is the [B, H, W, C] tensor,
+    the value is resize_nearest_neighbor(low, [2H, 2W]).  nn.conv2d consumes it with the fused upsample + convolution
+    kernels (the generator's resize -> conv pairs, models/dcgan.py:37-46); anything else calls .materialize()."""
+
+    def __init__(self, low):
+        self.low = low
+
+    @property
+    def shape(self):
+        B, H, W, C = self.low.shape
+        return torch.Size((B, 2 * H, 2 * W, C))
+
+    @property
+    def is_cuda(self):
+        return self.low.is_cuda
+
+    @property
+    def dtype(self):
+        return self.low.dtype
+
+    @property
+    def device(self):
+        return self.low.device
+
+    def dim(self):
+        return 4
+
+    def materialize(self):
+        return resize_nearest_neighbor(self.low, [2 * self.low.shape[1], 2 * self.low.shape[2]])
+
+
+def upsample2x(x, lazy=True):
+    """tf.image.resize_nearest_neighbor(x, [2H, 2W]) (models/dcgan.py:38,42,46).  With lazy=True on the GPU path the result
+    is an Upsampled2x handle that the following nn.conv2d fuses with its convolution."""
+    if lazy and UPSAMPLE_FUSION and CONV_BACKEND == "tcgen05" and x.is_cuda and x.dtype == torch.float32:
+        return Upsampled2x(x.contiguous())
+    return resize_nearest_neighbor(x, [2 * x.shape[1], 2 * x.shape[2]])
+
+
+def conv_up2_supported(lowshape, cout, kh, kw, stride, pad):
+    """Shapes the fused upsample + convolution kernels tile."""
+    B, H, W, cin = lowshape
+    if pad != "SAME" or tuple(stride) != (1, 1) or kh != kw or kh % 2 == 0:
+        return False
+    if cin % 128 or cout % 128 or not (_pow2(H) and _pow2(W)) or W > 32:
+        return False
+    if _lib.load().otgan_up2_subtaps(kh, (kh - 1) // 2) == 0:
+        return False
+    img = H * W
+    return (img >= 128 or (B * img) % 128 == 0) and (img >= 32 or (B * img) % 32 == 0)
+
+
+class _ConvUp2TC(torch.autograd.Function):
+    """conv2d(resize_nearest_neighbor(x_low, 2x), W, 'SAME') + bias on the fused kernels (otgan_conv2d_up2_{fprop,dgrad,wgrad}_tf32):
+    four 3x3 convolutions of the low-resolution input with pre-summed sub-filters, one per output parity class."""
+
+    @staticmethod
+    def forward(ctx, x_low, wt, bias, geom):
+        lib = _lib.load()
+        kh, kw, pt, pl = geom
+        B, H, W, cin = x_low.shape
+        cout = wt.shape[0]
+        n1 = lib.otgan_up2_subtaps(kh, pt)
+        slots = n1 * n1
+        x_low, wt = x_low.contiguous(), wt.contiguous()
+        if bias is not None and bias.data_ptr() % 16:
+            bias = bias.clone()
+        stream = torch.cuda.current_stream().cuda_stream
+        w_sub = torch.empty((4, cout, slots * cin), device=x_low.device, dtype=torch.float32)
+        _lib.check(lib.otgan_up2_weight_presum_f32(cout, kh, kw, cin, pt, pl, wt.data_ptr(), w_sub.data_ptr(), stream), "otgan_up2_weight_presum_f32")
+        y = torch.empty((B, 2 * H, 2 * W, cout), device=x_low.device, dtype=torch.float32)
+        ws = _workspace(x_low.device, lib.otgan_workspace_bytes_conv_gemm(B, 2 * H, 2 * W, cout))
+        rc = lib.otgan_conv2d_up2_fprop_tf32(B, H, W, cin, cout, kh, kw, pt, pl, x_low.data_ptr(), w_sub.data_ptr(),
+                                             bias.data_ptr() if bias is not None else None, y.data_ptr(), ws.data_ptr(),
+                                             ws.numel() * 4, stream)
+        _lib.check(rc, "otgan_conv2d_up2_fprop_tf32")
+        ctx.save_for_backward(x_low, w_sub)
+        ctx.geom, ctx.has_bias, ctx.cout, ctx.slots = geom, bias is not None, cout, slots
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x_low, w_sub = ctx.saved_tensors
+        kh, kw, pt, pl = ctx.geom
+        B, H, W, cin = x_low.shape
+        cout, slots = ctx.cout, ctx.slots
+        dy = dy.contiguous()
+        stream = torch.cuda.current_stream().cuda_stream
+        dx = dwt = db = None
+        if ctx.needs_input_grad[0]:
+            w_sub_t = torch.empty((4, cin, slots * cout), device=dy.device, dtype=torch.float32)
+            for c in range(4):
+                _lib.check(lib.otgan_ohwi_to_ihwo_f32(cout, slots, cin, w_sub[c].data_ptr(), w_sub_t[c].data_ptr(), stream), "otgan_ohwi_to_ihwo_f32")
+            dx = torch.empty_like(x_low)
+            ws = _workspace(dy.device, lib.otgan_workspace_bytes_conv_gemm(B, H, W, cin))
+            rc = lib.otgan_conv2d_up2_dgrad_tf32(B, H, W, cin, cout, kh, kw, pt, pl, dy.data_ptr(), w_sub_t.data_ptr(), dx.data_ptr(),
+                                                 ws.data_ptr(), ws.numel() * 4, stream)
+            _lib.check(rc, "otgan_conv2d_up2_dgrad_tf32")
+        if ctx.needs_input_grad[1]:
+            ws = _workspace(dy.device, lib.otgan_workspace_bytes_conv_up2_wgrad(B, H, W, cin, cout, kh, kw, pt, pl))
+            dw_sub = torch.empty_like(w_sub)
+            rc = lib.otgan_conv2d_up2_wgrad_tf32(B, H, W, cin, cout, kh, kw, pt, pl, dy.data_ptr(), x_low.data_ptr(), dw_sub.data_ptr(),
+                                                 ws.data_ptr(), ws.numel() * 4, stream)
+            _lib.check(rc, "otgan_conv2d_up2_wgrad_tf32")
+            dwt = torch.empty((cout, kh * kw * cin), device=dy.device, dtype=torch.float32)
+            _lib.check(lib.otgan_up2_weight_unsum_f32(cout, kh, kw, cin, pt, pl, dw_sub.data_ptr(), dwt.data_ptr(), stream), "otgan_up2_weight_unsum_f32")
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            P = dy.numel() // cout
+            ws = _workspace(dy.device, lib.otgan_workspace_bytes_colsum(P, cout))
+            db = torch.empty((cout,), device=dy.device, dtype=torch.float32)
+            _lib.check(lib.otgan_colsum_f32(P, cout, dy.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream), "otgan_colsum_f32")
+        return dx, dwt, db, None
+
+
 class _CreluL2Norm(torch.autograd.Function):
     """Critic head on this library's CUDA kernels (otgan_crelu_l2norm_{fwd,bwd}_f32)."""
 
@@ -661,8 +778,11 @@ class _GluUp(torch.autograd.Function):
 
 def glu(y, upsample=False):
     """x, l = tf.split(y, 2, 3); x *= tf.nn.sigmoid(l)  [; x = resize_nearest_neighbor(x, 2x)]   (models/dcgan.py:39-48).
-    One fused CUDA kernel on the GPU; the literal ops for CPU tensors."""
+    One fused CUDA kernel on the GPU; the literal ops for CPU tensors.  With upsample=True on the GPU path the result is an
+    un-materialised Upsampled2x handle (see upsample2x) so that the following nn.conv2d fuses the resize."""
     if y.is_cuda and y.dtype == torch.float32 and y.dim() == 4 and (y.shape[3] // 2) % 4 == 0:
+        if upsample and UPSAMPLE_FUSION and CONV_BACKEND == "tcgen05":
+            return Upsampled2x(_GluUp.apply(y.contiguous(), 1))
         return _GluUp.apply(y.contiguous(), 2 if upsample else 1)
     x, l = torch.chunk(y, 2, 3)
     x = x * torch.sigmoid(l)
@@ -786,7 +906,14 @@ def _dense(x, W, pre_activation=None):
 
 def _conv2d(x, W, stride=(1, 1), pad="SAME", dilate=1, pre_activation=None, upsample=False, bias=None):
     """utils/nn.py:234-275 (__list_conv2d): optional NN-upsample of the concatenated list, pre-activation, conv."""
+    if isinstance(x, Upsampled2x):
+        if (pre_activation is None and not upsample and isinstance(W, TransposedWeight) and CONV_BACKEND == "tcgen05"
+                and conv_up2_supported(tuple(x.low.shape), W.vshape[3], W.vshape[0], W.vshape[1], stride, pad)):
+            kh, kw = W.vshape[0], W.vshape[1]
+            return _ConvUp2TC.apply(x.low, W.wt, bias, (kh, kw, (kh - 1) // 2, (kw - 1) // 2))
+        x = x.materialize()
     xl = _as_list(x)
+    xl = [xi.materialize() if isinstance(xi, Upsampled2x) else xi for xi in xl]
     if dilate != 1:
         raise NotImplementedError("dilated conv is dead code in the reference (SURVEY 2.1 #16)")
     if upsample:

@@ -167,7 +167,8 @@ def test_dcgan_networks_every_conv_call_checked_against_float64():
         torch.autograd.grad([f2], [generator.flat], [gy])
     finally:
         nn._ConvTC.forward, nn._ConvTC.backward = staticmethod(orig_fwd), staticmethod(orig_bwd)
-    assert len(calls) == 3 + 3 + 3                     # critic c1-c3, generator g1-g3, critic c1-c3 on the generated images
+    assert len(calls) == 3 + 3                         # critic c1-c3 on the real images, critic c1-c3 on the generated images
+                                                       # (the generator's layers run on _ConvUp2TC / _ConvNarrow, tested separately)
     n_dx = n_dw = 0
     for rec in calls:
         kh, kw, s, pt, pl = rec["geom"]
@@ -187,7 +188,7 @@ def test_dcgan_networks_every_conv_call_checked_against_float64():
             n_dw += 1
             assert float((rec["dw"].double().view_as(dwr) - dwr).abs().max() / dwr.abs().max()) <= 4e-3, ("wgrad", tag)
             assert float((rec["db"].double() - dbr).abs().max() / dbr.abs().max()) <= 4e-3, ("bias-grad", tag)
-    assert n_dx == 9 and n_dw == 6                     # the critic inside the generator step builds no filter gradients
+    assert n_dx == 6 and n_dw == 3                     # the critic inside the generator step builds no filter gradients
 
 
 def test_dcgan_networks_agree_with_library_convolutions():
@@ -258,3 +259,82 @@ def test_narrow_channel_convolutions(shape, exact):
             assert err == 0.0, (name, shape, err)
         else:
             assert err <= 4e-3, (name, shape, err)
+
+
+UP2_SHAPES = [  # (B, Hl, Wl, Cin, Cout, k): low-resolution input, output is [B, 2Hl, 2Wl, Cout]
+    (8, 4, 4, 128, 128, 5),
+    (4, 8, 8, 256, 256, 5),
+    (2, 16, 16, 128, 256, 5),
+    (16, 4, 4, 1024, 1024, 5),      # generator conv2d_0 at batch 16
+    (16, 8, 8, 512, 512, 5),        # generator conv2d_1
+    (4, 8, 8, 128, 128, 3),         # DenseNet-style 3x3
+]
+
+
+@pytest.mark.parametrize("shape", UP2_SHAPES)
+@pytest.mark.parametrize("exact", [True, False])
+def test_fused_upsample_convolution(shape, exact):
+    """conv2d(resize_nearest_neighbor(x, 2x), W) on the fused sub-pixel kernels (4 parity classes x 3x3 pre-summed
+    sub-filters on the low-resolution input) vs float64 upsample + convolution: forward, input gradient (w.r.t. the
+    low-resolution tensor), filter gradient (after the un-sum), bias gradient.  Integer inputs: exact; N(0,1): 4e-3."""
+    from otgan_b200.utils import nn
+    B, Hl, Wl, Cin, Cout, k = shape
+    assert nn.conv_up2_supported((B, Hl, Wl, Cin), Cout, k, k, [1, 1], "SAME")
+    g = torch.Generator(device="cuda").manual_seed(9)
+    if exact:
+        x = torch.randint(-2, 3, (B, Hl, Wl, Cin), device="cuda", generator=g).float()
+        w = torch.randint(-1, 2, (Cout, k, k, Cin), device="cuda", generator=g).float()
+        b = torch.randint(-4, 5, (Cout,), device="cuda", generator=g).float()
+        dy = torch.randint(-2, 3, (B, 2 * Hl, 2 * Wl, Cout), device="cuda", generator=g).float()
+    else:
+        x = torch.randn((B, Hl, Wl, Cin), device="cuda", generator=g)
+        w = torch.randn((Cout, k, k, Cin), device="cuda", generator=g) * 0.05
+        b = torch.randn((Cout,), device="cuda", generator=g)
+        dy = torch.randn((B, 2 * Hl, 2 * Wl, Cout), device="cuda", generator=g)
+    xr = x.clone().requires_grad_(True)
+    wr = w.reshape(Cout, -1).clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    p = (k - 1) // 2
+    y = nn._ConvUp2TC.apply(xr, wr, br, (k, k, p, p))
+    dx, dw, db = torch.autograd.grad([y], [xr, wr, br], [dy])
+    xd, wd, bd = (t.double().requires_grad_(True) for t in (x, w, b))
+    xu = xd.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    yr = _ref_conv(xu, wd, bd, k, 1)
+    dxr, dwr, dbr = torch.autograd.grad([yr], [xd, wd, bd], [dy.double()])
+    for name, o, r in zip(("fprop", "dgrad", "wgrad", "bias-grad"), (y.detach(), dx, dw.view(Cout, k, k, Cin), db), (yr.detach(), dxr, dwr, dbr)):
+        err = float((o.double() - r).abs().max() / r.abs().max())
+        if exact:
+            assert err == 0.0, (name, shape, err)
+        else:
+            assert err <= 4e-3, (name, shape, err)
+
+
+def test_generator_uses_the_fused_upsample_path():
+    """models/dcgan.py through nn.upsample2x / nn.glu(upsample=True): the three resize -> conv pairs run on _ConvUp2TC and
+    the generated images equal the materialised-upsample path to TF32 accuracy."""
+    from otgan_b200.models.dcgan import generator
+    from otgan_b200.utils import nn
+    dev = torch.device("cuda", 0)
+    generator.reset()
+    torch.manual_seed(3)
+    with torch.no_grad():
+        generator(init=True, device=dev, batch_size=16)
+        u = torch.rand(16, 100, device=dev) * 2 - 1
+        calls = []
+        orig = nn._ConvUp2TC.forward
+
+        def fwd(ctx, *a):
+            calls.append(a[0].shape)
+            return orig(ctx, *a)
+
+        nn._ConvUp2TC.forward = staticmethod(fwd)
+        try:
+            img = generator(batch_size=16, u=u)
+            nn.UPSAMPLE_FUSION = False
+            ref = generator(batch_size=16, u=u)
+        finally:
+            nn.UPSAMPLE_FUSION = True
+            nn._ConvUp2TC.forward = staticmethod(orig)
+    assert [tuple(c) for c in calls] == [(16, 4, 4, 1024), (16, 8, 8, 512), (16, 16, 16, 256)]
+    assert float((img - ref).abs().max() / ref.abs().max()) <= 5e-3
+    generator.reset()
