@@ -311,40 +311,63 @@ def matching_benchmark(torch, devv, steps, warmup):
     return res, roof
 
 
-CONV_LAYERS = {  # DCGAN layers on the tcgen05 kernels at the N=256 step: (B, H, W, Cin, Cout, k, stride)   SURVEY App. B.1
+CONV_LAYERS = {  # DCGAN layers on the tcgen05 kernels at the N=256 step.  Critic: (B, H, W, Cin, Cout, k, stride).
     "critic conv2d_1": (2 * N_TOTAL, 32, 32, 256, 256, 5, 2), "critic conv2d_2": (2 * N_TOTAL, 16, 16, 512, 512, 5, 2),
-    "critic conv2d_3": (2 * N_TOTAL, 8, 8, 1024, 1024, 5, 2), "generator conv2d_0": (N_TOTAL, 8, 8, 1024, 1024, 5, 1),
-    "generator conv2d_1": (N_TOTAL, 16, 16, 512, 512, 5, 1), "generator conv2d_2": (N_TOTAL, 32, 32, 256, 256, 5, 1)}
+    "critic conv2d_3": (2 * N_TOTAL, 8, 8, 1024, 1024, 5, 2),
+    # generator: resize_nearest_neighbor(2x) -> conv 5x5, run as the fused sub-pixel kernels on the LOW-resolution input
+    # (B, Hlow, Wlow, Cin, Cout, k, "up2"): 4 parity classes x 9 pre-summed taps instead of 25 taps at the high resolution
+    "generator conv2d_0": (N_TOTAL, 4, 4, 1024, 1024, 5, "up2"), "generator conv2d_1": (N_TOTAL, 8, 8, 512, 512, 5, "up2"),
+    "generator conv2d_2": (N_TOTAL, 16, 16, 256, 256, 5, "up2")}
 # dram__bytes_read.sum + dram__bytes_write.sum of the profiled launch (profiles/r01_h_conv_fprop_ncu_full.txt)
 CONV_ROOFLINE_LAUNCH, CONV_ROOFLINE_TRAFFIC = "critic conv2d_3", 743.63e6 + 23.21e6
 
 
 def conv_benchmark(torch, iters=5):
-    """Live per-launch times (CUDA events on the launching stream, 2 warm-up + `iters` launches, tensors >> L2 per layer
-    sweep) of this library's convolution kernels on every DCGAN layer of the N=256 step.  Algorithmic FLOPs per launch =
-    2 * B*Ho*Wo * Cout * k*k*Cin."""
+    """Live per-launch times (CUDA events on the launching stream, 2 warm-up + `iters` launches, every layer's tensors are
+    far larger than L2 in total) of this library's convolution kernels on every DCGAN layer of the N=256 step.
+    `gflop` = FLOPs the launch EXECUTES (critic: 2*B*Ho*Wo*Cout*25*Cin; fused generator layers:
+    2*B*Ho*Wo*Cout*9*Cin); `gflop_reference_form` = what the reference's resize + 25-tap convolution would spend."""
     from otgan_b200 import _lib
     lib = _lib.load()
     st = torch.cuda.current_stream().cuda_stream
     out = {}
     for name, (B, H, W, Cin, Cout, k, s) in CONV_LAYERS.items():
-        Ho, Wo = H // s, W // s
-        flops = 2.0 * B * Ho * Wo * Cout * k * k * Cin
-        pad = (max((Ho - 1) * s + k - H, 0)) // 2
+        up2 = s == "up2"
+        Ho, Wo = (2 * H, 2 * W) if up2 else (H // s, W // s)
+        pad = (k - 1) // 2 if up2 else (max((Ho - 1) * s + k - H, 0)) // 2
+        ref_flops = 2.0 * B * Ho * Wo * Cout * k * k * Cin
         x = torch.randn(B, H, W, Cin, device="cuda")
         w = torch.randn(Cout, k * k * Cin, device="cuda") * 0.02
         b = torch.randn(Cout, device="cuda")
         dy = torch.randn(B, Ho, Wo, Cout, device="cuda")
         y, dx, dw = torch.empty_like(dy), torch.empty_like(x), torch.empty_like(w)
-        wt = torch.empty(Cin, k * k * Cout, device="cuda")
-        ws = torch.empty(lib.otgan_workspace_bytes_conv_wgrad(B, H, W, Cin, Cout, k, k, s) // 4 + 64, device="cuda")
-        _lib.check(lib.otgan_ohwi_to_ihwo_f32(Cout, k * k, Cin, w.data_ptr(), wt.data_ptr(), st), "ohwi_to_ihwo")
-        ops = {
-            "fprop": lambda: lib.otgan_conv2d_fprop_tf32(B, H, W, Cin, Cout, k, k, s, pad, pad, x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), None, 0, st),
-            "dgrad": lambda: lib.otgan_conv2d_dgrad_tf32(B, H, W, Cin, Cout, k, k, s, pad, pad, dy.data_ptr(), wt.data_ptr(), dx.data_ptr(), None, 0, st),
-            "wgrad": lambda: lib.otgan_conv2d_wgrad_tf32(B, H, W, Cin, Cout, k, k, s, pad, pad, dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel() * 4, st),
-        }
-        row = {"shape": [B, H, W, Cin, Cout, k, s], "gflop": flops / 1e9}
+        if up2:
+            n1 = lib.otgan_up2_subtaps(k, pad)
+            slots = n1 * n1
+            flops = 2.0 * B * Ho * Wo * Cout * slots * Cin
+            w_sub = torch.empty(4, Cout, slots * Cin, device="cuda")
+            w_sub_t = torch.empty(4, Cin, slots * Cout, device="cuda")
+            dw_sub = torch.empty_like(w_sub)
+            _lib.check(lib.otgan_up2_weight_presum_f32(Cout, k, k, Cin, pad, pad, w.data_ptr(), w_sub.data_ptr(), st), "presum")
+            for c in range(4):
+                _lib.check(lib.otgan_ohwi_to_ihwo_f32(Cout, slots, Cin, w_sub[c].data_ptr(), w_sub_t[c].data_ptr(), st), "ohwi_to_ihwo")
+            ws = torch.empty(lib.otgan_workspace_bytes_conv_up2_wgrad(B, H, W, Cin, Cout, k, k, pad, pad) // 4 + 64, device="cuda")
+            ops = {
+                "fprop": lambda: lib.otgan_conv2d_up2_fprop_tf32(B, H, W, Cin, Cout, k, k, pad, pad, x.data_ptr(), w_sub.data_ptr(), b.data_ptr(), y.data_ptr(), None, 0, st),
+                "dgrad": lambda: lib.otgan_conv2d_up2_dgrad_tf32(B, H, W, Cin, Cout, k, k, pad, pad, dy.data_ptr(), w_sub_t.data_ptr(), dx.data_ptr(), None, 0, st),
+                "wgrad": lambda: lib.otgan_conv2d_up2_wgrad_tf32(B, H, W, Cin, Cout, k, k, pad, pad, dy.data_ptr(), x.data_ptr(), dw_sub.data_ptr(), ws.data_ptr(), ws.numel() * 4, st),
+            }
+        else:
+            flops = ref_flops
+            wt = torch.empty(Cin, k * k * Cout, device="cuda")
+            ws = torch.empty(lib.otgan_workspace_bytes_conv_wgrad(B, H, W, Cin, Cout, k, k, s) // 4 + 64, device="cuda")
+            _lib.check(lib.otgan_ohwi_to_ihwo_f32(Cout, k * k, Cin, w.data_ptr(), wt.data_ptr(), st), "ohwi_to_ihwo")
+            ops = {
+                "fprop": lambda: lib.otgan_conv2d_fprop_tf32(B, H, W, Cin, Cout, k, k, s, pad, pad, x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), None, 0, st),
+                "dgrad": lambda: lib.otgan_conv2d_dgrad_tf32(B, H, W, Cin, Cout, k, k, s, pad, pad, dy.data_ptr(), wt.data_ptr(), dx.data_ptr(), None, 0, st),
+                "wgrad": lambda: lib.otgan_conv2d_wgrad_tf32(B, H, W, Cin, Cout, k, k, s, pad, pad, dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel() * 4, st),
+            }
+        row = {"shape": [B, H, W, Cin, Cout, k, s], "gflop": flops / 1e9, "gflop_reference_form": ref_flops / 1e9}
         for op, fn in ops.items():
             for _ in range(2):
                 _lib.check(fn(), op)
@@ -358,7 +381,7 @@ def conv_benchmark(torch, iters=5):
             ms = e0.elapsed_time(e1) / iters
             row[op] = {"ms": ms, "tflops": flops / ms / 1e9}
         out[name] = row
-        del x, w, b, dy, y, dx, dw, wt, ws
+        del x, w, b, dy, y, dx, dw, ws, ops
         torch.cuda.empty_cache()
     return out
 

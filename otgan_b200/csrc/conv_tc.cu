@@ -803,14 +803,14 @@ int ohwi_to_ihwo_launch(int Cout, int T, int Cin, const float* w, float* wt, cud
 size_t colsum_workspace_bytes(int P, int C)
 {
     (void)P;
-    return (size_t)64 * C * sizeof(float) + 256;
+    return (size_t)512 * C * sizeof(float) + 256;
 }
 
 int colsum_launch(int P, int C, const float* x, float* out, void* ws, size_t ws_bytes, cudaStream_t stream)
 {
     OTGAN_REQUIRE(ws && ws_bytes >= colsum_workspace_bytes(P, C), "colsum: workspace too small");
-    int slabs = ceil_div(P, 256);
-    slabs = slabs > 64 ? 64 : slabs;
+    int slabs = ceil_div(P, 128);                      // enough CTAs to stream the [P, C] matrix at HBM speed
+    slabs = slabs > 512 ? 512 : slabs;
     const int rows_per_slab = ceil_div(P, slabs);
     slabs = ceil_div(P, rows_per_slab);
     float* partial = reinterpret_cast<float*>(ws);
