@@ -80,10 +80,14 @@ def test_fused_activation_kernels_vs_torch():
         (gr,) = torch.autograd.grad([zr], [xd], [gz.double()])
         assert torch.equal(z.double(), zr) and float((gx.double() - gr).abs().max()) == 0.0
     y = torch.randn(2, 5, 5, 16, device="cuda", requires_grad=True)
-    for up in (False, True):
-        o = nn.glu(y, upsample=up)
+    for up, fusion in ((False, True), (True, True), (True, False)):
+        nn.UPSAMPLE_FUSION = fusion                  # False: the GLU kernel writes the upsampled tensor itself (otgan_glu_up, up = 2)
+        try:
+            o = nn.glu(y, upsample=up)
+        finally:
+            nn.UPSAMPLE_FUSION = True
         if isinstance(o, nn.Upsampled2x):            # un-materialised handle for the fused upsample + conv path
-            assert up and o.low.shape[1] == y.shape[1]
+            assert up and fusion and o.low.shape[1] == y.shape[1]
             o = o.materialize()
         go = torch.randn_like(o)
         (gy,) = torch.autograd.grad([o], [y], [go])
