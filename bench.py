@@ -96,9 +96,10 @@ def workload_config(world, workload):
                        % (T_ITERS, N_TOTAL, N_TOTAL, N_TOTAL // 2, D_FEAT, LAMBDA),
            "N": N_TOTAL, "h": N_TOTAL // 2, "D": D_FEAT, "T": T_ITERS, "lambda": LAMBDA, "ranks": world,
            "images_per_rank": N_TOTAL // world, "towers": 2 * world if world > 1 else 2,
-           "conv_backend": "libotgan tcgen05 implicit-GEMM kernels (fprop / dgrad / wgrad, TF32 operands, fp32 accumulation) for the "
-                           "six 5x5 layers that carry 99.6% of the FLOPs; the 3-channel first critic / last generator convolution "
-                           "and the 100-wide dense layer run on cuDNN / cuBLAS through torch",
+           "conv_backend": "libotgan tcgen05 implicit-GEMM kernels (fprop / dgrad / wgrad, TF32 operands, fp32 accumulation) for every "
+                           "convolution of the step; the generator's resize_nearest_neighbor + 5x5 convolution pairs run as the fused "
+                           "sub-pixel form (4 parity classes x 3x3 pre-summed sub-filters on the low-resolution input: same algebra, "
+                           "9 instead of 25 taps); the 100-wide dense layer is a cuBLAS call",
            "precision": "fp32 storage everywhere; matching kernels are fp32-exact (3xTF32 operands + fp32 register accumulation); "
                         "convolutions read the fp32 tensors as TF32 on the tensor cores (the math class of cuDNN's default fp32 convolution)",
            "l2_policy": "per-step working set (activations + 72 M parameters + Adam state, > 1 GB) exceeds the 126 MB L2; the "
@@ -431,6 +432,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.workload == "conv":                    # profiling aid: the per-layer convolution launches only (ncu -k regex:conv_)
+        if rank == 0:
+            res = conv_benchmark(torch)
+            print(json.dumps({"conv_layers": res, "roofline": conv_roofline(res)}))
+        return
     match_res, roof, conv_res = (None, None, None)
     if rank == 0:
         match_res, match_roof = matching_benchmark(torch, devv, 100, 5)
@@ -576,7 +582,8 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "matching"])
+    ap.add_argument("--workload", default="train", choices=["train", "matching", "conv"],
+                    help="train: the contract workload; matching / conv: only that sub-benchmark (profiling aid)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cuda-graphs", type=int, default=1, help="replay the training step from captured CUDA graphs (1) or launch eagerly (0)")
     ap.add_argument("--n-total", type=int, default=0, help="diagnostics only: override N (images per step); the contract workload is N=256")

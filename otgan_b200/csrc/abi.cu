@@ -415,7 +415,8 @@ int otgan_im2col_narrow_f32(int B, int H, int W, int C, int kh, int kw, int pad_
                             float* col, int ldc, void* stream)
 {
     OTGAN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 1 && C <= 16 && kh >= 1 && kw >= 1 && x && col, "im2col_narrow: bad arguments");
-    OTGAN_REQUIRE(ldc >= kh * kw * C && ldc % 4 == 0 && aligned16(col), "im2col_narrow: ldc must be a multiple of 4 and >= kh*kw*C, col 16-byte aligned");
+    OTGAN_REQUIRE(ldc >= kh * kw * C && ldc % 4 == 0 && ldc <= 256 && kh <= 32 && kw <= 32 && aligned16(col),
+                  "im2col_narrow: ldc must be a multiple of 4 in [kh*kw*C, 256], col 16-byte aligned");
     return im2col_narrow_launch(B, H, W, C, kh, kw, pad_top, pad_left, flip ? 1 : 0, x, col, ldc, (cudaStream_t)stream);
 }
 

@@ -15,27 +15,39 @@ namespace otgan {
 
 namespace {
 
-// col: [P, ldc]; one thread per float4 of a row
+// col: [P, ldc]; one thread per float4 of a row.  The column -> (row shift, column shift, channel) decode is the same for
+// every pixel, so it is tabulated once per block in shared memory (ldc <= 256) instead of being re-derived with integer
+// divisions for each of the 4 elements a thread writes.
 __global__ void __launch_bounds__(256)
 im2col_narrow_kernel(size_t n4, int H, int W, int C, int kh, int kw, int pt, int pl, int flip, int ldc,
                      const float* __restrict__ x, float* __restrict__ col)
 {
+    __shared__ int tab[256];                                  // (dh + 64) | (dw + 64) << 8 | c << 16, or -1 past the last column
     const int g4 = ldc >> 2, ncol = kh * kw * C;
+    for (int cidx = threadIdx.x; cidx < ldc; cidx += blockDim.x) {
+        int v = -1;
+        if (cidx < ncol) {
+            const int t = cidx / C, c = cidx - t * C;
+            const int a = t / kw, b = t - a * kw;
+            const int dh = flip ? pt - a : a - pt, dw = flip ? pl - b : b - pl;
+            v = (dh + 64) | ((dw + 64) << 8) | (c << 16);
+        }
+        tab[cidx] = v;
+    }
+    __syncthreads();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const int j = (int)(i % g4);
         const size_t px = i / g4;
         const int w = (int)(px % W), h = (int)((px / W) % H);
-        const size_t img = px / ((size_t)W * H);
+        const float* xpx = x + px * C;                        // x[n, h, w, 0]
         float v[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const int cidx = 4 * j + e;
+            const int code = tab[4 * j + e];
             float val = 0.f;
-            if (cidx < ncol) {
-                const int t = cidx / C, c = cidx - t * C;
-                const int a = t / kw, b = t - a * kw;
-                const int hh = h + (flip ? pt - a : a - pt), ww = w + (flip ? pl - b : b - pl);
-                if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __ldg(x + ((img * H + hh) * W + ww) * C + c);
+            if (code >= 0) {
+                const int dh = (code & 0xff) - 64, dw = ((code >> 8) & 0xff) - 64, c = code >> 16;
+                if (h + dh >= 0 && h + dh < H && w + dw >= 0 && w + dw < W) val = __ldg(xpx + ((long long)dh * W + dw) * C + c);
             }
             v[e] = val;
         }
