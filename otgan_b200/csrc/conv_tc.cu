@@ -464,25 +464,30 @@ struct SubMap {
 };
 
 // w_sub[cls = 2a+b][co][(ri * n1w + ci) * Cin + c] = sum_{kh: idx_h[a][kh] == ri} sum_{kw: idx_w[b][kw] == ci} w[co][(kh * KW + kw) * Cin + c]
+// One thread per float4 of channels (Cin % 4 == 0): streams the filter once (read w, write 1.44x as much).
 __global__ void __launch_bounds__(256)
 up2_presum_kernel(SubMap m, int Cout, int Cin, const float* __restrict__ w, float* __restrict__ w_sub)
 {
-    const int slots = m.n1h * m.n1w;
-    const size_t total = (size_t)4 * Cout * slots * Cin;
+    const int slots = m.n1h * m.n1w, C4 = Cin >> 2;
+    const size_t total = (size_t)4 * Cout * slots * C4;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % Cin);
-        size_t r = i / Cin;
+        const int c4 = (int)(i % C4);
+        size_t r = i / C4;
         const int slot = (int)(r % slots); r /= slots;
         const int co = (int)(r % Cout);
         const int cls = (int)(r / Cout);
         const int a = cls >> 1, b = cls & 1, ri = slot / m.n1w, ci = slot % m.n1w;
-        float acc = 0.f;
+        const float4* wrow = reinterpret_cast<const float4*>(w + (size_t)co * m.kh * m.kw * Cin) + c4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int kh = 0; kh < m.kh; ++kh) {
             if (m.idx_h[a][kh] != ri) continue;
-            for (int kw = 0; kw < m.kw; ++kw)
-                if (m.idx_w[b][kw] == ci) acc += w[((size_t)co * m.kh * m.kw + kh * m.kw + kw) * Cin + c];
+            for (int kw = 0; kw < m.kw; ++kw) {
+                if (m.idx_w[b][kw] != ci) continue;
+                const float4 v = __ldg(wrow + (size_t)(kh * m.kw + kw) * C4);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
         }
-        w_sub[i] = acc;
+        reinterpret_cast<float4*>(w_sub)[i] = acc;
     }
 }
 
@@ -490,21 +495,48 @@ up2_presum_kernel(SubMap m, int Cout, int Cin, const float* __restrict__ w, floa
 __global__ void __launch_bounds__(256)
 up2_unsum_kernel(SubMap m, int Cout, int Cin, const float* __restrict__ dw_sub, float* __restrict__ dw)
 {
-    const int slots = m.n1h * m.n1w, taps = m.kh * m.kw;
-    const size_t total = (size_t)Cout * taps * Cin;
+    const int slots = m.n1h * m.n1w, taps = m.kh * m.kw, C4 = Cin >> 2;
+    const size_t total = (size_t)Cout * taps * C4;
+    const float4* src = reinterpret_cast<const float4*>(dw_sub);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % Cin);
-        size_t r = i / Cin;
+        const int c4 = (int)(i % C4);
+        size_t r = i / C4;
         const int t = (int)(r % taps);
         const int co = (int)(r / taps);
         const int kh = t / m.kw, kw = t % m.kw;
-        float acc = 0.f;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
         for (int a = 0; a < 2; ++a)
+#pragma unroll
             for (int b = 0; b < 2; ++b) {
                 const int slot = m.idx_h[a][kh] * m.n1w + m.idx_w[b][kw];
-                acc += dw_sub[(((size_t)(2 * a + b) * Cout + co) * slots + slot) * Cin + c];
+                const float4 v = __ldg(src + (((size_t)(2 * a + b) * Cout + co) * slots + slot) * C4 + c4);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             }
-        dw[i] = acc;
+        reinterpret_cast<float4*>(dw)[i] = acc;
+    }
+}
+
+// out[c] = sum_s partial[s][c]: 8 float4 columns x 32 slab lanes per block, fixed-order tree (deterministic)
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(int C4, int S, const float4* __restrict__ partial, float4* __restrict__ out)
+{
+    __shared__ float4 red[32][8];
+    const int cx = threadIdx.x & 7, sy = threadIdx.x >> 3, col = blockIdx.x * 8 + cx;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < C4)
+        for (int s = sy; s < S; s += 32) {
+            const float4 v = partial[(size_t)s * C4 + col];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    red[sy][cx] = acc;
+    __syncthreads();
+    if (sy == 0 && col < C4) {
+        for (int i = 1; i < 32; ++i) {
+            const float4 v = red[i][cx];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        out[col] = acc;
     }
 }
 
@@ -816,9 +848,9 @@ int colsum_launch(int P, int C, const float* x, float* out, void* ws, size_t ws_
     float* partial = reinterpret_cast<float*>(ws);
     colsum_partial_kernel<<<dim3(ceil_div(C, 128), slabs), 256, 0, stream>>>(P, C, rows_per_slab, x, partial);
     OTGAN_CHECK_LAUNCH("colsum_partial_kernel");
-    const size_t n4 = (size_t)C / 4;
-    split_reduce_kernel<<<(int)((n4 + 255) / 256), 256, 0, stream>>>(n4, slabs, n4, reinterpret_cast<const float4*>(partial), reinterpret_cast<float4*>(out));
-    OTGAN_CHECK_LAUNCH("split_reduce_kernel");
+    const int C4 = C / 4;
+    colsum_final_kernel<<<ceil_div(C4, 8), 256, 0, stream>>>(C4, slabs, reinterpret_cast<const float4*>(partial), reinterpret_cast<float4*>(out));
+    OTGAN_CHECK_LAUNCH("colsum_final_kernel");
     return OTGAN_OK;
 }
 
@@ -868,7 +900,8 @@ int up2_presum_launch(int Cout, int kh, int kw, int Cin, int pt, int pl, const f
 {
     SubMap m;
     if (!make_submap(m, kh, kw, pt, pl)) { set_error("up2_presum: unsupported filter geometry %dx%d pad %d,%d", kh, kw, pt, pl); return OTGAN_EUNSUPPORTED; }
-    up2_presum_kernel<<<ew_grid((size_t)4 * Cout * m.n1h * m.n1w * Cin), 256, 0, stream>>>(m, Cout, Cin, w, w_sub);
+    OTGAN_REQUIRE(Cin % 4 == 0 && aligned16(w) && aligned16(w_sub), "up2_presum: Cin must be a multiple of 4, buffers 16-byte aligned");
+    up2_presum_kernel<<<ew_grid((size_t)4 * Cout * m.n1h * m.n1w * (Cin / 4)), 256, 0, stream>>>(m, Cout, Cin, w, w_sub);
     OTGAN_CHECK_LAUNCH("up2_presum_kernel");
     return OTGAN_OK;
 }
@@ -877,7 +910,8 @@ int up2_unsum_launch(int Cout, int kh, int kw, int Cin, int pt, int pl, const fl
 {
     SubMap m;
     if (!make_submap(m, kh, kw, pt, pl)) { set_error("up2_unsum: unsupported filter geometry %dx%d pad %d,%d", kh, kw, pt, pl); return OTGAN_EUNSUPPORTED; }
-    up2_unsum_kernel<<<ew_grid((size_t)Cout * kh * kw * Cin), 256, 0, stream>>>(m, Cout, Cin, dw_sub, dw);
+    OTGAN_REQUIRE(Cin % 4 == 0 && aligned16(dw_sub) && aligned16(dw), "up2_unsum: Cin must be a multiple of 4, buffers 16-byte aligned");
+    up2_unsum_kernel<<<ew_grid((size_t)Cout * kh * kw * (Cin / 4)), 256, 0, stream>>>(m, Cout, Cin, dw_sub, dw);
     OTGAN_CHECK_LAUNCH("up2_unsum_kernel");
     return OTGAN_OK;
 }
