@@ -258,12 +258,22 @@ class Trainer:
                     'generator': {n: p.detach().cpu() for n, p in self.generator.named_parameters()}}, path)
 
     def load(self, path):
-        ck = torch.load(path, map_location='cpu')
+        """saver.restore (train.py:190-193): V, g, b of both networks by TensorFlow variable name -- a Trainer.save() file,
+        an .npz keyed by variable name, or (where TensorFlow is importable) a reference checkpoint prefix.  Like the
+        reference, Adam moments, Adam's t and the EMA shadow restart."""
+        from .utils import checkpoint
+        checkpoint.assign((self.discriminator, self.generator), checkpoint.load_variables(path))
+        self.ema.attach(self.generator)
+
+    def sample_tiles(self, path, path_ema=None, n=100):
+        """train.py:233-243: PNG tile of generated samples (and of the EMA generator's samples)."""
+        from .utils import plotting
         with torch.no_grad():
-            for tpl in (self.discriminator, self.generator):
-                for n, p in tpl.named_parameters():
-                    p.copy_(ck[tpl.name][n])
-                tpl.store.version += 1                     # cached weights are stale
+            x = self.generator(**self.model_opts)
+            plotting.save_tile_img(plotting.img_tile(x[:n].cpu().numpy(), aspect_ratio=1.0, border_color=1.0, stretch=False), path)
+            if path_ema is not None:
+                xe = self.generator(ema=self.ema, **self.model_opts)
+                plotting.save_tile_img(plotting.img_tile(xe[:n].cpu().numpy(), aspect_ratio=1.0, border_color=1.0, stretch=False), path_ema)
 
 
 def gather_features(f_gen, f_dat, world):
@@ -350,6 +360,8 @@ def main(argv=None):
                   % (epoch, time.time() - begin, np.mean(dist_gen) if dist_gen else float('nan'),
                      np.mean(dist_disc) if dist_disc else float('nan'), np.mean(entropy)))
             sys.stdout.flush()
+        if rank == 0 and not args.synthetic:                                                     # :233-243
+            trainer.sample_tiles(os.path.join(args.save_dir, 'sample%d.png' % epoch), os.path.join(args.save_dir, 'ema_sample%d.png' % epoch))
         if (epoch + 1) % 200 == 0 and rank == 0 and not args.synthetic:                          # :275-277
             trainer.save(os.path.join(args.save_dir, 'med_gan_params-%d' % epoch))
         if args.max_steps and trainer.step_counter >= args.max_steps:

@@ -338,3 +338,30 @@ def test_generator_uses_the_fused_upsample_path():
     assert [tuple(c) for c in calls] == [(16, 4, 4, 1024), (16, 8, 8, 512), (16, 16, 16, 256)]
     assert float((img - ref).abs().max() / ref.abs().max()) <= 5e-3
     generator.reset()
+
+
+@pytest.mark.parametrize("cout", [3, 16])
+def test_narrow_output_variant_of_the_gemm_kernel(cout):
+    """otgan_conv2d_fprop_tf32 with Cout <= 16 (the TN = 16 instantiation: weight box = the real rows, masked store) and
+    otgan_conv2d_dgrad_tf32 with Cin <= 16, called directly through the C ABI; integer inputs, exact."""
+    from otgan_b200 import _lib
+    lib = _lib.load()
+    B, H, W, Cin, k, s = 4, 16, 16, 128, 5, 1
+    shape = (B, H, W, Cin, cout, k, s)
+    x, w, b, dy = _make(shape, True, 6)
+    ref = _run_ref(shape, x, w, b, dy)
+    st = torch.cuda.current_stream().cuda_stream
+    y = torch.full((B, H, W, cout), float("nan"), device="cuda")
+    rc = lib.otgan_conv2d_fprop_tf32(B, H, W, Cin, cout, k, k, s, 2, 2, x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), None, 0, st)
+    _lib.check(rc, "fprop")
+    assert float((y.double() - ref[0]).abs().max()) == 0.0
+    # dgrad with a narrow INPUT side: the roles of Cin / Cout swap (dy has 128 channels, dx has `cout` channels)
+    shape2 = (B, H, W, cout, 128, k, s)
+    x2, w2, b2, dy2 = _make(shape2, True, 7)
+    ref2 = _run_ref(shape2, x2, w2, b2, dy2)
+    wt = w2.view(128, k * k, cout).permute(2, 1, 0).reshape(cout, -1).contiguous()          # IHWO [Cin, k*k*Cout]
+    dx = torch.full((B, H, W, cout), float("nan"), device="cuda")
+    rc = lib.otgan_conv2d_dgrad_tf32(B, H, W, cout, 128, k, k, s, 2, 2, dy2.data_ptr(), wt.data_ptr(), dx.data_ptr(), None, 0, st)
+    _lib.check(rc, "dgrad")
+    torch.cuda.synchronize()
+    assert float((dx.double() - ref2[1]).abs().max()) == 0.0
