@@ -225,3 +225,20 @@ def test_critic_weight_cache_matches_recomputed_weights():
         f2 = discriminator(x)
     assert not torch.equal(f1, f2)
     discriminator.reset(); generator.reset()
+
+
+def test_densenet_train_steps_on_gpu():
+    """--model densenet (BASELINE config 4's model family): one critic and one generator step of the re-hosted loop run
+    and give a finite distance and an entropy in (0, ln h]; D = 7296.  (Its 16-filter convolutions run on the library
+    rung; the matching, head, weight-norm and optimiser kernels are this library's.)"""
+    from otgan_b200 import train as T
+    args = T.build_parser().parse_args(["--synthetic", "--model", "densenet", "--nr_gpu", "2", "--batch_size", "8",
+                                        "--nr_sinkhorn_iter", "20"])
+    tr = T.Trainer(args, torch.device("cuda", 0))
+    assert tr.num_features == 7296
+    p0 = tr.discriminator.flat.detach().clone()
+    for expect in ("disc", "gen"):
+        kind, stats = tr.step(torch.rand(16, 32, 32, 3, device="cuda") * 2 - 1)
+        d, e = stats.tolist()
+        assert kind == expect and np.isfinite(d) and 0.0 < e <= np.log(8) + 1e-4
+    assert not torch.equal(tr.discriminator.flat.detach(), p0)
