@@ -342,6 +342,8 @@ def conv_benchmark(torch, iters=5):
         b = torch.randn(Cout, device="cuda")
         dy = torch.randn(B, Ho, Wo, Cout, device="cuda")
         y, dx, dw = torch.empty_like(dy), torch.empty_like(x), torch.empty_like(w)
+        gws = torch.empty(max(lib.otgan_workspace_bytes_conv_gemm(B, Ho, Wo, Cout), lib.otgan_workspace_bytes_conv_gemm(B, H, W, Cin)) // 4 + 64, device="cuda")
+        gwa = (gws.data_ptr(), gws.numel() * 4)          # split-K / tail-split workspace, as nn._ConvTC passes it
         if up2:
             n1 = lib.otgan_up2_subtaps(k, pad)
             slots = n1 * n1
@@ -354,8 +356,8 @@ def conv_benchmark(torch, iters=5):
                 _lib.check(lib.otgan_ohwi_to_ihwo_f32(Cout, slots, Cin, w_sub[c].data_ptr(), w_sub_t[c].data_ptr(), st), "ohwi_to_ihwo")
             ws = torch.empty(lib.otgan_workspace_bytes_conv_up2_wgrad(B, H, W, Cin, Cout, k, k, pad, pad) // 4 + 64, device="cuda")
             ops = {
-                "fprop": lambda: lib.otgan_conv2d_up2_fprop_tf32(B, H, W, Cin, Cout, k, k, pad, pad, x.data_ptr(), w_sub.data_ptr(), b.data_ptr(), y.data_ptr(), None, 0, st),
-                "dgrad": lambda: lib.otgan_conv2d_up2_dgrad_tf32(B, H, W, Cin, Cout, k, k, pad, pad, dy.data_ptr(), w_sub_t.data_ptr(), dx.data_ptr(), None, 0, st),
+                "fprop": lambda: lib.otgan_conv2d_up2_fprop_tf32(B, H, W, Cin, Cout, k, k, pad, pad, x.data_ptr(), w_sub.data_ptr(), b.data_ptr(), y.data_ptr(), gwa[0], gwa[1], st),
+                "dgrad": lambda: lib.otgan_conv2d_up2_dgrad_tf32(B, H, W, Cin, Cout, k, k, pad, pad, dy.data_ptr(), w_sub_t.data_ptr(), dx.data_ptr(), gwa[0], gwa[1], st),
                 "wgrad": lambda: lib.otgan_conv2d_up2_wgrad_tf32(B, H, W, Cin, Cout, k, k, pad, pad, dy.data_ptr(), x.data_ptr(), dw_sub.data_ptr(), ws.data_ptr(), ws.numel() * 4, st),
             }
         else:
@@ -364,8 +366,8 @@ def conv_benchmark(torch, iters=5):
             ws = torch.empty(lib.otgan_workspace_bytes_conv_wgrad(B, H, W, Cin, Cout, k, k, s) // 4 + 64, device="cuda")
             _lib.check(lib.otgan_ohwi_to_ihwo_f32(Cout, k * k, Cin, w.data_ptr(), wt.data_ptr(), st), "ohwi_to_ihwo")
             ops = {
-                "fprop": lambda: lib.otgan_conv2d_fprop_tf32(B, H, W, Cin, Cout, k, k, s, pad, pad, x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), None, 0, st),
-                "dgrad": lambda: lib.otgan_conv2d_dgrad_tf32(B, H, W, Cin, Cout, k, k, s, pad, pad, dy.data_ptr(), wt.data_ptr(), dx.data_ptr(), None, 0, st),
+                "fprop": lambda: lib.otgan_conv2d_fprop_tf32(B, H, W, Cin, Cout, k, k, s, pad, pad, x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), gwa[0], gwa[1], st),
+                "dgrad": lambda: lib.otgan_conv2d_dgrad_tf32(B, H, W, Cin, Cout, k, k, s, pad, pad, dy.data_ptr(), wt.data_ptr(), dx.data_ptr(), gwa[0], gwa[1], st),
                 "wgrad": lambda: lib.otgan_conv2d_wgrad_tf32(B, H, W, Cin, Cout, k, k, s, pad, pad, dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel() * 4, st),
             }
         row = {"shape": [B, H, W, Cin, Cout, k, s], "gflop": flops / 1e9, "gflop_reference_form": ref_flops / 1e9}
@@ -382,7 +384,7 @@ def conv_benchmark(torch, iters=5):
             ms = e0.elapsed_time(e1) / iters
             row[op] = {"ms": ms, "tflops": flops / ms / 1e9}
         out[name] = row
-        del x, w, b, dy, y, dx, dw, ws, ops
+        del x, w, b, dy, y, dx, dw, ws, gws, ops
         torch.cuda.empty_cache()
     return out
 

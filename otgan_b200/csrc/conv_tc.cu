@@ -65,6 +65,10 @@ struct GemmParams {
     int n_cls, m_tiles, n_tiles, n_items;
     int splits;                               // split-K over the taps of a class (small-M launches); partials split_stride apart
     long long split_stride;
+    // tail split: the tiles of the last, partial wave (tiles % 148) are each cut into tail_splits shares of their taps so that
+    // the wave fills all SMs; their raw partial tiles go to tail_ws ([tail tile][share][128][TN]) and conv_tail_fixup sums them
+    int n_full, tail_splits;
+    float* tail_ws;
     int bw, bh, bn, tiles_w, tiles_h;         // pixel box (bw*bh*bn = 128) and tile grid of one class
     int kchunks;                              // 32-channel chunks per tap
     int n_valid;                              // real output channels (TN = 16 variant: N <= 16, rest of the tile is ignored)
@@ -105,15 +109,25 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
-    // item -> (split, class, N tile, M tile); a split sums a contiguous share of the class's taps
-    auto decode = [&](int item, int& mt, int& nt, int& cls, int& sp, int& t0, int& t1) {
+    // item -> (split, class, N tile, M tile); a split sums a contiguous share of the class's taps.  Items >= n_full are the
+    // shares of the tail tiles (sp = share, tail = index of the tail tile, -1 for a whole tile).
+    auto decode = [&](int item, int& mt, int& nt, int& cls, int& sp, int& t0, int& t1, int& tail) {
+        int nsplit = p.splits;
+        tail = -1;
+        if (item >= p.n_full) {
+            const int q = item - p.n_full;
+            tail = q / p.tail_splits;
+            sp = q - tail * p.tail_splits;
+            item = p.n_full + tail;
+            nsplit = p.tail_splits;
+        }
         mt = item % p.m_tiles; item /= p.m_tiles;
         nt = item % p.n_tiles; item /= p.n_tiles;
         cls = item % p.n_cls;
-        sp = item / p.n_cls;
+        if (tail < 0) sp = item / p.n_cls;
         const int tb = p.cls_tap_begin[cls], T = p.cls_tap_begin[cls + 1] - tb;
-        t0 = tb + (T * sp) / p.splits;
-        t1 = tb + (T * (sp + 1)) / p.splits;
+        t0 = tb + (T * sp) / nsplit;
+        t1 = tb + (T * (sp + 1)) / nsplit;
     };
 
     if (warp == 0) {
@@ -121,8 +135,8 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
         if (lane == 0) {
             int c = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                int mt, nt, cls, sp, t0, t1;
-                decode(item, mt, nt, cls, sp, t0, t1);
+                int mt, nt, cls, sp, t0, t1, tail;
+                decode(item, mt, nt, cls, sp, t0, t1, tail);
                 const int w0 = (mt % p.tiles_w) * p.bw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
                 const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
                 for (int t = t0; t < t1; ++t) {
@@ -145,8 +159,8 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
             const uint32_t idesc = umma_idesc_tf32(TM, TN);
             int c = 0, n = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
-                int mt, nt, cls, sp, t0, t1;
-                decode(item, mt, nt, cls, sp, t0, t1);
+                int mt, nt, cls, sp, t0, t1, tail;
+                decode(item, mt, nt, cls, sp, t0, t1, tail);
                 const int b = n & 1;
                 mbar_wait(tempty_bar(b), (((uint32_t)(n >> 1)) & 1u) ^ 1u);
                 tcgen05_fence_after();
@@ -175,14 +189,18 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
         const int rw = r % p.bw, rh = (r / p.bw) % p.bh, rn = r / (p.bw * p.bh);
         int n = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
-            int mt, nt, cls, sp, t0, t1;
-            decode(item, mt, nt, cls, sp, t0, t1);
+            int mt, nt, cls, sp, t0, t1, tail;
+            decode(item, mt, nt, cls, sp, t0, t1, tail);
             const int b = n & 1;
             const int w0 = (mt % p.tiles_w) * p.bw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
             const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
             float* out = p.out + sp * p.split_stride + p.cls_out_off[cls] + (long long)(n0 + rn) * p.osN +
                          (long long)(h0 + rh) * p.osH + (long long)(w0 + rw) * p.osW + nt * TN;
             const float* bias = (p.bias && sp == 0) ? p.bias + nt * TN : nullptr;     // the first partial carries the bias
+            if (tail >= 0) {                             // share of a tail tile: raw partial, compact [128][TN], bias in the fix-up
+                out = p.tail_ws + ((size_t)tail * p.tail_splits + sp) * (size_t)(TM * TN) + (size_t)r * TN;
+                bias = nullptr;
+            }
             mbar_wait(tfull_bar(b), ((uint32_t)(n >> 1)) & 1u);
             tcgen05_fence_after();
             if constexpr (TN == 16) {
@@ -225,6 +243,38 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
         __syncwarp();
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// Sums the shares of every tail tile (fixed order), adds the bias and scatters the rows to their output pixels.
+template <int TN>
+__global__ void __launch_bounds__(256)
+conv_tail_fixup_kernel(const __grid_constant__ GemmParams p)
+{
+    const int tail = blockIdx.x;
+    int item = p.n_full + tail;
+    const int mt = item % p.m_tiles; item /= p.m_tiles;
+    const int nt = item % p.n_tiles; item /= p.n_tiles;
+    const int cls = item % p.n_cls;
+    const int w0 = (mt % p.tiles_w) * p.bw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
+    const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
+    const float4* src = reinterpret_cast<const float4*>(p.tail_ws + (size_t)tail * p.tail_splits * (size_t)(TM * TN));
+    constexpr int C4 = TN / 4;
+    for (int idx = threadIdx.x; idx < TM * C4; idx += blockDim.x) {
+        const int r = idx / C4, c4 = idx - r * C4;
+        float4 a = src[idx];
+        for (int s = 1; s < p.tail_splits; ++s) {
+            const float4 b = src[(size_t)s * (TM * C4) + idx];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        if (p.bias) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nt * TN) + c4);
+            a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+        }
+        const int rw = r % p.bw, rh = (r / p.bw) % p.bh, rn = r / (p.bw * p.bh);
+        float* out = p.out + p.cls_out_off[cls] + (long long)(n0 + rn) * p.osN + (long long)(h0 + rh) * p.osH +
+                     (long long)(w0 + rw) * p.osW + nt * TN;
+        *reinterpret_cast<float4*>(out + 4 * c4) = a;
     }
 }
 
@@ -574,6 +624,22 @@ int gemm_splits(int tiles, int min_taps)
     return S < 1 ? 1 : S;
 }
 
+// Shares per tail tile: r = tiles % 148 tiles are left for the last wave; cutting each into S shares of its taps makes the
+// wave last ceil(r S / 148) / S of a tile time instead of 1.  Pick the S (<= 8, <= taps) with the shortest tail, preferring
+// small S (each share costs a partial tile of workspace traffic); 1 = leave the tail alone.
+int tail_splits_for(int r, int min_taps)
+{
+    if (r <= 0) return 1;
+    int best = 1;
+    double best_t = 0.9;                                 // at least a 10% shorter tail wave, else leave it alone
+    const int smax = min_taps < 8 ? min_taps : 8;
+    for (int S = 2; S <= smax; ++S) {
+        const double t = (double)((r * S + kNumSMs - 1) / kNumSMs) / S + 0.02 * S;
+        if (t < best_t - 1e-9) { best_t = t; best = S; }
+    }
+    return best;
+}
+
 // finish a fprop / dgrad launch: pick the split, point the kernel at the workspace, launch, reduce
 template <int TN>
 int launch_gemm(const GemmParams& p, cudaStream_t stream);
@@ -589,10 +655,32 @@ int run_gemm(GemmParams& p, int TN, size_t out_numel, float* out, void* ws, size
     p.splits = (out_numel % 4) ? 1 : gemm_splits(tiles, min_taps);
     if (p.splits > 1 && (!ws || ws_bytes < (size_t)p.splits * out_numel * sizeof(float))) p.splits = 1;   // no room: unsplit
     p.split_stride = (long long)out_numel;
-    p.n_items = tiles * p.splits;
     p.out = p.splits > 1 ? reinterpret_cast<float*>(ws) : out;
+    p.n_full = tiles * p.splits;
+    p.tail_splits = 1;
+    p.tail_ws = nullptr;
+    int n_tail = 0;
+    if (p.splits == 1 && TN >= 128 && ws) {              // cut the last, partial wave of tiles along the taps
+        n_tail = tiles % kNumSMs;
+        const int S = tail_splits_for(n_tail, min_taps);
+        if (S > 1 && ws_bytes >= (size_t)n_tail * S * TM * TN * sizeof(float)) {
+            p.n_full = tiles - n_tail;
+            p.tail_splits = S;
+            p.tail_ws = reinterpret_cast<float*>(ws);
+        } else {
+            n_tail = 0;
+        }
+    }
+    p.n_items = p.n_full + n_tail * p.tail_splits;
     const int rc = TN == 256 ? launch_gemm<256>(p, stream) : TN == 128 ? launch_gemm<128>(p, stream) : launch_gemm<16>(p, stream);
-    if (rc != OTGAN_OK || p.splits == 1) return rc;
+    if (rc != OTGAN_OK) return rc;
+    if (n_tail > 0) {
+        if (TN == 256) conv_tail_fixup_kernel<256><<<n_tail, 256, 0, stream>>>(p);
+        else conv_tail_fixup_kernel<128><<<n_tail, 256, 0, stream>>>(p);
+        OTGAN_CHECK_LAUNCH("conv_tail_fixup_kernel");
+        return OTGAN_OK;
+    }
+    if (p.splits == 1) return rc;
     const size_t n4 = out_numel / 4;
     const size_t blocks = (n4 + 255) / 256;
     const int grid = (int)(blocks < (size_t)(8 * kNumSMs) ? blocks : (size_t)(8 * kNumSMs));
@@ -668,9 +756,11 @@ size_t conv_gemm_workspace_bytes(int B, int H, int W, int C)
     if (C % 128) return 256;                                          // narrow (TN = 16) outputs are never split
     const int TN = (C % 256 == 0) ? 256 : 128;
     const long long tiles = (pix / TM) * (C / TN);
-    if (tiles < 1 || tiles >= kNumSMs) return 256;
+    if (tiles < 1) return 256;
     const int S = gemm_splits((int)tiles, 8);
-    return S > 1 ? (size_t)S * pix * C * sizeof(float) + 256 : 256;
+    if (S > 1) return (size_t)S * pix * C * sizeof(float) + 256;      // whole-launch split-K partials
+    const int r = (int)(tiles % kNumSMs);                             // tail split: r tiles x up to 8 shares
+    return r ? (size_t)r * 8 * TM * TN * sizeof(float) + 256 : 256;
 }
 
 int conv_fprop_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo,

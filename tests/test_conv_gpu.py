@@ -28,6 +28,8 @@ SHAPES = [
     (16, 16, 16, 512, 512, 5, 2),
     (16, 8, 8, 1024, 1024, 5, 1),        # DCGAN generator layers
     (16, 16, 16, 512, 512, 5, 1),
+    (80, 16, 16, 128, 256, 5, 1),        # 160 tiles: one full wave + a 12-tile tail that is cut into shares of the taps
+    (96, 32, 32, 128, 128, 5, 2),        # stride 2 with a tail (fprop 192 tiles; dgrad 768 tiles in 4 parity classes)
 ]
 
 

@@ -25,6 +25,8 @@ SHAPES = [
     (16, 8, 8, 1024, 1024, 5, 1),
     (16, 16, 16, 512, 512, 5, 1),
     (16, 32, 32, 256, 256, 5, 1),
+    (80, 16, 16, 128, 256, 5, 1),        # tail split: 160 tiles = one wave + 12
+    (96, 32, 32, 128, 128, 5, 2),
 ]
 OPS = ("fprop", "dgrad", "wgrad")
 
