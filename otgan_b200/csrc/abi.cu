@@ -73,6 +73,7 @@ int conv_wgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
                       const float* dy, const float* x, float* dw, void* ws, size_t ws_bytes, cudaStream_t stream);
 int ohwi_to_ihwo_launch(int Cout, int T, int Cin, const float* w, float* wt, cudaStream_t stream);
 size_t colsum_workspace_bytes(int P, int C);
+int conv_set_option(int option, int value);
 int up2_subtaps(int k, int pad);
 int up2_presum_launch(int Cout, int kh, int kw, int Cin, int pt, int pl, const float* w, float* w_sub, cudaStream_t stream);
 int up2_unsum_launch(int Cout, int kh, int kw, int Cin, int pt, int pl, const float* dw_sub, float* dw, cudaStream_t stream);
@@ -477,5 +478,7 @@ int otgan_conv2d_up2_wgrad_tf32(int B, int Hl, int Wl, int Cin, int Cout, int kh
     OTGAN_REQUIRE(aligned16(dy) && aligned16(x_low) && aligned16(dw_sub) && (!ws || aligned16(ws)), "conv2d_up2_wgrad: buffers must be 16-byte aligned");
     return conv_up2_wgrad_launch(B, Hl, Wl, Cin, Cout, kh, kw, pad_top, pad_left, dy, x_low, dw_sub, ws, ws_bytes, (cudaStream_t)stream);
 }
+
+int otgan_conv_set_option(int option, int value) { return conv_set_option(option, value); }
 
 }  // extern "C"

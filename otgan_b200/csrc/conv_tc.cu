@@ -246,6 +246,170 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
     }
 }
 
+// ---------------------------------------------------------------------------------------------- fprop / dgrad, 256 x 256 tiles
+// Measured on the kernel above (ncu, fused-upsample fprop of generator conv2d_0): every SM ingests 81 B/clk of operand tiles
+// from L2 while it is active and the tensor pipe is busy exactly 81/96 = 84.5% of that time -- 96 B/clk (48 KB per 512-cycle
+// K-chunk) is what a 128 x 256 tile needs at the full MMA rate, so the kernel is bound by operand delivery, not by the tensor
+// pipe or by wave quantisation (cutting the last wave into shares changed nothing).  This variant gives each CTA TWO 128-pixel
+// sub-tiles that share one 256-row weight tile: 64 KB per 1024 cycles of MMA = 64 B/clk.  Both accumulators (2 x 256 columns)
+// fill TMEM, so the epilogue no longer overlaps the next tile's MMAs; it is used when a tile has >= 100 K-chunks (epilogue
+// <= 10% of the tile) and the launch still has >= 0.75 waves of the bigger tiles.
+constexpr int G2_TN = 256;
+constexpr int G2_B_TILE = G2_TN * BK * 4;                     // 32 KB
+constexpr int G2_STAGE_BYTES = 2 * A_TILE + G2_B_TILE;        // 64 KB
+constexpr int G2_STAGES = 3;
+constexpr size_t G2_SMEM_BYTES = 1024 + (size_t)G2_STAGES * G2_STAGE_BYTES + 256;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm2_tc_kernel(const __grid_constant__ GemmParams p)
+{
+    constexpr int STAGES = G2_STAGES, TN = G2_TN;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bars = smem_base + STAGES * G2_STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    const uint32_t tfull_bar = bars + 8u * (2 * STAGES), tempty_bar = bars + 8u * (2 * STAGES + 1);
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 2);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * G2_STAGE_BYTES + 8 * (2 * STAGES + 2));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.amap[i]);
+        tma_prefetch_desc(&p.bmap);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty_bar, NUM_EPI_THREADS);
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    // item -> (split, class, N tile, pair of M tiles): sub-tile j of pair m2 is the 128-pixel tile 2 m2 + j
+    const int m_pairs = p.m_tiles >> 1;
+    auto decode = [&](int item, int& m2, int& nt, int& cls, int& sp, int& t0, int& t1) {
+        m2 = item % m_pairs; item /= m_pairs;
+        nt = item % p.n_tiles; item /= p.n_tiles;
+        cls = item % p.n_cls;
+        sp = item / p.n_cls;
+        const int tb = p.cls_tap_begin[cls], T = p.cls_tap_begin[cls + 1] - tb;
+        t0 = tb + (T * sp) / p.splits;
+        t1 = tb + (T * (sp + 1)) / p.splits;
+    };
+    auto tile_origin = [&](int mt, int& w0, int& h0, int& n0) {
+        w0 = (mt % p.tiles_w) * p.bw;
+        h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
+        n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
+    };
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                int m2, nt, cls, sp, t0, t1, wa, ha, na, wb, hb, nb;
+                decode(item, m2, nt, cls, sp, t0, t1);
+                tile_origin(2 * m2, wa, ha, na);
+                tile_origin(2 * m2 + 1, wb, hb, nb);
+                for (int t = t0; t < t1; ++t) {
+                    const Tap tap = p.taps[t];
+                    const CUtensorMap* am = &p.amap[tap.map];
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(empty_bar(s), ph ^ 1u);
+                        mbar_arrive_expect_tx(full_bar(s), (uint32_t)G2_STAGE_BYTES);
+                        const uint32_t dst = smem_base + s * G2_STAGE_BYTES;
+                        tma_load_4d(dst, am, full_bar(s), kc * BK, wa + tap.dw, ha + tap.dh, na);
+                        tma_load_4d(dst + A_TILE, am, full_bar(s), kc * BK, wb + tap.dw, hb + tap.dh, nb);
+                        tma_load_2d(dst + 2 * A_TILE, &p.bmap, full_bar(s), tap.wcol + kc * BK, tap.brow + nt * TN);
+                        if (++s == STAGES) { s = 0; ph ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(TM, TN);
+            int s = 0, n = 0;
+            uint32_t ph = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
+                int m2, nt, cls, sp, t0, t1;
+                decode(item, m2, nt, cls, sp, t0, t1);
+                mbar_wait(tempty_bar, ((uint32_t)n & 1u) ^ 1u);          // both accumulators drained by the epilogue
+                tcgen05_fence_after();
+                const int nst = (t1 - t0) * p.kchunks;
+                for (int st = 0; st < nst; ++st) {
+                    mbar_wait(full_bar(s), ph);
+                    tcgen05_fence_after();
+                    const uint32_t a0 = smem_base + s * G2_STAGE_BYTES, a1 = a0 + A_TILE, b0 = a0 + 2 * A_TILE;
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint64_t bd = umma_desc_kmajor(b0 + k * 32, 1024, SW128);
+                        umma_tf32(tmem_base, umma_desc_kmajor(a0 + k * 32, 1024, SW128), bd, idesc, (st > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32(tmem_base + TN, umma_desc_kmajor(a1 + k * 32, 1024, SW128), bd, idesc, (st > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(s));
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(tfull_bar);
+            }
+        }
+    } else {
+        // ===================================================== epilogue warps: both accumulators -> (+bias) -> global
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
+        const int rw = r % p.bw, rh = (r / p.bw) % p.bh, rn = r / (p.bw * p.bh);
+        int n = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
+            int m2, nt, cls, sp, t0, t1;
+            decode(item, m2, nt, cls, sp, t0, t1);
+            const float* bias = (p.bias && sp == 0) ? p.bias + nt * TN : nullptr;
+            mbar_wait(tfull_bar, (uint32_t)n & 1u);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int j = 0; j < 2; ++j) {
+                int w0, h0, n0;
+                tile_origin(2 * m2 + j, w0, h0, n0);
+                float* out = p.out + sp * p.split_stride + p.cls_out_off[cls] + (long long)(n0 + rn) * p.osN +
+                             (long long)(h0 + rh) * p.osH + (long long)(w0 + rw) * p.osW + nt * TN;
+#pragma unroll 1
+                for (int cc = 0; cc < TN / 32; ++cc) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(j * TN + cc * 32), v);
+                    tmem_ld_wait();
+                    if (bias) {
+#pragma unroll
+                        for (int q = 0; q < 32; q += 4) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + q));
+                            v[q] = __float_as_uint(__uint_as_float(v[q]) + bb.x);
+                            v[q + 1] = __float_as_uint(__uint_as_float(v[q + 1]) + bb.y);
+                            v[q + 2] = __float_as_uint(__uint_as_float(v[q + 2]) + bb.z);
+                            v[q + 3] = __float_as_uint(__uint_as_float(v[q + 3]) + bb.w);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 32; q += 4)
+                        *reinterpret_cast<uint4*>(out + cc * 32 + q) = make_uint4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(tempty_bar);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // Sums the shares of every tail tile (fixed order), adds the bias and scatters the rows to their output pixels.
 template <int TN>
 __global__ void __launch_bounds__(256)
@@ -640,6 +804,8 @@ int tail_splits_for(int r, int min_taps)
     return best;
 }
 
+bool g_use_gemm2 = true;      // A/B switch for the 256 x 256 variant (otgan_conv_set_option)
+
 // finish a fprop / dgrad launch: pick the split, point the kernel at the workspace, launch, reduce
 template <int TN>
 int launch_gemm(const GemmParams& p, cudaStream_t stream);
@@ -659,6 +825,20 @@ int run_gemm(GemmParams& p, int TN, size_t out_numel, float* out, void* ws, size
     p.n_full = tiles * p.splits;
     p.tail_splits = 1;
     p.tail_ws = nullptr;
+    // 256 x 256 tiles (two sub-tiles share the weight tile) when the launch keeps >= 0.75 waves of them and a tile is long
+    // enough to amortise the un-overlapped epilogue
+    if (g_use_gemm2 && p.splits == 1 && TN == 256 && (p.m_tiles & 1) == 0 && tiles / 2 >= (kNumSMs * 3) / 4 && min_taps * p.kchunks >= 100) {
+        p.n_items = tiles / 2;
+        static bool attr2 = false;
+        if (!attr2) {
+            OTGAN_CUDA(cudaFuncSetAttribute(conv_gemm2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM_BYTES));
+            attr2 = true;
+        }
+        const int grid2 = p.n_items < kNumSMs ? p.n_items : kNumSMs;
+        conv_gemm2_tc_kernel<<<grid2, NUM_THREADS, G2_SMEM_BYTES, stream>>>(p);
+        OTGAN_CHECK_LAUNCH("conv_gemm2_tc_kernel");
+        return OTGAN_OK;
+    }
     int n_tail = 0;
     if (p.splits == 1 && TN >= 128 && ws) {              // cut the last, partial wave of tiles along the taps
         n_tail = tiles % kNumSMs;
@@ -1150,6 +1330,14 @@ int conv_up2_wgrad_launch(int B, int Hl, int Wl, int Cin, int Cout, int kh, int 
     split_reduce_kernel<<<grid, 256, 0, stream>>>(n4, p.splits, n4, reinterpret_cast<const float4*>(p.out), reinterpret_cast<float4*>(dw_sub));
     OTGAN_CHECK_LAUNCH("split_reduce_kernel");
     return OTGAN_OK;
+}
+
+// A/B switches for benchmarking: option 0 = use the 256 x 256 tile variant of the fprop / dgrad kernel (default 1)
+int conv_set_option(int option, int value)
+{
+    if (option == 0) { g_use_gemm2 = value != 0; return OTGAN_OK; }
+    set_error("conv_set_option: unknown option %d", option);
+    return OTGAN_EINVAL;
 }
 
 }  // namespace otgan

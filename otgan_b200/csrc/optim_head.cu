@@ -57,6 +57,9 @@ __device__ __forceinline__ float block_sum(float s, float* red)
 }
 
 // x: [B, HW, C] (NHWC) -> y: [B, HW * 2C] = normalise(concat(relu(x), relu(-x)) over channels), inv[b] = 1/||z_b||
+// VEC = 4: C % 4 == 0 and 16-byte aligned tensors -> float4 loads / stores (4x fewer memory instructions per byte; the scalar
+// version ran at ~1.2 TB/s).  The summation order differs between VEC = 1 and VEC = 4 but is fixed for either.
+template <int VEC>
 __global__ void __launch_bounds__(256)
 crelu_l2norm_fwd_kernel(int HW, int C, const float* __restrict__ x, float* __restrict__ y, float* __restrict__ inv)
 {
@@ -64,20 +67,38 @@ crelu_l2norm_fwd_kernel(int HW, int C, const float* __restrict__ x, float* __res
     const int b = blockIdx.x, n = HW * C;
     const float* xb = x + (size_t)b * n;
     float s = 0.f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(xb[i], xb[i], s);      // relu(x)^2 + relu(-x)^2 = x^2
+    if (VEC == 4) {
+        for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4) {
+            const float4 v = *reinterpret_cast<const float4*>(xb + i);
+            s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(xb[i], xb[i], s);  // relu(x)^2 + relu(-x)^2 = x^2
+    }
     const float tot = block_sum(s, red);
     const float r = 1.0f / sqrtf(tot);                                                // no epsilon (models/dcgan.py:19)
     if (threadIdx.x == 0) inv[b] = r;
     float* yb = y + (size_t)b * 2 * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int hw = i / C, c = i - hw * C;
-        const float v = xb[i];
-        yb[(size_t)hw * 2 * C + c] = fmaxf(v, 0.f) * r;
-        yb[(size_t)hw * 2 * C + C + c] = fmaxf(-v, 0.f) * r;
+    if (VEC == 4) {
+        for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4) {
+            const int hw = i / C, c = i - hw * C;
+            const float4 v = *reinterpret_cast<const float4*>(xb + i);
+            float* dst = yb + (size_t)hw * 2 * C + c;
+            *reinterpret_cast<float4*>(dst) = make_float4(fmaxf(v.x, 0.f) * r, fmaxf(v.y, 0.f) * r, fmaxf(v.z, 0.f) * r, fmaxf(v.w, 0.f) * r);
+            *reinterpret_cast<float4*>(dst + C) = make_float4(fmaxf(-v.x, 0.f) * r, fmaxf(-v.y, 0.f) * r, fmaxf(-v.z, 0.f) * r, fmaxf(-v.w, 0.f) * r);
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int hw = i / C, c = i - hw * C;
+            const float v = xb[i];
+            yb[(size_t)hw * 2 * C + c] = fmaxf(v, 0.f) * r;
+            yb[(size_t)hw * 2 * C + C + c] = fmaxf(-v, 0.f) * r;
+        }
     }
 }
 
 // dz = (dy - y <y, dy>) * inv ; dx = dz[pos] * [x > 0] - dz[neg] * [x < 0]
+template <int VEC>
 __global__ void __launch_bounds__(256)
 crelu_l2norm_bwd_kernel(int HW, int C, const float* __restrict__ x, const float* __restrict__ y,
                         const float* __restrict__ inv, const float* __restrict__ dy, float* __restrict__ dx)
@@ -87,17 +108,38 @@ crelu_l2norm_bwd_kernel(int HW, int C, const float* __restrict__ x, const float*
     const float* yb = y + (size_t)b * 2 * n;
     const float* dyb = dy + (size_t)b * 2 * n;
     float s = 0.f;
-    for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) s = fmaf(yb[i], dyb[i], s);
+    if (VEC == 4) {
+        for (int i = threadIdx.x * 4; i < 2 * n; i += blockDim.x * 4) {
+            const float4 a = *reinterpret_cast<const float4*>(yb + i), d = *reinterpret_cast<const float4*>(dyb + i);
+            s = fmaf(a.x, d.x, s); s = fmaf(a.y, d.y, s); s = fmaf(a.z, d.z, s); s = fmaf(a.w, d.w, s);
+        }
+    } else {
+        for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) s = fmaf(yb[i], dyb[i], s);
+    }
     const float dot = block_sum(s, red);
     const float r = inv[b];
     const float* xb = x + (size_t)b * n;
     float* dxb = dx + (size_t)b * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int hw = i / C, c = i - hw * C;
-        const size_t ip = (size_t)hw * 2 * C + c, in_ = ip + C;
-        const float v = xb[i];
-        const float dzp = (dyb[ip] - yb[ip] * dot) * r, dzn = (dyb[in_] - yb[in_] * dot) * r;
-        dxb[i] = (v > 0.f ? dzp : 0.f) - (v < 0.f ? dzn : 0.f);
+    auto one = [&](float v, float yp, float yn, float dp, float dn) {
+        const float dzp = (dp - yp * dot) * r, dzn = (dn - yn * dot) * r;
+        return (v > 0.f ? dzp : 0.f) - (v < 0.f ? dzn : 0.f);
+    };
+    if (VEC == 4) {
+        for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4) {
+            const int hw = i / C, c = i - hw * C;
+            const size_t ip = (size_t)hw * 2 * C + c;
+            const float4 v = *reinterpret_cast<const float4*>(xb + i);
+            const float4 yp = *reinterpret_cast<const float4*>(yb + ip), yn = *reinterpret_cast<const float4*>(yb + ip + C);
+            const float4 dp = *reinterpret_cast<const float4*>(dyb + ip), dn = *reinterpret_cast<const float4*>(dyb + ip + C);
+            *reinterpret_cast<float4*>(dxb + i) = make_float4(one(v.x, yp.x, yn.x, dp.x, dn.x), one(v.y, yp.y, yn.y, dp.y, dn.y),
+                                                              one(v.z, yp.z, yn.z, dp.z, dn.z), one(v.w, yp.w, yn.w, dp.w, dn.w));
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int hw = i / C, c = i - hw * C;
+            const size_t ip = (size_t)hw * 2 * C + c, in_ = ip + C;
+            dxb[i] = one(xb[i], yb[ip], yb[in_], dyb[ip], dyb[in_]);
+        }
     }
 }
 
@@ -118,7 +160,9 @@ int adam_ema_launch(size_t n, float* p, const float* g, float* v, float* mg, flo
 
 int crelu_l2norm_fwd_launch(int B, int HW, int C, const float* x, float* y, float* inv, cudaStream_t stream)
 {
-    crelu_l2norm_fwd_kernel<<<B, 256, 0, stream>>>(HW, C, x, y, inv);
+    const bool vec = (C % 4 == 0) && aligned16(x) && aligned16(y);
+    if (vec) crelu_l2norm_fwd_kernel<4><<<B, 256, 0, stream>>>(HW, C, x, y, inv);
+    else crelu_l2norm_fwd_kernel<1><<<B, 256, 0, stream>>>(HW, C, x, y, inv);
     OTGAN_CHECK_LAUNCH("crelu_l2norm_fwd_kernel");
     return OTGAN_OK;
 }
@@ -126,7 +170,9 @@ int crelu_l2norm_fwd_launch(int B, int HW, int C, const float* x, float* y, floa
 int crelu_l2norm_bwd_launch(int B, int HW, int C, const float* x, const float* y, const float* inv, const float* dy,
                             float* dx, cudaStream_t stream)
 {
-    crelu_l2norm_bwd_kernel<<<B, 256, 0, stream>>>(HW, C, x, y, inv, dy, dx);
+    const bool vec = (C % 4 == 0) && aligned16(x) && aligned16(y) && aligned16(dy) && aligned16(dx);
+    if (vec) crelu_l2norm_bwd_kernel<4><<<B, 256, 0, stream>>>(HW, C, x, y, inv, dy, dx);
+    else crelu_l2norm_bwd_kernel<1><<<B, 256, 0, stream>>>(HW, C, x, y, inv, dy, dx);
     OTGAN_CHECK_LAUNCH("crelu_l2norm_bwd_kernel");
     return OTGAN_OK;
 }

@@ -367,3 +367,65 @@ def test_narrow_output_variant_of_the_gemm_kernel(cout):
     _lib.check(rc, "dgrad")
     torch.cuda.synchronize()
     assert float((dx.double() - ref2[1]).abs().max()) == 0.0
+
+
+def test_256_row_tile_variant_matches_the_128_row_kernel():
+    """conv_gemm2_tc_kernel (two 128-pixel sub-tiles per CTA sharing one weight tile; chosen for launches with >= 111 of the
+    bigger tiles and >= 100 K-chunks per tile) against the 128 x 256-tile kernel (itself checked against float64 above) on
+    integer inputs, where both are exact: outputs must be identical.  Covers fprop, stride-1 and stride-2 dgrad (parity
+    classes) and the fused-upsample fprop / dgrad."""
+    from otgan_b200 import _lib
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(21)
+
+    def ints(*shape, lo=-2, hi=3):
+        return torch.randint(lo, hi, shape, device="cuda", generator=g).float()
+
+    def both(fn, out):
+        res = []
+        for v in (1, 0):
+            assert lib.otgan_conv_set_option(0, v) == 0
+            out.fill_(float("nan"))
+            _lib.check(fn(), "launch")
+            torch.cuda.synchronize()
+            res.append(out.clone())
+        lib.otgan_conv_set_option(0, 1)
+        assert not torch.isnan(res[0]).any() and torch.equal(res[0], res[1])
+
+    def ws_for(*dims):
+        n = lib.otgan_workspace_bytes_conv_gemm(*dims)
+        t = torch.empty(n // 4 + 64, device="cuda")
+        return t, t.data_ptr(), t.numel() * 4
+
+    try:
+        # fprop, stride 1: 512 tiles of 128 x 256, 100 K-chunks per tile
+        B, H, W, Cin, Cout, k = 64, 32, 32, 128, 256, 5
+        x, w, b = ints(B, H, W, Cin), ints(Cout, k * k * Cin), ints(Cout, lo=-4, hi=5)
+        y = torch.empty(B, H, W, Cout, device="cuda")
+        t, wp, wb = ws_for(B, H, W, Cout)
+        both(lambda: lib.otgan_conv2d_fprop_tf32(B, H, W, Cin, Cout, k, k, 1, 2, 2, x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), wp, wb, st), y)
+        # dgrad, stride 1 (N = Cin = 256)
+        Cin, Cout = 256, 128
+        dy, wt = ints(B, H, W, Cout), ints(Cin, k * k * Cout)
+        dx = torch.empty(B, H, W, Cin, device="cuda")
+        t, wp, wb = ws_for(B, H, W, Cin)
+        both(lambda: lib.otgan_conv2d_dgrad_tf32(B, H, W, Cin, Cout, k, k, 1, 2, 2, dy.data_ptr(), wt.data_ptr(), dx.data_ptr(), wp, wb, st), dx)
+        # dgrad, stride 2: four parity classes with 4 / 6 / 6 / 9 taps, 32 K-chunks per tap
+        B, H, W, Cin, Cout = 128, 8, 8, 1024, 1024
+        dy, wt = ints(B, H // 2, W // 2, Cout), ints(Cin, k * k * Cout, lo=-1, hi=2)
+        dx = torch.empty(B, H, W, Cin, device="cuda")
+        t, wp, wb = ws_for(B, H, W, Cin)
+        both(lambda: lib.otgan_conv2d_dgrad_tf32(B, H, W, Cin, Cout, k, k, 2, 1, 1, dy.data_ptr(), wt.data_ptr(), dx.data_ptr(), wp, wb, st), dx)
+        # fused upsample: fprop (4 classes x 9 taps, strided output rows) and dgrad (36 taps over the parity views of dy)
+        B, Hl, Wl, Cin, Cout = 256, 8, 8, 512, 256
+        x, w_sub, b = ints(B, Hl, Wl, Cin), ints(4, Cout, 9 * Cin, lo=-1, hi=2), ints(Cout, lo=-4, hi=5)
+        y = torch.empty(B, 2 * Hl, 2 * Wl, Cout, device="cuda")
+        t, wp, wb = ws_for(B, 2 * Hl, 2 * Wl, Cout)
+        both(lambda: lib.otgan_conv2d_up2_fprop_tf32(B, Hl, Wl, Cin, Cout, k, k, 2, 2, x.data_ptr(), w_sub.data_ptr(), b.data_ptr(), y.data_ptr(), wp, wb, st), y)
+        dy, w_sub_t = ints(B, 2 * Hl, 2 * Wl, Cout), ints(4, Cin, 9 * Cout, lo=-1, hi=2)
+        dx = torch.empty(B, Hl, Wl, Cin, device="cuda")
+        t, wp, wb = ws_for(B, Hl, Wl, Cin)
+        both(lambda: lib.otgan_conv2d_up2_dgrad_tf32(B, Hl, Wl, Cin, Cout, k, k, 2, 2, dy.data_ptr(), w_sub_t.data_ptr(), dx.data_ptr(), wp, wb, st), dx)
+    finally:
+        lib.otgan_conv_set_option(0, 1)

@@ -28,10 +28,12 @@ def test_adam_ema_kernel_vs_oracle():
     np.testing.assert_allclose(opt.state["mg"].cpu().numpy(), mg, rtol=1e-4, atol=1e-9)    # fp32 state vs fp64 oracle
 
 
-def test_crelu_l2norm_kernel_fwd_bwd():
+@pytest.mark.parametrize("C", [96, 6])
+def test_crelu_l2norm_kernel_fwd_bwd(C):
+    """C = 96: float4 path; C = 6: scalar path of otgan_crelu_l2norm_{fwd,bwd}_f32."""
     from otgan_b200.utils import nn
     torch.manual_seed(0)
-    x = torch.randn(5, 4, 4, 96, device="cuda", requires_grad=True)
+    x = torch.randn(5, 4, 4, C, device="cuda", requires_grad=True)
     y = nn.crelu_l2norm(x)
     gy = torch.randn_like(y)
     (gx,) = torch.autograd.grad([y], [x], [gy])
