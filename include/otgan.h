@@ -192,8 +192,10 @@ OTGAN_API size_t otgan_workspace_bytes_conv_wgrad(int B, int H, int W, int Cin, 
 OTGAN_API int otgan_conv2d_wgrad_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top,
                                       int pad_left, const float* dy, const float* x, float* dw_ohwi, void* ws,
                                       size_t ws_bytes, void* stream);
-/* A/B switch for measurements (process-wide): option 0 = let fprop / dgrad use the 256 x 256-tile kernel variant where it
- * applies (default 1); 0 forces the 128 x 256-tile kernel.  Results are identical either way up to the summation order. */
+/* A/B switches for measurements and tests (process-wide).  option 0: let fprop / dgrad use the 256 x 256-tile kernel variant
+ * where it applies (default 1); option 1: cut the last partial wave of tiles into shares of the filter taps (default 0: no
+ * measured gain); option 2: minimum K-chunks per tile for option 0 (default 500).  Results are identical either way up to
+ * the floating-point summation order. */
 OTGAN_API int otgan_conv_set_option(int option, int value);
 OTGAN_API int otgan_ohwi_to_ihwo_f32(int Cout, int taps, int Cin, const float* w_ohwi, float* w_ihwo, void* stream);
 /* ---- fused 2x nearest-neighbour upsample + convolution (models/dcgan.py:37-46: resize_nearest_neighbor -> nn.conv2d) -----------

@@ -252,8 +252,9 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
 // K-chunk) is what a 128 x 256 tile needs at the full MMA rate, so the kernel is bound by operand delivery, not by the tensor
 // pipe or by wave quantisation (cutting the last wave into shares changed nothing).  This variant gives each CTA TWO 128-pixel
 // sub-tiles that share one 256-row weight tile: 64 KB per 1024 cycles of MMA = 64 B/clk.  Both accumulators (2 x 256 columns)
-// fill TMEM, so the epilogue no longer overlaps the next tile's MMAs; it is used when a tile has >= 100 K-chunks (epilogue
-// <= 10% of the tile) and the launch still has >= 0.75 waves of the bigger tiles.
+// fill TMEM, so the epilogue no longer overlaps the next tile's MMAs.  Measured: +12% on launches whose tiles have >= 500
+// K-chunks, -10% on short tiles -- the convolutions run power-capped (~1.7 GHz), so less data movement only pays where the
+// un-overlapped epilogue is negligible.  Used for tiles of >= 500 K-chunks in launches with >= 0.75 waves of the bigger tiles.
 constexpr int G2_TN = 256;
 constexpr int G2_B_TILE = G2_TN * BK * 4;                     // 32 KB
 constexpr int G2_STAGE_BYTES = 2 * A_TILE + G2_B_TILE;        // 64 KB
@@ -804,7 +805,14 @@ int tail_splits_for(int r, int min_taps)
     return best;
 }
 
-bool g_use_gemm2 = true;      // A/B switch for the 256 x 256 variant (otgan_conv_set_option)
+// A/B switches (otgan_conv_set_option).  Both experiments were measured on B200 with the kernels power-capped (sw_power_cap,
+// SM clock ~1.7 GHz, 700-780 TFLOP/s TF32):
+//  * 256 x 256 tiles: +12% on launches with very long tiles (critic conv2d_3 fprop, fused-upsample dgrad of generator
+//    conv2d_1), -10% on short ones (un-overlapped epilogue) -> used only for tiles of >= 500 K-chunks;
+//  * tail split: no measurable change (the chip, not the per-SM schedule, limits throughput) -> off by default.
+bool g_use_gemm2 = true;
+bool g_tail_split = false;
+int g_gemm2_min_chunks = 500;
 
 // finish a fprop / dgrad launch: pick the split, point the kernel at the workspace, launch, reduce
 template <int TN>
@@ -827,7 +835,7 @@ int run_gemm(GemmParams& p, int TN, size_t out_numel, float* out, void* ws, size
     p.tail_ws = nullptr;
     // 256 x 256 tiles (two sub-tiles share the weight tile) when the launch keeps >= 0.75 waves of them and a tile is long
     // enough to amortise the un-overlapped epilogue
-    if (g_use_gemm2 && p.splits == 1 && TN == 256 && (p.m_tiles & 1) == 0 && tiles / 2 >= (kNumSMs * 3) / 4 && min_taps * p.kchunks >= 100) {
+    if (g_use_gemm2 && p.splits == 1 && TN == 256 && (p.m_tiles & 1) == 0 && tiles / 2 >= (kNumSMs * 3) / 4 && min_taps * p.kchunks >= g_gemm2_min_chunks) {
         p.n_items = tiles / 2;
         static bool attr2 = false;
         if (!attr2) {
@@ -840,7 +848,7 @@ int run_gemm(GemmParams& p, int TN, size_t out_numel, float* out, void* ws, size
         return OTGAN_OK;
     }
     int n_tail = 0;
-    if (p.splits == 1 && TN >= 128 && ws) {              // cut the last, partial wave of tiles along the taps
+    if (g_tail_split && p.splits == 1 && TN >= 128 && ws) {   // cut the last, partial wave of tiles along the taps
         n_tail = tiles % kNumSMs;
         const int S = tail_splits_for(n_tail, min_taps);
         if (S > 1 && ws_bytes >= (size_t)n_tail * S * TM * TN * sizeof(float)) {
@@ -1332,10 +1340,13 @@ int conv_up2_wgrad_launch(int B, int Hl, int Wl, int Cin, int Cout, int kh, int 
     return OTGAN_OK;
 }
 
-// A/B switches for benchmarking: option 0 = use the 256 x 256 tile variant of the fprop / dgrad kernel (default 1)
+// A/B switches for benchmarking / tests: 0 = use the 256 x 256 tile variant of the fprop / dgrad kernel (default 1),
+// 1 = cut the last partial wave of tiles into shares of the taps (default 0), 2 = minimum K-chunks per tile for option 0 (500)
 int conv_set_option(int option, int value)
 {
     if (option == 0) { g_use_gemm2 = value != 0; return OTGAN_OK; }
+    if (option == 1) { g_tail_split = value != 0; return OTGAN_OK; }
+    if (option == 2) { g_gemm2_min_chunks = value < 1 ? 1 : value; return OTGAN_OK; }
     set_error("conv_set_option: unknown option %d", option);
     return OTGAN_EINVAL;
 }

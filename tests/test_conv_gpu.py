@@ -88,8 +88,14 @@ def _run_ref(shape, x, w, b, dy):
 
 @pytest.mark.parametrize("shape", SHAPES)
 def test_conv_kernels_exact_on_integer_inputs(shape):
+    from otgan_b200 import _lib
     x, w, b, dy = _make(shape, True, 1)
-    ours = _run_ours(shape, x, w, b, dy)
+    tail = shape[0] >= 80                       # the two shapes with a partial last wave: also exercise the tail-split option
+    _lib.load().otgan_conv_set_option(1, 1 if tail else 0)
+    try:
+        ours = _run_ours(shape, x, w, b, dy)
+    finally:
+        _lib.load().otgan_conv_set_option(1, 0)
     ref = _run_ref(shape, x, w, b, dy)
     for name, o, r in zip(("fprop", "dgrad", "wgrad", "bias-grad"), ours, ref):
         diff = (o.double() - r).abs()
@@ -384,6 +390,7 @@ def test_256_row_tile_variant_matches_the_128_row_kernel():
 
     def both(fn, out):
         res = []
+        assert lib.otgan_conv_set_option(2, 100) == 0        # admit every launch of this test to the 256-row variant
         for v in (1, 0):
             assert lib.otgan_conv_set_option(0, v) == 0
             out.fill_(float("nan"))
@@ -429,3 +436,4 @@ def test_256_row_tile_variant_matches_the_128_row_kernel():
         both(lambda: lib.otgan_conv2d_up2_dgrad_tf32(B, Hl, Wl, Cin, Cout, k, k, 2, 2, dy.data_ptr(), w_sub_t.data_ptr(), dx.data_ptr(), wp, wb, st), dx)
     finally:
         lib.otgan_conv_set_option(0, 1)
+        lib.otgan_conv_set_option(2, 500)
