@@ -197,6 +197,14 @@ OTGAN_API int otgan_conv2d_wgrad_tf32(int B, int H, int W, int Cin, int Cout, in
  * measured gain); option 2: minimum K-chunks per tile for option 0 (default 500).  Results are identical either way up to
  * the floating-point summation order. */
 OTGAN_API int otgan_conv_set_option(int option, int value);
+/* Host-only introspection (no GPU, no driver): the kernel parameters -- tile boxes, parity classes, filter-tap tables
+ * (view, pixel shift, weight column / row), output strides, split factors, kernel variant -- that one convolution pass would
+ * be launched with.  op: 0 fprop, 1 dgrad, 2 wgrad, 3 / 4 / 5 the fused-upsample fprop / dgrad / wgrad (H, W = the LOW-
+ * resolution extent).  Writes long long values into out_host (layout documented at conv_plan_describe in conv_tc.cu) and
+ * returns their number, or a negative error.  tests/test_conv_plan_host.py replays these tables in numpy against the
+ * reference convolution, so the host logic of the kernels is checked on a machine without a GPU. */
+OTGAN_API int otgan_conv_plan_describe(int op, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top,
+                                       int pad_left, long long* out_host, int capacity);
 OTGAN_API int otgan_ohwi_to_ihwo_f32(int Cout, int taps, int Cin, const float* w_ohwi, float* w_ihwo, void* stream);
 /* ---- fused 2x nearest-neighbour upsample + convolution (models/dcgan.py:37-46: resize_nearest_neighbor -> nn.conv2d) -----------
  * y [B, 2Hl, 2Wl, Cout] = conv(upsample2x(x_low [B, Hl, Wl, Cin]), W, stride 1, 'SAME') + bias without materialising the

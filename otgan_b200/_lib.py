@@ -60,6 +60,7 @@ SIGNATURES = {
     "otgan_workspace_bytes_conv_wgrad": (_sz, [_i] * 8),
     "otgan_conv2d_wgrad_tf32": (_i, [_i] * 10 + [_vp, _vp, _vp, _vp, _sz, _vp]),
     "otgan_conv_set_option": (_i, [_i, _i]),
+    "otgan_conv_plan_describe": (_i, [_i] * 11 + [ctypes.POINTER(ctypes.c_longlong), _i]),
     "otgan_ohwi_to_ihwo_f32": (_i, [_i, _i, _i, _vp, _vp, _vp]),
     "otgan_up2_subtaps": (_i, [_i, _i]),
     "otgan_up2_weight_presum_f32": (_i, [_i] * 6 + [_vp, _vp, _vp]),

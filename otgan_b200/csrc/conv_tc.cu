@@ -769,10 +769,30 @@ bool pixel_box(int npix, int Wt, int Ht, int Bt, int* bw, int* bh, int* bn)
     return (*bw) * (*bh) * (*bn) == npix && Bt % *bn == 0 && *bn <= 256;
 }
 
+// ---- plan capture (otgan_conv_plan_describe): the launch functions run unchanged up to the point of the kernel launch, with
+// tensor-map encoding skipped (no driver needed), and hand their kernel parameters over instead of launching.  Lets the
+// CPU tests check the very tap tables / classes / strides / splits the GPU kernels would receive.
+struct PlanCapture {
+    bool active = false;
+    int kind = -1;            // 0: conv_gemm_tc_kernel, 1: conv_gemm2_tc_kernel, 2: conv_wgrad_tc_kernel
+    int TN = 0, n_tail = 0;
+    GemmParams gemm;
+    WgradParams wgrad;
+};
+thread_local PlanCapture* t_capture = nullptr;
+inline bool capturing() { return t_capture && t_capture->active; }
+
+bool conv_map_2d(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows, int box_cols, CUtensorMapSwizzle swz)
+{
+    if (capturing()) return true;
+    return make_tensor_map_2d(map, base, rows, cols, ld, box_rows, box_cols, swz);
+}
+
 // 4-D view of an NHWC tensor [B, H, W, C] sub-sampled by `s` starting at pixel (ph, pw): dims [C, W/s, H/s, B]
 bool make_view_map(CUtensorMap* map, const float* base, int B, int H, int W, int C, int s, int ph, int pw,
                    const unsigned box[4], CUtensorMapSwizzle swz)
 {
+    if (capturing()) return true;
     const unsigned long long dims[4] = {(unsigned long long)C, (unsigned long long)(W / s), (unsigned long long)(H / s), (unsigned long long)B};
     const unsigned long long str[3] = {(unsigned long long)s * C * 4, (unsigned long long)s * W * C * 4, (unsigned long long)H * W * C * 4};
     return make_tensor_map_nd(map, base + ((size_t)ph * W + pw) * C, 4, dims, str, box, swz);
@@ -837,6 +857,7 @@ int run_gemm(GemmParams& p, int TN, size_t out_numel, float* out, void* ws, size
     // enough to amortise the un-overlapped epilogue
     if (g_use_gemm2 && p.splits == 1 && TN == 256 && (p.m_tiles & 1) == 0 && tiles / 2 >= (kNumSMs * 3) / 4 && min_taps * p.kchunks >= g_gemm2_min_chunks) {
         p.n_items = tiles / 2;
+        if (capturing()) { t_capture->kind = 1; t_capture->TN = 256; t_capture->gemm = p; return OTGAN_OK; }
         static bool attr2 = false;
         if (!attr2) {
             OTGAN_CUDA(cudaFuncSetAttribute(conv_gemm2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM_BYTES));
@@ -862,6 +883,7 @@ int run_gemm(GemmParams& p, int TN, size_t out_numel, float* out, void* ws, size
     p.n_items = p.n_full + n_tail * p.tail_splits;
     const int rc = TN == 256 ? launch_gemm<256>(p, stream) : TN == 128 ? launch_gemm<128>(p, stream) : launch_gemm<16>(p, stream);
     if (rc != OTGAN_OK) return rc;
+    if (capturing()) { t_capture->n_tail = n_tail; return OTGAN_OK; }
     if (n_tail > 0) {
         if (TN == 256) conv_tail_fixup_kernel<256><<<n_tail, 256, 0, stream>>>(p);
         else conv_tail_fixup_kernel<128><<<n_tail, 256, 0, stream>>>(p);
@@ -880,6 +902,7 @@ int run_gemm(GemmParams& p, int TN, size_t out_numel, float* out, void* ws, size
 template <int TN>
 int launch_gemm(const GemmParams& p, cudaStream_t stream)
 {
+    if (capturing()) { t_capture->kind = 0; t_capture->TN = TN; t_capture->gemm = p; return OTGAN_OK; }
     static bool attr_set = false;
     if (!attr_set) {
         OTGAN_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<TN>::SMEM_BYTES));
@@ -894,6 +917,7 @@ int launch_gemm(const GemmParams& p, cudaStream_t stream)
 template <int TN>
 int launch_wgrad(const WgradParams& p, cudaStream_t stream)
 {
+    if (capturing()) { t_capture->kind = 2; t_capture->TN = TN; t_capture->wgrad = p; return OTGAN_OK; }
     static bool attr_set = false;
     if (!attr_set) {
         OTGAN_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<TN>::SMEM_BYTES));
@@ -970,7 +994,7 @@ int conv_fprop_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
         for (int pw = 0; pw < s; ++pw)
             if (!make_view_map(&p.amap[ph * s + pw], x, B, H, W, Cin, s, ph, pw, box, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
     for (int i = s * s; i < 4; ++i) p.amap[i] = p.amap[0];
-    if (!make_tensor_map_2d(&p.bmap, w, Cout, kh * kw * Cin, kh * kw * Cin, brows, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
+    if (!conv_map_2d(&p.bmap, w, Cout, kh * kw * Cin, kh * kw * Cin, brows, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
     int nt = 0;
     for (int a = 0; a < kh; ++a)
         for (int b = 0; b < kw; ++b) {
@@ -1008,7 +1032,7 @@ int conv_dgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
     const unsigned box[4] = {(unsigned)BK, (unsigned)p.bw, (unsigned)p.bh, (unsigned)p.bn};
     if (!make_view_map(&p.amap[0], dy, B, Ho, Wo, Cout, 1, 0, 0, box, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
     for (int i = 1; i < 4; ++i) p.amap[i] = p.amap[0];
-    if (!make_tensor_map_2d(&p.bmap, wt, Cin, kh * kw * Cout, kh * kw * Cout, brows, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
+    if (!conv_map_2d(&p.bmap, wt, Cin, kh * kw * Cout, kh * kw * Cout, brows, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
     // parity classes of the input pixel (ih, iw): ih = s*j + ph gets the taps with (ph + pt - a) % s == 0, from output row
     // oh = j + (ph + pt - a) / s
     int nt = 0;
@@ -1094,7 +1118,7 @@ int conv_wgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
         p.out = dw;
     }
     const int rc = TN == 256 ? launch_wgrad<256>(p, stream) : launch_wgrad<128>(p, stream);
-    if (rc != OTGAN_OK || p.splits == 1) return rc;
+    if (rc != OTGAN_OK || p.splits == 1 || capturing()) return rc;
     const size_t n4 = (size_t)p.split_stride / 4;
     const int grid = (int)((n4 + 255) / 256 < (size_t)(8 * kNumSMs) ? (n4 + 255) / 256 : (size_t)(8 * kNumSMs));
     split_reduce_kernel<<<grid, 256, 0, stream>>>(n4, p.splits, n4, reinterpret_cast<const float4*>(p.out), reinterpret_cast<float4*>(dw));
@@ -1212,7 +1236,7 @@ int conv_up2_fprop_launch(int B, int Hl, int Wl, int Cin, int Cout, int kh, int 
     const unsigned box[4] = {(unsigned)BK, (unsigned)p.bw, (unsigned)p.bh, (unsigned)p.bn};
     if (!make_view_map(&p.amap[0], x_low, B, Hl, Wl, Cin, 1, 0, 0, box, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
     for (int i = 1; i < 4; ++i) p.amap[i] = p.amap[0];
-    if (!make_tensor_map_2d(&p.bmap, w_sub, 4 * Cout, slots * Cin, slots * Cin, TN, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
+    if (!conv_map_2d(&p.bmap, w_sub, 4 * Cout, slots * Cin, slots * Cin, TN, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
     p.n_valid = Cout; p.b_box_bytes = TN * BK * 4;
     int nt = 0;
     p.n_cls = 4;
@@ -1253,7 +1277,7 @@ int conv_up2_dgrad_launch(int B, int Hl, int Wl, int Cin, int Cout, int kh, int 
     for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 2; ++b)
             if (!make_view_map(&p.amap[2 * a + b], dy, B, 2 * Hl, 2 * Wl, Cout, 2, a, b, box, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
-    if (!make_tensor_map_2d(&p.bmap, w_sub_t, 4 * Cin, slots * Cout, slots * Cout, TN, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
+    if (!conv_map_2d(&p.bmap, w_sub_t, 4 * Cin, slots * Cout, slots * Cout, TN, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
     p.n_valid = Cin; p.b_box_bytes = TN * BK * 4;
     int nt = 0;
     p.n_cls = 1;
@@ -1332,12 +1356,70 @@ int conv_up2_wgrad_launch(int B, int Hl, int Wl, int Cin, int Cout, int kh, int 
         p.out = dw_sub;
     }
     const int rc = TN == 256 ? launch_wgrad<256>(p, stream) : launch_wgrad<128>(p, stream);
-    if (rc != OTGAN_OK || p.splits == 1) return rc;
+    if (rc != OTGAN_OK || p.splits == 1 || capturing()) return rc;
     const size_t n4 = (size_t)p.split_stride / 4;
     const int grid = (int)((n4 + 255) / 256 < (size_t)(8 * kNumSMs) ? (n4 + 255) / 256 : (size_t)(8 * kNumSMs));
     split_reduce_kernel<<<grid, 256, 0, stream>>>(n4, p.splits, n4, reinterpret_cast<const float4*>(p.out), reinterpret_cast<float4*>(dw_sub));
     OTGAN_CHECK_LAUNCH("split_reduce_kernel");
     return OTGAN_OK;
+}
+
+// Serialises the kernel parameters one of the six convolution passes WOULD be launched with (no GPU, no driver needed).
+// op: 0 fprop, 1 dgrad, 2 wgrad, 3 fused-upsample fprop, 4 fused-upsample dgrad, 5 fused-upsample wgrad (H, W = low-res then).
+// Layout of out[] (all long long):
+//   gemm kernels (kind 0 / 1): kind, TN, n_cls, n_items, splits, m_tiles, n_tiles, bw, bh, bn, tiles_w, tiles_h, kchunks,
+//        n_valid, osW, osH, osN, n_full, tail_splits, n_tail, ntaps, cls_tap_begin[5], cls_out_off[4], then ntaps x
+//        (map, dw, dh, wcol, brow, dmap)
+//   wgrad kernel (kind 2): kind, TN, ntaps, co_tiles, ci_tiles, splits, n_items, bw, bh, bn, tiles_w, tiles_h, nchunks,
+//        chunks_per_split, ldw, split_stride, then ntaps x (map, dw, dh, wcol, brow, dmap)
+int conv_plan_describe(int op, int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl,
+                       long long* out, int cap)
+{
+    static float dummy_storage[64];
+    float* dummy = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dummy_storage) + 63) & ~(uintptr_t)63);
+    void* big_ws = reinterpret_cast<void*>(dummy);            // never dereferenced: nothing is launched while capturing
+    const size_t big = (size_t)1 << 40;
+    PlanCapture cap_state;
+    cap_state.active = true;
+    t_capture = &cap_state;
+    int rc = OTGAN_EINVAL;
+    switch (op) {
+    case 0: rc = conv_fprop_launch(B, H, W, Cin, Cout, kh, kw, s, pt, pl, H / s, W / s, dummy, dummy, nullptr, dummy, big_ws, big, nullptr); break;
+    case 1: rc = conv_dgrad_launch(B, H, W, Cin, Cout, kh, kw, s, pt, pl, H / s, W / s, dummy, dummy, dummy, big_ws, big, nullptr); break;
+    case 2: rc = conv_wgrad_launch(B, H, W, Cin, Cout, kh, kw, s, pt, pl, H / s, W / s, dummy, dummy, dummy, big_ws, big, nullptr); break;
+    case 3: rc = conv_up2_fprop_launch(B, H, W, Cin, Cout, kh, kw, pt, pl, dummy, dummy, nullptr, dummy, big_ws, big, nullptr); break;
+    case 4: rc = conv_up2_dgrad_launch(B, H, W, Cin, Cout, kh, kw, pt, pl, dummy, dummy, dummy, big_ws, big, nullptr); break;
+    case 5: rc = conv_up2_wgrad_launch(B, H, W, Cin, Cout, kh, kw, pt, pl, dummy, dummy, dummy, big_ws, big, nullptr); break;
+    default: set_error("conv_plan_describe: unknown op %d", op);
+    }
+    t_capture = nullptr;
+    if (rc != OTGAN_OK) return rc;
+    int n = 0;
+    auto put = [&](long long v) { if (n < cap) out[n] = v; ++n; };
+    auto put_taps = [&](const Tap* taps, int nt) {
+        for (int t = 0; t < nt; ++t) { put(taps[t].map); put(taps[t].dw); put(taps[t].dh); put(taps[t].wcol); put(taps[t].brow); put(taps[t].dmap); }
+    };
+    if (cap_state.kind == 0 || cap_state.kind == 1) {
+        const GemmParams& g = cap_state.gemm;
+        const int nt = g.cls_tap_begin[g.n_cls];
+        put(cap_state.kind); put(cap_state.TN); put(g.n_cls); put(g.n_items); put(g.splits); put(g.m_tiles); put(g.n_tiles);
+        put(g.bw); put(g.bh); put(g.bn); put(g.tiles_w); put(g.tiles_h); put(g.kchunks); put(g.n_valid);
+        put(g.osW); put(g.osH); put(g.osN); put(g.n_full); put(g.tail_splits); put(cap_state.n_tail); put(nt);
+        for (int c = 0; c < 5; ++c) put(g.cls_tap_begin[c]);
+        for (int c = 0; c < 4; ++c) put(g.cls_out_off[c]);
+        put_taps(g.taps, nt);
+    } else if (cap_state.kind == 2) {
+        const WgradParams& g = cap_state.wgrad;
+        put(2); put(cap_state.TN); put(g.ntaps); put(g.co_tiles); put(g.ci_tiles); put(g.splits); put(g.n_items);
+        put(g.bw); put(g.bh); put(g.bn); put(g.tiles_w); put(g.tiles_h); put(g.nchunks); put(g.chunks_per_split);
+        put(g.ldw); put(g.split_stride);
+        put_taps(g.taps, g.ntaps);
+    } else {
+        set_error("conv_plan_describe: nothing was captured");
+        return OTGAN_EINVAL;
+    }
+    if (n > cap) { set_error("conv_plan_describe: needs %d values, buffer holds %d", n, cap); return OTGAN_ENOSPC; }
+    return n;
 }
 
 // A/B switches for benchmarking / tests: 0 = use the 256 x 256 tile variant of the fprop / dgrad kernel (default 1),

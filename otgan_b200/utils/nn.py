@@ -17,8 +17,12 @@ TensorFlow semantics that differ from PyTorch defaults are restated explicitly: 
 `tf.nn.l2_normalize` (x * rsqrt(max(sum x^2, 1e-12))), nearest-neighbour resize (src = dst // 2), CReLU over a LIST of
 inputs interleaved per element ([x0, -x0, x1, -x1, ...], utils/nn.py:198-200).
 
-Convolutions / matmuls currently run on cuDNN / cuBLAS through torch (library rung); the
-optimiser update (adam_updates + EMA) runs in this library's fused CUDA kernel (otgan_adam_ema_f32).
+On the GPU the layers run on this library's CUDA kernels through the C ABI (include/otgan.h): nn.conv2d on the tcgen05
+implicit-GEMM convolutions (_ConvTC: fprop / dgrad / wgrad; _ConvUp2TC: the generator's resize + convolution pairs in the
+fused sub-pixel form; _ConvNarrow: the two 3-channel layers), weight norm, CReLU, GLU, the critic head and Adam+EMA on
+their fused kernels.  Shapes the convolution kernels do not tile (DenseNet's 16-filter layers, odd batch sizes) and the
+100-wide dense layer go to cuDNN / cuBLAS through torch (CONV_BACKEND = "cudnn" forces that rung everywhere, for A/B
+tests).  CPU tensors take the literal torch op sequence (host-side tests only; there is no CPU product path).
 """
 import contextlib
 import math
