@@ -226,3 +226,40 @@ def test_launch_configuration_choices(lib):
     buf = (ctypes.c_longlong * 4)()
     assert lib.otgan_conv_plan_describe(0, 8, 8, 8, 32, 128, 5, 5, 1, 2, 2, buf, 4) == -3            # OTGAN_ENOSPC
     assert lib.otgan_conv_plan_describe(0, 8, 8, 8, 3, 128, 5, 5, 1, 2, 2, buf, 4) == -4             # unsupported channels
+    assert lib.otgan_conv_plan_describe(0, 8, 8, 8, 32, 128, 7, 7, 1, 3, 3, buf, 4) == -1            # 49 taps > tap table
+
+
+GEOMS = [  # (B, H, W, k, s): rectangular images, 1x1 / 3x3 / 5x5 filters, boxes spanning several images or several rows
+    (4, 16, 8, 5, 1), (4, 16, 8, 5, 2), (2, 32, 32, 3, 1), (16, 4, 4, 5, 1), (32, 4, 4, 3, 2), (1, 16, 8, 1, 1),
+    (2, 8, 32, 5, 1), (16, 8, 4, 5, 2), (2, 32, 16, 3, 2), (64, 2, 2, 3, 1),
+]
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_tap_tables_on_rectangular_and_small_geometries(lib, geom):
+    """fprop, dgrad and wgrad tables over a spread of geometries (H != W, boxes covering several images, k in 1..5; 7x7 = 49 taps exceeds the 40-entry tap table and is rejected)."""
+    B, H, W, k, s = geom
+    rng = np.random.RandomState(sum(geom))
+    pad_t, pad_l = same_pad(H, k, s)[0], same_pad(W, k, s)[0]
+    assert pad_t == pad_l
+    C1, C2 = 128, 128
+    x = torch.from_numpy(rng.randn(B, H, W, C1)).requires_grad_(True)
+    w = torch.from_numpy(rng.randn(C2, k, k, C1)).requires_grad_(True)
+    dy = rng.randn(B, H // s, W // s, C2)
+    y_ref = ref_conv(x, w, k, s)
+    dx_ref, dw_ref = torch.autograd.grad([y_ref], [x, w], [torch.from_numpy(dy)])
+    d = describe(lib, "fprop", B, H, W, C1, C2, k, s, pad_t)
+    structural_checks(d, B * (H // s) * (W // s), C1)
+    out = replay_gemm(d, x.detach().numpy(), s, w.detach().numpy().reshape(C2, -1), C2, C1, (B, H // s, W // s), y_ref.numel())
+    np.testing.assert_allclose(out.reshape(y_ref.shape), y_ref.detach().numpy(), rtol=0, atol=1e-9)
+    d = describe(lib, "dgrad", B, H, W, C1, C2, k, s, pad_t)
+    structural_checks(d, B * (H // s) * (W // s), C2)
+    w_ihwo = w.detach().numpy().reshape(C2, k * k, C1).transpose(2, 1, 0).reshape(C1, -1)
+    out = replay_gemm(d, dy, 1, w_ihwo, C1, C2, (B, H // s, W // s), B * H * W * C1)
+    np.testing.assert_allclose(out.reshape(B, H, W, C1), dx_ref.numpy(), rtol=0, atol=1e-9)
+    d = describe(lib, "wgrad", B, H, W, C1, C2, k, s, pad_t)
+    dw = np.zeros((C2, d["ldw"]))
+    for t in d["taps"]:
+        a = shifted(view(x.detach().numpy(), s, t["map"]), t["dh"], t["dw"])
+        dw[t["brow"]:t["brow"] + C2, t["wcol"]:t["wcol"] + C1] += np.einsum("nijo,nijc->oc", view(dy, 1, t["dmap"]), a)
+    np.testing.assert_allclose(dw.reshape(C2, k, k, C1), dw_ref.numpy(), rtol=0, atol=1e-8)
