@@ -75,10 +75,6 @@ OTGAN_API int otgan_sinkhorn_f32(int nblk, int rows, int cols, int T, float lam,
                        const float* L0 /* [nblk, rows, cols] */, float* P /* [nblk, rows, cols] */,
                        float* entropy /* [nblk] */, float* pc /* [nblk] */, int impl, void* stream);
 
-/* A/B switch of the persistent kernel's register tiling (process-wide): 4 rows per thread = 256 threads per block, 2 rows =
- * 512 threads (twice the warps per scheduler to hide the half-step's latency chain).  Same arithmetic and summation order. */
-OTGAN_API int otgan_sinkhorn_set_tile_rows(int rows_per_thread);
-
 /* Same, additionally reporting per block how many half-steps took the slow (log-domain, max-subtracted) path of the
  * scaling-form kernel (slow_steps: [nblk] ints or NULL); impl = OTGAN_IMPL_SIMT selects the literal log-domain kernel. */
 OTGAN_API int otgan_sinkhorn_ex_f32(int nblk, int rows, int cols, int T, float lam, const float* L0, float* P,

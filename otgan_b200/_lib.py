@@ -34,7 +34,6 @@ SIGNATURES = {
     "otgan_workspace_bytes_cost": (_sz, [_i, _i, _i, _i, _i]),
     "otgan_cost_blocks_f32": (_i, [_i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _f, _vp, _vp, _sz, _i, _vp]),
     "otgan_sinkhorn_f32": (_i, [_i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _i, _vp]),
-    "otgan_sinkhorn_set_tile_rows": (_i, [_i]),
     "otgan_sinkhorn_ex_f32": (_i, [_i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "otgan_workspace_bytes_plan": (_sz, []),
     "otgan_plan_apply_f32": (_i, [ctypes.POINTER(Plan), _i, _i, _vp, _vp, _i, _vp, _i, _vp, _sz, _i, _vp]),

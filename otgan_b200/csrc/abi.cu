@@ -74,7 +74,6 @@ int conv_wgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
 int ohwi_to_ihwo_launch(int Cout, int T, int Cin, const float* w, float* wt, cudaStream_t stream);
 size_t colsum_workspace_bytes(int P, int C);
 int conv_set_option(int option, int value);
-extern int g_sinkhorn_tile_rows;
 int conv_plan_describe(int op, int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, long long* out, int cap);
 int up2_subtaps(int k, int pad);
 int up2_presum_launch(int Cout, int kh, int kw, int Cin, int pt, int pl, const float* w, float* w_sub, cudaStream_t stream);
@@ -489,13 +488,6 @@ int otgan_conv_plan_describe(int op, int B, int H, int W, int Cin, int Cout, int
     OTGAN_REQUIRE(out_host && capacity > 0, "conv_plan_describe: null output");
     OTGAN_REQUIRE(op >= 3 || stride == 1 || stride == 2, "conv_plan_describe: stride %d not in {1, 2}", stride);
     return conv_plan_describe(op, B, H, W, Cin, Cout, kh, kw, op >= 3 ? 1 : stride, pad_top, pad_left, out_host, capacity);
-}
-
-int otgan_sinkhorn_set_tile_rows(int rows_per_thread)
-{
-    OTGAN_REQUIRE(rows_per_thread == 2 || rows_per_thread == 4, "sinkhorn_set_tile_rows: %d not in {2, 4}", rows_per_thread);
-    g_sinkhorn_tile_rows = rows_per_thread;
-    return OTGAN_OK;
 }
 
 }  // extern "C"

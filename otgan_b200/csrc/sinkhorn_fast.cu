@@ -22,13 +22,7 @@ namespace otgan {
 
 namespace {
 
-constexpr int H = 128, LDS_ = 132;                   // 132-word rows: float4 aligned, conflict-free for both copies
-constexpr int MAX_WARPS = 16;
-// R = rows of the register tile per thread: 4 -> 256 threads (8 warps, 2 per scheduler), 2 -> 512 threads (16 warps, 4 per
-// scheduler).  The half-step is a latency chain (LDS -> FMAs -> shuffles -> rcp -> STS -> barrier) issued by only two warps per
-// scheduler at R = 4 (ncu: issue slots 38 % used, ~850 cycles per half-step for 182 instructions per warp); R = 2 halves the
-// instructions per warp and doubles the warps that can fill each other's stalls.
-template <int R> struct Tile { static constexpr int NT = 1024 / R; };
+constexpr int H = 128, NTHREADS = 256, LDS_ = 132;   // 132-word rows: float4 aligned, conflict-free for both copies
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 constexpr float S_LO = 9.094947017729282e-13f /* 2^-40 */, S_HI = 1099511627776.f /* 2^40 */;
 
@@ -37,7 +31,7 @@ struct Smem {
     float L0T[H * LDS_];       // L0T[c][r]
     float f[H], g[H];          // absorbed potentials (natural-log units)
     float u[2][H], v[2][H];    // scaling vectors, double buffered
-    float red[2][MAX_WARPS];
+    float red[2][NTHREADS / 32];
 };
 
 // s[4]: per-lane partials for the 4 tile lines; returns the total over the 8 lanes that share them for tile line
@@ -56,17 +50,7 @@ __device__ __forceinline__ float oct_reduce_scatter4(const float (&s)[4], int la
     t += __shfl_xor_sync(0xffffffffu, t, 1);
     return t;
 }
-// s[2]: per-lane partials for the 2 tile lines; all four lanes with the same (lane & 4) hold the total of line (lane >> 2) & 1
-__device__ __forceinline__ float oct_reduce_scatter2(const float (&s)[2], int lane)
-{
-    const bool b2 = lane & 4;
-    float t = (b2 ? s[1] : s[0]) + __shfl_xor_sync(0xffffffffu, b2 ? s[0] : s[1], 4);
-    t += __shfl_xor_sync(0xffffffffu, t, 2);
-    t += __shfl_xor_sync(0xffffffffu, t, 1);
-    return t;
-}
-template <int R>
-__global__ void __launch_bounds__(Tile<R>::NT, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float* __restrict__ entropy,
                      float* __restrict__ pc, int* __restrict__ slow_steps, int rows, int cols, int T, float lam)
 {
@@ -74,11 +58,9 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int lg = lane >> 3, g8 = lane & 7;
-    constexpr int NTHREADS = Tile<R>::NT;
-    const int base4 = 4 * R * warp + R * lg;     // first of the R tile rows (row copy) / tile columns (column copy)
+    const int base4 = 16 * warp + 4 * lg;        // first of the 4 tile rows (row copy) / tile columns (column copy)
     // the 4 x 4 columns (row copy) / rows (column copy) of this lane: float4 groups g8 + 8m, m = 0..3
-    const int my_idx = R == 4 ? (lane >> 1) & 3 : (lane >> 2) & 1;     // tile line whose total this lane holds after the reduce-scatter
-    const bool writer = R == 4 ? (lane & 1) == 0 : (lane & 3) == 0;    // one of the lanes that hold it stores it
+    const int my_idx = (lane >> 1) & 3;          // tile line whose total this lane holds after the reduce-scatter
     const int my_line = base4 + my_idx;
     const size_t boff = (size_t)blockIdx.x * rows * cols;
     const float* __restrict__ Lb = L0g + boff;
@@ -87,10 +69,9 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
     // ---- stage L0 into shared memory, plain and transposed; lanes = 32 consecutive rows -> conflict-free.
     // All 16 loads of a thread are issued before the first store (one L2 round trip instead of sixteen).
     {
-        constexpr int NLD = 4096 / NTHREADS;
-        float4 x[NLD];
+        float4 x[16];
 #pragma unroll
-        for (int j = 0; j < NLD; ++j) {
+        for (int j = 0; j < 16; ++j) {
             const int t = tid + j * NTHREADS;
             const int r = (t >> 10) * 32 + (t & 31), c4 = ((t >> 5) & 31) * 4;
             x[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
@@ -106,7 +87,7 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
             }
         }
 #pragma unroll
-        for (int j = 0; j < NLD; ++j) {
+        for (int j = 0; j < 16; ++j) {
             const int t = tid + j * NTHREADS;
             const int r = (t >> 10) * 32 + (t & 31), c4 = ((t >> 5) & 31) * 4;
             float4 y = x[j];
@@ -121,8 +102,8 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
     }
     __syncthreads();
 
-    float Kr[R][16];    // row copy:    Kr[i][4m + e] = K[base4 + i][4 (g8 + 8m) + e]
-    float Kc[R][16];    // column copy: Kc[j][4m + e] = K[4 (g8 + 8m) + e][base4 + j]
+    float Kr[4][16];    // row copy:    Kr[i][4m + e] = K[base4 + i][4 (g8 + 8m) + e]
+    float Kc[4][16];    // column copy: Kc[j][4m + e] = K[4 (g8 + 8m) + e][base4 + j]
     int ub = 0, vb = 0, n_slow = 0;
 
     auto absorb = [&]() {   // f -= log2 u, g -= log2 v; afterwards u = v = 1 in the current buffers
@@ -135,13 +116,13 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
         __syncthreads();
     };
     // tile of exponents a = (M[line][o] - p_line) - q_o for the 4 tile lines; M = L0 (rows) or L0T (columns)
-    auto load_exponents = [&](const float* M, const float* pl, const float* qo, float (&a)[R][16]) {
+    auto load_exponents = [&](const float* M, const float* pl, const float* qo, float (&a)[4][16]) {
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const int o = 4 * (g8 + 8 * m);
             const float4 q = *reinterpret_cast<const float4*>(&qo[o]);
 #pragma unroll
-            for (int i = 0; i < R; ++i) {
+            for (int i = 0; i < 4; ++i) {
                 const float p = pl[base4 + i];
                 const float4 l = *reinterpret_cast<const float4*>(&M[(base4 + i) * LDS_ + o]);
                 a[i][4 * m + 0] = (l.x - p) - q.x; a[i][4 * m + 1] = (l.y - p) - q.y;
@@ -151,10 +132,10 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
     };
     // max-subtracted log-sum-exp over each of the 4 tile lines; on return a = 2^(a - lse) (line-normalised) and the
     // lane holding line my_idx returns its lse.  nvalid = number of valid lines (rows or cols).
-    auto normalise_lines = [&](float (&a)[R][16], int nvalid) -> float {
+    auto normalise_lines = [&](float (&a)[4][16], int nvalid) -> float {
         float lse = 0.f;
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
+        for (int i = 0; i < 4; ++i) {
             float m = a[i][0];
 #pragma unroll
             for (int e = 1; e < 16; ++e) m = fmaxf(m, a[i][e]);
@@ -173,10 +154,10 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
         }
         return lse;
     };
-    auto rebuild = [&](const float* M, const float* pl, const float* qo, float (&K)[R][16]) {
+    auto rebuild = [&](const float* M, const float* pl, const float* qo, float (&K)[4][16]) {
         load_exponents(M, pl, qo, K);
 #pragma unroll
-        for (int i = 0; i < R; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int e = 0; e < 16; ++e) K[i][e] = ex2_approx(K[i][e] * LOG2E);
     };
@@ -184,7 +165,7 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
         absorb();
         load_exponents(sm.L0, sm.f, sm.g, Kr);
         const float lse = normalise_lines(Kr, rows);
-        if (writer && my_line < rows) sm.f[my_line] += lse;
+        if ((lane & 1) == 0 && my_line < rows) sm.f[my_line] += lse;
         __syncthreads();
         rebuild(sm.L0T, sm.g, sm.f, Kc);
         ++n_slow;
@@ -193,27 +174,26 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
         absorb();
         load_exponents(sm.L0T, sm.g, sm.f, Kc);
         const float lse = normalise_lines(Kc, cols);
-        if (writer && my_line < cols) sm.g[my_line] += lse;
+        if ((lane & 1) == 0 && my_line < cols) sm.g[my_line] += lse;
         __syncthreads();
         rebuild(sm.L0, sm.f, sm.g, Kr);
         ++n_slow;
     };
     // fast half-step: total_line = sum_o K[line][o] * x_o  (the caller takes the reciprocal)
-    auto matvec = [&](const float (&K)[R][16], const float* x) -> float {
+    auto matvec = [&](const float (&K)[4][16], const float* x) -> float {
         float4 xv[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m) xv[m] = *reinterpret_cast<const float4*>(&x[4 * (g8 + 8 * m)]);
-        float s[R];
+        float s[4];
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
+        for (int i = 0; i < 4; ++i) {
             float t0 = K[i][0] * xv[0].x, t1 = K[i][4] * xv[1].x, t2 = K[i][8] * xv[2].x, t3 = K[i][12] * xv[3].x;
             t0 = fmaf(K[i][1], xv[0].y, t0); t1 = fmaf(K[i][5], xv[1].y, t1); t2 = fmaf(K[i][9], xv[2].y, t2); t3 = fmaf(K[i][13], xv[3].y, t3);
             t0 = fmaf(K[i][2], xv[0].z, t0); t1 = fmaf(K[i][6], xv[1].z, t1); t2 = fmaf(K[i][10], xv[2].z, t2); t3 = fmaf(K[i][14], xv[3].z, t3);
             t0 = fmaf(K[i][3], xv[0].w, t0); t1 = fmaf(K[i][7], xv[1].w, t1); t2 = fmaf(K[i][11], xv[2].w, t2); t3 = fmaf(K[i][15], xv[3].w, t3);
             s[i] = (t0 + t1) + (t2 + t3);
         }
-        if constexpr (R == 4) return oct_reduce_scatter4(s, lane);
-        else return oct_reduce_scatter2(s, lane);
+        return oct_reduce_scatter4(s, lane);
     };
 
     for (int it = 0; it < T; ++it) {
@@ -224,7 +204,7 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
             const float s = matvec(Kr, sm.v[vb]);
             const bool ok_line = my_line < rows;
             const bool bad = ok_line && !(s >= S_LO && s <= S_HI);
-            if (writer) sm.u[ub ^ 1][my_line] = ok_line ? __fdividef(1.f, s) : 1.f;
+            if ((lane & 1) == 0) sm.u[ub ^ 1][my_line] = ok_line ? __fdividef(1.f, s) : 1.f;
             if (__syncthreads_or(bad)) slow_row(); else ub ^= 1;
         }
         // ================= column half-step: log_a -= reduce_logsumexp(log_a, axis=0)   utils/matching.py:54
@@ -232,7 +212,7 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
             const float s = matvec(Kc, sm.u[ub]);
             const bool ok_line = my_line < cols;
             const bool bad = ok_line && !(s >= S_LO && s <= S_HI);
-            if (writer) sm.v[vb ^ 1][my_line] = ok_line ? __fdividef(1.f, s) : 1.f;
+            if ((lane & 1) == 0) sm.v[vb ^ 1][my_line] = ok_line ? __fdividef(1.f, s) : 1.f;
             if (__syncthreads_or(bad)) slow_col(); else vb ^= 1;
         }
     }
@@ -243,10 +223,10 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
     __syncthreads();
     float ent = 0.f, pcs = 0.f;
     {
-        float a[R][16];
+        float a[4][16];
         load_exponents(sm.L0, sm.f, sm.g, a);
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
+        for (int i = 0; i < 4; ++i) {
             const int r = base4 + i;
             float m = a[i][0];
 #pragma unroll
@@ -300,21 +280,15 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
 
 }  // namespace
 
-int g_sinkhorn_tile_rows = 4;      // 4: 256-thread kernel (measured default); 2: 512-thread variant (otgan_sinkhorn_set_tile_rows)
-
 int sinkhorn_fast_launch(int nblk, int rows, int cols, int T, float lam, const float* L0, float* P, float* entropy,
                          float* pc, int* slow_steps, cudaStream_t stream)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        OTGAN_CUDA(cudaFuncSetAttribute(sinkhorn_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-        OTGAN_CUDA(cudaFuncSetAttribute(sinkhorn_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        OTGAN_CUDA(cudaFuncSetAttribute(sinkhorn_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         attr_set = true;
     }
-    if (g_sinkhorn_tile_rows == 2)
-        sinkhorn_fast_kernel<2><<<nblk, Tile<2>::NT, sizeof(Smem), stream>>>(L0, P, entropy, pc, slow_steps, rows, cols, T, lam);
-    else
-        sinkhorn_fast_kernel<4><<<nblk, Tile<4>::NT, sizeof(Smem), stream>>>(L0, P, entropy, pc, slow_steps, rows, cols, T, lam);
+    sinkhorn_fast_kernel<<<nblk, NTHREADS, sizeof(Smem), stream>>>(L0, P, entropy, pc, slow_steps, rows, cols, T, lam);
     OTGAN_CHECK_LAUNCH("sinkhorn_fast_kernel");
     return OTGAN_OK;
 }

@@ -384,33 +384,3 @@ def test_errors_surface_as_exceptions(M):
     big = torch.zeros(1, 1100, 1100, device="cuda")
     with pytest.raises(_lib.OtganError, match="not supported"):
         M.sinkhorn(big, 1.0, 1)
-
-
-@pytest.mark.parametrize("nblk,rows,cols,lam,T", [(6, 128, 128, 500.0, 100), (3, 32, 32, 50.0, 10), (2, 17, 23, 100.0, 5),
-                                                  (6, 125, 125, 500.0, 30), (2, 100, 128, 2000.0, 50), (1, 128, 128, 500.0, 0)])
-def test_sinkhorn_512_thread_tiling_gives_the_same_plans(M, nblk, rows, cols, lam, T):
-    """otgan_sinkhorn_set_tile_rows(2): the 512-thread register tiling of the persistent kernel (2 x 16 tiles, 4 warps per
-    scheduler) does the same arithmetic in the same summation order as the 256-thread one -> identical P / entropy / <P,C>,
-    and both sit inside the fp64-oracle gate."""
-    lib = _lib.load()
-    D = 256
-    C = np.stack([mo.cosine_cost(mo.synth_embeddings(rows, D, 70 + k, "clustered", sigma=1.0).astype(np.float64),
-                                 mo.synth_embeddings(cols, D, 80 + k, "clustered", sigma=1.0).astype(np.float64))
-                  for k in range(nblk)])
-    L0 = dev((-lam * C).astype(np.float32))
-    res = {}
-    try:
-        for r in (4, 2):
-            assert lib.otgan_sinkhorn_set_tile_rows(r) == 0
-            P, ent, pc, slow = M.sinkhorn(L0, lam, T, True, 0, want_stats=True)
-            torch.cuda.synchronize()
-            res[r] = (P.clone(), ent.clone(), pc.clone(), slow.clone())
-    finally:
-        lib.otgan_sinkhorn_set_tile_rows(4)
-    assert lib.otgan_sinkhorn_set_tile_rows(3) == -1
-    for a, b in zip(res[4], res[2]):
-        assert torch.equal(a, b)
-    C32 = L0.cpu().double().numpy() / -lam
-    for k in range(nblk):
-        p, e, _ = mo.sinkhorn(C32[k], lam, T, np.float64)
-        assert relerr(res[2][0][k], p) < TOL_P * max(1.0, lam / 500.0)
