@@ -319,8 +319,10 @@ CONV_LAYERS = {  # DCGAN layers on the tcgen05 kernels at the N=256 step (SURVEY
     # (B, Hlow, Wlow, Cin, Cout, k, "up2"): 4 parity classes x 9 pre-summed taps instead of 25 taps at the high resolution
     "generator conv2d_0": (N_TOTAL, 4, 4, 1024, 1024, 5, "up2"), "generator conv2d_1": (N_TOTAL, 8, 8, 512, 512, 5, "up2"),
     "generator conv2d_2": (N_TOTAL, 16, 16, 256, 256, 5, "up2")}
-# dram__bytes_read.sum + dram__bytes_write.sum of the profiled launch (profiles/r01_h_conv_fprop_ncu_full.txt)
-CONV_ROOFLINE_LAUNCH, CONV_ROOFLINE_TRAFFIC = "critic conv2d_3", 743.63e6 + 23.21e6
+# The roofline object quotes the launch that was captured with ncu --set full: generator conv2d_0 fprop (fused upsample form,
+# conv_gemm_tc_kernel<256>; profiles/r01_l_conv_up2_fprop_ncu_full.txt): dram__bytes_read.sum + dram__bytes_write.sum =
+# 182.5 + 44.6 MB per launch, against 235 MB algorithmic (x_low 16.8 MB + the four sub-filters 151 MB + y 67 MB).
+CONV_ROOFLINE_LAUNCH, CONV_ROOFLINE_TRAFFIC = "generator conv2d_0", 182.51e6 + 44.59e6
 
 
 def conv_benchmark(torch, iters=5):
@@ -390,15 +392,15 @@ def conv_benchmark(torch, iters=5):
 
 
 def conv_roofline(conv):
-    """Roofline object of the step's dominant kernel, conv_gemm_tc_kernel<256> (fprop / dgrad; 41% of the step in the ncu
-    launch list), on the launch that was also captured with ncu --set full: critic conv2d_3 fprop."""
+    """Roofline object of the step's dominant kernel, conv_gemm_tc_kernel<256> (fprop / dgrad; 52% of the step in the ncu
+    launch list profiles/r01_m_train_launches.txt), on the launch that was also captured with ncu --set full."""
     pk = peaks()
     full = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     r = conv[CONV_ROOFLINE_LAUNCH]["fprop"]
     gemm = [conv[n][op] for n in conv for op in ("fprop", "dgrad")]
     flops = [conv[n]["gflop"] for n in conv for _ in ("fprop", "dgrad")]
     mean_tf = sum(flops) / sum(g["ms"] for g in gemm)                        # GFLOP / ms = TFLOP/s
-    return {"bound": "tensor", "kernel": "conv_gemm_tc_kernel<256> (%s fprop, 429.5 GFLOP per launch)" % CONV_ROOFLINE_LAUNCH,
+    return {"bound": "tensor", "kernel": "conv_gemm_tc_kernel<256> (%s fprop, %.1f GFLOP executed per launch)" % (CONV_ROOFLINE_LAUNCH, conv[CONV_ROOFLINE_LAUNCH]["gflop"]),
             "achieved": r["tflops"], "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": r["tflops"] / pk["bf16_tflops"],
             "traffic": CONV_ROOFLINE_TRAFFIC,
             "frac_of_tf32_ceiling": r["tflops"] / (pk["bf16_tflops"] / 2.0),
@@ -408,7 +410,8 @@ def conv_roofline(conv):
             "peak_source": pk["source"],
             "note": "operands are fp32 tensors consumed as TF32 (kind::tf32): the tensor pipe runs TF32 at half the bf16 rate, so "
                     "the ceiling of this kernel is peak/2; `frac` is against the measured dense bf16 burst peak as the contract "
-                    "asks, frac_of_tf32_ceiling against half of it.  ncu: tensor pipe 84.5% active, DRAM 15% (traffic field)."}
+                    "asks, frac_of_tf32_ceiling against half of it.  ncu: tensor pipe 84.5% active, DRAM 6% of peak (traffic field); "
+                    "the kernel runs power-capped (sw_power_cap, ~1.7 GHz)."}
 
 
 def run_ours(args):
