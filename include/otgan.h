@@ -9,8 +9,9 @@
  * Conventions
  *   - every pointer is a DEVICE pointer owned by the caller (row-major fp32) unless the name ends in _host;
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), launches only this library's own
- *     kernels, allocates nothing (workspace is sized by otgan_workspace_bytes and passed in) and keeps no global
- *     mutable state except the thread-local last-error string;
+ *     kernels, allocates nothing (workspace is sized by otgan_workspace_bytes_* and passed in) and keeps no global
+ *     mutable state except the thread-local last-error string / launch counter and the process-wide A/B switches of
+ *     otgan_conv_set_option (measurement aids; they select between kernel variants that compute the same result);
  *   - return value 0 = OTGAN_OK, negative = error (nothing was launched for OTGAN_EINVAL); otgan_last_error() gives text;
  *   - results are deterministic (fixed reduction orders, no floating-point atomics): the same inputs give the same bits.
  */
