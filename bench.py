@@ -134,7 +134,6 @@ class CpuTrainer:
     def __init__(self, n_total, T, lam):
         import torch
         from otgan_b200.models import dcgan
-        from otgan_b200.utils import nn as onn
         self.torch, self.n, self.T, self.lam = torch, n_total, T, lam
         torch.manual_seed(1)
         dcgan.generator.reset(); dcgan.discriminator.reset()
