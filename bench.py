@@ -391,8 +391,8 @@ def conv_benchmark(torch, iters=5):
 
 
 def conv_roofline(conv):
-    """Roofline object of the step's dominant kernel, conv_gemm_tc_kernel<256> (fprop / dgrad; 52% of the step in the ncu
-    launch list profiles/r01_m_train_launches.txt), on the launch that was also captured with ncu --set full."""
+    """Roofline object of the step's dominant kernel, conv_gemm_tc_kernel<256> (fprop / dgrad; 49% of the step in the ncu
+    launch list profiles/r01_p_train_launches.txt), on the launch that was also captured with ncu --set full."""
     pk = peaks()
     full = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     r = conv[CONV_ROOFLINE_LAUNCH]["fprop"]
