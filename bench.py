@@ -556,10 +556,11 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             mt, ph, cores = cpu_matching_time(N_TOTAL, D_FEAT, T_ITERS, LAMBDA, 5, 1)
             best = float(np.min(mt))
-            tt, tcores = cpu_train_time(32, 2, 1)
+            tt, tcores = cpu_train_time(32, 6, 1)
             line["cpu_baseline"] = {"value": 32 / float(np.mean(tt)), "unit": "images/sec", "cores": tcores, "kind": "port",
-                                    "sample": "2 training steps on a bounded batch of 32 real + 32 generated images (torch-CPU "
-                                              "conv stacks + oracle/ C+OpenMP matching; TensorFlow 1.x not installable offline)",
+                                    "sample": "6 training steps (one full 1 critic : 5 generator cycle, ~10 s of CPU work) on a bounded "
+                                              "batch of 32 real + 32 generated images (torch-CPU conv stacks + oracle/ C+OpenMP "
+                                              "matching; TensorFlow 1.x not installable offline)",
                                     "ms_per_step": float(np.mean(tt)) * 1e3,
                                     "matching_phase_n256": {"ms": best * 1e3, "images_per_sec": N_TOTAL / best, "cores": cores,
                                                             "phase_ms": {"cost": ph[0], "sinkhorn": ph[1], "matched_distance": ph[2]},
