@@ -20,9 +20,15 @@
 // Precision: operands are the fp32 tensors read as TF32 by the tensor core (10-bit mantissa, the same math class as the
 // cuDNN TF32 kernels this replaces), fp32 accumulation in TMEM.
 //
-// Kernel shape (both kernels): 192 threads = warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 2-5 epilogue
-// (TMEM lane quadrant = warp & 3).  Persistent CTAs (one per SM) walk the tile list; 4-6 smem stages of BK = 32;
-// accumulator 128 x TN fp32 in TMEM, double buffered so the epilogue of one tile overlaps the MMAs of the next.
+// Kernel shape: warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 2-5 epilogue (TMEM lane quadrant = warp & 3);
+// the wgrad kernel adds two more producer warps (its 12 small boxes per stage need three issuing threads).  Persistent CTAs
+// (one per SM) walk the tile list; 4-8 smem stages of BK = 32; accumulator 128 x TN fp32 in TMEM, double buffered so the
+// epilogue of one tile overlaps the MMAs of the next.
+//
+// Also in this file: the fused 2x-upsample + convolution forms (same kernels, sub-pixel tap tables, make_submap), the
+// 256 x 256-tile variant conv_gemm2_tc_kernel, split-K over filter taps for launches with fewer tiles than SMs, the
+// weight-layout helpers (OHWI -> IHWO, sub-filter pre-sum / un-sum), the bias-gradient column sum, and the host-only plan
+// capture behind otgan_conv_plan_describe that lets CPU tests replay the exact tap tables a launch would use.
 #include "tc_common.cuh"
 #include <string.h>
 
