@@ -73,6 +73,20 @@ def test_invalid_arguments_are_rejected_before_launch(lib):
     assert lib.otgan_distance_from_pc_f32(null, null, 4, null, null) == -1
     assert lib.otgan_workspace_bytes_cost(6, 128, 128, 32768, 0) > 0
     assert lib.otgan_workspace_bytes_cost(0, 128, 128, 32768, 0) == 0
+    # convolution entry points: null / misaligned pointers, bad stride, bad geometry are refused on the host
+    assert lib.otgan_conv2d_fprop_tf32(8, 8, 8, 128, 128, 5, 5, 1, 2, 2, null, null, null, null, null, 0, null) == -1
+    assert b"null" in lib.otgan_last_error()
+    assert lib.otgan_conv2d_fprop_tf32(8, 8, 8, 128, 128, 5, 5, 3, 2, 2, 16, 16, null, 16, null, 0, null) == -1      # stride 3
+    assert lib.otgan_conv2d_fprop_tf32(8, 8, 8, 128, 128, 5, 5, 1, 2, 2, 20, 16, null, 16, null, 0, null) == -1      # x misaligned
+    assert lib.otgan_conv2d_dgrad_tf32(8, 8, 8, 128, 128, 5, 5, 1, 2, 2, null, 16, 16, null, 0, null) == -1
+    assert lib.otgan_conv2d_wgrad_tf32(8, 8, 8, 128, 128, 5, 5, 1, 2, 2, 16, null, 16, null, 0, null) == -1
+    assert lib.otgan_conv2d_wgrad_tf32(8, 8, 8, 128, 128, 5, 5, 1, 7, 2, 16, 16, 16, null, 0, null) == -1            # pad >= k
+    assert lib.otgan_conv2d_up2_fprop_tf32(8, 4, 4, 128, 128, 5, 5, 2, 2, null, 16, null, 16, null, 0, null) == -1
+    assert lib.otgan_im2col_narrow_f32(8, 32, 32, 3, 5, 5, 2, 2, 0, 16, 16, 64, null) == -1                          # ldc < 75
+    assert lib.otgan_col2im_narrow_f32(8, 32, 32, 17, 5, 5, 2, 2, 0, 16, 512, null, 16, null) == -1                  # C > 16
+    assert lib.otgan_colsum_f32(128, 6, 16, 16, 16, 1 << 20, null) == -1                                             # C % 4
+    assert lib.otgan_conv_set_option(9, 1) == -1 and lib.otgan_up2_subtaps(5, 2) == 3 and lib.otgan_up2_subtaps(7, 3) == 0
+    assert lib.otgan_workspace_bytes_conv_wgrad(512, 32, 32, 256, 256, 5, 5, 2) > 256 and lib.otgan_workspace_bytes_conv_gemm(0, 1, 1, 1) == 0
 
 
 def test_product_path_has_no_cpu_fallback():
