@@ -54,6 +54,7 @@ def build_parser():
     parser.add_argument('--max_steps', type=int, default=0, help='stop after this many steps (0 = run like the reference)')
     parser.add_argument('--log_every', type=int, default=0, help='also print a line every N steps')
     parser.add_argument('--cuda_graphs', action='store_true', help='replay each step from a captured CUDA graph')
+    parser.add_argument('--image_size', type=int, default=32, help='synthetic image side (extension: the reference is hard-wired to 32; dcgan only)')
     return parser
 
 
@@ -75,9 +76,13 @@ class Trainer:
         generator.reset(); discriminator.reset()
         self.generator, self.discriminator = generator, discriminator
         self.model_opts = {'batch_size': self.bs_local, 'nonlinearity': args.nonlinearity}      # train.py:45
+        self.image_size = getattr(args, 'image_size', 32)
+        if self.image_size != 32:
+            assert args.model == 'dcgan', "--image_size is an extension of the DCGAN models only"
+            self.model_opts['image_size'] = self.image_size
         torch.manual_seed(args.seed)                                                            # :48-49
         # run once for (data dependent) initialization of parameters                              :52-54
-        x_init = torch.zeros((args.batch_size, 32, 32, 3), device=device)
+        x_init = torch.zeros((args.batch_size, self.image_size, self.image_size, 3), device=device)
         with torch.no_grad():
             f = discriminator(x_init + 0.1, init=True, device=device, **self.model_opts)
             generator(init=True, device=device, **dict(self.model_opts, batch_size=args.batch_size))
@@ -189,7 +194,7 @@ class Trainer:
         assert a.optimizer == 'adam', "CUDA-graph replay needs the fused Adam kernel (device-resident step scalars)"
         dev = self.device
         bs = self.bs_local
-        self.g_x = torch.zeros((bs, 32, 32, 3), device=dev)
+        self.g_x = torch.zeros((bs, self.image_size, self.image_size, 3), device=dev)
         self.g_u = torch.zeros((bs, 100), device=dev)
         self.g_hyper = {k: torch.zeros(3, device=dev) for k in ('disc', 'gen')}
         opts = {'disc': self.disc_optimizer, 'gen': self.gen_optimizer}
@@ -321,7 +326,7 @@ def main(argv=None):
         print('model has a hidden representation with %d features' % trainer.num_features)        # train.py:56
     rng = np.random.RandomState(args.seed + rank)
     if args.synthetic:
-        trainx = cifar10_data.synthetic(max(args.nr_gpu * args.batch_size * 4, 2048), seed=args.seed)
+        trainx = cifar10_data.synthetic(max(args.nr_gpu * args.batch_size * 4, 2048), seed=args.seed, size=args.image_size)
     else:
         trainx, _ = cifar10_data.load(args.data_dir + '/cifar-10-python')
         trainx = np.transpose(trainx, (0, 2, 3, 1)) / 127.5 - 1.                                  # :158

@@ -137,3 +137,20 @@ def test_adam_oracle_formula():
     p1, v1, mg1 = no.adam_step(p, g, np.zeros(2), np.zeros(2), 1, 3e-4, 0.5, 0.999)
     # t = 1: v_hat = g, mg_hat = g^2  ->  step = lr * g / sqrt(g^2 + 1e-8)
     np.testing.assert_allclose(p1, p - 3e-4 * g / np.sqrt(g * g + 1e-8), rtol=1e-12)
+
+
+def test_dcgan_image_size_extension_shapes():
+    """BASELINE config 5 (64 x 64 synthetic images; not in the reference, whose shapes are hard-wired to 32 x 32): the
+    generator seeded at 8 x 8 emits [B, 64, 64, 3]; the fully convolutional critic maps it to 8*8*2048 = 131072 unit-norm
+    features; image_size = 32 leaves the reference's parameter counts untouched."""
+    dcgan.discriminator.reset(); dcgan.generator.reset()
+    torch.manual_seed(0)
+    with torch.no_grad():
+        x = dcgan.generator(2, init=True, device="cpu", image_size=64)
+        assert tuple(x.shape) == (2, 64, 64, 3) and float(x.abs().max()) <= 1.0
+        f = dcgan.discriminator(x, init=True, device="cpu")
+    assert tuple(f.shape) == (2, 131072)
+    np.testing.assert_allclose(f.pow(2).sum(1).numpy(), 1.0, rtol=1e-5)
+    assert dcgan.discriminator.store.num_params() == 34419840                  # the critic has no size-dependent variable
+    assert dcgan.generator.store.num_params() == 37761926 + (4 - 1) * (100 + 2) * 2 * 4 * 4 * 1024     # only the seed dense layer grows
+    dcgan.discriminator.reset(); dcgan.generator.reset()
