@@ -244,3 +244,19 @@ def test_densenet_train_steps_on_gpu():
         d, e = stats.tolist()
         assert kind == expect and np.isfinite(d) and 0.0 < e <= np.log(8) + 1e-4
     assert not torch.equal(tr.discriminator.flat.detach(), p0)
+
+
+def test_dcgan_64x64_extension_trains_on_gpu():
+    """--image_size 64 (BASELINE config 5's image shape; an extension, the reference is hard-wired to 32 x 32): D = 131072
+    features, one critic and two generator steps with finite distance / entropy.  The stride-2 critic layers and the three
+    fused upsample + convolution layers run on the tcgen05 kernels at these extents; the two 3-channel layers (64 pixels wide)
+    fall back to the library rung."""
+    from otgan_b200 import train as T
+    args = T.build_parser().parse_args(["--synthetic", "--image_size", "64", "--nr_gpu", "2", "--batch_size", "8",
+                                        "--nr_sinkhorn_iter", "20"])
+    tr = T.Trainer(args, torch.device("cuda", 0))
+    assert tr.num_features == 131072
+    for expect in ("disc", "gen", "gen"):
+        kind, stats = tr.step(torch.rand(16, 64, 64, 3, device="cuda") * 2 - 1)
+        d, e = stats.tolist()
+        assert kind == expect and np.isfinite(d) and 0.0 < e <= np.log(8) + 1e-4
