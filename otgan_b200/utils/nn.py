@@ -370,7 +370,7 @@ def conv_tc_supported(xshape, cout, kh, kw, stride, pad):
     if pad != "SAME" or stride[0] != stride[1] or stride[0] not in (1, 2) or kh * kw > 32:
         return False
     s = stride[0]
-    if cin % 128 or cout % 128 or H % s or W % s:
+    if cin % 128 or cout % 128 or H % s or W % s or kh < s or kw < s:        # k < stride: dgrad would have an empty parity class
         return False
     ho, wo = H // s, W // s
     if not (_pow2(ho) and _pow2(wo)) or wo > 32:

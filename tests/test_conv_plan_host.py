@@ -263,3 +263,45 @@ def test_tap_tables_on_rectangular_and_small_geometries(lib, geom):
         a = shifted(view(x.detach().numpy(), s, t["map"]), t["dh"], t["dw"])
         dw[t["brow"]:t["brow"] + C2, t["wcol"]:t["wcol"] + C1] += np.einsum("nijo,nijc->oc", view(dy, 1, t["dmap"]), a)
     np.testing.assert_allclose(dw.reshape(C2, k, k, C1), dw_ref.numpy(), rtol=0, atol=1e-8)
+
+
+def test_python_support_predicates_agree_with_the_host_launch_code(lib):
+    """nn.conv_tc_supported / conv_up2_supported / conv_narrow_supported decide in Python whether a layer goes to the tcgen05
+    kernels; if one of them said yes for a shape the C++ launch code refuses, training would raise at run time.  Sweep
+    batches, extents, channels, filters and strides: every shape a predicate accepts must be accepted by ALL the passes it
+    routes to (checked with the launch code itself, in plan-capture mode)."""
+    from otgan_b200.utils import nn
+    buf = (ctypes.c_longlong * 1024)()
+
+    def ok(op, B, H, W, Cin, Cout, k, s, pad):
+        return lib.otgan_conv_plan_describe(op, B, H, W, Cin, Cout, k, k, s, pad, pad, buf, 1024) > 0
+
+    n_tc = n_up2 = n_narrow = n_rejected = 0
+    for B in (1, 2, 3, 4, 6, 8, 16, 24, 32, 64):
+        for H, W in ((4, 4), (8, 8), (16, 16), (32, 32), (16, 8), (8, 32), (64, 64), (12, 12)):
+            for k in (1, 3, 5):
+                for s in (1, 2):
+                    pad = same_pad(H, k, s)[0]
+                    if pad != same_pad(W, k, s)[0] or pad >= k:
+                        continue
+                    for Cin, Cout in ((128, 128), (256, 128), (128, 256), (1024, 1024), (96, 128), (128, 144)):
+                        if nn.conv_tc_supported((B, H, W, Cin), Cout, k, k, [s, s], "SAME"):
+                            n_tc += 1
+                            assert all(ok(op, B, H, W, Cin, Cout, k, s, pad) for op in (0, 1, 2)), (B, H, W, Cin, Cout, k, s)
+                        else:
+                            n_rejected += 1
+                        if s == 1 and k % 2 == 1 and nn.conv_up2_supported((B, H, W, Cin), Cout, k, k, [1, 1], "SAME"):
+                            n_up2 += 1
+                            assert all(ok(op, B, H, W, Cin, Cout, k, 1, (k - 1) // 2) for op in (3, 4, 5)), (B, H, W, Cin, Cout, k)
+                    if s == 1:
+                        for Cin, Cout in ((3, 128), (128, 3)):
+                            if nn.conv_narrow_supported((B, H, W, Cin), Cout, k, k, [1, 1], "SAME"):
+                                n_narrow += 1
+                                wide = 128
+                                # the passes _ConvNarrow launches: padded-32 GEMM, 1x1 GEMM over [pixels, 128], 1x1 wgrad
+                                if Cin <= 16:
+                                    assert ok(0, B, H, W, 32, Cout, k, 1, pad)
+                                else:
+                                    assert ok(1, B, H, W, Cin, 32, k, 1, pad)
+                                assert ok(0, B, H, W, wide, 128, 1, 1, 0) and ok(2, B, H, W, 128, wide, 1, 1, 0), (B, H, W, Cin, Cout, k)
+    assert n_tc > 100 and n_up2 > 30 and n_narrow > 20 and n_rejected > 100
