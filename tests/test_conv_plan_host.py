@@ -305,3 +305,39 @@ def test_python_support_predicates_agree_with_the_host_launch_code(lib):
                                     assert ok(1, B, H, W, Cin, 32, k, 1, pad)
                                 assert ok(0, B, H, W, wide, 128, 1, 1, 0) and ok(2, B, H, W, 128, wide, 1, 1, 0), (B, H, W, Cin, Cout, k)
     assert n_tc > 100 and n_up2 > 30 and n_narrow > 20 and n_rejected > 100
+
+
+def test_workspace_queries_cover_what_the_launch_code_uses(lib):
+    """otgan_workspace_bytes_conv_{gemm,wgrad,up2_wgrad} must be >= the partial buffers the chosen split factors need
+    (wgrad REQUIRES the space; fprop / dgrad would silently run unsplit, i.e. slower, if the query under-estimated)."""
+    from otgan_b200.utils import nn
+    for B in (8, 32, 64, 256, 512):
+        for (H, W, Cin, Cout, k, s) in ((32, 32, 256, 256, 5, 2), (16, 16, 512, 512, 5, 2), (8, 8, 1024, 1024, 5, 2),
+                                       (8, 8, 1024, 1024, 5, 1), (32, 32, 128, 128, 1, 1), (16, 16, 128, 256, 3, 1)):
+            pad = same_pad(H, k, s)[0]
+            if not nn.conv_tc_supported((B, H, W, Cin), Cout, k, k, [s, s], "SAME"):
+                continue
+            Ho, Wo = H // s, W // s
+            d = describe(lib, "fprop", B, H, W, Cin, Cout, k, s, pad)
+            if d["splits"] > 1:
+                assert lib.otgan_workspace_bytes_conv_gemm(B, Ho, Wo, Cout) >= d["splits"] * B * Ho * Wo * Cout * 4
+            d = describe(lib, "dgrad", B, H, W, Cin, Cout, k, s, pad)
+            if d["splits"] > 1:
+                assert lib.otgan_workspace_bytes_conv_gemm(B, H, W, Cin) >= d["splits"] * B * H * W * Cin * 4
+            d = describe(lib, "wgrad", B, H, W, Cin, Cout, k, s, pad)
+            if d["splits"] > 1:
+                assert lib.otgan_workspace_bytes_conv_wgrad(B, H, W, Cin, Cout, k, k, s) >= d["splits"] * d["split_stride"] * 4
+                assert d["split_stride"] == Cout * k * k * Cin
+        for (Hl, Wl, Cin, Cout) in ((4, 4, 1024, 1024), (8, 8, 512, 512), (16, 16, 256, 256)):
+            if not nn.conv_up2_supported((B, Hl, Wl, Cin), Cout, 5, 5, [1, 1], "SAME"):
+                continue
+            d = describe(lib, "up2_wgrad", B, Hl, Wl, Cin, Cout, 5, 1, 2)
+            assert d["split_stride"] == 4 * Cout * 9 * Cin
+            if d["splits"] > 1:
+                assert lib.otgan_workspace_bytes_conv_up2_wgrad(B, Hl, Wl, Cin, Cout, 5, 5, 2, 2) >= d["splits"] * d["split_stride"] * 4
+            d = describe(lib, "up2_fprop", B, Hl, Wl, Cin, Cout, 5, 1, 2)
+            if d["splits"] > 1:
+                assert lib.otgan_workspace_bytes_conv_gemm(B, 2 * Hl, 2 * Wl, Cout) >= d["splits"] * B * 4 * Hl * Wl * Cout * 4
+            d = describe(lib, "up2_dgrad", B, Hl, Wl, Cin, Cout, 5, 1, 2)
+            if d["splits"] > 1:
+                assert lib.otgan_workspace_bytes_conv_gemm(B, Hl, Wl, Cin) >= d["splits"] * B * Hl * Wl * Cin * 4
