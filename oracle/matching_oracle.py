@@ -4,13 +4,15 @@ This file is an op-for-op numpy restatement of the reference's algorithm.  Only
 ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
 ``--impl reference`` legs may import it; the product path (``otgan_b200``) never does.
 
-PARITY UNPINNED: the reference (openai/ot-gan) ships no tests, golden vectors or
-known-answer values, and its arithmetic lives in TensorFlow 1.x (un-vendored,
-un-pinned, not installable here: python 3.12, no wheel, no network), so this oracle
-cannot be checked against the reference executing.  It is pinned instead by
-(i) algebraic invariants of the algorithm (tests/test_oracle.py), (ii) an independent
-C restatement (oracle/matching_oracle.c) and (iii) committed golden vectors generated
-by the fp64 path of this file (tests/golden/, generator script committed).
+PARITY PIN: the reference (openai/ot-gan) ships no tests, golden vectors or known-answer values, and TensorFlow 1.x
+(un-vendored, un-pinned) is not installable here (python 3.12, no wheel, no network).  The oracle is pinned instead to
+the reference's own CODE: tests/golden/make_reference_golden.py imports /root/reference/utils/matching.py,
+toy_example/matching_cpu.py, utils/nn.py and models/*.py UNMODIFIED over tests/golden/tf1_numpy_shim.py (a float64 numpy
+emulation of the ~35 TensorFlow-1.x primitives they call, semantics documented there) and commits the outputs as
+tests/golden/ref_*.npz; tests/test_reference_golden.py checks this oracle against them to 1e-11 (and the CUDA path on
+the GPU).  What remains unpinned is only the arithmetic INSIDE the TensorFlow primitives (matmul, logsumexp, softmax,
+conv2d), restated in the shim.  Further pins: (i) algebraic invariants of the algorithm (tests/test_oracle.py), (ii) an
+independent C restatement (oracle/matching_oracle.c), (iii) fp64 golden vectors of this file (tests/golden/*.npz).
 
 Reference lines followed (paths relative to /root/reference):
   get_matched_features_random          utils/matching.py:3-9

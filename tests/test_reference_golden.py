@@ -1,0 +1,187 @@
+"""Parity against fixtures produced by EXECUTING THE REFERENCE'S OWN FILES (tests/golden/ref_*.npz, written by
+tests/golden/make_reference_golden.py: /root/reference/utils/matching.py, toy_example/matching_cpu.py, utils/nn.py and
+models/*.py imported unmodified over a float64 numpy emulation of the TensorFlow-1.x primitives they call).
+
+CPU (-m "not gpu"): the oracle (oracle/matching_oracle.py, oracle/nn_oracle.py) and the host mirror of the models on CPU
+tensors must reproduce the fixtures -- this is what pins the oracle to the reference's code.
+GPU (-m gpu): the CUDA path, through the C ABI, against the same fixtures.
+"""
+import glob
+import os
+import sys
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import matching_oracle as mo
+from oracle import nn_oracle as no
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+MATCHING = sorted(p for p in glob.glob(os.path.join(GOLDEN, "ref_*.npz")) if "ref_model_" not in p)
+MODELS = sorted(glob.glob(os.path.join(GOLDEN, "ref_model_*.npz")))
+
+
+def seeded_variable(name, shape):
+    """Same function as tests/golden/make_reference_golden.py: model variables are derived from their names."""
+    rng = np.random.RandomState(zlib.crc32(name.encode()) & 0x7FFFFFFF)
+    leaf = name.rsplit("/", 1)[-1]
+    if leaf == "V":
+        return rng.normal(0.0, 0.05, size=shape).astype(np.float32)
+    if leaf == "g":
+        return rng.uniform(0.5, 1.5, size=shape).astype(np.float32)
+    return rng.normal(0.0, 0.1, size=shape).astype(np.float32)
+
+
+def relerr(a, ref):
+    a = a.detach().cpu().double().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float64)
+    return float(np.abs(a - ref).max() / max(np.abs(ref).max(), 1e-300))
+
+
+def test_fixtures_exist():
+    assert len(MATCHING) == 6 and len(MODELS) == 2
+
+
+# ----------------------------------------------------------------------------------------------- CPU: oracle == reference code
+@pytest.mark.parametrize("path", MATCHING)
+def test_oracle_reproduces_the_reference_matching(path):
+    g = np.load(path)
+    kind, A, B, lam, T, G = str(g["kind"]), g["A"], g["B"], float(g["lam"]), int(g["T"]), int(g["G"])
+    if kind == "two":
+        fa, fb = list(np.split(A, G)), list(np.split(B, G))
+        res = mo.get_matched_features(fa, fb, lam, T)
+        dist = mo.calc_distance(fa, fb, res)
+        cat = np.concatenate
+        r = mo.get_matched_features_random(fa, fb)
+        np.testing.assert_array_equal(np.concatenate(r[0]), g["rand_aa"])
+        np.testing.assert_array_equal(np.concatenate(r[1]), g["rand_bb"])
+    elif kind == "single":
+        fa, fb = list(np.split(A, G)), list(np.split(B, G))
+        res = mo.get_matched_features_single_batch(fa, fb, lam, T)
+        dist = mo.calc_distance(fa, fb, res)
+        cat = np.concatenate
+    elif kind == "toy":
+        res = mo.toy_get_matched_features(A, B, lam, T)
+        dist = mo.toy_calc_distance(A, B, res)
+        cat = lambda x: x
+    else:
+        res = mo.toy_get_matched_features_single_batch([A], [B], lam, T, A.shape[0])
+        res = tuple(np.concatenate(x) if isinstance(x, list) else x for x in res)
+        dist = mo.toy_calc_distance(A, B, res)
+        cat = lambda x: x
+    for i, k in enumerate(["f_aa", "f_bb", "f_ab", "f_ba"]):
+        np.testing.assert_allclose(cat(res[i]), g[k], rtol=0, atol=1e-11 * max(1.0, np.abs(g[k]).max()))
+    assert abs(res[4] - float(g["entropy"])) < 1e-11 and abs(dist - float(g["dist"])) < 1e-12
+
+
+def _assign_by_name(template):
+    with torch.no_grad():
+        for n, p in template.named_parameters():
+            p.copy_(torch.from_numpy(seeded_variable(n, tuple(p.shape))))
+
+
+def _models(name):
+    from otgan_b200.models import dcgan, densenet
+    return dcgan if name == "dcgan" else densenet
+
+
+@pytest.mark.parametrize("path", MODELS)
+def test_oracle_and_host_mirror_reproduce_the_reference_models(path):
+    g = np.load(path)
+    name = os.path.basename(path)[len("ref_model_"):-4]
+    mod = _models(name)
+    mod.discriminator.reset(); mod.generator.reset()
+    x = torch.from_numpy(g["x"])
+    us = [torch.from_numpy(g["u%d" % i]) for i in range(int(g["n_latents"]))]
+    u = us[0] if name == "dcgan" else us
+    with torch.no_grad():
+        mod.discriminator(torch.zeros(2, 32, 32, 3) + 0.1, init=True, device="cpu")
+        mod.generator(2, init=True, device="cpu")
+    # same variables, same names, same creation order as the reference graph (tf.trainable_variables())
+    names = [n for n, _ in mod.discriminator.named_parameters()] + [n for n, _ in mod.generator.named_parameters()]
+    sizes = [p.numel() for _, p in mod.discriminator.named_parameters()] + [p.numel() for _, p in mod.generator.named_parameters()]
+    assert names == [str(s) for s in g["var_names"]] and sizes == [int(s) for s in g["var_sizes"]]
+    _assign_by_name(mod.discriminator); _assign_by_name(mod.generator)
+    with torch.no_grad():
+        f = mod.discriminator(x)
+        img = mod.generator(2, u=u)
+    assert relerr(f, g["features"]) < 2e-5 and float(np.abs(img.double().numpy() - g["image"]).max()) < 2e-5     # fp32 torch-CPU vs fp64
+    # the numpy model oracle (fp64) on the same variables
+    td = {n: p.detach().double().numpy() for n, p in mod.discriminator.named_parameters()}
+    tg = {n: p.detach().double().numpy() for n, p in mod.generator.named_parameters()}
+    if name == "dcgan":
+        fo, io = no.dcgan_discriminator(x.double().numpy(), td), no.dcgan_generator(u.double().numpy(), tg)
+    else:
+        fo, io = no.densenet_discriminator(x.double().numpy(), td), no.densenet_generator([t.double().numpy() for t in us], tg)
+    assert relerr(fo, g["features"]) < 1e-10 and float(np.abs(io - g["image"]).max()) < 1e-10
+    mod.discriminator.reset(); mod.generator.reset()
+
+
+# ----------------------------------------------------------------------------------------------- GPU: CUDA path == reference code
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", MATCHING)
+def test_cuda_matching_reproduces_the_reference(path):
+    from otgan_b200.utils import matching as M
+    from otgan_b200.toy_example import matching_cpu as Tm
+    g = np.load(path)
+    kind, A, B, lam, T, G = str(g["kind"]), g["A"], g["B"], float(g["lam"]), int(g["T"]), int(g["G"])
+    if kind == "toy_single":
+        pytest.skip("the toy single-batch tensor API is not on the hot path (SURVEY 8f-2 covers the two-batch toy form)")
+    if kind == "toy":
+        got = Tm.get_matched_features(dev(A), dev(B), lam, T)
+        dist = Tm.calc_distance(dev(A), dev(B), got)
+        cat = lambda x: x
+    else:
+        ta, tb = list(torch.chunk(dev(A), G, 0)), list(torch.chunk(dev(B), G, 0))
+        fn = M.get_matched_features if kind == "two" else M.get_matched_features_single_batch
+        got = fn(ta, tb, lam, T)
+        dist = M.calc_distance(ta, tb, got)
+        cat = torch.cat
+    for i, k in enumerate(["f_aa", "f_bb", "f_ab", "f_ba"]):
+        assert relerr(cat(got[i]), g[k]) < 1e-5, k                                   # north star: 1e-5 relative
+    assert abs(float(got[4]) - float(g["entropy"])) <= 5e-6 * max(abs(float(g["entropy"])), 0.1)
+    assert abs(float(dist) - float(g["dist"])) < 1e-6
+    if kind == "two":
+        fa = [torch.full((2, 3), float(i), device="cuda") for i in range(4)]
+        r = M.get_matched_features_random(ta, tb)
+        assert torch.equal(torch.cat(r[0]).cpu(), torch.from_numpy(g["rand_aa"]).float())
+        assert torch.equal(torch.cat(r[1]).cpu(), torch.from_numpy(g["rand_bb"]).float())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", MODELS)
+@pytest.mark.parametrize("backend", ["tcgen05", "cudnn"])
+def test_cuda_models_reproduce_the_reference(path, backend):
+    """Forward of the reference's models/*.py (critic features, generator image) on this library's kernels.  tcgen05 rung:
+    TF32 operands (10-bit mantissa) -> 2e-3 of the largest feature; strict-fp32 library rung: 2e-5."""
+    from otgan_b200.utils import nn
+    g = np.load(path)
+    name = os.path.basename(path)[len("ref_model_"):-4]
+    mod = _models(name)
+    mod.discriminator.reset(); mod.generator.reset()
+    prev, prev_tf32 = nn.CONV_BACKEND, torch.backends.cudnn.allow_tf32
+    nn.CONV_BACKEND = backend
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        x = dev(g["x"])
+        us = [dev(g["u%d" % i]) for i in range(int(g["n_latents"]))]
+        u = us[0] if name == "dcgan" else us
+        with torch.no_grad():
+            mod.discriminator(torch.zeros(2, 32, 32, 3, device="cuda") + 0.1, init=True)
+            mod.generator(2, init=True, device=torch.device("cuda"))
+        _assign_by_name(mod.discriminator); _assign_by_name(mod.generator)
+        with torch.no_grad():
+            f = mod.discriminator(x)
+            img = mod.generator(2, u=u)
+        tol = 2e-3 if backend == "tcgen05" else 2e-5
+        assert relerr(f, g["features"]) < tol
+        assert float(np.abs(img.cpu().double().numpy() - g["image"]).max()) < tol
+    finally:
+        nn.CONV_BACKEND = prev
+        torch.backends.cudnn.allow_tf32 = prev_tf32
+        mod.discriminator.reset(); mod.generator.reset()
