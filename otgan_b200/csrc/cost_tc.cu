@@ -276,11 +276,8 @@ int cost_tc_launch(int nblk, int rows, int cols, int D, const float* const* X, c
     float* partial = reinterpret_cast<float*>(ws);
     float* sq = partial + (size_t)pl.splits * nblk * rows * cols;
     pl.prm.partial = partial;
-    static bool attr_set = false;
-    if (!attr_set) {
-        OTGAN_CUDA(cudaFuncSetAttribute(cost_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        attr_set = true;
-    }
+    // per-device attribute: set on every launch (a process-wide flag would miss a second GPU)
+    OTGAN_CUDA(cudaFuncSetAttribute(cost_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     dim3 grid(pl.splits, nblk);
     cost_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(pl.prm);
     OTGAN_CHECK_LAUNCH("cost_tc_kernel");

@@ -195,7 +195,10 @@ class Trainer:
         dev = self.device
         bs = self.bs_local
         self.g_x = torch.zeros((bs, self.image_size, self.image_size, 3), device=dev)
-        self.g_u = torch.zeros((bs, 100), device=dev)
+        if a.model == 'densenet':                          # models/densenet.py:53-56: four noise inputs
+            self.g_u = [torch.zeros((bs, 100), device=dev)] + [torch.zeros((bs, s, s, 16), device=dev) for s in (8, 16, 32)]
+        else:
+            self.g_u = torch.zeros((bs, 100), device=dev)
         self.g_hyper = {k: torch.zeros(3, device=dev) for k in ('disc', 'gen')}
         opts = {'disc': self.disc_optimizer, 'gen': self.gen_optimizer}
         # snapshot everything a training step mutates
@@ -249,10 +252,13 @@ class Trainer:
         hd = self.g_hyper[kind]
         hd[0:1].fill_(lr); hd[1:2].fill_(d1); hd[2:3].fill_(d2)
         self.g_x.copy_(x_real, non_blocking=True)
+        bufs = self.g_u if isinstance(self.g_u, list) else [self.g_u]
         if u is None:
-            self.g_u.uniform_(-1.0, 1.0)                                                         # tf.random_uniform  dcgan.py:30
+            for b in bufs:
+                b.uniform_(-1.0, 1.0)                                                            # tf.random_uniform  dcgan.py:30
         else:
-            self.g_u.copy_(u, non_blocking=True)
+            for b, src in zip(bufs, u if isinstance(u, (list, tuple)) else [u]):
+                b.copy_(src, non_blocking=True)
         self.graphs[kind].replay()
         self.replayed_launches += self.g_launches[kind]
         self.step_counter += 1
@@ -332,15 +338,18 @@ def main(argv=None):
         trainx = np.transpose(trainx, (0, 2, 3, 1)) / 127.5 - 1.                                  # :158
         trainx = trainx.astype(np.float32)
     nr_batches_train_per_gpu = trainx.shape[0] // (args.nr_gpu * args.batch_size)                # :159
+    current_epoch = 0
     if args.load_params:
         trainer.load(os.path.join(args.save_dir, args.model_name))
+        ix = args.model_name.rfind('-')                                                          # :191-193
+        current_epoch = int(args.model_name[ix + 1:]) if ix >= 0 and args.model_name[ix + 1:].isdigit() else 0
     if args.cuda_graphs:
         trainer.enable_cuda_graphs()
     os.makedirs(args.save_dir, exist_ok=True) if rank == 0 and not args.synthetic else None
     if rank == 0:
         print('starting training')
     start_time = time.time()
-    for epoch in range(1000000):
+    for epoch in range(current_epoch, 1000000):                                                  # :196
         begin = time.time()
         inds = np.random.RandomState(args.seed + epoch).permutation(trainx.shape[0])             # :200 (same on every rank)
         trainx = trainx[inds]
@@ -367,7 +376,7 @@ def main(argv=None):
             sys.stdout.flush()
         if rank == 0 and not args.synthetic:                                                     # :233-243
             trainer.sample_tiles(os.path.join(args.save_dir, 'sample%d.png' % epoch), os.path.join(args.save_dir, 'ema_sample%d.png' % epoch))
-        if (epoch + 1) % 200 == 0 and rank == 0 and not args.synthetic:                          # :275-277
+        if (epoch + 1) % 200 == 0 and epoch != current_epoch and rank == 0 and not args.synthetic:   # :275-277
             trainer.save(os.path.join(args.save_dir, 'med_gan_params-%d' % epoch))
         if args.max_steps and trainer.step_counter >= args.max_steps:
             break

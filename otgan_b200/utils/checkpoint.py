@@ -5,11 +5,11 @@ and EMA shadows are NOT saved, train.py:190-193 restarts them) named `med_gan_pa
 same names and layouts (`discriminator/conv2d_1/V` is the HWIO kernel, `generator/dense_0/V` is [in, out]), so a
 checkpoint maps one-to-one:
 
-    load_variables(path) -> {name: np.ndarray}
-        *.npz                 a numpy archive keyed by variable name (what `np.savez(**{v.name[:-2]: sess.run(v)})` writes
-                              on the TensorFlow side -- the portable exchange format)
-        *.pt / *.pth          Trainer.save() output
-        anything else         a TensorFlow checkpoint prefix, read with tf.train.load_checkpoint when TensorFlow is importable
+    load_variables(path) -> {name: np.ndarray}      the file FORMAT is sniffed, not the extension:
+        numpy archive         keyed by variable name (what `np.savez(**{v.op.name: sess.run(v)})` writes on the TensorFlow
+                              side -- the portable exchange format; a trailing ":0" on the keys is accepted)
+        torch archive         Trainer.save() output (the reference's extensionless name `med_gan_params-<epoch>` included)
+        <prefix>.index exists a TensorFlow checkpoint prefix, read with tf.train.load_checkpoint when TensorFlow is importable
                               (it is not in this image: a clear error is raised instead)
     assign(templates, variables)   copy into the flat parameter buffers (shape-checked), invalidating cached weights
     export_npz(templates, path)    the inverse, for loading these parameters back into the reference
@@ -18,11 +18,33 @@ import numpy as np
 import torch
 
 
+def _sniff(path):
+    """'npz' | 'torch' | 'tf' from the file contents (both numpy and torch archives are zip files)."""
+    import os
+    import zipfile
+    if os.path.isfile(path) and zipfile.is_zipfile(path):
+        with zipfile.ZipFile(path) as z:
+            names = z.namelist()
+        return "torch" if any(n.endswith("data.pkl") for n in names) else "npz"
+    if os.path.isfile(path):
+        return "torch"                              # legacy (non-zip) torch pickle
+    for ext in (".pt", ".npz"):
+        if os.path.isfile(path + ext):
+            return _sniff(path + ext) + ":" + ext
+    if os.path.isfile(path + ".index"):
+        return "tf"
+    raise FileNotFoundError("no checkpoint at %r (tried the path itself, +.pt, +.npz and the TensorFlow prefix +.index)" % path)
+
+
 def load_variables(path):
-    if path.endswith(".npz"):
+    kind = _sniff(path)
+    if ":" in kind:
+        kind, ext = kind.split(":")
+        path = path + ext
+    if kind == "npz":
         with np.load(path) as z:
             return {k[:-2] if k.endswith(":0") else k: np.asarray(z[k]) for k in z.files}
-    if path.endswith((".pt", ".pth")):
+    if kind == "torch":
         ck = torch.load(path, map_location="cpu")
         return {n: t.numpy() for group in ck.values() for n, t in group.items()}
     try:

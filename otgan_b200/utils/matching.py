@@ -33,8 +33,9 @@ def _stream():
 
 
 def _buf(key, shape, device, dtype=torch.float32):
-    """Persistent scratch tensors (cost blocks, plans, split-K workspace) reused across calls: no per-step allocation."""
-    k = (key, tuple(shape), device.index, dtype)
+    """Persistent INTERNAL scratch (split-K partials, pre-split plan planes), one per (device, stream): never handed to the
+    caller, so a later call cannot overwrite an earlier call's result; calls on different streams do not share scratch."""
+    k = (key, tuple(shape), device.index, dtype, torch.cuda.current_stream(device).cuda_stream)
     t = _buffers.get(k)
     if t is None:
         t = torch.empty(shape, device=device, dtype=dtype)
@@ -88,7 +89,7 @@ def cost_blocks(X, Y, lam, cost_kind=_lib.COST_COSINE, diag_add=None, impl=_lib.
     assert all(t.stride(0) == ldx for t in X) and all(t.stride(0) == ldy for t in Y)
     ws_bytes = lib.otgan_workspace_bytes_cost(nblk, rows, cols, D, impl)
     ws = _buf("cost_ws", ((ws_bytes + 3) // 4,), dev)
-    L = _buf("L", (nblk, rows, cols), dev)
+    L = torch.empty((nblk, rows, cols), device=dev, dtype=torch.float32)      # caller-owned result (fresh every call)
     diag = _lib.float_array(diag_add) if diag_add is not None else None
     rc = lib.otgan_cost_blocks_f32(nblk, rows, cols, D, _lib.ptr_array([t.data_ptr() for t in X]),
                                    _lib.ptr_array([t.data_ptr() for t in Y]), ldx, ldy, cost_kind, diag,
@@ -103,12 +104,11 @@ def sinkhorn(L, lam, nr_iter, want_plan=True, impl=_lib.IMPL_AUTO, want_stats=Fa
     lib = _lib.load()
     nblk, rows, cols = L.shape
     assert L.is_cuda and L.dtype == torch.float32 and L.is_contiguous()
-    P = _buf("P", (nblk, rows, cols), L.device) if want_plan else None
-    ent = _buf("ent", (nblk,), L.device)
-    pc = _buf("pc", (nblk,), L.device)
-    slow = _buf("slow", (nblk,), L.device, torch.int32) if want_stats else None
-    if slow is not None:
-        slow.zero_()
+    # results are fresh tensors owned by the caller; blocks larger than one SM need P as working storage
+    P = torch.empty((nblk, rows, cols), device=L.device, dtype=torch.float32) if (want_plan or max(rows, cols) > 128) else None
+    ent = torch.empty((nblk,), device=L.device, dtype=torch.float32)
+    pc = torch.empty((nblk,), device=L.device, dtype=torch.float32)
+    slow = torch.zeros((nblk,), device=L.device, dtype=torch.int32) if want_stats else None
     rc = lib.otgan_sinkhorn_ex_f32(nblk, rows, cols, int(nr_iter), float(lam), L.data_ptr(),
                                    P.data_ptr() if P is not None else None, ent.data_ptr(), pc.data_ptr(),
                                    slow.data_ptr() if slow is not None else None, impl, _stream())

@@ -157,10 +157,7 @@ class VariableStore:
                         wt_t = torch.empty((shape[2], shape[0] * shape[1] * C), device=self.device, dtype=torch.float32)
                     ent = self.wcache[scope] = (wt, inv, wt_t)
                 wt, inv, wt_t = ent
-                need = lib.otgan_workspace_bytes_weightnorm(K, C) // 4
-                ws = _wn_ws.get(self.device.index)
-                if ws is None or ws.numel() < need:
-                    ws = _wn_ws[self.device.index] = torch.empty((max(need, 64 * 32768),), device=self.device, dtype=torch.float32)
+                ws = _wn_workspace(self.device, lib.otgan_workspace_bytes_weightnorm(K, C) // 4)
                 rc = lib.otgan_weightnorm_fwd_f32(K, C, V.data_ptr(), g.data_ptr(), wt.data_ptr(), inv.data_ptr(), ws.data_ptr(),
                                                   ws.numel() * 4, stream)
                 _lib.check(rc, "otgan_weightnorm_fwd_f32")
@@ -349,13 +346,27 @@ CONV_BACKEND = "tcgen05"      # "tcgen05": this library's implicit-GEMM kernels 
 UPSAMPLE_FUSION = True        # nn.upsample2x / nn.glu(upsample=True) hand the following conv2d an un-materialised Upsampled2x
 CONV_NARROW = True            # route the two 3-channel layers through _ConvNarrow (False: cuDNN, for A/B timing)
 _conv_ws = {}
+_wn_ws = {}
+_retired_ws = []              # outgrown scratch buffers stay alive: a captured CUDA graph may still hold their addresses
 
 
 def _workspace(device, nbytes):
     """Grow-only per-device scratch buffer for the convolution kernels (split-K partials, bias-gradient partials)."""
     ws = _conv_ws.get(device.index)
     if ws is None or ws.numel() * 4 < nbytes:
+        if ws is not None:
+            _retired_ws.append(ws)
         ws = _conv_ws[device.index] = torch.empty((max(nbytes // 4 + 64, 1 << 20),), device=device, dtype=torch.float32)
+    return ws
+
+
+def _wn_workspace(device, need_floats):
+    """Scratch of the weight-norm kernels (same retirement rule as _workspace)."""
+    ws = _wn_ws.get(device.index)
+    if ws is None or ws.numel() < need_floats:
+        if ws is not None:
+            _retired_ws.append(ws)
+        ws = _wn_ws[device.index] = torch.empty((max(need_floats, 64 * 32768),), device=device, dtype=torch.float32)
     return ws
 
 
@@ -807,9 +818,6 @@ class TransposedWeight:
         return self.wt.view(co, kh, kw, ci).permute(0, 3, 1, 2)      # logical OIHW, channels-last memory: no copy
 
 
-_wn_ws = {}
-
-
 class _WeightNorm(torch.autograd.Function):
     """utils/nn.py:176-180 on this library's fused CUDA kernels (otgan_weightnorm_{fwd,bwd}_f32)."""
 
@@ -821,10 +829,7 @@ class _WeightNorm(torch.autograd.Function):
         Vc, gc = V.contiguous(), g.contiguous()
         wt = torch.empty((C, K), device=V.device, dtype=torch.float32)
         inv = torch.empty((C,), device=V.device, dtype=torch.float32)
-        need = lib.otgan_workspace_bytes_weightnorm(K, C) // 4
-        ws = _wn_ws.get(V.device.index)
-        if ws is None or ws.numel() < need:
-            ws = _wn_ws[V.device.index] = torch.empty((max(need, 64 * 32768),), device=V.device, dtype=torch.float32)
+        ws = _wn_workspace(V.device, lib.otgan_workspace_bytes_weightnorm(K, C) // 4)
         rc = lib.otgan_weightnorm_fwd_f32(K, C, Vc.data_ptr(), gc.data_ptr(), wt.data_ptr(), inv.data_ptr(), ws.data_ptr(),
                                           ws.numel() * 4, torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "otgan_weightnorm_fwd_f32")
@@ -840,7 +845,7 @@ class _WeightNorm(torch.autograd.Function):
         K = V.numel() // C
         dwt = dwt.contiguous()
         dV, dg = torch.empty_like(V), torch.empty_like(g)
-        ws = _wn_ws[V.device.index]
+        ws = _wn_workspace(V.device, lib.otgan_workspace_bytes_weightnorm(K, C) // 4)
         rc = lib.otgan_weightnorm_bwd_f32(K, C, V.data_ptr(), g.data_ptr(), inv.data_ptr(), dwt.data_ptr(), dV.data_ptr(),
                                           dg.data_ptr(), ws.data_ptr(), ws.numel() * 4, torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "otgan_weightnorm_bwd_f32")

@@ -58,6 +58,41 @@ def test_checkpoint_round_trip_by_tensorflow_variable_names(tmp_path):
     del bad["generator/conv2d_0/V"]
     with pytest.raises(KeyError):
         checkpoint.assign(tpls, bad)
+    open(os.path.join(tmp_path, "med_gan_params-2399.index"), "wb").write(b"\0")         # looks like a TF checkpoint prefix
     with pytest.raises(ImportError):
-        checkpoint.load_variables(os.path.join(tmp_path, "med_gan_params-2399"))         # TF checkpoint prefix, no tensorflow here
+        checkpoint.load_variables(os.path.join(tmp_path, "med_gan_params-2399"))         # ... and there is no tensorflow here
+    with pytest.raises(FileNotFoundError):
+        checkpoint.load_variables(os.path.join(tmp_path, "nothing-here"))
+    # the reference's extensionless torch archive (what Trainer.save writes as `med_gan_params-<epoch>`) is sniffed, not guessed
+    ext_less = os.path.join(tmp_path, "med_gan_params-199")
+    torch.save({"discriminator": {n: p.detach().clone() for n, p in dcgan.discriminator.named_parameters()},
+                "generator": {n: p.detach().clone() for n, p in dcgan.generator.named_parameters()}}, ext_less)
+    again = checkpoint.load_variables(ext_less)
+    assert sorted(again) == names and np.array_equal(again["generator/dense_0/g"], saved["generator/dense_0/g"])
+    dcgan.discriminator.reset(); dcgan.generator.reset()
+
+
+def test_reference_style_variable_dump_loads_and_reproduces_the_reference_features(tmp_path):
+    """a `med_gan_params-*` style dump keyed by TensorFlow variable names (`<scope>/<layer>/V:0`, HWIO kernels,
+    [in, out] dense matrices) -- written here from the same name-seeded variables the reference graph was evaluated with in
+    tests/golden/make_reference_golden.py -- goes through checkpoint.load_variables / assign and must reproduce the features
+    and the generated image of the REFERENCE's own models/dcgan.py (tests/golden/ref_model_dcgan.npz)."""
+    from otgan_b200.models import dcgan
+    from otgan_b200.utils import checkpoint
+    from tests.test_reference_golden import seeded_variable
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_model_dcgan.npz"))
+    dcgan.discriminator.reset(); dcgan.generator.reset()
+    with torch.no_grad():
+        dcgan.discriminator(torch.zeros(2, 32, 32, 3) + 0.1, init=True, device="cpu")
+        dcgan.generator(2, init=True, device="cpu")
+    tpls = (dcgan.discriminator, dcgan.generator)
+    dump = {n + ":0": seeded_variable(n, tuple(p.shape)) for t in tpls for n, p in t.named_parameters()}
+    path = os.path.join(tmp_path, "med_gan_params-2399.npz")
+    np.savez(path, **dump)
+    checkpoint.assign(tpls, checkpoint.load_variables(os.path.join(tmp_path, "med_gan_params-2399")))    # prefix form
+    with torch.no_grad():
+        f = dcgan.discriminator(torch.from_numpy(g["x"])).double().numpy()
+        img = dcgan.generator(2, u=torch.from_numpy(g["u0"])).double().numpy()
+    assert np.abs(f - g["features"]).max() / np.abs(g["features"]).max() < 2e-5
+    assert np.abs(img - g["image"]).max() < 2e-5
     dcgan.discriminator.reset(); dcgan.generator.reset()

@@ -5,7 +5,9 @@ BASELINE.json sizes.
 Tolerance model (everything is max-abs-error / max-abs-value against the fp64 oracle):
   cost blocks C          <= 2e-6        (the fp32 oracle sits at ~1.2e-7 .. 1e-6 depending on D)
   plans P                <= 1e-4        (lambda = 500 amplifies the fp32 rounding of C 500x; fp32 oracle: 1.5e-5 .. 6e-5)
-  matched features/grads <= 3e-5        (fp32 oracle: 2e-6 .. 2e-5)
+  matched features/grads <= max(1e-5, 1.5 x the fp32 oracle's own error on the same inputs)   (SURVEY 8d gate; the fp32
+                            oracle sits at 2e-6 .. 2e-5 -- lambda = 500 amplifies fp32 rounding of C inside log P);
+                            kernel-level plan-apply tests use fixed 3e-6 / 1e-5 gates
   entropy                <= 5e-6 relative
   distance               <= 1e-6 ABSOLUTE (it is a cancellation of O(1) terms down to ~1e-4)
 """
@@ -21,7 +23,16 @@ from oracle import matching_oracle as mo
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-TOL_C, TOL_P, TOL_F, TOL_ENT, TOL_DIST = 2e-6, 1e-4, 3e-5, 5e-6, 1e-6
+TOL_C, TOL_P, TOL_F, TOL_ENT, TOL_DIST = 2e-6, 1e-4, 1e-5, 5e-6, 1e-6
+
+
+def tol_f(ref64, ref32):
+    """SURVEY 8d parity gate for matched features / grad_ys: max(1e-5, 1.5 x the fp32 oracle's own error vs fp64)."""
+    worst = 0.0
+    for a, b in zip(ref64, ref32):
+        a, b = np.concatenate(a) if isinstance(a, list) else a, np.concatenate(b) if isinstance(b, list) else b
+        worst = max(worst, float(np.abs(b.astype(np.float64) - a).max() / np.abs(a).max()))
+    return max(TOL_F, 1.5 * worst)
 
 
 def relerr(a, ref):
@@ -186,25 +197,29 @@ def test_sinkhorn_large_blocks(M, nblk, rows, cols, lam, T):
 
 def test_single_batch_at_headline_size(M):
     """utils/matching.py:88-136 at N = 256: three 256 x 256 blocks with +999 on the aa/bb diagonals."""
-    N, D, G = 256, 2048, 4
+    N, D, G = 256, 32768, 4
     A, B = mo.synth_embeddings(N, D, 1, "clustered", sigma=1.0), mo.synth_embeddings(N, D, 2, "clustered", sigma=1.0)
-    ref = mo.get_matched_features_single_batch(list(np.split(A, G)), list(np.split(B, G)), 500.0, 50)
-    got = M.get_matched_features_single_batch(towers(A, G), towers(B, G), 500.0, 50)
+    fa, fb = list(np.split(A, G)), list(np.split(B, G))
+    ref = mo.get_matched_features_single_batch(fa, fb, 500.0, 100)
+    tol = tol_f(ref[:4], mo.get_matched_features_single_batch(fa, fb, 500.0, 100, np.float32)[:4])
+    got = M.get_matched_features_single_batch(towers(A, G), towers(B, G), 500.0, 100)
     for i in range(4):
-        assert relerr(torch.cat(got[i]), np.concatenate(ref[i])) < TOL_F
+        assert relerr(torch.cat(got[i]), np.concatenate(ref[i])) < tol, (i, tol)
     assert abs(float(got[4]) - ref[4]) <= TOL_ENT * abs(ref[4])
 
 
-def test_two_batch_h256(M):
-    """BASELINE config 5 block size (h = 256) through the public API."""
-    N, D, G = 512, 4096, 8
+@pytest.mark.parametrize("D", [4096, 131072])
+def test_two_batch_h256(M, D):
+    """BASELINE config 5 (N = 512, h = 256, D = 131072 = the 64 x 64 critic's feature count, 8 towers) through the public API."""
+    N, G = 512, 8
     A, B = mo.synth_embeddings(N, D, 1, "clustered", sigma=1.0), mo.synth_embeddings(N, D, 2, "clustered", sigma=1.0)
     fa, fb = list(np.split(A, G)), list(np.split(B, G))
     ref = mo.get_matched_features(fa, fb, 500.0, 100)
+    tol = tol_f(ref[:4], mo.get_matched_features(fa, fb, 500.0, 100, np.float32)[:4])
     ta, tb = towers(A, G), towers(B, G)
     got = M.get_matched_features(ta, tb, 500.0, 100)
     for i in range(4):
-        assert relerr(torch.cat(got[i]), np.concatenate(ref[i])) < TOL_F
+        assert relerr(torch.cat(got[i]), np.concatenate(ref[i])) < tol, (i, tol)
     assert abs(float(M.calc_distance(ta, tb, got)) - mo.calc_distance(fa, fb, ref)) < TOL_DIST
 
 
@@ -258,6 +273,8 @@ CONFIGS = [
     (256, 32768, 2, 500.0, 100, "iid"),
     (256, 32768, 8, 500.0, 100, "clustered"),
     (256, 7296, 4, 500.0, 100, "clustered"),
+    (256, 32768, 2, 500.0, 500, "clustered"),       # BASELINE config 3 at its real size: T = 500
+    (256, 32768, 2, 500.0, 500, "iid"),
     (64, 512, 4, 500.0, 500, "clustered"),
     (12, 37, 2, 100.0, 7, "iid"),
 ]
@@ -270,11 +287,12 @@ def test_get_matched_features_vs_fp64_oracle(M, N, D, G, lam, T, kind):
     fa, fb = list(np.split(A, G)), list(np.split(B, G))
     ref = mo.get_matched_features(fa, fb, lam, T)
     ref_dist = mo.calc_distance(fa, fb, ref)
+    tol = tol_f(ref[:4], mo.get_matched_features(fa, fb, lam, T, np.float32)[:4])
     ta, tb = towers(A, G), towers(B, G)
     got = M.get_matched_features(ta, tb, lam, T)
     assert len(got) == 5 and all(len(got[i]) == G and got[i][0].shape == (N // G, D) for i in range(4))
     for i in range(4):
-        assert relerr(torch.cat(got[i]), np.concatenate(ref[i])) < TOL_F
+        assert relerr(torch.cat(got[i]), np.concatenate(ref[i])) < tol, (i, tol)
     assert abs(float(got[4]) - ref[4]) <= TOL_ENT * abs(ref[4])
     dist = M.calc_distance(ta, tb, got)
     assert abs(float(dist) - ref_dist) < TOL_DIST
@@ -282,8 +300,8 @@ def test_get_matched_features_vs_fp64_oracle(M, N, D, G, lam, T, kind):
     ga, gb, stats = M.matching_step(ta, tb, lam, T)
     rga, rgb = mo.grad_features(ref)
     scale = max(np.abs(np.concatenate(ref[0])).max(), np.abs(np.concatenate(ref[1])).max())
-    assert np.abs(torch.cat(ga).cpu().double().numpy() - np.concatenate(rga)).max() / scale < TOL_F
-    assert np.abs(torch.cat(gb).cpu().double().numpy() - np.concatenate(rgb)).max() / scale < TOL_F
+    assert np.abs(torch.cat(ga).cpu().double().numpy() - np.concatenate(rga)).max() / scale < tol
+    assert np.abs(torch.cat(gb).cpu().double().numpy() - np.concatenate(rgb)).max() / scale < tol
     assert abs(float(stats[0]) - ref_dist) < TOL_DIST
     assert abs(float(stats[1]) - ref[4]) <= TOL_ENT * abs(ref[4])
 
@@ -312,10 +330,12 @@ def test_tower_list_layouts_agree(M):
 def test_single_batch_vs_oracle(M):
     N, D, G = 96, 1024, 3
     A, B = mo.synth_embeddings(N, D, 1, "clustered", sigma=1.0), mo.synth_embeddings(N, D, 2, "clustered", sigma=1.0)
-    ref = mo.get_matched_features_single_batch(list(np.split(A, G)), list(np.split(B, G)), 500.0, 50)
+    fa, fb = list(np.split(A, G)), list(np.split(B, G))
+    ref = mo.get_matched_features_single_batch(fa, fb, 500.0, 50)
+    tol = tol_f(ref[:4], mo.get_matched_features_single_batch(fa, fb, 500.0, 50, np.float32)[:4])
     got = M.get_matched_features_single_batch(towers(A, G), towers(B, G), 500.0, 50)
     for i in range(4):
-        assert relerr(torch.cat(got[i]), np.concatenate(ref[i])) < TOL_F
+        assert relerr(torch.cat(got[i]), np.concatenate(ref[i])) < tol, (i, tol)
     assert abs(float(got[4]) - ref[4]) <= TOL_ENT * abs(ref[4])
 
 
@@ -333,13 +353,7 @@ def test_toy_matching_cpu_mirror():
     A = rng.randn(512, 16).astype(np.float32)                 # notebook-2 shape: batch 512, D=16, lambda 50, T 10
     B = (rng.randn(512, 16) * 0.5 + 1.0).astype(np.float32)
     ref = mo.toy_get_matched_features(A, B, 50.0, 10)
-    # h = 256 exceeds the single-CTA Sinkhorn kernel: use the 64-row toy shape of BASELINE config 1 when unsupported
-    try:
-        got = T.get_matched_features(dev(A), dev(B), 50.0, 10)
-    except Exception:
-        A, B = A[:64], B[:64]
-        ref = mo.toy_get_matched_features(A, B, 50.0, 10)
-        got = T.get_matched_features(dev(A), dev(B), 50.0, 10)
+    got = T.get_matched_features(dev(A), dev(B), 50.0, 10)
     for i in range(4):
         assert relerr(got[i], ref[i]) < TOL_F
     assert abs(float(got[4]) - ref[4]) <= TOL_ENT * abs(ref[4])
@@ -347,7 +361,7 @@ def test_toy_matching_cpu_mirror():
     assert abs(float(d) - mo.toy_calc_distance(A, B, ref)) < 1e-6
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))))
+@pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith("ref_")))
 def test_golden_vectors_on_gpu(M, path):
     g = np.load(path)
     name = os.path.basename(path)
@@ -381,6 +395,30 @@ def test_errors_surface_as_exceptions(M):
     with pytest.raises(TypeError):
         M.get_matched_features([torch.zeros(2, 4, device="cuda", dtype=torch.float64)] * 2,
                                [torch.zeros(2, 4, device="cuda", dtype=torch.float64)] * 2, 1.0, 1)
-    big = torch.zeros(1, 1100, 1100, device="cuda")
-    with pytest.raises(_lib.OtganError, match="not supported"):
-        M.sinkhorn(big, 1.0, 1)
+
+
+def test_results_are_caller_owned(M):
+    """A second call must not overwrite the tensors the first call returned (round-1 hazard: shared persistent buffers)."""
+    rng = np.random.RandomState(3)
+    X1, X2 = dev(rng.rand(16, 64).astype(np.float32)), dev(rng.rand(16, 64).astype(np.float32))
+    L1 = M.cost_blocks([X1], [X1], 10.0)
+    keep = L1.clone()
+    L2 = M.cost_blocks([X2], [X2], 10.0)
+    assert L1.data_ptr() != L2.data_ptr() and torch.equal(L1, keep)
+    P1, e1, _ = M.sinkhorn(L1, 10.0, 5)
+    keepP = P1.clone()
+    P2, e2, _ = M.sinkhorn(L2, 10.0, 5)
+    assert P1.data_ptr() != P2.data_ptr() and torch.equal(P1, keepP) and e1.data_ptr() != e2.data_ptr()
+
+
+@pytest.mark.parametrize("rows,cols,T", [(1100, 1100, 3), (1300, 2500, 2)])
+def test_sinkhorn_any_size(M, rows, cols, T):
+    """Blocks above 1024 (the reference's default flags give h = 2500): the online-LSE streaming kernels."""
+    rng = np.random.RandomState(rows)
+    C = rng.rand(1, rows, cols)
+    L0 = dev((-50.0 * C).astype(np.float32))
+    P, ent, pc = M.sinkhorn(L0, 50.0, T)
+    C32 = L0.cpu().double().numpy() / -50.0
+    p, e, _ = mo.sinkhorn(C32[0], 50.0, T, np.float64)
+    assert relerr(P[0], p) < TOL_P and abs(float(ent[0]) - e) <= TOL_ENT * abs(e)
+    assert abs(float(pc[0]) - np.sum(p * C32[0])) < 2e-5 * rows

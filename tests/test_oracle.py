@@ -128,7 +128,7 @@ def test_fp32_oracle_is_within_the_parity_gate_of_fp64():
     assert abs(mo.calc_distance(fa, fb, r32, np.float32) - mo.calc_distance(fa, fb, r64)) < 1e-6
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))))
+@pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith("ref_")))
 def test_golden_vectors(path):
     g = np.load(path)
     name = os.path.basename(path)
