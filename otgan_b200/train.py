@@ -164,6 +164,7 @@ class Trainer:
         Ga, Gb, stats = self._match(A.detach(), B.detach())
         lo, hi = local_rows(self.rank, bs)
         ga, gb = Ga[lo:hi], Gb[lo:hi]                                                            # this rank's towers
+        self.last_grad_ys = (Ga, Gb)
         if train_disc:
             (grad,) = torch.autograd.grad([feats], [disc.flat], grad_outputs=[torch.cat([ga, gb], 0)])   # :122-128
             if self.world > 1:
@@ -304,6 +305,58 @@ def gather_features(f_gen, f_dat, world):
 def local_rows(rank, bs_local):
     """Row range of this rank's towers inside the gathered [N, D] feature / grad_ys matrices."""
     return rank * bs_local, (rank + 1) * bs_local
+
+
+def parity_check(world, rank, device, n_total=64, backends=(("cudnn", 1e-3), ("tcgen05", 5e-3))):
+    """Multi-rank parity of one critic step and one generator step (used by tests/mgpu_parity.py and `bench.py --gpus N`):
+    the summed tower gradient, distance and entropy computed by `world` ranks (all-gather + own-row backward + all-reduce)
+    against the same step computed by ONE rank on the full batch with identical images, latents and parameters, plus a
+    BITWISE check that every rank derives identical grad_ys / distance / entropy from the gathered embeddings (the
+    replicated cost + Sinkhorn partition is deterministic).  Not bitwise on the gradients: per-rank batch sizes change the
+    tile / split-K configuration of the convolution kernels, i.e. the fp32 summation order, so the gate is relative
+    (1e-3 strict-fp32 library rung, 5e-3 TF32 tensor-core rung) at lambda = 10 where Sinkhorn does not amplify that noise.
+    Collective on every rank; returns {"ok": bool, "rows": [...], "matching_bitwise": bool}."""
+    prev_tf32, prev_backend = torch.backends.cudnn.allow_tf32, nn.CONV_BACKEND
+    torch.backends.cudnn.allow_tf32 = False
+    towers = 2 * world
+    argv = ["--synthetic", "--nr_gpu", str(towers), "--batch_size", str(n_total // towers), "--nr_sinkhorn_iter", "50",
+            "--sinkhorn_lambda", "10"]
+    g = torch.Generator().manual_seed(1234)
+    x_all = (torch.rand((n_total, 32, 32, 3), generator=g) * 2 - 1).to(device)
+    u_all = (torch.rand((n_total, 100), generator=g) * 2 - 1).to(device)
+    ok, rows, bitwise = True, [], True
+    try:
+        for backend, gate in backends:
+            nn.CONV_BACKEND = backend
+            for step_kind in ("disc", "gen"):
+                res = {}
+                for mode in ("multi", "single"):
+                    w, r = (world, rank) if mode == "multi" else (1, 0)
+                    tr = Trainer(build_parser().parse_args(argv), device, r, w)                  # same seed -> identical parameters
+                    tr.step_counter = 0 if step_kind == "disc" else 1
+                    bs = tr.bs_local
+                    lo = r * bs
+                    kind, stats = tr.step(x_all[lo:lo + bs], u=u_all[lo:lo + bs], apply_update=False)
+                    assert kind == step_kind
+                    res[mode] = (tr.last_grad.clone(), stats.clone(), tr.last_grad_ys)
+                gm, sm, ys = res["multi"]
+                gs, ss, _ = res["single"]
+                if world > 1:                                   # every rank must hold the same bits of grad_ys / stats
+                    for t in (ys[0], ys[1], sm):
+                        hi, lo_ = t.clone(), t.clone()
+                        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+                        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+                        bitwise = bitwise and bool(torch.equal(hi, lo_))
+                rel = float((gm - gs).abs().max() / gs.abs().max())
+                dd, de = abs(float(sm[0] - ss[0])), abs(float(sm[1] - ss[1]))
+                rows.append({"backend": backend, "step": step_kind, "grad_rel_err": rel, "d_distance": dd, "d_entropy": de, "gate": gate})
+                ok = ok and rel < gate and dd < 1e-6 and de < 1e-5
+    finally:
+        nn.CONV_BACKEND, torch.backends.cudnn.allow_tf32 = prev_backend, prev_tf32
+    flag = torch.tensor([1.0 if (ok and bitwise) else 0.0], device=device)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return {"ok": bool(flag.item() == 1.0), "world": world, "rows": rows, "matching_bitwise": bitwise}
 
 
 def maybe_flip(x, rng):

@@ -75,6 +75,20 @@ def test_oracle_reproduces_the_reference_matching(path):
     assert abs(res[4] - float(g["entropy"])) < 1e-11 and abs(dist - float(g["dist"])) < 1e-12
 
 
+@pytest.mark.parametrize("path", [p for p in MATCHING if "two_batch" in p and "toy" not in p])
+def test_torch_cpu_restatement_reproduces_the_reference_matching(path):
+    """oracle/torch_oracle.py (the CPU baseline bench.py times: one torch op per TensorFlow op, fp32) against the fixtures."""
+    from oracle import torch_oracle as to
+    g = np.load(path)
+    A, B, lam, T, G = g["A"], g["B"], float(g["lam"]), int(g["T"]), int(g["G"])
+    fa = [torch.from_numpy(x) for x in np.split(A, G)]
+    fb = [torch.from_numpy(x) for x in np.split(B, G)]
+    res = to.get_matched_features(fa, fb, lam, T)
+    for i, k in enumerate(["f_aa", "f_bb", "f_ab", "f_ba"]):
+        assert relerr(torch.cat(res[i]), g[k]) < 3e-5, k                      # fp32 noise floor of this path (SURVEY App. C)
+    assert abs(float(res[4]) - float(g["entropy"])) < 1e-5 and abs(float(to.calc_distance(fa, fb, res)) - float(g["dist"])) < 1e-6
+
+
 def _assign_by_name(template):
     with torch.no_grad():
         for n, p in template.named_parameters():
