@@ -244,6 +244,64 @@ OTGAN_API int otgan_col2im_narrow_f32(int B, int H, int W, int C, int kh, int kw
 OTGAN_API size_t otgan_workspace_bytes_colsum(int P, int C);
 OTGAN_API int otgan_colsum_f32(int P, int C, const float* x, float* out, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- generic convolutions (any channel counts / batch; utils/nn.py:234-241, 328-338 accept any shape) ---------------------------------
+ * The same tcgen05 kernels in their generic mode: channel counts are multiples of 4, spatial extents powers of two, the batch is
+ * arbitrary; x / y / dy / dx may be channel SLICES of wider NHWC buffers (pixel strides ldx / ldy in floats, pointers at the first
+ * channel used) -- this is how DenseNet's growing list input (models/densenet.py:10-15) is read without a concatenation.
+ * Weights: w [Cout][kh*kw][Cin] (fprop), w_ihwo [Cin][kh*kw][Cout] (dgrad), dense.  TMA zero-fills the K tail of every tap and the
+ * rows past Cout, partial tiles are masked in the epilogue.
+ * epilogue (fprop): OTGAN_EPI_NONE  y = conv + bias                                       [.., Cout] at pixel stride ldy
+ *                   OTGAN_EPI_CRELU8 y = crelu8(conv + bias): channel c -> relu at (c/8)*16 + c%8, relu(-.) at (c/8)*16 + 8 + c%8
+ *                                                                                          [.., 2 Cout] at pixel stride ldy (Cout % 8 == 0)
+ * The crelu8 order is this library's layout of CReLU-activated tensors (utils/nn.py:198-200 concatenates [x, -x] per list
+ * element); otgan_crelu8_perm_host gives the matching permutation of a filter's input channels. */
+enum { OTGAN_EPI_NONE = 0, OTGAN_EPI_CRELU8 = 1 };
+OTGAN_API int otgan_conv2d_fprop_ex_tf32(int B, int H, int W, int Cin, int ldx, int Cout, int ldy, int kh, int kw, int stride,
+                                         int pad_top, int pad_left, const float* x, const float* w, const float* bias, float* y,
+                                         int epilogue, void* stream);
+OTGAN_API int otgan_conv2d_dgrad_ex_tf32(int B, int H, int W, int Cin, int ldx, int Cout, int ldy, int kh, int kw, int stride,
+                                         int pad_top, int pad_left, const float* dy, const float* w_ihwo, float* dx, void* stream);
+OTGAN_API size_t otgan_workspace_bytes_conv_wgrad_ex(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride);
+OTGAN_API int otgan_conv2d_wgrad_ex_tf32(int B, int H, int W, int Cin, int ldx, int Cout, int ldy, int kh, int kw, int stride,
+                                         int pad_top, int pad_left, const float* dy, const float* x, float* dw, void* ws,
+                                         size_t ws_bytes, void* stream);
+/* crelu8 activation of a [P, C] tensor (row stride ldx) into a 2C-channel slot (row stride ldz), and its backward:
+ * dx[c] = (z_pos > 0 ? dz_pos : 0) - (z_neg > 0 ? dz_neg : 0).  C % 8 == 0. */
+OTGAN_API int otgan_crelu8_fwd_f32(long long P, int C, const float* x, int ldx, float* z, int ldz, void* stream);
+OTGAN_API int otgan_crelu8_bwd_f32(long long P, int C, const float* z, int ldz, const float* dz, int lddz, float* dx, int lddx,
+                                   void* stream);
+/* perm_host[t * C2 + cz] = t * C2 + cref: row of the reference's HWIO kernel (input channel order [x_0, -x_0, x_1, -x_1, ...] over
+ * the list elements, utils/nn.py:198-200) that feeds crelu8 channel cz; C2 = 2 * sum(elem_ch).  Returns taps * C2 or < 0. */
+OTGAN_API int otgan_crelu8_perm_host(int n_elem, const int* elem_ch, int taps, int* perm_host, int capacity);
+/* Weight norm with an optional row permutation (device int array, NULL = identity) and an optionally strided Wt / dWt
+ * ([C][taps][cin] with strides ldrow / ldtap floats when cin > 0): the generic form of otgan_weightnorm_{fwd,bwd}_f32. */
+OTGAN_API int otgan_weightnorm_fwd_ex_f32(int K, int C, const float* V, const float* g, const int* perm_dev, int cin,
+                                          long long ldtap, long long ldrow, float* Wt, float* inv_norm, void* ws, size_t ws_bytes,
+                                          void* stream);
+OTGAN_API int otgan_weightnorm_bwd_ex_f32(int K, int C, const float* V, const float* g, const float* inv_norm, const int* perm_dev,
+                                          int cin, long long ldtap, long long ldrow, const float* dWt, float* dV, float* dg, void* ws,
+                                          size_t ws_bytes, void* stream);
+
+/* ---- DenseNet dense block (models/densenet.py:10-15, 56-61: `block`) ---------------------------------------------------------------
+ * x = [e_0 .. e_{n_base-1}] (base elements, base_ch[i] channels each, multiples of 8); L times: x.append(conv3x3(crelu(x), 16)).
+ * Z [B,H,W,Ctot], Ctot = otgan_dense_channels = 2 (sum base_ch + 16 L): the crelu8-activated list, element after element.  The
+ * caller fills the base slots (otgan_crelu8_fwd_f32); fprop runs the L layers, each reading the channel prefix of Z and writing
+ * its own slot from the convolution's epilogue.  wf_host[r]: W_r as [16][9][cin_r], cin_r = 2 (sum base_ch + 16 r), input channels
+ * in Z order (otgan_weightnorm_fwd_ex_f32 with the otgan_crelu8_perm_host permutation); bias_host[r]: [16] or NULL.
+ * bgrad: dZ = gradient w.r.t. Z from the block's consumer; writes dY [B,H,W,16L] (gradients of the L pre-activations),
+ * dbase_host[i] [B,H,W,base_ch[i]], dW_all [16L][9][Ctot] (row block r valid for ci < cin_r) and db_all [16L] (either may be NULL).
+ * WB [Ctot][9][16L] = otgan_dense_build_wb_f32(wf_host): the weight operand of the backward "gather" convolutions. */
+typedef struct { int B, H, W, n_base, base_ch[4], L, growth; } otgan_dense_geom_t;
+OTGAN_API int otgan_dense_channels(const otgan_dense_geom_t* geom);
+OTGAN_API size_t otgan_dense_wb_floats(const otgan_dense_geom_t* geom);
+OTGAN_API int otgan_dense_build_wb_f32(const otgan_dense_geom_t* geom, const float* const* wf_host, float* WB, void* stream);
+OTGAN_API int otgan_dense_block_fprop_tf32(const otgan_dense_geom_t* geom, const float* const* wf_host,
+                                           const float* const* bias_host, float* Z, void* stream);
+OTGAN_API size_t otgan_workspace_bytes_dense_bgrad(const otgan_dense_geom_t* geom);
+OTGAN_API int otgan_dense_block_bgrad_tf32(const otgan_dense_geom_t* geom, const float* Z, const float* dZ, const float* WB,
+                                           float* dY, float* const* dbase_host, float* dW_all, float* db_all, void* ws,
+                                           size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

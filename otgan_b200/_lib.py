@@ -25,6 +25,14 @@ class Plan(ctypes.Structure):
                 ("coef", (_f * OTGAN_MAX_TERMS) * OTGAN_MAX_OUTPUTS)]
 
 
+class DenseGeom(ctypes.Structure):
+    """otgan_dense_geom_t"""
+    _fields_ = [("B", _i), ("H", _i), ("W", _i), ("n_base", _i), ("base_ch", _i * 4), ("L", _i), ("growth", _i)]
+
+
+_ll = ctypes.c_longlong
+_gp = ctypes.POINTER(DenseGeom)
+
 # name -> (restype, argtypes); must list every symbol include/otgan.h declares (tests/test_abi.py checks this)
 SIGNATURES = {
     "otgan_abi_version": (_i, []),
@@ -73,6 +81,21 @@ SIGNATURES = {
     "otgan_col2im_narrow_f32": (_i, [_i] * 9 + [_vp, _i, _vp, _vp, _vp]),
     "otgan_workspace_bytes_colsum": (_sz, [_i, _i]),
     "otgan_colsum_f32": (_i, [_i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "otgan_conv2d_fprop_ex_tf32": (_i, [_i] * 12 + [_vp, _vp, _vp, _vp, _i, _vp]),
+    "otgan_conv2d_dgrad_ex_tf32": (_i, [_i] * 12 + [_vp, _vp, _vp, _vp]),
+    "otgan_workspace_bytes_conv_wgrad_ex": (_sz, [_i] * 8),
+    "otgan_conv2d_wgrad_ex_tf32": (_i, [_i] * 12 + [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "otgan_crelu8_fwd_f32": (_i, [_ll, _i, _vp, _i, _vp, _i, _vp]),
+    "otgan_crelu8_bwd_f32": (_i, [_ll, _i, _vp, _i, _vp, _i, _vp, _i, _vp]),
+    "otgan_crelu8_perm_host": (_i, [_i, ctypes.POINTER(_i), _i, ctypes.POINTER(_i), _i]),
+    "otgan_weightnorm_fwd_ex_f32": (_i, [_i, _i, _vp, _vp, _vp, _i, _ll, _ll, _vp, _vp, _vp, _sz, _vp]),
+    "otgan_weightnorm_bwd_ex_f32": (_i, [_i, _i, _vp, _vp, _vp, _vp, _i, _ll, _ll, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "otgan_dense_channels": (_i, [_gp]),
+    "otgan_dense_wb_floats": (_sz, [_gp]),
+    "otgan_dense_build_wb_f32": (_i, [_gp, _vp, _vp, _vp]),
+    "otgan_dense_block_fprop_tf32": (_i, [_gp, _vp, _vp, _vp, _vp]),
+    "otgan_workspace_bytes_dense_bgrad": (_sz, [_gp]),
+    "otgan_dense_block_bgrad_tf32": (_i, [_gp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -1,6 +1,6 @@
 // abi.cu -- extern "C" entry points of libotgan.so (declared in include/otgan.h): argument validation, implementation
 // selection and the plans that express the reference's matched-feature regrouping.  No torch types, no allocation.
-#include "common.cuh"
+#include "conv_ex.cuh"
 #include <string.h>
 
 namespace otgan {
@@ -53,6 +53,19 @@ int crelu_l2norm_fwd_launch(int B, int HW, int C, const float* x, float* y, floa
 int crelu_l2norm_bwd_launch(int B, int HW, int C, const float* x, const float* y, const float* inv, const float* dy,
                             float* dx, cudaStream_t stream);
 
+int weightnorm_fwd_ex_launch(int K, int C, const float* V, const float* g, const int* perm, int cin, long long ldtap, long long ldrow,
+                             float* Wt, float* inv, void* ws, cudaStream_t stream);
+int weightnorm_bwd_ex_launch(int K, int C, const float* V, const float* g, const float* inv, const int* perm, int cin, long long ldtap,
+                             long long ldrow, const float* dWt, float* dV, float* dg, void* ws, cudaStream_t stream);
+int crelu8_fwd_launch(long long P, int C, const float* x, int ldx, float* z, int ldz, cudaStream_t stream);
+int crelu8_bwd_launch(long long P, int C, const float* z, int ldz, const float* dz, int lddz, float* dx, int lddx, cudaStream_t stream);
+int dense_channels(const otgan_dense_geom_t* g);
+size_t dense_wb_floats(const otgan_dense_geom_t* g);
+int dense_build_wb_launch(const otgan_dense_geom_t* g, const float* const* wf, float* WB, cudaStream_t stream);
+int dense_block_fprop_launch(const otgan_dense_geom_t* g, const float* const* wf, const float* const* bias, float* Z, cudaStream_t stream);
+size_t dense_bgrad_workspace_bytes(const otgan_dense_geom_t* g);
+int dense_block_bgrad_launch(const otgan_dense_geom_t* g, const float* Z, const float* dZ, const float* WB, float* dY,
+                             float* const* dbase, float* dW_all, float* db_all, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t weightnorm_workspace_bytes(int K, int C);
 int weightnorm_fwd_launch(int K, int C, const float* V, const float* g, float* Wt, float* inv, void* ws, cudaStream_t stream);
 int weightnorm_bwd_launch(int K, int C, const float* V, const float* g, const float* inv, const float* dWt, float* dV,
@@ -488,6 +501,138 @@ int otgan_conv_plan_describe(int op, int B, int H, int W, int Cin, int Cout, int
     OTGAN_REQUIRE(out_host && capacity > 0, "conv_plan_describe: null output");
     OTGAN_REQUIRE(op >= 3 || stride == 1 || stride == 2, "conv_plan_describe: stride %d not in {1, 2}", stride);
     return conv_plan_describe(op, B, H, W, Cin, Cout, kh, kw, op >= 3 ? 1 : stride, pad_top, pad_left, out_host, capacity);
+}
+
+// ---- generic convolutions / crelu8 / DenseNet dense block -------------------------------------------------------------------
+static void conv_ex_fill(ConvEx& c, int B, int H, int W, int kh, int kw, int stride, int pt, int pl)
+{
+    memset(&c, 0, sizeof(c));
+    c.B = B; c.H = H; c.W = W; c.kh = kh; c.kw = kw; c.stride = stride; c.pt = pt; c.pl = pl;
+}
+
+int otgan_conv2d_fprop_ex_tf32(int B, int H, int W, int Cin, int ldx, int Cout, int ldy, int kh, int kw, int stride, int pad_top,
+                               int pad_left, const float* x, const float* w, const float* bias, float* y, int epilogue, void* stream)
+{
+    OTGAN_REQUIRE(x && w && y, "conv2d_fprop_ex: null pointer");
+    OTGAN_REQUIRE(epilogue == OTGAN_EPI_NONE || epilogue == OTGAN_EPI_CRELU8, "conv2d_fprop_ex: unknown epilogue %d", epilogue);
+    OTGAN_REQUIRE(Cin >= 4 && !(Cin & 3) && Cout >= 1 && ldx >= Cin && ldy >= (epilogue == OTGAN_EPI_CRELU8 ? 2 * Cout : Cout),
+                  "conv2d_fprop_ex: bad channel counts / strides (Cin=%d ldx=%d Cout=%d ldy=%d)", Cin, ldx, Cout, ldy);
+    ConvEx c;
+    conv_ex_fill(c, B, H, W, kh, kw, stride, pad_top, pad_left);
+    c.a = x; c.Ka = Cin; c.lda = ldx;
+    c.out = y; c.N = Cout; c.ldo = ldy;
+    c.w = w; c.w_K = Cin; c.w_taps = kh * kw; c.w_rows = Cout; c.w_ldtap = Cin; c.w_ldrow = (long long)kh * kw * Cin;
+    c.bias = bias;
+    c.epi_mode = epilogue == OTGAN_EPI_CRELU8 ? EPI_CRELU8 : EPI_PLAIN;
+    return conv_fprop_ex_launch(c, (cudaStream_t)stream);
+}
+
+int otgan_conv2d_dgrad_ex_tf32(int B, int H, int W, int Cin, int ldx, int Cout, int ldy, int kh, int kw, int stride, int pad_top,
+                               int pad_left, const float* dy, const float* w_ihwo, float* dx, void* stream)
+{
+    OTGAN_REQUIRE(dy && w_ihwo && dx, "conv2d_dgrad_ex: null pointer");
+    OTGAN_REQUIRE(Cout >= 4 && !(Cout & 3) && Cin >= 1 && ldx >= Cin && ldy >= Cout,
+                  "conv2d_dgrad_ex: bad channel counts / strides (Cin=%d ldx=%d Cout=%d ldy=%d)", Cin, ldx, Cout, ldy);
+    ConvEx c;
+    conv_ex_fill(c, B, H, W, kh, kw, stride, pad_top, pad_left);
+    c.a = dy; c.Ka = Cout; c.lda = ldy;
+    c.out = dx; c.N = Cin; c.ldo = ldx;
+    c.w = w_ihwo; c.w_K = Cout; c.w_taps = kh * kw; c.w_rows = Cin; c.w_ldtap = Cout; c.w_ldrow = (long long)kh * kw * Cout;
+    c.epi_mode = EPI_PLAIN;
+    return conv_dgrad_ex_launch(c, (cudaStream_t)stream);
+}
+
+size_t otgan_workspace_bytes_conv_wgrad_ex(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride)
+{
+    if (B < 1 || H < 1 || W < 1 || Cin < 1 || Cout < 1 || kh < 1 || kw < 1 || (stride != 1 && stride != 2)) return 0;
+    return conv_wgrad_ex_workspace_bytes(B, H / stride, W / stride, Cin, Cout, kh, kw);
+}
+
+int otgan_conv2d_wgrad_ex_tf32(int B, int H, int W, int Cin, int ldx, int Cout, int ldy, int kh, int kw, int stride, int pad_top,
+                               int pad_left, const float* dy, const float* x, float* dw, void* ws, size_t ws_bytes, void* stream)
+{
+    OTGAN_REQUIRE(dy && x && dw, "conv2d_wgrad_ex: null pointer");
+    OTGAN_REQUIRE(ldx >= Cin && ldy >= Cout, "conv2d_wgrad_ex: pixel stride smaller than the channel count");
+    return conv_wgrad_ex_launch(B, H, W, Cin, ldx, Cout, ldy, kh, kw, stride, pad_top, pad_left, dy, x, dw, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int otgan_crelu8_fwd_f32(long long P, int C, const float* x, int ldx, float* z, int ldz, void* stream)
+{
+    OTGAN_REQUIRE(x && z && ldx >= C && ldz >= 2 * C, "crelu8_fwd: null pointer / row stride too small");
+    return crelu8_fwd_launch(P, C, x, ldx, z, ldz, (cudaStream_t)stream);
+}
+
+int otgan_crelu8_bwd_f32(long long P, int C, const float* z, int ldz, const float* dz, int lddz, float* dx, int lddx, void* stream)
+{
+    OTGAN_REQUIRE(z && dz && dx && ldz >= 2 * C && lddz >= 2 * C && lddx >= C, "crelu8_bwd: null pointer / row stride too small");
+    return crelu8_bwd_launch(P, C, z, ldz, dz, lddz, dx, lddx, (cudaStream_t)stream);
+}
+
+int otgan_crelu8_perm_host(int n_elem, const int* elem_ch, int taps, int* perm_host, int capacity)
+{
+    OTGAN_REQUIRE(n_elem >= 1 && elem_ch && perm_host && taps >= 1, "crelu8_perm: bad arguments");
+    int c2 = 0;
+    for (int i = 0; i < n_elem; ++i) {
+        OTGAN_REQUIRE(elem_ch[i] >= 8 && !(elem_ch[i] & 7), "crelu8_perm: element %d has %d channels (needs a multiple of 8)", i, elem_ch[i]);
+        c2 += 2 * elem_ch[i];
+    }
+    if (taps * c2 > capacity) { set_error("crelu8_perm: needs %d entries, buffer holds %d", taps * c2, capacity); return OTGAN_ENOSPC; }
+    for (int t = 0; t < taps; ++t) {
+        int off = 0;
+        for (int i = 0; i < n_elem; ++i) {
+            const int ci = elem_ch[i];
+            for (int c = 0; c < ci; ++c)
+                for (int sgn = 0; sgn < 2; ++sgn) {
+                    const int cz = 2 * off + (c / 8) * 16 + sgn * 8 + (c % 8);       // crelu8 order (this library)
+                    const int cref = 2 * off + sgn * ci + c;                          // [x_i, -x_i] per element (utils/nn.py:198-200)
+                    perm_host[t * c2 + cz] = t * c2 + cref;
+                }
+            off += ci;
+        }
+    }
+    return taps * c2;
+}
+
+int otgan_weightnorm_fwd_ex_f32(int K, int C, const float* V, const float* g, const int* perm_dev, int cin, long long ldtap,
+                                long long ldrow, float* Wt, float* inv_norm, void* ws, size_t ws_bytes, void* stream)
+{
+    OTGAN_REQUIRE(K >= 1 && C >= 1 && V && g && Wt && inv_norm && ws, "weightnorm_fwd_ex: bad arguments");
+    OTGAN_REQUIRE(cin == 0 || (cin > 0 && K % cin == 0 && ldtap >= cin && ldrow >= (K / cin - 1) * ldtap + cin), "weightnorm_fwd_ex: bad strides");
+    OTGAN_REQUIRE(ws_bytes >= weightnorm_workspace_bytes(K, C), "weightnorm_fwd_ex: workspace too small");
+    return weightnorm_fwd_ex_launch(K, C, V, g, perm_dev, cin, ldtap, ldrow, Wt, inv_norm, ws, (cudaStream_t)stream);
+}
+
+int otgan_weightnorm_bwd_ex_f32(int K, int C, const float* V, const float* g, const float* inv_norm, const int* perm_dev, int cin,
+                                long long ldtap, long long ldrow, const float* dWt, float* dV, float* dg, void* ws, size_t ws_bytes,
+                                void* stream)
+{
+    OTGAN_REQUIRE(K >= 1 && C >= 1 && V && g && inv_norm && dWt && dV && dg && ws, "weightnorm_bwd_ex: bad arguments");
+    OTGAN_REQUIRE(cin == 0 || (cin > 0 && K % cin == 0 && ldtap >= cin && ldrow >= (K / cin - 1) * ldtap + cin), "weightnorm_bwd_ex: bad strides");
+    OTGAN_REQUIRE(ws_bytes >= weightnorm_workspace_bytes(K, C), "weightnorm_bwd_ex: workspace too small");
+    return weightnorm_bwd_ex_launch(K, C, V, g, inv_norm, perm_dev, cin, ldtap, ldrow, dWt, dV, dg, ws, (cudaStream_t)stream);
+}
+
+int otgan_dense_channels(const otgan_dense_geom_t* geom)
+{
+    const int c = dense_channels(geom);
+    if (c < 0) { set_error("dense: bad geometry (base channels multiples of 8, 1 <= L <= 32, growth 16)"); return OTGAN_EINVAL; }
+    return c;
+}
+size_t otgan_dense_wb_floats(const otgan_dense_geom_t* geom) { return dense_wb_floats(geom); }
+int otgan_dense_build_wb_f32(const otgan_dense_geom_t* geom, const float* const* wf_host, float* WB, void* stream)
+{
+    return dense_build_wb_launch(geom, wf_host, WB, (cudaStream_t)stream);
+}
+int otgan_dense_block_fprop_tf32(const otgan_dense_geom_t* geom, const float* const* wf_host, const float* const* bias_host, float* Z,
+                                 void* stream)
+{
+    return dense_block_fprop_launch(geom, wf_host, bias_host, Z, (cudaStream_t)stream);
+}
+size_t otgan_workspace_bytes_dense_bgrad(const otgan_dense_geom_t* geom) { return dense_bgrad_workspace_bytes(geom); }
+int otgan_dense_block_bgrad_tf32(const otgan_dense_geom_t* geom, const float* Z, const float* dZ, const float* WB, float* dY,
+                                 float* const* dbase_host, float* dW_all, float* db_all, void* ws, size_t ws_bytes, void* stream)
+{
+    return dense_block_bgrad_launch(geom, Z, dZ, WB, dY, dbase_host, dW_all, db_all, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -30,6 +30,7 @@
 // weight-layout helpers (OHWI -> IHWO, sub-filter pre-sum / un-sum), the bias-gradient column sum, and the host-only plan
 // capture behind otgan_conv_plan_describe that lets CPU tests replay the exact tap tables a launch would use.
 #include "tc_common.cuh"
+#include "conv_ex.cuh"
 #include <string.h>
 
 namespace otgan {
@@ -82,7 +83,104 @@ struct GemmParams {
     long long osW, osH, osN;                  // output pixel strides (floats)
     float* out;
     const float* bias;                        // [N] or null
+    // ---- generic mode (any channel counts / batch, channel slices of wider buffers, fused epilogues): DenseNet and every
+    // shape outside the DCGAN family.  The weight operand is a 3-D tensor [K, taps, rows] so that TMA zero-fills both the K
+    // tail of a tap and the rows past N; the accumulator N is a run-time multiple of 16 (n_inst <= TN); rows / columns outside
+    // the tensor are masked in the epilogue.
+    int generic;
+    int b_k0;                                 // K coordinate of the first weight column used (a K-slice of a wider weight tensor)
+    int n_inst;                               // UMMA N of this launch (= the N tile stride: tile nt covers columns [nt * n_inst, ..))
+    int m_w, m_h, m_b;                        // valid extents of the tile grid (row mask)
+    int epi_mode;                             // EPI_PLAIN / EPI_CRELU8 / EPI_CRELU8_BWD
+    const float* e_add;                       // EPI_CRELU8_BWD: g = acc + e_add (may be null), sign pattern from e_z; both are
+    const float* e_z;                         //   [.., 2 * N_out] slices addressed with the strides below
+    long long esW, esH, esN;
 };
+
+// Epilogues of the generic mode.  CReLU slot layout ("crelu8"): channel c of a tensor with C channels is stored as
+// relu(x_c) at (c / 8) * 16 + c % 8 and relu(-x_c) at (c / 8) * 16 + 8 + c % 8 -- blocks of 8 positive then 8 negative parts,
+// so that one thread's 32 accumulator columns map to 64 (forward) / 16 (backward) contiguous output floats.
+
+template <int TN>
+__device__ __forceinline__ void epilogue_generic(const GemmParams& p, uint32_t tmem_acc, int nt, float* orow, long long epix, bool row_ok)
+{
+    int lim = (nt + 1) * p.n_inst;                                // first column this tile does NOT own
+    lim = lim > p.n_valid ? p.n_valid : lim;
+    const int ncols = lim - nt * p.n_inst;
+#pragma unroll 1
+    for (int cc = 0; cc * 32 < ncols; ++cc) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_acc + (uint32_t)(cc * 32), v);        // warp-collective: every lane executes it, masked rows included
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        const int col0 = nt * p.n_inst + cc * 32;
+        if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (col0 + j < lim) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(p.bias + col0 + j));
+        }
+        if (p.epi_mode == EPI_PLAIN) {
+            float* o = orow + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                if (col0 + j + 3 < lim) {
+                    *reinterpret_cast<uint4*>(o + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (col0 + j + e < lim) o[j + e] = __uint_as_float(v[j + e]);
+                }
+            }
+        } else if (p.epi_mode == EPI_CRELU8) {
+            float* o = orow + 2 * col0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (col0 + 8 * q < lim) {
+                    float pos[8], neg[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float x = __uint_as_float(v[8 * q + i]);
+                        pos[i] = fmaxf(x, 0.f);
+                        neg[i] = fmaxf(-x, 0.f);
+                    }
+                    *reinterpret_cast<float4*>(o + 16 * q) = make_float4(pos[0], pos[1], pos[2], pos[3]);
+                    *reinterpret_cast<float4*>(o + 16 * q + 4) = make_float4(pos[4], pos[5], pos[6], pos[7]);
+                    *reinterpret_cast<float4*>(o + 16 * q + 8) = make_float4(neg[0], neg[1], neg[2], neg[3]);
+                    *reinterpret_cast<float4*>(o + 16 * q + 12) = make_float4(neg[4], neg[5], neg[6], neg[7]);
+                }
+            }
+        } else {    // EPI_CRELU8_BWD: 32 accumulator columns (gradient of a crelu8 slot) -> 16 gradients of the pre-activation
+            float* o = orow + (col0 >> 1);
+            const float* z = p.e_z + epix + col0;
+            const float* a = p.e_add ? p.e_add + epix + col0 : nullptr;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (col0 + 16 * q < lim) {
+                    float d[8];
+#pragma unroll
+                    for (int i4 = 0; i4 < 8; i4 += 4) {
+                        const float4 zp = __ldg(reinterpret_cast<const float4*>(z + 16 * q + i4));
+                        const float4 zn = __ldg(reinterpret_cast<const float4*>(z + 16 * q + 8 + i4));
+                        float4 ap = make_float4(0.f, 0.f, 0.f, 0.f), an = ap;
+                        if (a) {
+                            ap = __ldg(reinterpret_cast<const float4*>(a + 16 * q + i4));
+                            an = __ldg(reinterpret_cast<const float4*>(a + 16 * q + 8 + i4));
+                        }
+                        const float gp[4] = {__uint_as_float(v[16 * q + i4]) + ap.x, __uint_as_float(v[16 * q + i4 + 1]) + ap.y,
+                                             __uint_as_float(v[16 * q + i4 + 2]) + ap.z, __uint_as_float(v[16 * q + i4 + 3]) + ap.w};
+                        const float gn[4] = {__uint_as_float(v[16 * q + 8 + i4]) + an.x, __uint_as_float(v[16 * q + 8 + i4 + 1]) + an.y,
+                                             __uint_as_float(v[16 * q + 8 + i4 + 2]) + an.z, __uint_as_float(v[16 * q + 8 + i4 + 3]) + an.w};
+                        const float zpv[4] = {zp.x, zp.y, zp.z, zp.w}, znv[4] = {zn.x, zn.y, zn.z, zn.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) d[i4 + e] = (zpv[e] > 0.f ? gp[e] : 0.f) - (znv[e] > 0.f ? gn[e] : 0.f);
+                    }
+                    *reinterpret_cast<float4*>(o + 8 * q) = make_float4(d[0], d[1], d[2], d[3]);
+                    *reinterpret_cast<float4*>(o + 8 * q + 4) = make_float4(d[4], d[5], d[6], d[7]);
+                }
+            }
+        }
+    }
+}
 
 template <int TN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -154,7 +252,8 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
                         mbar_arrive_expect_tx(full_bar(s), (uint32_t)(A_TILE + p.b_box_bytes));
                         const uint32_t dst = smem_base + s * C::STAGE_BYTES;
                         tma_load_4d(dst, am, full_bar(s), kc * BK, w0 + tap.dw, h0 + tap.dh, n0);
-                        tma_load_2d(dst + A_TILE, &p.bmap, full_bar(s), tap.wcol + kc * BK, tap.brow + nt * TN);
+                        if (p.generic) tma_load_3d(dst + A_TILE, &p.bmap, full_bar(s), p.b_k0 + kc * BK, tap.dmap, tap.brow + nt * p.n_inst);
+                        else tma_load_2d(dst + A_TILE, &p.bmap, full_bar(s), tap.wcol + kc * BK, tap.brow + nt * TN);
                     }
                 }
             }
@@ -162,7 +261,7 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
     } else if (warp == 1) {
         // ===================================================== MMA issuer (one thread)
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(TM, TN);
+            const uint32_t idesc = umma_idesc_tf32(TM, p.generic ? p.n_inst : TN);
             int c = 0, n = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
                 int mt, nt, cls, sp, t0, t1, tail;
@@ -209,7 +308,15 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
             }
             mbar_wait(tfull_bar(b), ((uint32_t)(n >> 1)) & 1u);
             tcgen05_fence_after();
-            if constexpr (TN == 16) {
+            if (p.generic) {
+                if constexpr (TN != 16) {
+                    const bool row_ok = (w0 + rw < p.m_w) && (h0 + rh < p.m_h) && (n0 + rn < p.m_b);
+                    const long long epix = (long long)(n0 + rn) * p.esN + (long long)(h0 + rh) * p.esH + (long long)(w0 + rw) * p.esW;
+                    float* orow = p.out + p.cls_out_off[cls] + (long long)(n0 + rn) * p.osN + (long long)(h0 + rh) * p.osH +
+                                  (long long)(w0 + rw) * p.osW;
+                    epilogue_generic<TN>(p, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TN), nt, orow, epix, row_ok);
+                }
+            } else if constexpr (TN == 16) {
                 // narrow outputs (the generator's 3-channel image, the critic's image gradient): only n_valid columns exist;
                 // the weight box has n_valid rows, the other accumulator columns hold garbage and are never stored
                 uint32_t v[16];
@@ -460,6 +567,7 @@ struct WgradParams {
     int ldw;                                  // row stride of dW (= ntaps * Cin)
     long long split_stride;                   // floats between split partials
     float* out;
+    int masked, m_valid, n_valid;             // generic shapes: rows (co) >= m_valid / columns (ci) >= n_valid are not stored
 };
 
 // wgrad thread layout: warp 0 = producer of the dy boxes (+ expect_tx), warp 1 = MMA issuer, warps 2-5 = epilogue,
@@ -592,14 +700,23 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradParams p)
             float* out = p.out + (long long)sp * p.split_stride + (long long)(p.taps[t].brow + cot * TM + r) * p.ldw + p.taps[t].wcol + cit * TN;
             mbar_wait(tfull_bar(b), ((uint32_t)(n >> 1)) & 1u);
             tcgen05_fence_after();
+            const bool row_ok = !p.masked || (cot * TM + r < p.m_valid);
 #pragma unroll 1
             for (int cc = 0; cc < TN / 32; ++cc) {
+                if (p.masked && cit * TN + cc * 32 >= p.n_valid) break;          // warp-uniform
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TN + cc * 32), v);
                 tmem_ld_wait();
+                if (!row_ok) continue;
+                if (!p.masked || cit * TN + cc * 32 + 32 <= p.n_valid) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<uint4*>(out + cc * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<uint4*>(out + cc * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (cit * TN + cc * 32 + j < p.n_valid) out[cc * 32 + j] = __uint_as_float(v[j]);
+                }
             }
             tcgen05_fence_before();
             mbar_arrive(tempty_bar(b));
@@ -795,13 +912,37 @@ bool conv_map_2d(CUtensorMap* map, const float* base, int rows, int cols, int ld
 }
 
 // 4-D view of an NHWC tensor [B, H, W, C] sub-sampled by `s` starting at pixel (ph, pw): dims [C, W/s, H/s, B]
+// `ld` = pixel stride in floats (0: the tensor is dense, ld = C); with ld > C the view is a channel SLICE of a wider buffer
+// (DenseNet's concatenated feature buffer): channels past C are outside the tensor and zero-filled like the spatial padding.
 bool make_view_map(CUtensorMap* map, const float* base, int B, int H, int W, int C, int s, int ph, int pw,
-                   const unsigned box[4], CUtensorMapSwizzle swz)
+                   const unsigned box[4], CUtensorMapSwizzle swz, int ld = 0)
 {
     if (capturing()) return true;
+    const unsigned long long L = (unsigned long long)(ld > 0 ? ld : C);
     const unsigned long long dims[4] = {(unsigned long long)C, (unsigned long long)(W / s), (unsigned long long)(H / s), (unsigned long long)B};
-    const unsigned long long str[3] = {(unsigned long long)s * C * 4, (unsigned long long)s * W * C * 4, (unsigned long long)H * W * C * 4};
-    return make_tensor_map_nd(map, base + ((size_t)ph * W + pw) * C, 4, dims, str, box, swz);
+    const unsigned long long str[3] = {(unsigned long long)s * L * 4, (unsigned long long)s * W * L * 4, (unsigned long long)H * W * L * 4};
+    return make_tensor_map_nd(map, base + ((size_t)ph * W + pw) * L, 4, dims, str, box, swz);
+}
+
+// 3-D weight tensor of the generic mode: [K (innermost), taps, rows], row stride ldrow floats, tap stride ldtap floats
+bool make_weight_map_3d(CUtensorMap* map, const float* base, int K, int taps, int rows, long long ldtap, long long ldrow, int box_rows)
+{
+    if (capturing()) return true;
+    const unsigned long long dims[3] = {(unsigned long long)K, (unsigned long long)taps, (unsigned long long)rows};
+    const unsigned long long str[2] = {(unsigned long long)ldtap * 4, (unsigned long long)ldrow * 4};
+    const unsigned box[3] = {(unsigned)BK, 1u, (unsigned)box_rows};
+    return make_tensor_map_nd(map, base, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+// generic pixel box: like pixel_box, but the batch need not be a multiple of bn (the overhang is zero-filled / masked)
+bool pixel_box_generic(int npix, int Wt, int Ht, int* bw, int* bh, int* bn)
+{
+    if (!is_pow2(Wt) || !is_pow2(Ht)) return false;
+    *bw = Wt < npix ? Wt : npix;
+    const int rem = npix / *bw;
+    *bh = Ht < rem ? Ht : rem;
+    *bn = rem / *bh;
+    return (*bw) * (*bh) * (*bn) == npix && *bn <= 256;
 }
 
 // Split-K of fprop / dgrad: when a launch has fewer tiles than SMs (small batch per GPU), the taps of each class are
@@ -852,7 +993,7 @@ int run_gemm(GemmParams& p, int TN, size_t out_numel, float* out, void* ws, size
         min_taps = T < min_taps ? T : min_taps;
     }
     const int tiles = p.m_tiles * p.n_tiles * p.n_cls;
-    p.splits = (out_numel % 4) ? 1 : gemm_splits(tiles, min_taps);
+    p.splits = ((out_numel % 4) || p.generic) ? 1 : gemm_splits(tiles, min_taps);   // generic: slices / fused epilogues are not split
     if (p.splits > 1 && (!ws || ws_bytes < (size_t)p.splits * out_numel * sizeof(float))) p.splits = 1;   // no room: unsplit
     p.split_stride = (long long)out_numel;
     p.out = p.splits > 1 ? reinterpret_cast<float*>(ws) : out;
@@ -861,7 +1002,7 @@ int run_gemm(GemmParams& p, int TN, size_t out_numel, float* out, void* ws, size
     p.tail_ws = nullptr;
     // 256 x 256 tiles (two sub-tiles share the weight tile) when the launch keeps >= 0.75 waves of them and a tile is long
     // enough to amortise the un-overlapped epilogue
-    if (g_use_gemm2 && p.splits == 1 && TN == 256 && (p.m_tiles & 1) == 0 && tiles / 2 >= (kNumSMs * 3) / 4 && min_taps * p.kchunks >= g_gemm2_min_chunks) {
+    if (g_use_gemm2 && !p.generic && p.splits == 1 && TN == 256 && (p.m_tiles & 1) == 0 && tiles / 2 >= (kNumSMs * 3) / 4 && min_taps * p.kchunks >= g_gemm2_min_chunks) {
         p.n_items = tiles / 2;
         if (capturing()) { t_capture->kind = 1; t_capture->TN = 256; t_capture->gemm = p; return OTGAN_OK; }
         // per-device attribute: set on every launch (a process-wide flag would miss a second GPU)
@@ -872,7 +1013,7 @@ int run_gemm(GemmParams& p, int TN, size_t out_numel, float* out, void* ws, size
         return OTGAN_OK;
     }
     int n_tail = 0;
-    if (g_tail_split && p.splits == 1 && TN >= 128 && ws) {   // cut the last, partial wave of tiles along the taps
+    if (g_tail_split && !p.generic && p.splits == 1 && TN >= 128 && ws) {   // cut the last, partial wave of tiles along the taps
         n_tail = tiles % kNumSMs;
         const int S = tail_splits_for(n_tail, min_taps);
         if (S > 1 && ws_bytes >= (size_t)n_tail * S * TM * TN * sizeof(float)) {
@@ -884,7 +1025,8 @@ int run_gemm(GemmParams& p, int TN, size_t out_numel, float* out, void* ws, size
         }
     }
     p.n_items = p.n_full + n_tail * p.tail_splits;
-    const int rc = TN == 256 ? launch_gemm<256>(p, stream) : TN == 128 ? launch_gemm<128>(p, stream) : launch_gemm<16>(p, stream);
+    const int rc = TN == 256 ? launch_gemm<256>(p, stream) : TN == 128 ? launch_gemm<128>(p, stream)
+                 : TN == 32 ? launch_gemm<32>(p, stream) : launch_gemm<16>(p, stream);
     if (rc != OTGAN_OK) return rc;
     if (capturing()) { t_capture->n_tail = n_tail; return OTGAN_OK; }
     if (n_tail > 0) {
@@ -1058,6 +1200,119 @@ int conv_dgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
     return run_gemm(p, TN, (size_t)B * H * W * Cin, dx, ws, ws_bytes, stream);
 }
 
+// ---------------------------------------------------------------------------------------------- generic fprop / dgrad
+// Any channel counts (multiples of 4), any batch, power-of-two spatial extents; operands may be channel SLICES of wider NHWC
+// buffers (pixel strides lda / ldo); the weight operand is a K-slice / row-slice of a 3-D tensor [w_K, taps, w_rows].
+static int tn_for(int N, int* n_inst)
+{
+    if (N <= 32) { *n_inst = (N + 15) / 16 * 16; return 32; }
+    const int tiles = (N + 255) / 256;
+    *n_inst = ((N + tiles - 1) / tiles + 15) / 16 * 16;
+    return 256;
+}
+
+static bool ex_common(GemmParams& p, const ConvEx& c, int TN)
+{
+    p.generic = 1;
+    p.b_k0 = c.k0;
+    p.n_valid = c.N;
+    p.b_box_bytes = p.n_inst * BK * 4;
+    p.kchunks = (c.Ka + BK - 1) / BK;
+    p.n_tiles = (c.N + p.n_inst - 1) / p.n_inst;
+    p.bias = c.bias;
+    p.epi_mode = c.epi_mode; p.e_add = c.e_add; p.e_z = c.e_z;
+    (void)TN;
+    return make_weight_map_3d(&p.bmap, c.w, c.w_K, c.w_taps, c.w_rows, c.w_ldtap, c.w_ldrow, p.n_inst);
+}
+
+static bool ex_args_ok(const ConvEx& c)
+{
+    if (c.B < 1 || c.H < 1 || c.W < 1 || c.kh < 1 || c.kw < 1 || c.kh * c.kw > MAX_TAPS) return false;
+    if ((c.stride != 1 && c.stride != 2) || c.pt < 0 || c.pl < 0 || c.pt >= c.kh || c.pl >= c.kw || c.H % c.stride || c.W % c.stride) return false;
+    if (c.Ka < 1 || c.N < 1 || (c.lda & 3) || (c.ldo & 3) || (c.w_ldtap & 3) || (c.w_ldrow & 3) || (c.k0 & 3)) return false;
+    if (!aligned16(c.a) || !aligned16(c.out) || !aligned16(c.w)) return false;
+    if (c.epi_mode == EPI_CRELU8 && (c.N & 7)) return false;
+    if (c.epi_mode == EPI_CRELU8_BWD && ((c.N & 15) || c.stride != 1 || !c.e_z || (c.e_ld & 3))) return false;
+    return true;
+}
+
+// y[B, H/s, W/s, N] = conv(x[B, H, W, Ka], w) (+ bias) (+ epilogue)
+int conv_fprop_ex_launch(const ConvEx& c, cudaStream_t stream)
+{
+    OTGAN_REQUIRE(ex_args_ok(c), "conv_fprop_ex: bad arguments / alignment");
+    const int s = c.stride, Ho = c.H / s, Wo = c.W / s;
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    if (!pixel_box_generic(TM, Wo, Ho, &p.bw, &p.bh, &p.bn)) {
+        set_error("conv_fprop_ex(tcgen05): output extent %dx%d must be powers of two", Ho, Wo);
+        return OTGAN_EUNSUPPORTED;
+    }
+    const int TN = tn_for(c.N, &p.n_inst);
+    const unsigned box[4] = {(unsigned)BK, (unsigned)p.bw, (unsigned)p.bh, (unsigned)p.bn};
+    for (int ph = 0; ph < s; ++ph)
+        for (int pw = 0; pw < s; ++pw)
+            if (!make_view_map(&p.amap[ph * s + pw], c.a, c.B, c.H, c.W, c.Ka, s, ph, pw, box, CU_TENSOR_MAP_SWIZZLE_128B, c.lda)) return OTGAN_EUNSUPPORTED;
+    for (int i = s * s; i < 4; ++i) p.amap[i] = p.amap[0];
+    if (!ex_common(p, c, TN)) return OTGAN_EUNSUPPORTED;
+    int nt = 0;
+    for (int a = 0; a < c.kh; ++a)
+        for (int b = 0; b < c.kw; ++b) {
+            const int oh = a - c.pt, ow = b - c.pl;
+            const int ph = oh & (s - 1), pw = ow & (s - 1);
+            p.taps[nt++] = Tap{ph * s + pw, (ow - pw) / s, (oh - ph) / s, 0, c.row0, a * c.kw + b};
+        }
+    p.n_cls = 1;
+    p.cls_tap_begin[0] = 0; p.cls_tap_begin[1] = nt;
+    p.tiles_w = Wo / p.bw; p.tiles_h = Ho / p.bh;
+    p.m_tiles = p.tiles_w * p.tiles_h * ceil_div(c.B, p.bn);
+    p.m_w = Wo; p.m_h = Ho; p.m_b = c.B;
+    p.osW = c.ldo; p.osH = (long long)Wo * c.ldo; p.osN = (long long)Ho * Wo * c.ldo;
+    p.esW = c.e_ld; p.esH = (long long)Wo * c.e_ld; p.esN = (long long)Ho * Wo * c.e_ld;
+    return run_gemm(p, TN, 0, c.out, nullptr, 0, stream);
+}
+
+// dx[B, H, W, N] = conv_transpose(dy[B, H/s, W/s, Ka], w[N rows][taps][K]) (+ epilogue); the weight rows are the INPUT channels
+int conv_dgrad_ex_launch(const ConvEx& c, cudaStream_t stream)
+{
+    OTGAN_REQUIRE(ex_args_ok(c), "conv_dgrad_ex: bad arguments / alignment");
+    const int s = c.stride, Ho = c.H / s, Wo = c.W / s;
+    OTGAN_REQUIRE(c.kh >= s && c.kw >= s, "conv_dgrad_ex: filter smaller than the stride");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    if (!pixel_box_generic(TM, Wo, Ho, &p.bw, &p.bh, &p.bn)) {
+        set_error("conv_dgrad_ex(tcgen05): extent %dx%d must be powers of two", Ho, Wo);
+        return OTGAN_EUNSUPPORTED;
+    }
+    const int TN = tn_for(c.N, &p.n_inst);
+    const unsigned box[4] = {(unsigned)BK, (unsigned)p.bw, (unsigned)p.bh, (unsigned)p.bn};
+    if (!make_view_map(&p.amap[0], c.a, c.B, Ho, Wo, c.Ka, 1, 0, 0, box, CU_TENSOR_MAP_SWIZZLE_128B, c.lda)) return OTGAN_EUNSUPPORTED;
+    for (int i = 1; i < 4; ++i) p.amap[i] = p.amap[0];
+    if (!ex_common(p, c, TN)) return OTGAN_EUNSUPPORTED;
+    int nt = 0;
+    p.n_cls = s * s;
+    for (int ph = 0; ph < s; ++ph)
+        for (int pw = 0; pw < s; ++pw) {
+            const int cls = ph * s + pw;
+            p.cls_tap_begin[cls] = nt;
+            p.cls_out_off[cls] = ((long long)ph * c.W + pw) * c.ldo;
+            for (int a = 0; a < c.kh; ++a) {
+                if ((ph + c.pt - a) % s) continue;
+                for (int b = 0; b < c.kw; ++b) {
+                    if ((pw + c.pl - b) % s) continue;
+                    p.taps[nt++] = Tap{0, (pw + c.pl - b) / s, (ph + c.pt - a) / s, 0, c.row0, a * c.kw + b};
+                }
+            }
+            if (nt == p.cls_tap_begin[cls]) { set_error("conv_dgrad_ex: a parity class has no filter tap"); return OTGAN_EUNSUPPORTED; }
+        }
+    p.cls_tap_begin[p.n_cls] = nt;
+    p.tiles_w = Wo / p.bw; p.tiles_h = Ho / p.bh;
+    p.m_tiles = p.tiles_w * p.tiles_h * ceil_div(c.B, p.bn);
+    p.m_w = Wo; p.m_h = Ho; p.m_b = c.B;
+    p.osW = (long long)s * c.ldo; p.osH = (long long)s * c.W * c.ldo; p.osN = (long long)c.H * c.W * c.ldo;
+    p.esW = c.e_ld; p.esH = (long long)c.W * c.e_ld; p.esN = (long long)c.H * c.W * c.e_ld;      // epilogue inputs: stride 1 only
+    return run_gemm(p, TN, 0, c.out, nullptr, 0, stream);
+}
+
 size_t conv_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int kh, int kw)
 {
     const int TN = (Cin % 256 == 0) ? 256 : 128;
@@ -1114,6 +1369,80 @@ int conv_wgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
     } else {
         p.out = dw;
     }
+    const int rc = TN == 256 ? launch_wgrad<256>(p, stream) : launch_wgrad<128>(p, stream);
+    if (rc != OTGAN_OK || p.splits == 1 || capturing()) return rc;
+    const size_t n4 = (size_t)p.split_stride / 4;
+    const int grid = (int)((n4 + 255) / 256 < (size_t)(8 * kNumSMs) ? (n4 + 255) / 256 : (size_t)(8 * kNumSMs));
+    split_reduce_kernel<<<grid, 256, 0, stream>>>(n4, p.splits, n4, reinterpret_cast<const float4*>(p.out), reinterpret_cast<float4*>(dw));
+    OTGAN_CHECK_LAUNCH("split_reduce_kernel");
+    return OTGAN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- generic wgrad
+// dw[Cout][kh*kw][Cin] = sum over pixels dy[.., co] x[.. + tap, ci] for any channel counts (multiples of 4) / batch; dy and x may
+// be channel slices of wider buffers (pixel strides ldy / ldx).  Tiles past Cout / Cin read zeros (TMA) and are not stored.
+static int wgrad_ex_tn(int Cin)
+{
+    const int w256 = ceil_div(Cin, 256) * 256, w128 = ceil_div(Cin, 128) * 128;
+    return w128 < w256 ? 128 : 256;
+}
+
+size_t conv_wgrad_ex_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int kh, int kw)
+{
+    const int TN = wgrad_ex_tn(Cin);
+    const int items = ceil_div(Cout, TM) * ceil_div(Cin, TN) * kh * kw;
+    const long long P = (long long)B * Ho * Wo;
+    const double dw_bytes = 4.0 * Cout * kh * kw * Cin;
+    const int S = wgrad_splits(items, (int)((P + 31) / 32), 0.5 * dw_bytes * (double)P, dw_bytes);
+    return S > 1 ? (size_t)S * Cout * kh * kw * Cin * sizeof(float) + 256 : 256;
+}
+
+int conv_wgrad_ex_launch(int B, int H, int W, int Cin, int ldx, int Cout, int ldy, int kh, int kw, int s, int pt, int pl,
+                         const float* dy, const float* x, float* dw, void* ws, size_t ws_bytes, cudaStream_t stream)
+{
+    OTGAN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && kh >= 1 && kw >= 1 && kh * kw <= MAX_TAPS && (s == 1 || s == 2) && pt >= 0 && pl >= 0 &&
+                  pt < kh && pl < kw && H % s == 0 && W % s == 0, "conv_wgrad_ex: unsupported geometry");
+    OTGAN_REQUIRE(Cin >= 4 && Cout >= 4 && !(Cin & 3) && !(Cout & 3) && !(ldx & 3) && !(ldy & 3) && aligned16(dy) && aligned16(x) && aligned16(dw),
+                  "conv_wgrad_ex: channel counts / strides must be multiples of 4, pointers 16-byte aligned");
+    const int Ho = H / s, Wo = W / s;
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    if (!pixel_box_generic(32, Wo, Ho, &p.bw, &p.bh, &p.bn)) {
+        set_error("conv_wgrad_ex(tcgen05): output extent %dx%d must be powers of two", Ho, Wo);
+        return OTGAN_EUNSUPPORTED;
+    }
+    const int TN = wgrad_ex_tn(Cin);
+    const unsigned box[4] = {32u, (unsigned)p.bw, (unsigned)p.bh, (unsigned)p.bn};
+    if (!make_view_map(&p.dymap[0], dy, B, Ho, Wo, Cout, 1, 0, 0, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, ldy)) return OTGAN_EUNSUPPORTED;
+    for (int i = 1; i < 4; ++i) p.dymap[i] = p.dymap[0];
+    for (int ph = 0; ph < s; ++ph)
+        for (int pw = 0; pw < s; ++pw)
+            if (!make_view_map(&p.xmap[ph * s + pw], x, B, H, W, Cin, s, ph, pw, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, ldx)) return OTGAN_EUNSUPPORTED;
+    for (int i = s * s; i < 4; ++i) p.xmap[i] = p.xmap[0];
+    int nt = 0;
+    for (int a = 0; a < kh; ++a)
+        for (int b = 0; b < kw; ++b) {
+            const int oh = a - pt, ow = b - pl;
+            const int ph = oh & (s - 1), pw = ow & (s - 1);
+            p.taps[nt++] = Tap{ph * s + pw, (ow - pw) / s, (oh - ph) / s, (a * kw + b) * Cin, 0, 0};
+        }
+    p.ntaps = nt;
+    p.co_tiles = ceil_div(Cout, TM); p.ci_tiles = ceil_div(Cin, TN);
+    p.tiles_w = Wo / p.bw; p.tiles_h = Ho / p.bh;
+    p.nchunks = p.tiles_w * p.tiles_h * ceil_div(B, p.bn);
+    p.masked = 1; p.m_valid = Cout; p.n_valid = Cin;
+    const int items = p.co_tiles * p.ci_tiles * nt;
+    const double dw_bytes = 4.0 * Cout * nt * Cin;
+    p.splits = wgrad_splits(items, p.nchunks, 0.5 * dw_bytes * (double)B * Ho * Wo, dw_bytes);
+    p.chunks_per_split = ceil_div(p.nchunks, p.splits);
+    p.splits = ceil_div(p.nchunks, p.chunks_per_split);
+    p.n_items = items * p.splits;
+    p.ldw = nt * Cin;
+    p.split_stride = (long long)Cout * p.ldw;
+    if (p.splits > 1 && (!ws || ws_bytes < (size_t)p.splits * p.split_stride * sizeof(float))) {       // no room: unsplit
+        p.splits = 1; p.chunks_per_split = p.nchunks; p.n_items = items;
+    }
+    p.out = p.splits > 1 ? reinterpret_cast<float*>(ws) : dw;
     const int rc = TN == 256 ? launch_wgrad<256>(p, stream) : launch_wgrad<128>(p, stream);
     if (rc != OTGAN_OK || p.splits == 1 || capturing()) return rc;
     const size_t n4 = (size_t)p.split_stride / 4;

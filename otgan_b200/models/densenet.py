@@ -13,16 +13,16 @@ from ..utils.nn import arg_scope
 
 # //// discriminator ////
 def disc_spec(x, init=False, layers_per_block=16, filters_per_layer=16, nonlinearity='crelu', ema=None, **kwargs):
-    with arg_scope([nn.conv2d, nn.dense], counters={}, init=init, weight_norm=True, ema=ema):
+    with arg_scope([nn.conv2d, nn.dense, nn.dense_block], counters={}, init=init, weight_norm=True, ema=ema):
 
         def block(x):
             if type(x) is not list:
                 x = [x]
-            for rep in range(layers_per_block):
-                x.append(nn.conv2d(x, filters_per_layer, pre_activation=nonlinearity))
-            return x
+            return nn.dense_block(x, layers_per_block, filters_per_layer, pre_activation=nonlinearity)      # :10-15
 
         def downsample(x):
+            if isinstance(x, nn.Crelu8Tensor):
+                return nn.conv2d(x, x.raw_channels // 2, pre_activation=nonlinearity, stride=[2, 2])
             if type(x) is not list:
                 x = [x]
             return nn.conv2d(x, int(np.sum([int(xi.shape[-1]) for xi in x])) // 2, pre_activation=nonlinearity, stride=[2, 2])
@@ -52,16 +52,16 @@ def gen_spec(batch_size, init=False, layers_per_block=16, filters_per_layer=16, 
              torch.rand((batch_size, 16, 16, filters_per_layer), device=device) * 2.0 - 1.0,
              torch.rand((batch_size, 32, 32, filters_per_layer), device=device) * 2.0 - 1.0]
 
-    with arg_scope([nn.conv2d, nn.dense], counters={}, init=init, weight_norm=True, ema=ema):
+    with arg_scope([nn.conv2d, nn.dense, nn.dense_block], counters={}, init=init, weight_norm=True, ema=ema):
 
         def block(x):
             if type(x) is not list:
                 x = [x]
-            for rep in range(layers_per_block):
-                x.append(nn.conv2d(x, filters_per_layer, pre_activation=nonlinearity))
-            return x
+            return nn.dense_block(x, layers_per_block, filters_per_layer, pre_activation=nonlinearity)      # :56-61
 
         def upsample(x):
+            if isinstance(x, nn.Crelu8Tensor):           # resize commutes with the element-wise CReLU
+                return nn.conv2d(x.upsample2x(), x.raw_channels // 2, pre_activation=nonlinearity)
             if type(x) is list:
                 x = torch.cat(x, 3)
             xs = list(x.shape)

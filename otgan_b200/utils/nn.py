@@ -345,6 +345,7 @@ def _conv2d_nhwc(x, W, stride, pad, bias=None):
 CONV_BACKEND = "tcgen05"      # "tcgen05": this library's implicit-GEMM kernels where they tile the shape; "cudnn": library rung only
 UPSAMPLE_FUSION = True        # nn.upsample2x / nn.glu(upsample=True) hand the following conv2d an un-materialised Upsampled2x
 CONV_NARROW = True            # route the two 3-channel layers through _ConvNarrow (False: cuDNN, for A/B timing)
+DENSE_BLOCK_FUSION = True     # nn.dense_block runs DenseNet's blocks on the dense-block kernels (False: the literal list code)
 _conv_ws = {}
 _wn_ws = {}
 _retired_ws = []              # outgrown scratch buffers stay alive: a captured CUDA graph may still hold their addresses
@@ -852,14 +853,283 @@ class _WeightNorm(torch.autograd.Function):
         return dV.view(ctx.vshape), dg
 
 
+
+# ------------------------------------------------------------------------------------------------ generic convolutions / DenseNet
+def conv_gen_supported(xshape, cout, kh, kw, stride, pad):
+    """Shapes the GENERIC mode of the tcgen05 kernels takes (otgan_conv2d_*_ex_tf32): 'SAME' padding, stride 1 or 2, power-of-two
+    spatial extents; any batch and any channel counts (padded to multiples of 4 here)."""
+    B, H, W, cin = xshape
+    if pad != "SAME" or stride[0] != stride[1] or stride[0] not in (1, 2) or kh * kw > 40 or kh < stride[0] or kw < stride[0]:
+        return False
+    s = stride[0]
+    return H % s == 0 and W % s == 0 and _pow2(H // s) and _pow2(W // s) and B >= 1
+
+
+class _ConvGen(torch.autograd.Function):
+    """tf.nn.conv2d(x, W, [1,s,s,1], 'SAME') + bias_add on the generic mode of this library's tcgen05 kernels: any batch / channel
+    counts (multiples of 4; the caller pads), x may be any NHWC tensor including a crelu8 feature buffer.  wt: [Cout, kh*kw*Cin]."""
+
+    @staticmethod
+    def forward(ctx, x, wt, bias, geom):
+        lib = _lib.load()
+        kh, kw, s, pt, pl = geom
+        B, H, W, cin = x.shape
+        cout = wt.shape[0]
+        x, wt = x.contiguous(), wt.contiguous()
+        y = torch.empty((B, H // s, W // s, cout), device=x.device, dtype=torch.float32)
+        rc = lib.otgan_conv2d_fprop_ex_tf32(B, H, W, cin, cin, cout, cout, kh, kw, s, pt, pl, x.data_ptr(), wt.data_ptr(),
+                                            bias.data_ptr() if bias is not None else None, y.data_ptr(), 0,
+                                            torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "otgan_conv2d_fprop_ex_tf32")
+        ctx.save_for_backward(x, wt)
+        ctx.geom, ctx.has_bias = geom, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, wt = ctx.saved_tensors
+        kh, kw, s, pt, pl = ctx.geom
+        B, H, W, cin = x.shape
+        cout = wt.shape[0]
+        dy = dy.contiguous()
+        stream = torch.cuda.current_stream().cuda_stream
+        dx = dwt = db = None
+        if ctx.needs_input_grad[0]:
+            wt_t = torch.empty((cin, kh * kw * cout), device=x.device, dtype=torch.float32)
+            _lib.check(lib.otgan_ohwi_to_ihwo_f32(cout, kh * kw, cin, wt.data_ptr(), wt_t.data_ptr(), stream), "otgan_ohwi_to_ihwo_f32")
+            dx = torch.empty_like(x)
+            rc = lib.otgan_conv2d_dgrad_ex_tf32(B, H, W, cin, cin, cout, cout, kh, kw, s, pt, pl, dy.data_ptr(), wt_t.data_ptr(),
+                                                dx.data_ptr(), stream)
+            _lib.check(rc, "otgan_conv2d_dgrad_ex_tf32")
+        if ctx.needs_input_grad[1]:
+            ws = _workspace(x.device, lib.otgan_workspace_bytes_conv_wgrad_ex(B, H, W, cin, cout, kh, kw, s))
+            dwt = torch.empty_like(wt)
+            rc = lib.otgan_conv2d_wgrad_ex_tf32(B, H, W, cin, cin, cout, cout, kh, kw, s, pt, pl, dy.data_ptr(), x.data_ptr(),
+                                                dwt.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream)
+            _lib.check(rc, "otgan_conv2d_wgrad_ex_tf32")
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            P = dy.numel() // cout
+            ws = _workspace(x.device, lib.otgan_workspace_bytes_colsum(P, cout))
+            db = torch.empty((cout,), device=x.device, dtype=torch.float32)
+            _lib.check(lib.otgan_colsum_f32(P, cout, dy.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream), "otgan_colsum_f32")
+        return dx, dwt, db, None
+
+
+_perm_cache = {}
+
+
+def crelu8_perm(elem_ch, taps, device):
+    """Device int32 row permutation for a filter whose input is a crelu8 buffer of list elements with `elem_ch` channels:
+    Wt[c][k_z] = V[perm[k_z]][c] (otgan_crelu8_perm_host).  Cached per (elements, taps, device)."""
+    key = (tuple(int(c) for c in elem_ch), int(taps), device.index)
+    t = _perm_cache.get(key)
+    if t is None:
+        import ctypes
+        n = taps * 2 * sum(key[0])
+        buf = (ctypes.c_int * n)()
+        ch = (ctypes.c_int * len(key[0]))(*key[0])
+        rc = _lib.load().otgan_crelu8_perm_host(len(key[0]), ch, taps, buf, n)
+        if rc != n:
+            _lib.check(rc if rc < 0 else -1, "otgan_crelu8_perm_host")
+        t = _perm_cache[key] = torch.tensor(list(buf), dtype=torch.int32, device=device)
+    return t
+
+
+class _WeightNormPerm(torch.autograd.Function):
+    """W = g V / ||V|| (utils/nn.py:176-180) written output-channel-major with the K rows permuted into crelu8 order."""
+
+    @staticmethod
+    def forward(ctx, V, g, perm):
+        lib = _lib.load()
+        C = V.shape[-1]
+        K = V.numel() // C
+        Vc, gc = V.contiguous(), g.contiguous()
+        wt = torch.empty((C, K), device=V.device, dtype=torch.float32)
+        inv = torch.empty((C,), device=V.device, dtype=torch.float32)
+        ws = _wn_workspace(V.device, lib.otgan_workspace_bytes_weightnorm(K, C) // 4)
+        rc = lib.otgan_weightnorm_fwd_ex_f32(K, C, Vc.data_ptr(), gc.data_ptr(), perm.data_ptr(), 0, 0, 0, wt.data_ptr(), inv.data_ptr(),
+                                             ws.data_ptr(), ws.numel() * 4, torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "otgan_weightnorm_fwd_ex_f32")
+        ctx.save_for_backward(Vc, gc, inv, perm)
+        ctx.vshape = V.shape
+        return wt
+
+    @staticmethod
+    def backward(ctx, dwt):
+        lib = _lib.load()
+        V, g, inv, perm = ctx.saved_tensors
+        C = V.shape[-1]
+        K = V.numel() // C
+        dwt = dwt.contiguous()
+        dV, dg = torch.empty_like(V), torch.empty_like(g)
+        ws = _wn_workspace(V.device, lib.otgan_workspace_bytes_weightnorm(K, C) // 4)
+        rc = lib.otgan_weightnorm_bwd_ex_f32(K, C, V.data_ptr(), g.data_ptr(), inv.data_ptr(), perm.data_ptr(), 0, 0, 0, dwt.data_ptr(),
+                                             dV.data_ptr(), dg.data_ptr(), ws.data_ptr(), ws.numel() * 4,
+                                             torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "otgan_weightnorm_bwd_ex_f32")
+        return dV.view(ctx.vshape), dg, None
+
+
+class Crelu8Tensor:
+    """The CReLU-activated concatenation of a Python list of NHWC tensors, held as ONE buffer in this library's crelu8 slot
+    order (element i with c_i channels at raw offset o_i -> channels [2 o_i, 2 o_i + 2 c_i): blocks of 8 positive parts then
+    their 8 negative parts).  Equal, up to that fixed channel permutation, to the reference's
+    relu(concat([x_0, -x_0, x_1, -x_1, ...], 3)) (utils/nn.py:198-200); nn.conv2d consumes it with the filter's input channels
+    permuted to match.  Produced by nn.dense_block."""
+
+    def __init__(self, z, elem_ch):
+        self.z, self.elem_ch = z, [int(c) for c in elem_ch]
+
+    @property
+    def raw_channels(self):
+        return sum(self.elem_ch)
+
+    @property
+    def shape(self):
+        B, H, W, _ = self.z.shape
+        return torch.Size((B, H, W, self.raw_channels))
+
+    @property
+    def device(self):
+        return self.z.device
+
+    def upsample2x(self):
+        """tf.image.resize_nearest_neighbor of the (concatenated) list commutes with the element-wise CReLU."""
+        return Crelu8Tensor(resize_nearest_neighbor(self.z, [2 * self.z.shape[1], 2 * self.z.shape[2]]), self.elem_ch)
+
+
+class _DenseBlock(torch.autograd.Function):
+    """One dense block of models/densenet.py on otgan_dense_block_{fprop,bgrad}_tf32 (csrc/dense_block.cu).
+    Inputs: geometry, the base list elements [B,H,W,c_i], then (V_r, g_r, b_r) of the L layers.  Output: Z (crelu8 buffer)."""
+
+    @staticmethod
+    def forward(ctx, n_base, L, *tensors):
+        import ctypes
+        lib = _lib.load()
+        base = [t.contiguous() for t in tensors[:n_base]]
+        Vs, gs, bs = tensors[n_base::3], tensors[n_base + 1::3], tensors[n_base + 2::3]
+        B, H, W, _ = base[0].shape
+        dev = base[0].device
+        stream = torch.cuda.current_stream().cuda_stream
+        geom = _lib.DenseGeom()
+        geom.B, geom.H, geom.W, geom.n_base, geom.L, geom.growth = B, H, W, n_base, L, 16
+        base_ch = [int(t.shape[3]) for t in base]
+        for i, c in enumerate(base_ch):
+            geom.base_ch[i] = c
+        ctot = lib.otgan_dense_channels(ctypes.byref(geom))
+        if ctot < 0:
+            _lib.check(ctot, "otgan_dense_channels")
+        Z = torch.empty((B, H, W, ctot), device=dev, dtype=torch.float32)
+        P = B * H * W
+        off = 0
+        for t, c in zip(base, base_ch):
+            _lib.check(lib.otgan_crelu8_fwd_f32(P, c, t.data_ptr(), c, Z.data_ptr() + 4 * 2 * off, ctot, stream), "otgan_crelu8_fwd_f32")
+            off += c
+        c0 = off
+        wfs, invs = [], []
+        for r in range(L):
+            cin = 2 * (c0 + 16 * r)
+            K = 9 * cin
+            V, g = Vs[r].contiguous(), gs[r].contiguous()
+            wf = torch.empty((16, K), device=dev, dtype=torch.float32)
+            inv = torch.empty((16,), device=dev, dtype=torch.float32)
+            perm = crelu8_perm(base_ch + [16] * r, 9, dev)
+            ws = _wn_workspace(dev, lib.otgan_workspace_bytes_weightnorm(K, 16) // 4)
+            rc = lib.otgan_weightnorm_fwd_ex_f32(K, 16, V.data_ptr(), g.data_ptr(), perm.data_ptr(), 0, 0, 0, wf.data_ptr(), inv.data_ptr(),
+                                                 ws.data_ptr(), ws.numel() * 4, stream)
+            _lib.check(rc, "otgan_weightnorm_fwd_ex_f32")
+            wfs.append(wf); invs.append(inv)
+        bias = [b.contiguous() for b in bs]
+        rc = lib.otgan_dense_block_fprop_tf32(ctypes.byref(geom), _lib.ptr_array([w.data_ptr() for w in wfs]),
+                                              _lib.ptr_array([b.data_ptr() for b in bias]), Z.data_ptr(), stream)
+        _lib.check(rc, "otgan_dense_block_fprop_tf32")
+        ctx.geom, ctx.base_ch, ctx.L, ctx.n_base, ctx.ctot = geom, base_ch, L, n_base, ctot
+        ctx.wfs, ctx.invs = wfs, invs
+        ctx.save_for_backward(Z, *[t.contiguous() for t in Vs], *[t.contiguous() for t in gs])
+        return Z
+
+    @staticmethod
+    def backward(ctx, dZ):
+        import ctypes
+        lib = _lib.load()
+        saved = ctx.saved_tensors
+        L, n_base, ctot, base_ch, geom = ctx.L, ctx.n_base, ctx.ctot, ctx.base_ch, ctx.geom
+        Z, Vs, gs = saved[0], saved[1:1 + L], saved[1 + L:1 + 2 * L]
+        B, H, W, _ = Z.shape
+        dev = Z.device
+        stream = torch.cuda.current_stream().cuda_stream
+        dZ = dZ.contiguous()
+        WB = torch.empty((lib.otgan_dense_wb_floats(ctypes.byref(geom)),), device=dev, dtype=torch.float32)
+        _lib.check(lib.otgan_dense_build_wb_f32(ctypes.byref(geom), _lib.ptr_array([w.data_ptr() for w in ctx.wfs]), WB.data_ptr(), stream),
+                   "otgan_dense_build_wb_f32")
+        dY = torch.empty((B, H, W, 16 * L), device=dev, dtype=torch.float32)
+        dbase = [torch.empty((B, H, W, c), device=dev, dtype=torch.float32) for c in base_ch]
+        need_w = any(ctx.needs_input_grad[2 + n_base + 3 * r + j] for r in range(L) for j in range(3))
+        dW_all = torch.empty((16 * L, 9, ctot), device=dev, dtype=torch.float32) if need_w else None
+        db_all = torch.empty((16 * L,), device=dev, dtype=torch.float32) if need_w else None
+        ws = _workspace(dev, lib.otgan_workspace_bytes_dense_bgrad(ctypes.byref(geom)))
+        rc = lib.otgan_dense_block_bgrad_tf32(ctypes.byref(geom), Z.data_ptr(), dZ.data_ptr(), WB.data_ptr(), dY.data_ptr(),
+                                              _lib.ptr_array([t.data_ptr() for t in dbase]),
+                                              dW_all.data_ptr() if need_w else None, db_all.data_ptr() if need_w else None,
+                                              ws.data_ptr(), ws.numel() * 4, stream)
+        _lib.check(rc, "otgan_dense_block_bgrad_tf32")
+        c0 = sum(base_ch)
+        grads = []
+        for r in range(L):
+            if not need_w:
+                grads += [None, None, None]
+                continue
+            cin = 2 * (c0 + 16 * r)
+            K = 9 * cin
+            V, g = Vs[r], gs[r]
+            dV, dg = torch.empty_like(V), torch.empty_like(g)
+            perm = crelu8_perm(base_ch + [16] * r, 9, dev)
+            wsn = _wn_workspace(dev, lib.otgan_workspace_bytes_weightnorm(K, 16) // 4)
+            rc = lib.otgan_weightnorm_bwd_ex_f32(K, 16, V.data_ptr(), g.data_ptr(), ctx.invs[r].data_ptr(), perm.data_ptr(), cin, ctot,
+                                                 9 * ctot, dW_all.data_ptr() + 4 * 16 * r * 9 * ctot, dV.data_ptr(), dg.data_ptr(),
+                                                 wsn.data_ptr(), wsn.numel() * 4, stream)
+            _lib.check(rc, "otgan_weightnorm_bwd_ex_f32")
+            grads += [dV, dg, db_all[16 * r:16 * r + 16]]
+        return (None, None, *dbase, *grads)
+
+
+@add_arg_scope
+def dense_block(x, layers_per_block, filters_per_layer, pre_activation="crelu", counters=None, init=False, ema=None,
+                weight_norm=True, **kwargs):
+    """models/densenet.py:10-15 / 56-61 (`block`):  for rep in range(layers_per_block): x.append(nn.conv2d(x, filters_per_layer,
+    pre_activation=nonlinearity)).  Creates the same variables in the same order (conv2d_k/V, g, b) as those conv2d calls.
+    On the GPU with CReLU and growth 16 the whole block runs on this library's dense-block kernels and the result is a
+    Crelu8Tensor (the activated, concatenated list); otherwise the literal list code runs and the list is returned."""
+    x = list(x) if isinstance(x, (list, tuple)) else [x]
+    assert counters is not None, "dense_block needs the layer counters of the enclosing arg_scope"
+    fused = (CONV_BACKEND == "tcgen05" and DENSE_BLOCK_FUSION and weight_norm and pre_activation == "crelu" and filters_per_layer == 16
+             and not init and len(x) <= 4
+             and all(isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.shape[3] % 8 == 0 for t in x)
+             and _pow2(int(x[0].shape[1])) and _pow2(int(x[0].shape[2])) and layers_per_block <= 32 and _tls.store.frozen)
+    if not fused:
+        for rep in range(layers_per_block):
+            x.append(conv2d(x, filters_per_layer, pre_activation=pre_activation, counters=counters, init=init, ema=ema))
+        return x
+    tensors = list(x)
+    for rep in range(layers_per_block):
+        layer_name = get_name("conv2d", counters)
+        prm = get_params(layer_name, None, False, ema, raw=True)
+        tensors += [prm["V"], prm["g"], prm["b"]]
+    z = _DenseBlock.apply(len(x), layers_per_block, *tensors)
+    return Crelu8Tensor(z, [int(t.shape[3]) for t in x] + [16] * layers_per_block)
+
 # ------------------------------------------------------------------------------------------------ get_params
 def get_params(layer_name, x=None, init=False, ema=None, use_W=True, use_g=True, use_b=True, f=None, weight_norm=True,
-               init_scale=1.0, filter_size=None, num_units=None, pre_activation=None):
-    """utils/nn.py:103-183: variables V, g, b of one layer (created on the init pass), W = g * V / ||V||."""
+               init_scale=1.0, filter_size=None, num_units=None, pre_activation=None, raw=False):
+    """utils/nn.py:103-183: variables V, g, b of one layer (created on the init pass), W = g * V / ||V||.
+    raw=True returns the variables themselves ({"V", "g", "b"}, EMA-substituted) for kernels that fuse the weight norm."""
     store = _tls.store
     scope = store.name + "/" + layer_name
     ema_src = ema.shadow if ema is not None else None
     params = {}
+    if raw:
+        return {"V": store.get(scope + "/V", ema_src), "g": store.get(scope + "/g", ema_src), "b": store.get(scope + "/b", ema_src)}
     if init:
         xl = _as_list(x)
         nr_in = sum(int(xi.shape[-1]) for xi in xl)
@@ -915,6 +1185,8 @@ def _dense(x, W, pre_activation=None):
 
 def _conv2d(x, W, stride=(1, 1), pad="SAME", dilate=1, pre_activation=None, upsample=False, bias=None):
     """utils/nn.py:234-275 (__list_conv2d): optional NN-upsample of the concatenated list, pre-activation, conv."""
+    if isinstance(x, Crelu8Tensor):
+        raise TypeError("a Crelu8Tensor is consumed by nn.conv2d(..., pre_activation='crelu') on the GPU path only")
     if isinstance(x, Upsampled2x):
         if (pre_activation is None and not upsample and isinstance(W, TransposedWeight) and CONV_BACKEND == "tcgen05"
                 and conv_up2_supported(tuple(x.low.shape), W.vshape[3], W.vshape[0], W.vshape[1], stride, pad)):
@@ -940,6 +1212,10 @@ def _conv2d(x, W, stride=(1, 1), pad="SAME", dilate=1, pre_activation=None, upsa
         if pre_activation is None and CONV_NARROW and conv_narrow_supported((B, H, Wd, cin), cout, kh, kw, stride, pad):
             geom = (kh, kw, 1, same_padding(H, kh, 1)[0], same_padding(Wd, kw, 1)[0])
             return _ConvNarrow.apply(xl[0].contiguous(), W.wt, bias, geom)
+        if conv_gen_supported((B, H, Wd, cin), cout, kh, kw, stride, pad):
+            # every other shape: the generic mode of the same kernels (channel counts padded to multiples of 4)
+            z = xl[0].contiguous() if pre_activation is None else _CreluPad.apply(xl[0].contiguous(), (0, 0, 0, 0))
+            return _conv_gen(z, W.wt, bias, kh, kw, stride[0], cin, cout)
     if (pre_activation == "crelu" and len(xl) == 1 and pad == "SAME" and xl[0].is_cuda and xl[0].dtype == torch.float32
             and xl[0].shape[3] % 4 == 0):
         # CReLU written straight into the TensorFlow-'SAME'-padded input of the convolution (one fused kernel)
@@ -949,6 +1225,41 @@ def _conv2d(x, W, stride=(1, 1), pad="SAME", dilate=1, pre_activation=None, upsa
         z = _CreluPad.apply(xl[0].contiguous(), (pt, pl, pb, pr))
         return _conv2d_nhwc(z, W, list(stride), "VALID", bias)
     return _conv2d_nhwc(apply_pre_activation(xl, pre_activation, 3), W, list(stride), pad, bias)
+
+
+def _conv_gen(z, wt, bias, kh, kw, s, cin, cout):
+    """_ConvGen with the channel counts padded to multiples of 4 (TMA strides are multiples of 16 bytes): zero input channels /
+    zero filters change nothing; the padded output channels are sliced away."""
+    B, H, Wd, _ = z.shape
+    cin4, cout4 = -(-cin // 4) * 4, -(-cout // 4) * 4
+    if cin4 != cin:
+        z = F.pad(z, (0, cin4 - cin))
+        wt = F.pad(wt.view(cout, kh * kw, cin), (0, cin4 - cin)).reshape(cout, -1)
+    if cout4 != cout:
+        wt = F.pad(wt, (0, 0, 0, cout4 - cout))
+        bias = F.pad(bias, (0, cout4 - cout)) if bias is not None else None
+    geom = (kh, kw, s, same_padding(H, kh, s)[0], same_padding(Wd, kw, s)[0])
+    y = _ConvGen.apply(z, wt, bias, geom)
+    return y[..., :cout] if cout4 != cout else y
+
+
+def _conv2d_crelu8(x, V, g, bias, stride, pad):
+    """nn.conv2d(list, ..., pre_activation='crelu') where the activated list is a Crelu8Tensor: the filter's input channels are
+    permuted into crelu8 order while W = g V / ||V|| is built; the convolution reads the buffer as is."""
+    kh, kw, c2, cout = V.shape
+    assert c2 == 2 * x.raw_channels, "filter does not match the crelu8 buffer"
+    B, H, Wd, _ = x.z.shape
+    if not conv_gen_supported((B, H, Wd, c2), cout, kh, kw, stride, pad):
+        raise _lib.OtganError("conv2d on a crelu8 buffer: shape not supported (needs 'SAME', stride 1/2, power-of-two extents)")
+    cout4 = -(-cout // 4) * 4
+    if cout4 != cout:                                  # e.g. the generator's 3-channel output layer
+        V = F.pad(V, (0, cout4 - cout))
+        g = F.pad(g, (0, cout4 - cout), value=1.0)
+        bias = F.pad(bias, (0, cout4 - cout)) if bias is not None else None
+    wt = _WeightNormPerm.apply(V, g, crelu8_perm(x.elem_ch, kh * kw, x.z.device))
+    geom = (kh, kw, stride[0], same_padding(H, kh, stride[0])[0], same_padding(Wd, kw, stride[1])[0])
+    y = _ConvGen.apply(x.z, wt, bias, geom)
+    return y[..., :cout] if cout4 != cout else y
 
 
 @add_arg_scope
@@ -971,6 +1282,11 @@ def conv2d(x, num_filters, pre_activation="celu", filter_size=[3, 3], stride=[1,
            **kwargs):
     """utils/nn.py:328-338"""
     layer_name = get_name("conv2d", counters)
+    if isinstance(x, Crelu8Tensor):
+        if not (pre_activation == "crelu" and weight_norm and use_g and not upsample and dilate == 1 and not init):
+            raise ValueError("a Crelu8Tensor input needs pre_activation='crelu' with weight norm (models/densenet.py usage)")
+        prm = get_params(layer_name, None, False, ema, raw=True)
+        return _conv2d_crelu8(x, prm["V"], prm["g"], prm["b"] if use_b else None, stride, pad)
     f = lambda x, W: _conv2d(x, W, stride, pad, dilate, pre_activation, upsample)
     params = get_params(layer_name, x, init, ema, use_W=True, use_g=use_g, use_b=use_b, f=f, weight_norm=weight_norm,
                         init_scale=init_scale, filter_size=list(filter_size), num_units=num_filters,

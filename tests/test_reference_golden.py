@@ -156,8 +156,19 @@ def test_cuda_matching_reproduces_the_reference(path):
         got = fn(ta, tb, lam, T)
         dist = M.calc_distance(ta, tb, got)
         cat = torch.cat
+    # SURVEY 8d gate: max(1e-5, 1.5 x the error of correct fp32 implementations on the same inputs) -- here the numpy fp32
+    # oracle and (two-batch) the torch-CPU restatement against the reference-code fixture
+    floor = 0.0
+    if kind == "two":
+        from oracle import torch_oracle as to
+        fa, fb = list(np.split(A, G)), list(np.split(B, G))
+        r32 = mo.get_matched_features(fa, fb, lam, T, np.float32)
+        rt = to.get_matched_features([torch.from_numpy(x) for x in fa], [torch.from_numpy(x) for x in fb], lam, T)
+        for i, k in enumerate(["f_aa", "f_bb", "f_ab", "f_ba"]):
+            floor = max(floor, relerr(np.concatenate(r32[i]), g[k]), relerr(torch.cat(rt[i]), g[k]))
+    tol = max(1e-5, 1.5 * floor)
     for i, k in enumerate(["f_aa", "f_bb", "f_ab", "f_ba"]):
-        assert relerr(cat(got[i]), g[k]) < 1e-5, k                                   # north star: 1e-5 relative
+        assert relerr(cat(got[i]), g[k]) < tol, (k, tol)                             # north star: 1e-5 relative
     assert abs(float(got[4]) - float(g["entropy"])) <= 5e-6 * max(abs(float(g["entropy"])), 0.1)
     assert abs(float(dist) - float(g["dist"])) < 1e-6
     if kind == "two":
