@@ -139,7 +139,10 @@ int otgan_cost_blocks_f32(int nblk, int rows, int cols, int D, const float* cons
         set_error("cost: tcgen05 path needs square blocks <= 128, 16-byte aligned rows (ld %% 4 == 0) and D >= 16");
         return OTGAN_EUNSUPPORTED;
     }
-    if (tc_ok && impl != OTGAN_IMPL_SIMT)
+    // AUTO: short contractions (D < 2048: toy / test shapes, a few microseconds either way) stay on the exact-fp32 FMA kernel --
+    // measured on B200, its cost error is 1.6e-7 against 3.6e-7 for the 3xTF32 tensor-core kernel, and lambda = 500 amplifies
+    // that difference on small, peaked problems; at D = 32768 the two are equal (3.9e-7 / 4.3e-7) and tcgen05 is 3x faster.
+    if (tc_ok && impl != OTGAN_IMPL_SIMT && (impl == OTGAN_IMPL_TCGEN05 || D >= 2048))
         return cost_tc_launch(nblk, rows, cols, D, X_host, Y_host, ldx, ldy, cost_kind, diag_add_host, lam, L, ws,
                               ws_bytes, (cudaStream_t)stream);
     return cost_simt_launch(nblk, rows, cols, D, X_host, Y_host, ldx, ldy, cost_kind, diag_add_host, lam, L, ws,

@@ -9,6 +9,10 @@
 // __syncthreads_or); then the same half-step is redone on the slow path from the last good state.  The first row step is
 // always slow.  Exact algebra, fp32 rounding of the same class as the log-domain form (entries of K that underflow at an
 // absorption are < 2^-126 and can regain at most 2^80, i.e. stay < 2^-46 of a row sum).
+// The absorbed potentials f, g are kept in DOUBLE precision: with lambda = 500 they reach ~350, where one fp32 ulp is 3e-5, and
+// exp(L0 - f - g) is a difference of such numbers -- in fp32 that rounding went straight into P (measured 2.9e-5 on a peaked
+// h = 32 problem, 8x the log-domain kernel).  They are touched only on the slow path and in the epilogue (a few thousand fp64
+// operations per block in total), the fast half-steps are unchanged.
 //
 // Layout: one CTA (256 threads) per block.  K is held twice in registers -- a row-oriented copy and a column-oriented
 // copy, each as 4x16 tiles per thread -- so that a half-step is: 4 LDS.128 of the scaling vector, 64 FMAs, a 4-value
@@ -29,7 +33,7 @@ constexpr float S_LO = 9.094947017729282e-13f /* 2^-40 */, S_HI = 1099511627776.
 struct Smem {
     float L0[H * LDS_];        // L0[r][c] = -lambda*C (natural-log units, exactly the caller's fp32), -inf outside [rows, cols)
     float L0T[H * LDS_];       // L0T[c][r]
-    float f[H], g[H];          // absorbed potentials (natural-log units)
+    double f[H], g[H];         // absorbed potentials (natural-log units), double precision: see the header comment
     float u[2][H], v[2][H];    // scaling vectors, double buffered
     float red[2][NTHREADS / 32];
 };
@@ -97,7 +101,7 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
         }
     }
     if (tid < H) {
-        sm.f[tid] = 0.f; sm.g[tid] = 0.f;
+        sm.f[tid] = 0.0; sm.g[tid] = 0.0;
         sm.u[0][tid] = 1.f; sm.u[1][tid] = 1.f; sm.v[0][tid] = 1.f; sm.v[1][tid] = 1.f;
     }
     __syncthreads();
@@ -108,25 +112,26 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
 
     auto absorb = [&]() {   // f -= log2 u, g -= log2 v; afterwards u = v = 1 in the current buffers
         if (tid < H) {
-            sm.f[tid] -= LN2 * lg2_approx(sm.u[ub][tid]);
-            sm.g[tid] -= LN2 * lg2_approx(sm.v[vb][tid]);
+            sm.f[tid] -= log((double)sm.u[ub][tid]);
+            sm.g[tid] -= log((double)sm.v[vb][tid]);
             sm.u[ub][tid] = 1.f;
             sm.v[vb][tid] = 1.f;
         }
         __syncthreads();
     };
     // tile of exponents a = (M[line][o] - p_line) - q_o for the 4 tile lines; M = L0 (rows) or L0T (columns)
-    auto load_exponents = [&](const float* M, const float* pl, const float* qo, float (&a)[4][16]) {
+    auto load_exponents = [&](const float* M, const double* pl, const double* qo, float (&a)[4][16]) {
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const int o = 4 * (g8 + 8 * m);
-            const float4 q = *reinterpret_cast<const float4*>(&qo[o]);
+            const double q0 = qo[o], q1 = qo[o + 1], q2 = qo[o + 2], q3 = qo[o + 3];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float p = pl[base4 + i];
+                const double p = pl[base4 + i];
                 const float4 l = *reinterpret_cast<const float4*>(&M[(base4 + i) * LDS_ + o]);
-                a[i][4 * m + 0] = (l.x - p) - q.x; a[i][4 * m + 1] = (l.y - p) - q.y;
-                a[i][4 * m + 2] = (l.z - p) - q.z; a[i][4 * m + 3] = (l.w - p) - q.w;
+                // (-inf) - finite stays -inf in double; the difference of the large terms is taken before the rounding to fp32
+                a[i][4 * m + 0] = (float)(((double)l.x - p) - q0); a[i][4 * m + 1] = (float)(((double)l.y - p) - q1);
+                a[i][4 * m + 2] = (float)(((double)l.z - p) - q2); a[i][4 * m + 3] = (float)(((double)l.w - p) - q3);
             }
         }
     };
@@ -154,7 +159,7 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
         }
         return lse;
     };
-    auto rebuild = [&](const float* M, const float* pl, const float* qo, float (&K)[4][16]) {
+    auto rebuild = [&](const float* M, const double* pl, const double* qo, float (&K)[4][16]) {
         load_exponents(M, pl, qo, K);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -165,7 +170,7 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
         absorb();
         load_exponents(sm.L0, sm.f, sm.g, Kr);
         const float lse = normalise_lines(Kr, rows);
-        if ((lane & 1) == 0 && my_line < rows) sm.f[my_line] += lse;
+        if ((lane & 1) == 0 && my_line < rows) sm.f[my_line] += (double)lse;
         __syncthreads();
         rebuild(sm.L0T, sm.g, sm.f, Kc);
         ++n_slow;
@@ -174,7 +179,7 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
         absorb();
         load_exponents(sm.L0T, sm.g, sm.f, Kc);
         const float lse = normalise_lines(Kc, cols);
-        if ((lane & 1) == 0 && my_line < cols) sm.g[my_line] += lse;
+        if ((lane & 1) == 0 && my_line < cols) sm.g[my_line] += (double)lse;
         __syncthreads();
         rebuild(sm.L0, sm.f, sm.g, Kr);
         ++n_slow;
@@ -219,7 +224,7 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
 
     // ================= P = softmax(log_a, -1), entropy, <P,C>                            utils/matching.py:56-57
     // log_a_ij = L0_ij - f_i - (g_j - log v_j); the row potential (and u) cancels in the row softmax.
-    if (tid < H) sm.g[tid] -= LN2 * lg2_approx(sm.v[vb][tid]);
+    if (tid < H) sm.g[tid] -= log((double)sm.v[vb][tid]);
     __syncthreads();
     float ent = 0.f, pcs = 0.f;
     {

@@ -995,8 +995,11 @@ class Crelu8Tensor:
         return self.z.device
 
     def upsample2x(self):
-        """tf.image.resize_nearest_neighbor of the (concatenated) list commutes with the element-wise CReLU."""
-        return Crelu8Tensor(resize_nearest_neighbor(self.z, [2 * self.z.shape[1], 2 * self.z.shape[2]]), self.elem_ch)
+        """models/densenet.py:64-68 (`upsample`): tf.concat(x, 3) -> resize_nearest_neighbor -> conv2d(crelu).  The resize
+        commutes with the element-wise CReLU, and because the reference CONCATENATES the list before that convolution its CReLU
+        sees ONE tensor ([relu(cat), relu(-cat)], not the per-element interleave): the result is a single-element
+        Crelu8Tensor.  The crelu8 layout itself is unchanged (blocks of 8 raw channels; element offsets are multiples of 8)."""
+        return Crelu8Tensor(resize_nearest_neighbor(self.z, [2 * self.z.shape[1], 2 * self.z.shape[2]]), [self.raw_channels])
 
 
 class _DenseBlock(torch.autograd.Function):

@@ -400,8 +400,13 @@ def test_golden_vectors_on_gpu(M, path):
         got = M.get_matched_features(ta, tb, lam, T)
         dist = M.calc_distance(ta, tb, got)
         cat = torch.cat
+    tol = TOL_F
+    if not name.startswith("toy"):                     # SURVEY 8d gate: max(1e-5, 1.5 x the fp32 oracle's own error on these inputs)
+        fa, fb = list(np.split(A, G)), list(np.split(B, G))
+        fn32 = mo.get_matched_features_single_batch if name.startswith("single") else mo.get_matched_features
+        tol = tol_f([g[k] for k in ("f_aa", "f_bb", "f_ab", "f_ba")], fn32(fa, fb, lam, T, np.float32)[:4])
     for i, k in enumerate(["f_aa", "f_bb", "f_ab", "f_ba"]):
-        assert relerr(cat(got[i]), g[k]) < TOL_F
+        assert relerr(cat(got[i]), g[k]) < tol, (k, tol)
     # small-h fixtures: the entropy is a mean over a handful of rows, so use an absolute floor
     assert abs(float(got[4]) - float(g["entropy"])) <= TOL_ENT * max(abs(float(g["entropy"])), 0.1)
     assert abs(float(dist) - float(g["dist"])) < TOL_DIST
