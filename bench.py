@@ -592,6 +592,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.only_config:                           # profiling aid: one named configuration, e.g. densenet:256:100[:image_size]
+        model, n_total, t_iters = args.only_config.split(":")[:3]
+        isz = int(args.only_config.split(":")[3]) if args.only_config.count(":") >= 3 else 32
+        res = time_config(torch, dist, T, devv, rank, world, int(n_total), int(t_iters), model=model, image_size=isz,
+                          steps=args.steps, warmup=args.warmup, graphs=bool(args.cuda_graphs))
+        if rank == 0:
+            print(json.dumps(res))
+        if world > 1:
+            dist.barrier()
+            os._exit(0)
+        return
     if args.workload == "conv":                    # profiling aid: the per-layer convolution launches only (ncu -k regex:conv_)
         if rank == 0:
             res = conv_benchmark(torch)
@@ -794,6 +805,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cuda-graphs", type=int, default=1, help="replay the training step from captured CUDA graphs (1) or launch eagerly (0)")
     ap.add_argument("--n-total", type=int, default=0, help="diagnostics only: override N (images per step); the contract workload is N=256")
+    ap.add_argument("--only-config", default="", help="profiling aid: time one configuration model:N:T[:image_size] and print its line")
     ap.add_argument("--step-only", action="store_true", help="profiling aid: only the contract training step (no sub-benchmarks, extra configs or CPU leg)")
     args = ap.parse_args()
     if args.n_total:

@@ -95,9 +95,10 @@ typedef struct {
     float coef[OTGAN_MAX_OUTPUTS][OTGAN_MAX_TERMS];
 } otgan_plan_t;
 
-/* ws: otgan_workspace_bytes_plan() bytes (pre-split plan planes of the tensor-core path); may be NULL, which selects
- * the SIMT kernel. */
+/* ws: otgan_workspace_bytes_plan_h(h) bytes (pre-split plan planes of the tensor-core path, h rounded up to 128;
+ * otgan_workspace_bytes_plan() is the h <= 128 size); may be NULL, which selects the SIMT kernel. */
 OTGAN_API size_t otgan_workspace_bytes_plan(void);
+OTGAN_API size_t otgan_workspace_bytes_plan_h(int h);
 OTGAN_API int otgan_plan_apply_f32(const otgan_plan_t* plan_host, int h, int D,
                          const float* P /* [nblk, h, h] */, const float* const* F_host /* sources */, int ldf,
                          float* const* out_host /* outputs */, int ldo, void* ws, size_t ws_bytes, int impl, void* stream);

@@ -44,6 +44,7 @@ SIGNATURES = {
     "otgan_sinkhorn_f32": (_i, [_i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _i, _vp]),
     "otgan_sinkhorn_ex_f32": (_i, [_i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "otgan_workspace_bytes_plan": (_sz, []),
+    "otgan_workspace_bytes_plan_h": (_sz, [_i]),
     "otgan_plan_apply_f32": (_i, [ctypes.POINTER(Plan), _i, _i, _vp, _vp, _i, _vp, _i, _vp, _sz, _i, _vp]),
     "otgan_matched_two_batch_f32": (_i, [_i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _i, _vp]),
     "otgan_grad_features_f32": (_i, [_i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _sz, _i, _vp]),

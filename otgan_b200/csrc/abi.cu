@@ -40,7 +40,7 @@ int plan_apply_simt_launch(const otgan_plan_t* plan, int h, int D, const float* 
                            float* const* out, int ldo, cudaStream_t stream);
 bool plan_apply_tc_supported(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F, int ldf,
                              float* const* out, int ldo);
-size_t plan_apply_tc_workspace_bytes(int n_out);
+size_t plan_apply_tc_workspace_bytes(int n_out, int h);
 int plan_apply_tc_launch(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F, int ldf,
                          float* const* out, int ldo, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t distance_workspace_bytes(int n, int D);
@@ -136,7 +136,7 @@ int otgan_cost_blocks_f32(int nblk, int rows, int cols, int D, const float* cons
     OTGAN_REQUIRE(impl == OTGAN_IMPL_AUTO || impl == OTGAN_IMPL_SIMT || impl == OTGAN_IMPL_TCGEN05, "cost: unknown impl %d", impl);
     const bool tc_ok = cost_tc_supported(nblk, rows, cols, D, X_host, Y_host, ldx, ldy);
     if (impl == OTGAN_IMPL_TCGEN05 && !tc_ok) {
-        set_error("cost: tcgen05 path needs square blocks <= 128, 16-byte aligned rows (ld %% 4 == 0) and D >= 16");
+        set_error("cost: tcgen05 path needs 16-byte aligned rows (ld %% 4 == 0) and D >= 32");
         return OTGAN_EUNSUPPORTED;
     }
     // AUTO: short contractions (D < 2048: toy / test shapes, a few microseconds either way) stay on the exact-fp32 FMA kernel --
@@ -177,7 +177,8 @@ int otgan_sinkhorn_f32(int nblk, int rows, int cols, int T, float lam, const flo
     return otgan_sinkhorn_ex_f32(nblk, rows, cols, T, lam, L0, P, entropy, pc, nullptr, impl, stream);
 }
 
-size_t otgan_workspace_bytes_plan(void) { return plan_apply_tc_workspace_bytes(OTGAN_MAX_OUTPUTS); }
+size_t otgan_workspace_bytes_plan(void) { return plan_apply_tc_workspace_bytes(OTGAN_MAX_OUTPUTS, 128); }
+size_t otgan_workspace_bytes_plan_h(int h) { return plan_apply_tc_workspace_bytes(OTGAN_MAX_OUTPUTS, h); }
 
 int otgan_plan_apply_f32(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F_host, int ldf,
                          float* const* out_host, int ldo, void* ws, size_t ws_bytes, int impl, void* stream)
@@ -195,10 +196,10 @@ int otgan_plan_apply_f32(const otgan_plan_t* plan, int h, int D, const float* P,
         }
     }
     OTGAN_REQUIRE(impl == OTGAN_IMPL_AUTO || impl == OTGAN_IMPL_SIMT || impl == OTGAN_IMPL_TCGEN05, "plan_apply: unknown impl %d", impl);
-    const bool tc_ok = ws != nullptr && ws_bytes >= plan_apply_tc_workspace_bytes(plan->n_out) &&
+    const bool tc_ok = ws != nullptr && ws_bytes >= plan_apply_tc_workspace_bytes(plan->n_out, h) &&
                        plan_apply_tc_supported(plan, h, D, P, F_host, ldf, out_host, ldo);
     if (impl == OTGAN_IMPL_TCGEN05 && !tc_ok) {
-        set_error("plan_apply: tcgen05 path needs h <= 128, D >= 32, D/ld %% 4 == 0, 16-byte aligned pointers and a workspace");
+        set_error("plan_apply: tcgen05 path needs D >= 32, D/ld %% 4 == 0, 16-byte aligned pointers and a workspace of otgan_workspace_bytes_plan_h(h) bytes");
         return OTGAN_EUNSUPPORTED;
     }
     if (tc_ok && impl != OTGAN_IMPL_SIMT)

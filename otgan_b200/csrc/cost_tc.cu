@@ -3,9 +3,11 @@
 // tf.matmul(transpose_b=True) of utils/matching.py:29-43; the cost epilogue (1 - g, *(-lambda), +999 I, Euclidean form)
 // is the shared finalize kernel.
 //
-// Work decomposition: grid = (splits, nblk).  A CTA owns one 128x128 block and a K-slice of D/splits; splits is chosen so
-// that the grid fills the 148 SMs once (persistent over the K-slice).  Blocks that share an embedding tile run
-// concurrently on the same K range, so HBM sees every element once (3x through L2).
+// Work decomposition: grid = (splits, nblk * row tiles * column tiles).  A CTA owns one 128x128 tile of one block and a
+// K-slice of D/splits; splits is chosen so that the grid fills the 148 SMs once (persistent over the K-slice).  Blocks larger
+// than 128 (h = 256 of the 64x64-image configuration, N x N blocks of the single-batch variant) are simply more tiles: the TMA
+// box of tile (ti, tj) starts at row 128 ti / 128 tj of the same tensor maps, ragged edges are zero-filled.  Tiles that share
+// an embedding slab run concurrently on the same K range, so HBM sees every element once (the rest hits in L2).
 //
 // Accuracy.  (1) Operands: x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi); D += Ahi*Blo + Alo*Bhi + Ahi*Bhi
 // reproduces the fp32 product to 2^-22 (measured 2e-9 on the headline shape; a single TF32 pass is 1e-5 and would be
@@ -50,7 +52,8 @@ constexpr uint32_t SBO_BYTES = 8 * BK * 4;     // 8 rows x 128 B
 struct Params {
     CUtensorMap maps[MAX_MAPS];
     int map_m[OTGAN_MAX_BLOCKS], map_n[OTGAN_MAX_BLOCKS];   // tensor map of the M-side / N-side tile of each block
-    int nblk, rows, cols, nchunks, chunks_per_split, tile_tx_bytes;
+    int nblk, rows, cols, nchunks, chunks_per_split, tx_m, tx_n;
+    int tiles_r, tiles_c;                                    // 128-row / 128-column tiles per block
     float* partial;                                          // [splits][nblk][rows][cols]
 };
 
@@ -70,10 +73,12 @@ cost_tc_kernel(const __grid_constant__ Params p)
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int blk = blockIdx.y, split = blockIdx.x;
+    const int split = blockIdx.x;
+    const int blk = blockIdx.y / (p.tiles_r * p.tiles_c), tile = blockIdx.y % (p.tiles_r * p.tiles_c);
+    const int ti = tile / p.tiles_c, tj = tile % p.tiles_c;
     const CUtensorMap* map_m = &p.maps[p.map_m[blk]];
     const CUtensorMap* map_n = &p.maps[p.map_n[blk]];
-    const bool same_tile = p.map_m[blk] == p.map_n[blk];          // X == Y (single-batch aa / bb blocks): load once
+    const bool same_tile = p.map_m[blk] == p.map_n[blk] && ti == tj;   // X == Y (single-batch aa / bb blocks), diagonal tile: load once
     const int chunk0 = split * p.chunks_per_split;
     int nch = p.nchunks - chunk0;
     nch = nch > p.chunks_per_split ? p.chunks_per_split : nch;
@@ -109,10 +114,10 @@ cost_tc_kernel(const __grid_constant__ Params p)
                 const int s = c % STAGES;
                 const uint32_t ph = (uint32_t)(c / STAGES) & 1u;
                 mbar_wait(empty_bar(s), ph ^ 1u);
-                mbar_arrive_expect_tx(full_bar(s), (uint32_t)(ntiles * p.tile_tx_bytes));
+                mbar_arrive_expect_tx(full_bar(s), (uint32_t)(same_tile ? p.tx_m : p.tx_m + p.tx_n));
                 const uint32_t dst = smem_base + s * STAGE_BYTES;
-                tma_load_2d(dst, map_m, full_bar(s), (chunk0 + c) * BK, 0);
-                if (!same_tile) tma_load_2d(dst + TILE_BYTES, map_n, full_bar(s), (chunk0 + c) * BK, 0);
+                tma_load_2d(dst, map_m, full_bar(s), (chunk0 + c) * BK, ti * TILE_ROWS);
+                if (!same_tile) tma_load_2d(dst + TILE_BYTES, map_n, full_bar(s), (chunk0 + c) * BK, tj * TILE_ROWS);
             }
         }
     } else if (warp == 1) {
@@ -185,16 +190,17 @@ cost_tc_kernel(const __grid_constant__ Params p)
             tcgen05_fence_before();
             mbar_arrive(tempty_bar(b));
         }
-        if (m < p.rows) {
-            float* out = p.partial + (((size_t)split * p.nblk + blk) * p.rows + m) * p.cols;
+        const int row = ti * TILE_ROWS + m, col0 = tj * TILE_ROWS;
+        if (row < p.rows) {
+            float* out = p.partial + (((size_t)split * p.nblk + blk) * p.rows + row) * p.cols + col0;
             if ((p.cols & 3) == 0) {
 #pragma unroll
                 for (int j = 0; j < 128; j += 4)
-                    if (j < p.cols) *reinterpret_cast<float4*>(out + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                    if (col0 + j < p.cols) *reinterpret_cast<float4*>(out + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
             } else {
 #pragma unroll
                 for (int j = 0; j < 128; ++j)
-                    if (j < p.cols) out[j] = acc[j];
+                    if (col0 + j < p.cols) out[j] = acc[j];
             }
         }
     }
@@ -213,10 +219,10 @@ struct Plan {
     int splits;
 };
 
-int plan_splits(int nblk, int D, int* chunks_per_split)
+int plan_splits(int ntiles, int D, int* chunks_per_split)
 {
     const int nchunks = ceil_div(D, BK);
-    int S = kNumSMs / nblk;
+    int S = kNumSMs / ntiles;
     S = S < 1 ? 1 : (S > nchunks ? nchunks : S);
     const int cps = ceil_div(nchunks, S);
     if (chunks_per_split) *chunks_per_split = cps;
@@ -240,14 +246,17 @@ bool build_plan(Plan& pl, int nblk, int rows, int cols, int D, const float* cons
         p.map_m[k] = find_src(X[k], rows, ldx);
         p.map_n[k] = find_src(Y[k], cols, ldy);
     }
-    const int box_rows = rows < TILE_ROWS ? rows : TILE_ROWS;      // rows == cols (checked by cost_tc_supported)
-    for (int i = 0; i < nsrc; ++i)
+    for (int i = 0; i < nsrc; ++i) {
+        const int box_rows = srcs[i].nrows < TILE_ROWS ? srcs[i].nrows : TILE_ROWS;
         if (!make_tensor_map_2d(&p.maps[i], srcs[i].ptr, srcs[i].nrows, D, srcs[i].ld, box_rows, BK, CU_TENSOR_MAP_SWIZZLE_128B))
             return false;
-    p.tile_tx_bytes = box_rows * BK * 4;
+    }
+    p.tx_m = (rows < TILE_ROWS ? rows : TILE_ROWS) * BK * 4;
+    p.tx_n = (cols < TILE_ROWS ? cols : TILE_ROWS) * BK * 4;
     p.nblk = nblk; p.rows = rows; p.cols = cols;
+    p.tiles_r = ceil_div(rows, TILE_ROWS); p.tiles_c = ceil_div(cols, TILE_ROWS);
     p.nchunks = ceil_div(D, BK);
-    pl.splits = plan_splits(nblk, D, &p.chunks_per_split);
+    pl.splits = plan_splits(nblk * p.tiles_r * p.tiles_c, D, &p.chunks_per_split);
     return true;
 }
 
@@ -255,7 +264,7 @@ bool build_plan(Plan& pl, int nblk, int rows, int cols, int D, const float* cons
 
 bool cost_tc_supported(int nblk, int rows, int cols, int D, const float* const* X, const float* const* Y, int ldx, int ldy)
 {
-    if (rows > TILE_ROWS || cols > TILE_ROWS || rows != cols) return false;
+    if (rows < 1 || cols < 1 || (long long)nblk * ceil_div(rows, TILE_ROWS) * ceil_div(cols, TILE_ROWS) > 65535) return false;
     if ((ldx & 3) || (ldy & 3) || D < BK) return false;
     for (int k = 0; k < nblk; ++k)
         if (!aligned16(X[k]) || !aligned16(Y[k])) return false;
@@ -264,7 +273,8 @@ bool cost_tc_supported(int nblk, int rows, int cols, int D, const float* const* 
 
 size_t cost_tc_workspace_bytes(int nblk, int rows, int cols, int D)
 {
-    return (size_t)plan_splits(nblk, D, nullptr) * nblk * rows * cols * sizeof(float) + (size_t)nblk * (rows + cols) * sizeof(float) + 256;
+    const int ntiles = nblk * ceil_div(rows, TILE_ROWS) * ceil_div(cols, TILE_ROWS);
+    return (size_t)plan_splits(ntiles, D, nullptr) * nblk * rows * cols * sizeof(float) + (size_t)nblk * (rows + cols) * sizeof(float) + 256;
 }
 
 int cost_tc_launch(int nblk, int rows, int cols, int D, const float* const* X, const float* const* Y, int ldx, int ldy,
@@ -278,7 +288,7 @@ int cost_tc_launch(int nblk, int rows, int cols, int D, const float* const* X, c
     pl.prm.partial = partial;
     // per-device attribute: set on every launch (a process-wide flag would miss a second GPU)
     OTGAN_CUDA(cudaFuncSetAttribute(cost_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    dim3 grid(pl.splits, nblk);
+    dim3 grid(pl.splits, nblk * pl.prm.tiles_r * pl.prm.tiles_c);
     cost_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(pl.prm);
     OTGAN_CHECK_LAUNCH("cost_tc_kernel");
     return cost_finalize_launch(partial, pl.splits, nblk, rows, cols, D, cost_kind, X, Y, ldx, ldy, diag, lam, L, sq, stream);

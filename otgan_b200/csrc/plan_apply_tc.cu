@@ -2,7 +2,9 @@
 //
 //   out[o] ([h, D]) = sum_t coef[o][t] * op(P[blk[o][t]]) * F[src[o][t]]          (utils/matching.py:63-83, train.py:111,125-126)
 //
-// GEMM view per output group o:  D[M = 128 rows i][N = 128 columns d] += A[i][k] * B[k][d],  K = h per term.
+// GEMM view per output group o and 128-row tile:  D[M = 128 rows i][N = 128 columns d] += A[i][k] * B[k][d],  K = h per term
+// (blocks larger than 128 -- h = 256 of the 64x64-image configuration, N x N single-batch blocks -- are more row tiles and more
+// K chunks of the same kernel; the prepared A planes are [HP x HP] with HP = h rounded up to 128).
 //   A = coef * op(P)  : tiny, reused by every column tile.  A prep kernel writes it once per call, zero-padded to
 //                       128 x 128, already split into hi/lo TF32 planes and K-major (so transposes, the 0.5 averaging and
 //                       the f_aa - f_ab subtraction cost nothing in the main loop).
@@ -39,16 +41,16 @@ struct Params {
     CUtensorMap map_f[OTGAN_MAX_OUTPUTS];        // sources [h, D]
     otgan_plan_t plan;
     float* out[OTGAN_MAX_OUTPUTS];
-    int h, D, ldo, n_col_tiles, n_items, kchunks, box_bytes;
+    int h, hp, row_tiles, D, ldo, n_col_tiles, n_items, kchunks, box_bytes;
 };
 
 // Aop[(o*3 + t)*128 + i][k] = coef * op(P)[i][k] (zero padded), split into hi / lo TF32 planes
-__global__ void plan_prep_kernel(otgan_plan_t plan, int h, const float* __restrict__ P, float* __restrict__ a_hi,
+__global__ void plan_prep_kernel(otgan_plan_t plan, int h, int hp, const float* __restrict__ P, float* __restrict__ a_hi,
                                  float* __restrict__ a_lo)
 {
     const int o = blockIdx.y, t = blockIdx.z;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // over 128*128
-    const int i = idx >> 7, k = idx & 127;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // over hp*hp
+    const int i = idx / hp, k = idx - i * hp;
     float v = 0.f;
     if (t < plan.nterms[o] && i < h && k < h) {
         const float* Pm = P + (size_t)plan.blk[o][t] * h * h;
@@ -56,7 +58,7 @@ __global__ void plan_prep_kernel(otgan_plan_t plan, int h, const float* __restri
     }
     const uint32_t hi = cvt_rna_tf32(v);
     const uint32_t lo = cvt_rna_tf32(v - __uint_as_float(hi));
-    const size_t off = ((size_t)(o * OTGAN_MAX_TERMS + t) * 128 + i) * 128 + k;
+    const size_t off = ((size_t)(o * OTGAN_MAX_TERMS + t) * hp + i) * hp + k;
     a_hi[off] = __uint_as_float(hi);
     a_lo[off] = __uint_as_float(lo);
 }
@@ -112,7 +114,8 @@ plan_apply_tc_kernel(const __grid_constant__ Params p)
         if (lane == 0) {
             int c = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const int o = item / p.n_col_tiles, d0 = (item % p.n_col_tiles) * TN_;
+                const int rt = item % p.row_tiles, oc = item / p.row_tiles;
+                const int o = oc / p.n_col_tiles, d0 = (oc % p.n_col_tiles) * TN_;
                 for (int t = 0; t < p.plan.nterms[o]; ++t) {
                     const CUtensorMap* mf = &p.map_f[p.plan.src[o][t]];
                     for (int kc = 0; kc < p.kchunks; ++kc, ++c) {
@@ -122,7 +125,7 @@ plan_apply_tc_kernel(const __grid_constant__ Params p)
                         nbox = nbox > TN_ / 32 ? TN_ / 32 : nbox;
                         mbar_arrive_expect_tx(full_bar(s), 2 * A_TILE + nbox * p.box_bytes);
                         const uint32_t dst = smem_base + s * STAGE_BYTES;
-                        const int arow = (o * OTGAN_MAX_TERMS + t) * 128;
+                        const int arow = (o * OTGAN_MAX_TERMS + t) * p.hp + rt * TM_;
                         tma_load_2d(dst, &p.map_a_hi, full_bar(s), kc * BK, arow);
                         tma_load_2d(dst + A_TILE, &p.map_a_lo, full_bar(s), kc * BK, arow);
                         for (int j = 0; j < nbox; ++j)
@@ -137,7 +140,7 @@ plan_apply_tc_kernel(const __grid_constant__ Params p)
             const uint32_t idesc = umma_idesc_tf32(128, 128, /*a_mn_major=*/0, /*b_mn_major=*/1);
             int c = 0, n = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
-                const int o = item / p.n_col_tiles, b = n & 1;
+                const int o = (item / p.row_tiles) / p.n_col_tiles, b = n & 1;
                 mbar_wait(tempty_bar(b), (((uint32_t)(n >> 1)) & 1u) ^ 1u);
                 const uint32_t d = tmem_base + (uint32_t)(b * 128);
                 const int nst = p.plan.nterms[o] * p.kchunks;
@@ -170,7 +173,7 @@ plan_apply_tc_kernel(const __grid_constant__ Params p)
         const int st_id = threadIdx.x - 64;
         int c = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-            const int o = item / p.n_col_tiles;
+            const int o = (item / p.row_tiles) / p.n_col_tiles;
             const int nst = p.plan.nterms[o] * p.kchunks;
             for (int st = 0; st < nst; ++st, ++c) {
                 const int s = c % STAGES;
@@ -197,16 +200,18 @@ plan_apply_tc_kernel(const __grid_constant__ Params p)
         const int m = quad * 32 + lane;
         int n = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
-            const int o = item / p.n_col_tiles, d0 = (item % p.n_col_tiles) * TN_, b = n & 1;
+            const int rt = item % p.row_tiles, oc = item / p.row_tiles;
+            const int o = oc / p.n_col_tiles, d0 = (oc % p.n_col_tiles) * TN_, b = n & 1;
+            const int row = rt * TM_ + m;
             mbar_wait(tfull_bar(b), ((uint32_t)(n >> 1)) & 1u);
             tcgen05_fence_after();
-            float* out = p.out[o] + (size_t)m * p.ldo + d0;
+            float* out = p.out[o] + (size_t)row * p.ldo + d0;
 #pragma unroll 1
             for (int cc = 0; cc < 4; ++cc) {
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * 128 + cc * 32), r);
                 tmem_ld_wait();
-                if (m < p.h) {
+                if (row < p.h) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
                         if (d0 + cc * 32 + j < p.D)          // D % 4 == 0
@@ -231,7 +236,7 @@ plan_apply_tc_kernel(const __grid_constant__ Params p)
 bool plan_apply_tc_supported(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F, int ldf,
                              float* const* out, int ldo)
 {
-    if (h > TM_ || D < 32 || (D & 3) || (ldf & 3) || (ldo & 3) || !aligned16(P)) return false;
+    if (h < 1 || h > 4096 || D < 32 || (D & 3) || (ldf & 3) || (ldo & 3) || !aligned16(P)) return false;
     for (int o = 0; o < plan->n_out; ++o) {
         if (!aligned16(out[o])) return false;
         for (int t = 0; t < plan->nterms[o]; ++t)
@@ -240,24 +245,29 @@ bool plan_apply_tc_supported(const otgan_plan_t* plan, int h, int D, const float
     return true;
 }
 
-size_t plan_apply_tc_workspace_bytes(int n_out) { return (size_t)2 * n_out * OTGAN_MAX_TERMS * 128 * 128 * sizeof(float) + 256; }
+size_t plan_apply_tc_workspace_bytes(int n_out, int h)
+{
+    const size_t hp = (size_t)ceil_div(h < 1 ? 1 : h, TM_) * TM_;
+    return (size_t)2 * n_out * OTGAN_MAX_TERMS * hp * hp * sizeof(float) + 256;
+}
 
 int plan_apply_tc_launch(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F, int ldf,
                          float* const* out, int ldo, void* ws, size_t ws_bytes, cudaStream_t stream)
 {
-    OTGAN_REQUIRE(ws && ws_bytes >= plan_apply_tc_workspace_bytes(plan->n_out), "plan_apply(tcgen05): workspace too small");
-    const size_t plane = (size_t)plan->n_out * OTGAN_MAX_TERMS * 128 * 128;
+    OTGAN_REQUIRE(ws && ws_bytes >= plan_apply_tc_workspace_bytes(plan->n_out, h), "plan_apply(tcgen05): workspace too small");
+    const int hp = ceil_div(h, TM_) * TM_;
+    const size_t plane = (size_t)plan->n_out * OTGAN_MAX_TERMS * hp * hp;
     float* a_hi = reinterpret_cast<float*>(ws);
     float* a_lo = a_hi + plane;
-    plan_prep_kernel<<<dim3(128 * 128 / 256, plan->n_out, OTGAN_MAX_TERMS), 256, 0, stream>>>(*plan, h, P, a_hi, a_lo);
+    plan_prep_kernel<<<dim3(hp * hp / 256, plan->n_out, OTGAN_MAX_TERMS), 256, 0, stream>>>(*plan, h, hp, P, a_hi, a_lo);
     OTGAN_CHECK_LAUNCH("plan_prep_kernel");
 
     Params p;
     memset(&p, 0, sizeof(p));
     p.plan = *plan;
-    const int arows = plan->n_out * OTGAN_MAX_TERMS * 128;
-    if (!make_tensor_map_2d(&p.map_a_hi, a_hi, arows, 128, 128, 128, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
-    if (!make_tensor_map_2d(&p.map_a_lo, a_lo, arows, 128, 128, 128, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
+    const int arows = plan->n_out * OTGAN_MAX_TERMS * hp;
+    if (!make_tensor_map_2d(&p.map_a_hi, a_hi, arows, hp, hp, 128, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
+    if (!make_tensor_map_2d(&p.map_a_lo, a_lo, arows, hp, hp, 128, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return OTGAN_EUNSUPPORTED;
     bool used[OTGAN_MAX_OUTPUTS] = {false};
     for (int o = 0; o < plan->n_out; ++o) {
         p.out[o] = out[o];
@@ -269,9 +279,9 @@ int plan_apply_tc_launch(const otgan_plan_t* plan, int h, int D, const float* P,
     for (int s = 0; s < OTGAN_MAX_OUTPUTS; ++s)
         if (used[s] && !make_tensor_map_2d(&p.map_f[s], F[s], h, D, ldf, box_rows, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
             return OTGAN_EUNSUPPORTED;
-    p.h = h; p.D = D; p.ldo = ldo;
+    p.h = h; p.hp = hp; p.row_tiles = hp / TM_; p.D = D; p.ldo = ldo;
     p.n_col_tiles = ceil_div(D, TN_);
-    p.n_items = plan->n_out * p.n_col_tiles;
+    p.n_items = plan->n_out * p.n_col_tiles * p.row_tiles;
     p.kchunks = ceil_div(h, BK);
     // per-device attribute: set on every launch (a process-wide flag would miss a second GPU)
     OTGAN_CUDA(cudaFuncSetAttribute(plan_apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));

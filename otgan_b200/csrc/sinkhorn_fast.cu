@@ -119,67 +119,95 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
         }
         __syncthreads();
     };
-    // tile of exponents a = (M[line][o] - p_line) - q_o for the 4 tile lines; M = L0 (rows) or L0T (columns)
-    auto load_exponents = [&](const float* M, const double* pl, const double* qo, float (&a)[4][16]) {
+    // exp of a DOUBLE exponent to fp32 accuracy (~3e-7 relative) whatever its magnitude.  A plain fp32 exp(float(x)) carries half
+    // an ulp of |x| (4e-6 at |x| ~ 64) -- and entries that are negligible when K is rebuilt become the significant ones after the
+    // scalings have moved by e^+-55, so that rounding went straight into P (measured 1.2e-5 on a peaked h = 8 block).
+    // t = exponent in LOG2 units, double.  2^t to fp32 accuracy: t = n + r, |r| <= 1/2, 2^r by ex2.approx, 2^n by the exponent field.
+    auto exp2_d = [](double t) -> float {
+        if (!(t > -125.5)) return 0.f;                             // below the fp32 normal range (flush to zero), also -inf
+        if (t > 127.0) return INFINITY;
+        const int n = __double2int_rn(t);
+        const float r = ex2_approx((float)(t - (double)n));
+        return r * __int_as_float((n + 127) << 23);
+    };
+    constexpr double LOG2E_D = 1.4426950408889634074;
+    // approximate (fp32) line maxima of (M[line][o] - p_line) - q_o: only a shift that keeps the exponentials in range
+    auto line_max = [&](const float* M, const double* pl, const double* qo, float (&mx)[4]) {
+        float pf[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { mx[i] = -INFINITY; pf[i] = (float)pl[base4 + i]; }
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const int o = 4 * (g8 + 8 * m);
-            const double q0 = qo[o], q1 = qo[o + 1], q2 = qo[o + 2], q3 = qo[o + 3];
+            const float q0 = (float)qo[o], q1 = (float)qo[o + 1], q2 = (float)qo[o + 2], q3 = (float)qo[o + 3];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const double p = pl[base4 + i];
                 const float4 l = *reinterpret_cast<const float4*>(&M[(base4 + i) * LDS_ + o]);
-                // (-inf) - finite stays -inf in double; the difference of the large terms is taken before the rounding to fp32
-                a[i][4 * m + 0] = (float)(((double)l.x - p) - q0); a[i][4 * m + 1] = (float)(((double)l.y - p) - q1);
-                a[i][4 * m + 2] = (float)(((double)l.z - p) - q2); a[i][4 * m + 3] = (float)(((double)l.w - p) - q3);
+                mx[i] = fmaxf(mx[i], fmaxf(fmaxf((l.x - pf[i]) - q0, (l.y - pf[i]) - q1), fmaxf((l.z - pf[i]) - q2, (l.w - pf[i]) - q3)));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], o));
+            if (!(mx[i] > -INFINITY)) mx[i] = 0.f;                // fully masked line
+        }
+    };
+    // K[i][e] = exp((M[line][o] - p_line) - q_o - shift_i): the difference of the large terms is taken in double, in log2 units
+    // (one cvt, one DFMA, one DADD per element), then reduced and exponentiated (exp2_d)
+    auto exp_tile = [&](const float* M, const double* pl, const double* qo, const float (&shift)[4], float (&K)[4][16]) {
+        double pe[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pe[i] = -(pl[base4 + i] + (double)shift[i]) * LOG2E_D;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int o = 4 * (g8 + 8 * m);
+            const double q0 = qo[o] * LOG2E_D, q1 = qo[o + 1] * LOG2E_D, q2 = qo[o + 2] * LOG2E_D, q3 = qo[o + 3] * LOG2E_D;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 l = *reinterpret_cast<const float4*>(&M[(base4 + i) * LDS_ + o]);
+                K[i][4 * m + 0] = exp2_d(fma((double)l.x, LOG2E_D, pe[i]) - q0); K[i][4 * m + 1] = exp2_d(fma((double)l.y, LOG2E_D, pe[i]) - q1);
+                K[i][4 * m + 2] = exp2_d(fma((double)l.z, LOG2E_D, pe[i]) - q2); K[i][4 * m + 3] = exp2_d(fma((double)l.w, LOG2E_D, pe[i]) - q3);
             }
         }
     };
-    // max-subtracted log-sum-exp over each of the 4 tile lines; on return a = 2^(a - lse) (line-normalised) and the
-    // lane holding line my_idx returns its lse.  nvalid = number of valid lines (rows or cols).
-    auto normalise_lines = [&](float (&a)[4][16], int nvalid) -> float {
-        float lse = 0.f;
+    // max-subtracted log-sum-exp over each of the 4 tile lines of (M - p - q); on return K = exp(. - lse) (line-normalised) and
+    // the lane holding line my_idx returns its lse (double).  nvalid = number of valid lines (rows or cols).
+    auto normalise_lines = [&](const float* M, const double* pl, const double* qo, float (&K)[4][16], int nvalid) -> double {
+        float mx[4];
+        line_max(M, pl, qo, mx);
+        exp_tile(M, pl, qo, mx, K);
+        double lse = 0.0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float m = a[i][0];
-#pragma unroll
-            for (int e = 1; e < 16; ++e) m = fmaxf(m, a[i][e]);
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (!(m > -INFINITY)) m = 0.f;            // fully masked line
             float t = 0.f;
 #pragma unroll
-            for (int e = 0; e < 16; ++e) { a[i][e] = ex2_approx((a[i][e] - m) * LOG2E); t += a[i][e]; }
+            for (int e = 0; e < 16; ++e) t += K[i][e];
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            const float inv = (base4 + i < nvalid) ? __fdividef(1.f, t) : 0.f;
+            const float inv = (base4 + i < nvalid) ? __frcp_rn(t) : 0.f;
 #pragma unroll
-            for (int e = 0; e < 16; ++e) a[i][e] *= inv;
-            if (i == my_idx) lse = m + LN2 * lg2_approx(t);
+            for (int e = 0; e < 16; ++e) K[i][e] *= inv;
+            if (i == my_idx) lse = (double)mx[i] + log((double)t);
         }
         return lse;
     };
     auto rebuild = [&](const float* M, const double* pl, const double* qo, float (&K)[4][16]) {
-        load_exponents(M, pl, qo, K);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int e = 0; e < 16; ++e) K[i][e] = ex2_approx(K[i][e] * LOG2E);
+        const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+        exp_tile(M, pl, qo, zero, K);
     };
     auto slow_row = [&]() {   // f_i += LSE_j(L0 - f - g); K rebuilt; u = v = 1
         absorb();
-        load_exponents(sm.L0, sm.f, sm.g, Kr);
-        const float lse = normalise_lines(Kr, rows);
-        if ((lane & 1) == 0 && my_line < rows) sm.f[my_line] += (double)lse;
+        const double lse = normalise_lines(sm.L0, sm.f, sm.g, Kr, rows);
+        if ((lane & 1) == 0 && my_line < rows) sm.f[my_line] += lse;
         __syncthreads();
         rebuild(sm.L0T, sm.g, sm.f, Kc);
         ++n_slow;
     };
     auto slow_col = [&]() {
         absorb();
-        load_exponents(sm.L0T, sm.g, sm.f, Kc);
-        const float lse = normalise_lines(Kc, cols);
-        if ((lane & 1) == 0 && my_line < cols) sm.g[my_line] += (double)lse;
+        const double lse = normalise_lines(sm.L0T, sm.g, sm.f, Kc, cols);
+        if ((lane & 1) == 0 && my_line < cols) sm.g[my_line] += lse;
         __syncthreads();
         rebuild(sm.L0, sm.f, sm.g, Kr);
         ++n_slow;
@@ -228,23 +256,20 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
     __syncthreads();
     float ent = 0.f, pcs = 0.f;
     {
-        float a[4][16];
-        load_exponents(sm.L0, sm.f, sm.g, a);
+        float mx[4];
+        line_max(sm.L0, sm.f, sm.g, mx);
+        float e[4][16];
+        exp_tile(sm.L0, sm.f, sm.g, mx, e);                    // e = exp(log_a - row max), fp32-accurate for every magnitude
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int r = base4 + i;
-            float m = a[i][0];
+            float s = 0.f;
 #pragma unroll
-            for (int e = 1; e < 16; ++e) m = fmaxf(m, a[i][e]);
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (!(m > -INFINITY)) m = 0.f;
-            float e[16], s = 0.f;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) { e[k] = ex2_approx((a[i][k] - m) * LOG2E); s += e[k]; }
+            for (int k = 0; k < 16; ++k) s += e[i][k];
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             const float ls = LN2 * lg2_approx(s);
+            const double pr = sm.f[r] + (double)mx[i];
 #pragma unroll
             for (int mm = 0; mm < 4; ++mm) {
                 const int c = 4 * (g8 + 8 * mm);
@@ -252,10 +277,12 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const bool ok = (r < rows) && (c + k < cols);
-                    p[k] = ok ? __fdiv_rn(e[4 * mm + k], s) : 0.f;
-                    if (ok) {
-                        ent -= p[k] * ((a[i][4 * mm + k] - m) - ls);
-                        pcs += p[k] * sm.L0[r * LDS_ + c + k];
+                    p[k] = ok ? __fdiv_rn(e[i][4 * mm + k], s) : 0.f;
+                    if (ok && p[k] > 0.f) {
+                        const float l0 = sm.L0[r * LDS_ + c + k];
+                        const float am = (float)(((double)l0 - pr) - sm.g[c + k]);       // log_a - row max
+                        ent -= p[k] * (am - ls);
+                        pcs += p[k] * l0;
                     }
                 }
                 if (P && r < rows && c < cols) {

@@ -24,7 +24,7 @@ def get_matched_features(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_it
                                                  sinkhorn_lambda, nr_sinkhorn_iter, _lib.COST_EUCLID_MEAN, impl)
     N, D = A.shape
     outs = [torch.empty((N, D), device=A.device, dtype=torch.float32) for _ in range(4)]
-    ws, ws_bytes = _m._plan_ws(A.device)
+    ws, ws_bytes = _m._plan_ws(A.device, h)
     rc = lib.otgan_matched_two_batch_f32(h, D, P.data_ptr(), A.data_ptr(), B.data_ptr(), D, outs[0].data_ptr(),
                                          outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(), D, ws.data_ptr(),
                                          ws_bytes, impl, _m._stream())

@@ -43,9 +43,9 @@ def _buf(key, shape, device, dtype=torch.float32):
     return t
 
 
-def _plan_ws(device):
-    """Scratch for the pre-split plan planes of the tensor-core plan-apply kernel."""
-    n = _lib.load().otgan_workspace_bytes_plan()
+def _plan_ws(device, h=128):
+    """Scratch for the pre-split plan planes of the tensor-core plan-apply kernel (block side h)."""
+    n = _lib.load().otgan_workspace_bytes_plan_h(int(h))
     return _buf("plan_ws", ((n + 3) // 4,), device), n
 
 
@@ -148,7 +148,7 @@ def get_matched_features(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_it
     ngpu = len(features_a)
     N, D = A.shape
     outs = [torch.empty((N, D), device=A.device, dtype=torch.float32) for _ in range(4)]
-    ws, ws_bytes = _plan_ws(A.device)
+    ws, ws_bytes = _plan_ws(A.device, h)
     rc = lib.otgan_matched_two_batch_f32(h, D, P.data_ptr(), A.data_ptr(), B.data_ptr(), A.stride(0),
                                          outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(),
                                          D, ws.data_ptr(), ws_bytes, impl, _stream())
@@ -168,7 +168,7 @@ def get_matched_features_single_batch(features_a, features_b, sinkhorn_lambda, n
     L = cost_blocks([A, B, A], [A, B, B], sinkhorn_lambda, _lib.COST_COSINE, [999.0, 999.0, 0.0], impl)
     P, ent, _pc = sinkhorn(L, sinkhorn_lambda, nr_sinkhorn_iter, True, impl)
     outs = [torch.empty((N, D), device=A.device, dtype=torch.float32) for _ in range(4)]
-    ws, ws_bytes = _plan_ws(A.device)
+    ws, ws_bytes = _plan_ws(A.device, N)
     rc = lib.otgan_matched_single_batch_f32(N, D, P.data_ptr(), A.data_ptr(), B.data_ptr(), A.stride(0),
                                             outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
                                             outs[3].data_ptr(), D, ws.data_ptr(), ws_bytes, impl, _stream())
@@ -212,7 +212,7 @@ def matching_step(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, imp
     N, D = A.shape
     Ga = torch.empty((N, D), device=A.device, dtype=torch.float32)
     Gb = torch.empty((N, D), device=A.device, dtype=torch.float32)
-    ws, ws_bytes = _plan_ws(A.device)
+    ws, ws_bytes = _plan_ws(A.device, h)
     rc = lib.otgan_grad_features_f32(h, D, P.data_ptr(), A.data_ptr(), B.data_ptr(), A.stride(0), Ga.data_ptr(),
                                      Gb.data_ptr(), D, ws.data_ptr(), ws_bytes, impl, _stream())
     _lib.check(rc, "otgan_grad_features_f32")

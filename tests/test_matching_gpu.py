@@ -95,7 +95,7 @@ def test_cost_blocks_kernel(M, rows, cols, D, kind):
 
 
 @pytest.mark.parametrize("h,D,kind", [(128, 32768, 0), (128, 7296, 0), (64, 32768, 0), (128, 4096, 0), (96, 1000, 0),
-                                      (128, 48, 0), (32, 64, 1), (100, 520, 1)])
+                                      (128, 48, 0), (32, 64, 1), (100, 520, 1), (256, 8192, 0), (200, 1000, 0), (384, 2048, 1)])
 def test_cost_blocks_tcgen05_two_batch(M, h, D, kind):
     """TMA + tcgen05 3xTF32 cost kernel on the six-block two-batch pattern: against the fp64 oracle and against the
     exact-fp32 SIMT kernel (the two must agree to fp32 noise; lambda = 500 then keeps P within its gate)."""
@@ -252,13 +252,14 @@ def test_sinkhorn_rows_sum_to_one_at_full_size(M):
 
 
 @pytest.mark.parametrize("impl", [1, 2])          # 1 = SIMT (exact fp32), 2 = TMA + tcgen05 3xTF32
-@pytest.mark.parametrize("h,D", [(16, 64), (128, 4096), (20, 37), (64, 1000), (128, 32768), (100, 7296), (4, 32), (128, 160)])
+@pytest.mark.parametrize("h,D", [(16, 64), (128, 4096), (20, 37), (64, 1000), (128, 32768), (100, 7296), (4, 32), (128, 160),
+                                 (256, 4096), (200, 520), (384, 1024)])
 def test_plan_apply_kernels(M, h, D, impl):
     from otgan_b200 import _lib
     lib = _lib.load()
     if impl == 2 and D % 4 != 0:
         pytest.skip("tcgen05 path needs 16-byte aligned rows")
-    ws, ws_bytes = M._plan_ws(torch.device("cuda", 0))
+    ws, ws_bytes = M._plan_ws(torch.device("cuda", 0), h)
     rng = np.random.RandomState(h * 7 + D)
     P = rng.rand(6, h, h)
     P /= P.sum(axis=2, keepdims=True)
