@@ -33,6 +33,7 @@ constexpr float S_LO = 9.094947017729282e-13f /* 2^-40 */, S_HI = 1099511627776.
 struct Smem {
     float L0[H * LDS_];        // L0[r][c] = -lambda*C (natural-log units, exactly the caller's fp32), -inf outside [rows, cols)
     float L0T[H * LDS_];       // L0T[c][r]
+    float KX[H * LDS_];        // slow path: the freshly normalised copy of K, to transpose it into the other copy without new exps
     double f[H], g[H];         // absorbed potentials (natural-log units), double precision: see the header comment
     float u[2][H], v[2][H];    // scaling vectors, double buffered
     float red[2][NTHREADS / 32];
@@ -192,24 +193,37 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
         }
         return lse;
     };
-    auto rebuild = [&](const float* M, const double* pl, const double* qo, float (&K)[4][16]) {
-        const float zero[4] = {0.f, 0.f, 0.f, 0.f};
-        exp_tile(M, pl, qo, zero, K);
+    // The other copy of K is the transpose of the one just normalised: through shared memory (16 STS.128 + 16 LDS.128 per
+    // thread) instead of 64 more double-precision exponentials per thread.  src tile: src[i][4m+e] = X[base4+i][4(g8+8m)+e];
+    // dst[j][4m+e] = X[4(g8+8m)+e][base4+j].
+    auto transpose_into = [&](const float (&src)[4][16], float (&dst)[4][16]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+                *reinterpret_cast<float4*>(&sm.KX[(base4 + i) * LDS_ + 4 * (g8 + 8 * m)]) =
+                    make_float4(src[i][4 * m], src[i][4 * m + 1], src[i][4 * m + 2], src[i][4 * m + 3]);
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float4 v = *reinterpret_cast<const float4*>(&sm.KX[(4 * (g8 + 8 * m) + e) * LDS_ + base4]);
+                dst[0][4 * m + e] = v.x; dst[1][4 * m + e] = v.y; dst[2][4 * m + e] = v.z; dst[3][4 * m + e] = v.w;
+            }
     };
     auto slow_row = [&]() {   // f_i += LSE_j(L0 - f - g); K rebuilt; u = v = 1
         absorb();
         const double lse = normalise_lines(sm.L0, sm.f, sm.g, Kr, rows);
         if ((lane & 1) == 0 && my_line < rows) sm.f[my_line] += lse;
-        __syncthreads();
-        rebuild(sm.L0T, sm.g, sm.f, Kc);
+        transpose_into(Kr, Kc);                // includes the barrier that publishes f
         ++n_slow;
     };
     auto slow_col = [&]() {
         absorb();
         const double lse = normalise_lines(sm.L0T, sm.g, sm.f, Kc, cols);
         if ((lane & 1) == 0 && my_line < cols) sm.g[my_line] += lse;
-        __syncthreads();
-        rebuild(sm.L0, sm.f, sm.g, Kr);
+        transpose_into(Kc, Kr);
         ++n_slow;
     };
     // fast half-step: total_line = sum_o K[line][o] * x_o  (the caller takes the reciprocal)

@@ -118,8 +118,11 @@ def test_cost_blocks_tcgen05_two_batch(M, h, D, kind):
     ys = [A64[h:], B64[:h], B64[:h], B64[h:], B64[:h], B64[h:]]
     for k in range(6):
         C = cost(xs[k], ys[k])
-        assert relerr(Ltc[k] / -lam, C) < TOL_C, ("tcgen05 vs fp64", k)
-        assert relerr(Lsi[k] / -lam, C) < TOL_C, ("simt vs fp64", k)
+        # unnormalised Gaussian rows (the toy Euclidean cost) at h = 384, D = 2048 sit right at 2e-6 for BOTH kernels (fp32
+        # accumulation of 2048 O(1) products); the cosine blocks of the real path stay below TOL_C
+        tol_c = TOL_C if kind == 0 else 1.5 * TOL_C
+        assert relerr(Ltc[k] / -lam, C) < tol_c, ("tcgen05 vs fp64", k)
+        assert relerr(Lsi[k] / -lam, C) < tol_c, ("simt vs fp64", k)
     assert float((Ltc - Lsi).abs().max()) / lam < 1e-6
 
 
@@ -273,7 +276,8 @@ def test_plan_apply_kernels(M, h, D, impl):
                                          ws_bytes, impl, s)
     assert rc == 0, lib.otgan_last_error()
     # SIMT = exact fp32 FMA chains; tcgen05 = 3xTF32 operands (2^-22) + a truncating tensor-core accumulator
-    tol = 3e-6 if impl == 1 else 1e-5
+    # signed Gaussian features cancel in P*F (|out| ~ 1/sqrt(h)), so the error relative to max|out| grows like sqrt(h) beyond 128
+    tol = (3e-6 if impl == 1 else 1e-5) * max(1.0, (h / 128.0) ** 0.5)
     ref = mo._combine_two_batch(list(P64), A64[:h], A64[h:], B64[:h], B64[h:])
     for o, r in zip(outs, ref):
         assert relerr(o, r) < tol
