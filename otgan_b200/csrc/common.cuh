@@ -47,6 +47,19 @@ void count_launch(int n = 1);
     } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: set it once per (kernel, device).  `done` is the
+// caller's static bit mask (one bit per device ordinal < 64; higher ordinals set the attribute on every launch).
+#define OTGAN_SET_MAX_SMEM(kernel, bytes)                                                              \
+    do {                                                                                               \
+        static unsigned long long done__ = 0ull;                                                       \
+        int dev__ = 0;                                                                                 \
+        OTGAN_CUDA(cudaGetDevice(&dev__));                                                             \
+        if (dev__ >= 64 || !((done__ >> dev__) & 1ull)) {                                              \
+            OTGAN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            if (dev__ < 64) done__ |= 1ull << dev__;                                                   \
+        }                                                                                              \
+    } while (0)
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- device helpers ------------------------------------------------------------------------------------------

@@ -1005,8 +1005,7 @@ int run_gemm(GemmParams& p, int TN, size_t out_numel, float* out, void* ws, size
     if (g_use_gemm2 && !p.generic && p.splits == 1 && TN == 256 && (p.m_tiles & 1) == 0 && tiles / 2 >= (kNumSMs * 3) / 4 && min_taps * p.kchunks >= g_gemm2_min_chunks) {
         p.n_items = tiles / 2;
         if (capturing()) { t_capture->kind = 1; t_capture->TN = 256; t_capture->gemm = p; return OTGAN_OK; }
-        // per-device attribute: set on every launch (a process-wide flag would miss a second GPU)
-        OTGAN_CUDA(cudaFuncSetAttribute(conv_gemm2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM_BYTES));
+        OTGAN_SET_MAX_SMEM((conv_gemm2_tc_kernel), G2_SMEM_BYTES);
         const int grid2 = p.n_items < kNumSMs ? p.n_items : kNumSMs;
         conv_gemm2_tc_kernel<<<grid2, NUM_THREADS, G2_SMEM_BYTES, stream>>>(p);
         OTGAN_CHECK_LAUNCH("conv_gemm2_tc_kernel");
@@ -1048,8 +1047,7 @@ template <int TN>
 int launch_gemm(const GemmParams& p, cudaStream_t stream)
 {
     if (capturing()) { t_capture->kind = 0; t_capture->TN = TN; t_capture->gemm = p; return OTGAN_OK; }
-    // per-device attribute: set on every launch (a process-wide flag would miss a second GPU)
-    OTGAN_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<TN>::SMEM_BYTES));
+    OTGAN_SET_MAX_SMEM((conv_gemm_tc_kernel<TN>), Cfg<TN>::SMEM_BYTES);
     const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
     conv_gemm_tc_kernel<TN><<<grid, NUM_THREADS, Cfg<TN>::SMEM_BYTES, stream>>>(p);
     OTGAN_CHECK_LAUNCH("conv_gemm_tc_kernel");
@@ -1060,8 +1058,7 @@ template <int TN>
 int launch_wgrad(const WgradParams& p, cudaStream_t stream)
 {
     if (capturing()) { t_capture->kind = 2; t_capture->TN = TN; t_capture->wgrad = p; return OTGAN_OK; }
-    // per-device attribute: set on every launch (a process-wide flag would miss a second GPU)
-    OTGAN_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<TN>::SMEM_BYTES));
+    OTGAN_SET_MAX_SMEM((conv_wgrad_tc_kernel<TN>), Cfg<TN>::SMEM_BYTES);
     const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
     conv_wgrad_tc_kernel<TN><<<grid, WGRAD_THREADS, Cfg<TN>::SMEM_BYTES, stream>>>(p);
     OTGAN_CHECK_LAUNCH("conv_wgrad_tc_kernel");

@@ -232,9 +232,8 @@ int cost_simt_launch(int nblk, int rows, int cols, int D, const float* const* X,
     const Split p = plan_split(nblk, rows, cols, D);
     float* partial = reinterpret_cast<float*>(ws);
     float* sq = partial + (size_t)p.S * nblk * rows * cols;
-    // per-device attribute: set on every launch (a process-wide flag would miss a second GPU)
-    OTGAN_CUDA(cudaFuncSetAttribute(cost_gram_splitk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    OTGAN_CUDA(cudaFuncSetAttribute(cost_gram_splitk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    OTGAN_SET_MAX_SMEM((cost_gram_splitk_kernel<true>), SMEM_BYTES);
+    OTGAN_SET_MAX_SMEM((cost_gram_splitk_kernel<false>), SMEM_BYTES);
     dim3 grid(p.S, p.tiles_m * p.tiles_n, nblk);
     if (vec)
         cost_gram_splitk_kernel<true><<<grid, NT, SMEM_BYTES, stream>>>(args, rows, cols, D, ldx, ldy, p.ktiles_per_split, p.tiles_n, partial);

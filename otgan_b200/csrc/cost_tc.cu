@@ -286,8 +286,7 @@ int cost_tc_launch(int nblk, int rows, int cols, int D, const float* const* X, c
     float* partial = reinterpret_cast<float*>(ws);
     float* sq = partial + (size_t)pl.splits * nblk * rows * cols;
     pl.prm.partial = partial;
-    // per-device attribute: set on every launch (a process-wide flag would miss a second GPU)
-    OTGAN_CUDA(cudaFuncSetAttribute(cost_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    OTGAN_SET_MAX_SMEM((cost_tc_kernel), SMEM_BYTES);
     dim3 grid(pl.splits, nblk * pl.prm.tiles_r * pl.prm.tiles_c);
     cost_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(pl.prm);
     OTGAN_CHECK_LAUNCH("cost_tc_kernel");

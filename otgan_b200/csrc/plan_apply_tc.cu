@@ -283,8 +283,7 @@ int plan_apply_tc_launch(const otgan_plan_t* plan, int h, int D, const float* P,
     p.n_col_tiles = ceil_div(D, TN_);
     p.n_items = plan->n_out * p.n_col_tiles * p.row_tiles;
     p.kchunks = ceil_div(h, BK);
-    // per-device attribute: set on every launch (a process-wide flag would miss a second GPU)
-    OTGAN_CUDA(cudaFuncSetAttribute(plan_apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    OTGAN_SET_MAX_SMEM((plan_apply_tc_kernel), SMEM_BYTES);
     const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
     plan_apply_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
     OTGAN_CHECK_LAUNCH("plan_apply_tc_kernel");

@@ -329,8 +329,7 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
 int sinkhorn_fast_launch(int nblk, int rows, int cols, int T, float lam, const float* L0, float* P, float* entropy,
                          float* pc, int* slow_steps, cudaStream_t stream)
 {
-    // per-device attribute: set on every launch (a process-wide flag would miss a second GPU)
-    OTGAN_CUDA(cudaFuncSetAttribute(sinkhorn_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    OTGAN_SET_MAX_SMEM((sinkhorn_fast_kernel), sizeof(Smem));
     sinkhorn_fast_kernel<<<nblk, NTHREADS, sizeof(Smem), stream>>>(L0, P, entropy, pc, slow_steps, rows, cols, T, lam);
     OTGAN_CHECK_LAUNCH("sinkhorn_fast_kernel");
     return OTGAN_OK;

@@ -240,8 +240,7 @@ int sinkhorn_stream_launch(int nblk, int rows, int cols, int T, float lam, const
         OTGAN_CHECK_LAUNCH("sk_final_big_kernel");
         return OTGAN_OK;
     }
-    // the attribute is per device: set it on every launch (cheap) rather than caching a process-wide flag
-    OTGAN_CUDA(cudaFuncSetAttribute(sk_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAXS * 33 * sizeof(float))));
+    OTGAN_SET_MAX_SMEM(sk_col_kernel, MAXS * 33 * sizeof(float));
     for (int it = 0; it < T; ++it) {
         sk_row_kernel<<<ceil_div(nrows_total, 8), 256, 0, stream>>>(it == 0 ? L0 : P, P, nrows_total, cols);   // :53
         OTGAN_CHECK_LAUNCH("sk_row_kernel");

@@ -104,6 +104,7 @@ class Trainer:
         else:
             self.gen_optimizer = opt(generator, lr=args.learning_rate_gen, mom1=0.5)
             self.disc_optimizer = opt(discriminator, lr=-args.learning_rate_disc, mom1=0.5)
+        self.sync = {'disc': GradSync(discriminator, world), 'gen': GradSync(generator, world)}
         self.step_counter = 0
         self.gather_buf = None
         self.graphs = None                                 # set by enable_cuda_graphs()
@@ -166,17 +167,13 @@ class Trainer:
         ga, gb = Ga[lo:hi], Gb[lo:hi]                                                            # this rank's towers
         self.last_grad_ys = (Ga, Gb)
         if train_disc:
-            (grad,) = torch.autograd.grad([feats], [disc.flat], grad_outputs=[torch.cat([ga, gb], 0)])   # :122-128
-            if self.world > 1:
-                dist.all_reduce(grad, op=dist.ReduceOp.SUM)                                      # :134-139 (sum, not mean)
+            grad = self.sync['disc'].backward([feats], [torch.cat([ga, gb], 0)])                 # :122-128 + :134-139 (sum, not mean)
             if apply_update:
                 self.disc_optimizer.run(grad, lr=-a.learning_rate_disc, hyper_dev=hyper_dev)     # :143,215
                 if a.optimizer == 'adam':
                     disc.store.refresh_weight_cache()      # W of the updated critic, reused by the generator steps that follow
         else:
-            (grad,) = torch.autograd.grad([f_gen], [gen.flat], grad_outputs=[ga])                # :111-112
-            if self.world > 1:
-                dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+            grad = self.sync['gen'].backward([f_gen], [ga])                                      # :111-112 + :134-139
             if apply_update:
                 self.gen_optimizer.run(grad, lr=a.learning_rate_gen, hyper_dev=hyper_dev)        # :142,222 (+ EMA :223)
         self.last_grad = grad
@@ -286,6 +283,77 @@ class Trainer:
             if path_ema is not None:
                 xe = self.generator(ema=self.ema, **self.model_opts)
                 plotting.save_tile_img(plotting.img_tile(xe[:n].cpu().numpy(), aspect_ratio=1.0, border_color=1.0, stretch=False), path_ema)
+
+
+class GradSync:
+    """Backward pass of one network with the tower-gradient SUM (train.py:134-139) overlapped with it.
+
+    The gradient is taken with respect to the per-variable views of the flat parameter buffer (no final concatenation); a hook
+    on every view copies its gradient into a persistent flat gradient buffer, and as soon as all variables of a LAYER have
+    arrived the layer's slice is all-reduced on a side stream while the rest of the backward pass keeps running on the main
+    stream (layers finish last-to-first; each slice starts travelling as soon as its layer is done).  Works the same
+    eagerly and under CUDA-graph capture (the side stream forks from and joins into the capturing stream)."""
+
+    def __init__(self, template, world):
+        self.tpl, self.world = template, world
+        st = template.store
+        self.flat_grad = torch.zeros_like(st.flat.detach())
+        self.side = torch.cuda.Stream(device=st.flat.device) if world > 1 else None
+        self.layers = {}                                   # scope -> [lo, hi, n_vars]
+        self.var_layer = []
+        for name, shape, off, n in st.specs:
+            scope = name.rsplit("/", 1)[0]
+            ent = self.layers.setdefault(scope, [off, off + n, 0])
+            ent[0], ent[1], ent[2] = min(ent[0], off), max(ent[1], off + n), ent[2] + 1
+            self.var_layer.append(scope)
+
+    def backward(self, outputs, grad_outputs):
+        """Returns the flat gradient buffer holding d(outputs)/d(parameters) (summed over ranks when world > 1)."""
+        st = self.tpl.store
+        views = st.last_views
+        assert views is not None and len(views) == len(st.specs), "GradSync.backward needs the views of the network's last call"
+        pending = {k: v[2] for k, v in self.layers.items()}
+        done_events = []
+        main = torch.cuda.current_stream()
+        handles = []
+
+        def on_grad(i, g):
+            _, _, off, n = st.specs[i]
+            dst = self.flat_grad[off:off + n]
+            if g.data_ptr() != dst.data_ptr():
+                dst.copy_(g.reshape(-1))
+            scope = self.var_layer[i]
+            pending[scope] -= 1
+            if pending[scope] == 0 and self.world > 1:
+                lo, hi, _ = self.layers[scope]
+                self.side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self.side):
+                    dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM)
+            return None
+
+        for i, v in enumerate(views):
+            handles.append(v.register_hook(lambda g, i=i: on_grad(i, g)))
+        try:
+            grads = torch.autograd.grad(outputs, list(views), grad_outputs=grad_outputs, allow_unused=True)
+        finally:
+            for h in handles:
+                h.remove()
+        missing = [k for k, c in pending.items() if c > 0]
+        if missing:                                        # variables the outputs do not depend on: zero gradient, reduce now
+            for i, g in enumerate(grads):
+                if g is None:
+                    _, _, off, n = st.specs[i]
+                    self.flat_grad[off:off + n].zero_()
+            if self.world > 1:
+                self.side.wait_stream(main)
+                with torch.cuda.stream(self.side):
+                    for k in missing:
+                        lo, hi, _ = self.layers[k]
+                        dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM)
+        if self.world > 1:
+            main.wait_stream(self.side)
+        del done_events
+        return self.flat_grad
 
 
 def gather_features(f_gen, f_dat, world):

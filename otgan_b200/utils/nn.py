@@ -203,6 +203,7 @@ class Template:
             out = self.spec(*args, **kwargs)
         finally:
             _tls.store = prev
+            self.store.last_views = getattr(self.store, "_views", None)     # kept for gradient hooks (train.GradSync)
             self.store._views = None
         if not self.store.frozen:
             self.store.pack()

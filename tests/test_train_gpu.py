@@ -260,3 +260,23 @@ def test_dcgan_64x64_extension_trains_on_gpu():
         kind, stats = tr.step(torch.rand(16, 64, 64, 3, device="cuda") * 2 - 1)
         d, e = stats.tolist()
         assert kind == expect and np.isfinite(d) and 0.0 < e <= np.log(8) + 1e-4
+
+
+def test_loss_parity_tf32_convolutions_vs_strict_fp32():
+    """North star "loss parity to the reference": the same training trajectory (fixed seeds, images, latents; N = 64, T = 100,
+    lambda = 500, Adam 3e-4) on the tcgen05 convolution kernels (TF32 operands) and on the strict-fp32 library rung -- the
+    precision class of the reference's TensorFlow-1.x convolutions.  OT-GAN training is chaotic: a CONTROL run of the fp32 rung
+    with 1e-6 relative noise on its input images separates from the fp32 run just as fast (profiles/r02_loss_parity_dcgan.json:
+    mean distance gap over steps 20-60 0.099 for TF32-vs-fp32 against 0.128 for fp32-vs-perturbed-fp32).  So the gate is (i) the
+    first 20 steps, before chaos takes over, within a band measured at 3x margin (distance 0.03 = 5% of its scale, entropy 0.15),
+    and (ii) the later TF32-vs-fp32 gap no larger than 3x the control's own gap (+0.05)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("loss_parity", os.path.join(os.path.dirname(__file__), "..", "tools", "loss_parity.py"))
+    lp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(lp)
+    r = lp.compare(steps=60, n=64, t_iters=100, lam=500.0, model="dcgan")
+    a, c = r["tf32_vs_fp32"], r["fp32_vs_fp32_perturbed_1e-6"]
+    assert a["distance_gap_max_steps_0_20"] < 0.03 and a["entropy_gap_max_steps_0_20"] < 0.15, a
+    assert a["distance_gap_mean_steps_20_60"] < 3.0 * c["distance_gap_mean_steps_20_60"] + 0.05, (a, c)
+    assert a["entropy_gap_mean_steps_20_60"] < 3.0 * c["entropy_gap_mean_steps_20_60"] + 0.15, (a, c)

@@ -16,7 +16,7 @@ from otgan_b200 import train as T  # noqa: E402
 from otgan_b200.utils import nn  # noqa: E402
 
 
-def trajectory(backend, steps, n, t_iters, lam, model="dcgan"):
+def trajectory(backend, steps, n, t_iters, lam, model="dcgan", perturb=0.0):
     prev = (nn.CONV_BACKEND, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     nn.CONV_BACKEND = backend
     torch.backends.cudnn.allow_tf32 = False
@@ -29,6 +29,8 @@ def trajectory(backend, steps, n, t_iters, lam, model="dcgan"):
         out = []
         for s in range(steps):
             x = (torch.rand((n, 32, 32, 3), generator=g) * 2 - 1).cuda()
+            if perturb:                                  # control run: rounding-level noise on the inputs of every step
+                x = x * (1.0 + perturb * torch.randn(x.shape, device="cuda", generator=None))
             if model == "dcgan":
                 u = (torch.rand((n, 100), generator=g) * 2 - 1).cuda()
             else:
@@ -43,16 +45,28 @@ def trajectory(backend, steps, n, t_iters, lam, model="dcgan"):
 
 
 def compare(steps=200, n=64, t_iters=100, lam=500.0, model="dcgan"):
+    """A: tcgen05 (TF32 operands); B: strict fp32 library rung; C: B again with 1e-6 relative noise on the input images -- the
+    CONTROL that shows how fast this (chaotic) GAN trajectory separates from itself under fp32-rounding-level perturbations."""
     a = trajectory("tcgen05", steps, n, t_iters, lam, model)
     b = trajectory("cudnn", steps, n, t_iters, lam, model)
-    dd = [abs(x[1] - y[1]) for x, y in zip(a, b)]
-    de = [abs(x[2] - y[2]) for x, y in zip(a, b)]
-    scale_d = max(abs(y[1]) for y in b)
+    c = trajectory("cudnn", steps, n, t_iters, lam, model, perturb=1e-6)
+
+    def gaps(p, q):
+        dd = [abs(x[1] - y[1]) for x, y in zip(p, q)]
+        de = [abs(x[2] - y[2]) for x, y in zip(p, q)]
+        win = lambda v, lo, hi: sum(v[lo:hi]) / max(1, len(v[lo:hi]))
+        return {"distance_gap_mean_steps_0_20": win(dd, 0, 20), "distance_gap_mean_steps_20_60": win(dd, 20, 60),
+                "distance_gap_mean_rest": win(dd, 60, steps), "distance_gap_max_steps_0_20": max(dd[:20]),
+                "entropy_gap_mean_steps_0_20": win(de, 0, 20), "entropy_gap_mean_steps_20_60": win(de, 20, 60),
+                "entropy_gap_mean_rest": win(de, 60, steps), "entropy_gap_max_steps_0_20": max(de[:20])}
+
+    mean = lambda t, i, lo: sum(x[i] for x in t[lo:]) / max(1, len(t[lo:]))
     return {"model": model, "steps": steps, "N": n, "T": t_iters, "lambda": lam,
-            "max_abs_gap_distance": max(dd), "mean_abs_gap_distance": sum(dd) / len(dd), "max_abs_distance_fp32": scale_d,
-            "max_abs_gap_entropy": max(de), "mean_abs_gap_entropy": sum(de) / len(de),
-            "final": {"tcgen05": a[-1][1:], "fp32": b[-1][1:]},
-            "first_steps_gap_distance": dd[:12], "every_20th": [(s, a[s][1], b[s][1], a[s][2], b[s][2]) for s in range(0, steps, 20)]}
+            "distance_scale_fp32": max(abs(y[1]) for y in b),
+            "tf32_vs_fp32": gaps(a, b), "fp32_vs_fp32_perturbed_1e-6": gaps(b, c),
+            "late_means": {"tf32": [mean(a, 1, steps // 2), mean(a, 2, steps // 2)], "fp32": [mean(b, 1, steps // 2), mean(b, 2, steps // 2)],
+                           "fp32_perturbed": [mean(c, 1, steps // 2), mean(c, 2, steps // 2)]},
+            "every_10th": [(s, a[s][1], b[s][1], c[s][1], a[s][2], b[s][2], c[s][2]) for s in range(0, steps, 10)]}
 
 
 if __name__ == "__main__":
