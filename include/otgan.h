@@ -245,6 +245,30 @@ OTGAN_API int otgan_col2im_narrow_f32(int B, int H, int W, int C, int kh, int kw
 OTGAN_API size_t otgan_workspace_bytes_colsum(int P, int C);
 OTGAN_API int otgan_colsum_f32(int P, int C, const float* x, float* out, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- parameter-space pipeline in the variable's own layout ---------------------------------------------------------------------------
+ * The variables are HWIO (utils/nn.py:123: [kh, kw, Cin, Cout] == [K, C] with the OUTPUT channel contiguous).  These forms keep the
+ * whole gradient path in that layout, so that only ONE transpose (V -> the OHWI operand of fprop) is left per layer and step:
+ *   weightnorm_fwd2     W (OHWI) and, in the same pass over V, W_ihwo [Cin][taps][Cout] = the dgrad operand (a scaled row permutation
+ *                       of V -- no transpose); W_ihwo may be NULL
+ *   wgrad_hwio          the filter gradient written as [taps * Cin][Cout] (dV's layout; the 32 lanes of a warp own 32 consecutive
+ *                       output channels: 128-byte segments); the fused-upsample form writes [4][n1*n1 * Cin][Cout]
+ *   up2_..._ihwo/_hwio  the sub-filter pre-sum for dgrad built from W_ihwo, and the chain rule of the pre-sum on HWIO gradients
+ *   weightnorm_bwd_hwio dV, dg from an HWIO filter gradient: pure streaming, float4 along Cout */
+OTGAN_API int otgan_weightnorm_fwd2_f32(int K, int C, int taps, const float* V, const float* g, float* Wt, float* W_ihwo,
+                                        float* inv_norm, void* ws, size_t ws_bytes, void* stream);
+OTGAN_API int otgan_weightnorm_bwd_hwio_f32(int K, int C, const float* V, const float* g, const float* inv_norm, const float* dW_hwio,
+                                            float* dV, float* dg, void* ws, size_t ws_bytes, void* stream);
+OTGAN_API int otgan_conv2d_wgrad_hwio_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top,
+                                           int pad_left, const float* dy, const float* x, float* dw_hwio, void* ws, size_t ws_bytes,
+                                           void* stream);
+OTGAN_API int otgan_conv2d_up2_wgrad_hwio_tf32(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pad_top, int pad_left,
+                                               const float* dy, const float* x_low, float* dw_sub_hwio, void* ws, size_t ws_bytes,
+                                               void* stream);
+OTGAN_API int otgan_up2_weight_presum_ihwo_f32(int Cout, int kh, int kw, int Cin, int pad_top, int pad_left, const float* w_ihwo,
+                                               float* w_sub_ihwo, void* stream);
+OTGAN_API int otgan_up2_weight_unsum_hwio_f32(int Cout, int kh, int kw, int Cin, int pad_top, int pad_left, const float* dw_sub_hwio,
+                                              float* dw_hwio, void* stream);
+
 /* ---- generic convolutions (any channel counts / batch; utils/nn.py:234-241, 328-338 accept any shape) ---------------------------------
  * The same tcgen05 kernels in their generic mode: channel counts are multiples of 4, spatial extents powers of two, the batch is
  * arbitrary; x / y / dy / dx may be channel SLICES of wider NHWC buffers (pixel strides ldx / ldy in floats, pointers at the first

@@ -82,6 +82,12 @@ SIGNATURES = {
     "otgan_col2im_narrow_f32": (_i, [_i] * 9 + [_vp, _i, _vp, _vp, _vp]),
     "otgan_workspace_bytes_colsum": (_sz, [_i, _i]),
     "otgan_colsum_f32": (_i, [_i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "otgan_weightnorm_fwd2_f32": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "otgan_weightnorm_bwd_hwio_f32": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "otgan_conv2d_wgrad_hwio_tf32": (_i, [_i] * 10 + [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "otgan_conv2d_up2_wgrad_hwio_tf32": (_i, [_i] * 9 + [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "otgan_up2_weight_presum_ihwo_f32": (_i, [_i] * 6 + [_vp, _vp, _vp]),
+    "otgan_up2_weight_unsum_hwio_f32": (_i, [_i] * 6 + [_vp, _vp, _vp]),
     "otgan_conv2d_fprop_ex_tf32": (_i, [_i] * 12 + [_vp, _vp, _vp, _vp, _i, _vp]),
     "otgan_conv2d_dgrad_ex_tf32": (_i, [_i] * 12 + [_vp, _vp, _vp, _vp]),
     "otgan_workspace_bytes_conv_wgrad_ex": (_sz, [_i] * 8),

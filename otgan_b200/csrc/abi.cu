@@ -83,7 +83,7 @@ int conv_dgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
                       const float* dy, const float* wt, float* dx, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t conv_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int kh, int kw);
 int conv_wgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo,
-                      const float* dy, const float* x, float* dw, void* ws, size_t ws_bytes, cudaStream_t stream);
+                      const float* dy, const float* x, float* dw, void* ws, size_t ws_bytes, cudaStream_t stream, int hwio);
 int ohwi_to_ihwo_launch(int Cout, int T, int Cin, const float* w, float* wt, cudaStream_t stream);
 size_t colsum_workspace_bytes(int P, int C);
 int conv_set_option(int option, int value);
@@ -97,7 +97,12 @@ int conv_up2_dgrad_launch(int B, int Hl, int Wl, int Cin, int Cout, int kh, int 
                           const float* w_sub_t, float* dx_low, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t conv_up2_wgrad_workspace_bytes(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pt, int pl);
 int conv_up2_wgrad_launch(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pt, int pl, const float* dy,
-                          const float* x_low, float* dw_sub, void* ws, size_t ws_bytes, cudaStream_t stream);
+                          const float* x_low, float* dw_sub, void* ws, size_t ws_bytes, cudaStream_t stream, int hwio);
+int up2_presum_ihwo_launch(int Cout, int kh, int kw, int Cin, int pt, int pl, const float* w_ihwo, float* w_sub_t, cudaStream_t stream);
+int up2_unsum_hwio_launch(int Cout, int kh, int kw, int Cin, int pt, int pl, const float* dw_sub, float* dw, cudaStream_t stream);
+int weightnorm_fwd2_launch(int K, int C, int T, const float* V, const float* g, float* Wt, float* ihwo, float* inv, void* ws, cudaStream_t stream);
+int weightnorm_bwd_hwio_launch(int K, int C, const float* V, const float* g, const float* inv, const float* dW, float* dV, float* dg,
+                               void* ws, cudaStream_t stream);
 int im2col_narrow_launch(int B, int H, int W, int C, int kh, int kw, int pt, int pl, int flip, const float* x, float* col,
                          int ldc, cudaStream_t stream);
 int col2im_narrow_launch(int B, int H, int W, int C, int kh, int kw, int pt, int pl, int flip, const float* z, int ldz,
@@ -412,7 +417,17 @@ int otgan_conv2d_wgrad_tf32(int B, int H, int W, int Cin, int Cout, int kh, int 
     OTGAN_REQUIRE(stride == 1 || stride == 2, "conv2d_wgrad: stride %d not in {1, 2}", stride);
     OTGAN_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dw_ohwi) && (!ws || aligned16(ws)), "conv2d_wgrad: buffers must be 16-byte aligned");
     return conv_wgrad_launch(B, H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, H / stride, W / stride, dy, x, dw_ohwi, ws,
-                             ws_bytes, (cudaStream_t)stream);
+                             ws_bytes, (cudaStream_t)stream, 0);
+}
+
+int otgan_conv2d_wgrad_hwio_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top, int pad_left,
+                                 const float* dy, const float* x, float* dw_hwio, void* ws, size_t ws_bytes, void* stream)
+{
+    OTGAN_REQUIRE(dy && x && dw_hwio, "conv2d_wgrad_hwio: null pointer");
+    OTGAN_REQUIRE(stride == 1 || stride == 2, "conv2d_wgrad_hwio: stride %d not in {1, 2}", stride);
+    OTGAN_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dw_hwio) && (!ws || aligned16(ws)), "conv2d_wgrad_hwio: buffers must be 16-byte aligned");
+    return conv_wgrad_launch(B, H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, H / stride, W / stride, dy, x, dw_hwio, ws,
+                             ws_bytes, (cudaStream_t)stream, 1);
 }
 
 int otgan_ohwi_to_ihwo_f32(int Cout, int taps, int Cin, const float* w_ohwi, float* w_ihwo, void* stream)
@@ -494,7 +509,48 @@ int otgan_conv2d_up2_wgrad_tf32(int B, int Hl, int Wl, int Cin, int Cout, int kh
 {
     OTGAN_REQUIRE(dy && x_low && dw_sub, "conv2d_up2_wgrad: null pointer");
     OTGAN_REQUIRE(aligned16(dy) && aligned16(x_low) && aligned16(dw_sub) && (!ws || aligned16(ws)), "conv2d_up2_wgrad: buffers must be 16-byte aligned");
-    return conv_up2_wgrad_launch(B, Hl, Wl, Cin, Cout, kh, kw, pad_top, pad_left, dy, x_low, dw_sub, ws, ws_bytes, (cudaStream_t)stream);
+    return conv_up2_wgrad_launch(B, Hl, Wl, Cin, Cout, kh, kw, pad_top, pad_left, dy, x_low, dw_sub, ws, ws_bytes, (cudaStream_t)stream, 0);
+}
+
+int otgan_conv2d_up2_wgrad_hwio_tf32(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pad_top, int pad_left,
+                                     const float* dy, const float* x_low, float* dw_sub_hwio, void* ws, size_t ws_bytes, void* stream)
+{
+    OTGAN_REQUIRE(dy && x_low && dw_sub_hwio, "conv2d_up2_wgrad_hwio: null pointer");
+    OTGAN_REQUIRE(aligned16(dy) && aligned16(x_low) && aligned16(dw_sub_hwio) && (!ws || aligned16(ws)), "conv2d_up2_wgrad_hwio: buffers must be 16-byte aligned");
+    return conv_up2_wgrad_launch(B, Hl, Wl, Cin, Cout, kh, kw, pad_top, pad_left, dy, x_low, dw_sub_hwio, ws, ws_bytes, (cudaStream_t)stream, 1);
+}
+
+int otgan_up2_weight_presum_ihwo_f32(int Cout, int kh, int kw, int Cin, int pad_top, int pad_left, const float* w_ihwo, float* w_sub_ihwo,
+                                     void* stream)
+{
+    OTGAN_REQUIRE(Cout >= 1 && Cin >= 1 && w_ihwo && w_sub_ihwo, "up2_weight_presum_ihwo: bad arguments");
+    return up2_presum_ihwo_launch(Cout, kh, kw, Cin, pad_top, pad_left, w_ihwo, w_sub_ihwo, (cudaStream_t)stream);
+}
+
+int otgan_up2_weight_unsum_hwio_f32(int Cout, int kh, int kw, int Cin, int pad_top, int pad_left, const float* dw_sub_hwio, float* dw_hwio,
+                                    void* stream)
+{
+    OTGAN_REQUIRE(Cout >= 1 && Cin >= 1 && dw_sub_hwio && dw_hwio, "up2_weight_unsum_hwio: bad arguments");
+    return up2_unsum_hwio_launch(Cout, kh, kw, Cin, pad_top, pad_left, dw_sub_hwio, dw_hwio, (cudaStream_t)stream);
+}
+
+int otgan_weightnorm_fwd2_f32(int K, int C, int taps, const float* V, const float* g, float* Wt, float* W_ihwo, float* inv_norm, void* ws,
+                              size_t ws_bytes, void* stream)
+{
+    OTGAN_REQUIRE(K >= 4 && C >= 4 && !(K & 3) && !(C & 3) && taps >= 1 && K % taps == 0 && V && g && Wt && inv_norm && ws,
+                  "weightnorm_fwd2: bad arguments (K, C multiples of 4; K = taps * Cin)");
+    OTGAN_REQUIRE(aligned16(V) && aligned16(Wt) && (!W_ihwo || aligned16(W_ihwo)), "weightnorm_fwd2: buffers must be 16-byte aligned");
+    OTGAN_REQUIRE(ws_bytes >= weightnorm_workspace_bytes(K, C), "weightnorm_fwd2: workspace too small");
+    return weightnorm_fwd2_launch(K, C, taps, V, g, Wt, W_ihwo, inv_norm, ws, (cudaStream_t)stream);
+}
+
+int otgan_weightnorm_bwd_hwio_f32(int K, int C, const float* V, const float* g, const float* inv_norm, const float* dW_hwio, float* dV,
+                                  float* dg, void* ws, size_t ws_bytes, void* stream)
+{
+    OTGAN_REQUIRE(K >= 1 && C >= 4 && !(C & 3) && V && g && inv_norm && dW_hwio && dV && dg && ws, "weightnorm_bwd_hwio: bad arguments");
+    OTGAN_REQUIRE(aligned16(V) && aligned16(dW_hwio) && aligned16(dV), "weightnorm_bwd_hwio: buffers must be 16-byte aligned");
+    OTGAN_REQUIRE(ws_bytes >= weightnorm_workspace_bytes(K, C), "weightnorm_bwd_hwio: workspace too small");
+    return weightnorm_bwd_hwio_launch(K, C, V, g, inv_norm, dW_hwio, dV, dg, ws, (cudaStream_t)stream);
 }
 
 int otgan_conv_set_option(int option, int value) { return conv_set_option(option, value); }

@@ -568,6 +568,8 @@ struct WgradParams {
     long long split_stride;                   // floats between split partials
     float* out;
     int masked, m_valid, n_valid;             // generic shapes: rows (co) >= m_valid / columns (ci) >= n_valid are not stored
+    int hwio, hwio_c, hwio_rows;              // hwio != 0: write dW as [class][tap * Cin + ci][co] (the layout of the HWIO variable V,
+                                              // hwio_c = Cout, hwio_rows = Cout rows per class of `brow`): coalesced across the 32 lanes
 };
 
 // wgrad thread layout: warp 0 = producer of the dy boxes (+ expect_tx), warp 1 = MMA issuer, warps 2-5 = epilogue,
@@ -701,6 +703,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradParams p)
             mbar_wait(tfull_bar(b), ((uint32_t)(n >> 1)) & 1u);
             tcgen05_fence_after();
             const bool row_ok = !p.masked || (cot * TM + r < p.m_valid);
+            float* out_t = nullptr;
+            if (p.hwio) {          // [class][tap * Cin + ci][co]: lane r -> consecutive co, one 128-byte segment per ci column
+                const int cls = p.taps[t].brow / p.hwio_rows;
+                out_t = p.out + (long long)sp * p.split_stride + ((long long)cls * p.ldw + p.taps[t].wcol + cit * TN) * p.hwio_c + cot * TM + r;
+            }
 #pragma unroll 1
             for (int cc = 0; cc < TN / 32; ++cc) {
                 if (p.masked && cit * TN + cc * 32 >= p.n_valid) break;          // warp-uniform
@@ -708,7 +715,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradParams p)
                 tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TN + cc * 32), v);
                 tmem_ld_wait();
                 if (!row_ok) continue;
-                if (!p.masked || cit * TN + cc * 32 + 32 <= p.n_valid) {
+                if (p.hwio) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (!p.masked || cit * TN + cc * 32 + j < p.n_valid) out_t[(long long)(cc * 32 + j) * p.hwio_c] = __uint_as_float(v[j]);
+                } else if (!p.masked || cit * TN + cc * 32 + 32 <= p.n_valid) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
                         *reinterpret_cast<uint4*>(out + cc * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -849,6 +860,60 @@ up2_unsum_kernel(SubMap m, int Cout, int Cin, const float* __restrict__ dw_sub, 
             for (int b = 0; b < 2; ++b) {
                 const int slot = m.idx_h[a][kh] * m.n1w + m.idx_w[b][kw];
                 const float4 v = __ldg(src + (((size_t)(2 * a + b) * Cout + co) * slots + slot) * C4 + c4);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        reinterpret_cast<float4*>(dw)[i] = acc;
+    }
+}
+
+// The same two maps in the layouts whose contiguous axis is the OUTPUT channel (float4 along co):
+//   w_sub_t[cls][ci][slot][co] = sum_{taps t in (cls, slot)} w_ihwo[ci][t][co]      (the dgrad operand of the fused-upsample layers,
+//                                                                                  built from the IHWO filter in one pass)
+__global__ void __launch_bounds__(256)
+up2_presum_ihwo_kernel(SubMap m, int Cout, int Cin, const float* __restrict__ w_ihwo, float* __restrict__ w_sub_t)
+{
+    const int slots = m.n1h * m.n1w, C4 = Cout >> 2, taps = m.kh * m.kw;
+    const size_t total = (size_t)4 * Cin * slots * C4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        size_t r = i / C4;
+        const int slot = (int)(r % slots); r /= slots;
+        const int ci = (int)(r % Cin);
+        const int cls = (int)(r / Cin);
+        const int a = cls >> 1, b = cls & 1, ri = slot / m.n1w, cj = slot % m.n1w;
+        const float4* src = reinterpret_cast<const float4*>(w_ihwo + (size_t)ci * taps * Cout) + c4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kh = 0; kh < m.kh; ++kh) {
+            if (m.idx_h[a][kh] != ri) continue;
+            for (int kw = 0; kw < m.kw; ++kw) {
+                if (m.idx_w[b][kw] != cj) continue;
+                const float4 v = __ldg(src + (size_t)(kh * m.kw + kw) * C4);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        reinterpret_cast<float4*>(w_sub_t)[i] = acc;
+    }
+}
+//   dw_hwio[t][ci][co] = sum_{a, b} dw_sub_hwio[2a+b][slot(a, b, t)][ci][co]          (chain rule of the pre-sum on HWIO gradients)
+__global__ void __launch_bounds__(256)
+up2_unsum_hwio_kernel(SubMap m, int Cout, int Cin, const float* __restrict__ dw_sub, float* __restrict__ dw)
+{
+    const int slots = m.n1h * m.n1w, taps = m.kh * m.kw, C4 = Cout >> 2;
+    const size_t total = (size_t)taps * Cin * C4;
+    const float4* src = reinterpret_cast<const float4*>(dw_sub);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        size_t r = i / C4;
+        const int ci = (int)(r % Cin);
+        const int t = (int)(r / Cin);
+        const int kh = t / m.kw, kw = t % m.kw;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int slot = m.idx_h[a][kh] * m.n1w + m.idx_w[b][kw];
+                const float4 v = __ldg(src + (((size_t)(2 * a + b) * slots + slot) * Cin + ci) * C4 + c4);
                 acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             }
         reinterpret_cast<float4*>(dw)[i] = acc;
@@ -1322,7 +1387,7 @@ size_t conv_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int 
 
 // dw[Cout, kh*kw*Cin] = sum over pixels dy (x) x
 int conv_wgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo,
-                      const float* dy, const float* x, float* dw, void* ws, size_t ws_bytes, cudaStream_t stream)
+                      const float* dy, const float* x, float* dw, void* ws, size_t ws_bytes, cudaStream_t stream, int hwio)
 {
     OTGAN_REQUIRE(conv_dims_ok(B, H, W, Cin, Cout, kh, kw, s, pt, pl, Ho, Wo), "conv_wgrad: unsupported geometry");
     WgradParams p;
@@ -1360,6 +1425,7 @@ int conv_wgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
     p.n_items = items * p.splits;
     p.ldw = nt * Cin;
     p.split_stride = (long long)Cout * p.ldw;
+    p.hwio = hwio; p.hwio_c = Cout; p.hwio_rows = Cout;
     if (p.splits > 1) {
         OTGAN_REQUIRE(ws && ws_bytes >= (size_t)p.splits * p.split_stride * sizeof(float), "conv_wgrad: workspace too small");
         p.out = reinterpret_cast<float*>(ws);
@@ -1541,6 +1607,26 @@ int up2_unsum_launch(int Cout, int kh, int kw, int Cin, int pt, int pl, const fl
     return OTGAN_OK;
 }
 
+int up2_presum_ihwo_launch(int Cout, int kh, int kw, int Cin, int pt, int pl, const float* w_ihwo, float* w_sub_t, cudaStream_t stream)
+{
+    SubMap m;
+    if (!make_submap(m, kh, kw, pt, pl)) { set_error("up2_presum_ihwo: unsupported filter geometry %dx%d pad %d,%d", kh, kw, pt, pl); return OTGAN_EUNSUPPORTED; }
+    OTGAN_REQUIRE(Cout % 4 == 0 && aligned16(w_ihwo) && aligned16(w_sub_t), "up2_presum_ihwo: Cout must be a multiple of 4, buffers 16-byte aligned");
+    up2_presum_ihwo_kernel<<<ew_grid((size_t)4 * Cin * m.n1h * m.n1w * (Cout / 4)), 256, 0, stream>>>(m, Cout, Cin, w_ihwo, w_sub_t);
+    OTGAN_CHECK_LAUNCH("up2_presum_ihwo_kernel");
+    return OTGAN_OK;
+}
+
+int up2_unsum_hwio_launch(int Cout, int kh, int kw, int Cin, int pt, int pl, const float* dw_sub, float* dw, cudaStream_t stream)
+{
+    SubMap m;
+    if (!make_submap(m, kh, kw, pt, pl)) { set_error("up2_unsum_hwio: unsupported filter geometry %dx%d pad %d,%d", kh, kw, pt, pl); return OTGAN_EUNSUPPORTED; }
+    OTGAN_REQUIRE(Cout % 4 == 0 && aligned16(dw_sub) && aligned16(dw), "up2_unsum_hwio: Cout must be a multiple of 4, buffers 16-byte aligned");
+    up2_unsum_hwio_kernel<<<ew_grid((size_t)kh * kw * Cin * (Cout / 4)), 256, 0, stream>>>(m, Cout, Cin, dw_sub, dw);
+    OTGAN_CHECK_LAUNCH("up2_unsum_hwio_kernel");
+    return OTGAN_OK;
+}
+
 // y[B, 2Hl, 2Wl, Cout] = conv(upsample2x(x_low[B, Hl, Wl, Cin]), W) + bias, W given as the 4 pre-summed sub-filters
 // w_sub [4][Cout][n1h*n1w*Cin]
 int conv_up2_fprop_launch(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pt, int pl, const float* x_low,
@@ -1635,7 +1721,7 @@ size_t conv_up2_wgrad_workspace_bytes(int B, int Hl, int Wl, int Cin, int Cout, 
 
 // dw_sub [4][Cout][n1h*n1w*Cin]: filter gradients of the 4 sub-filters (up2_unsum turns them into dW of the 5x5 filter)
 int conv_up2_wgrad_launch(int B, int Hl, int Wl, int Cin, int Cout, int kh, int kw, int pt, int pl, const float* dy,
-                          const float* x_low, float* dw_sub, void* ws, size_t ws_bytes, cudaStream_t stream)
+                          const float* x_low, float* dw_sub, void* ws, size_t ws_bytes, cudaStream_t stream, int hwio)
 {
     OTGAN_REQUIRE(up2_dims_ok(B, Hl, Wl, Cin, Cout, kh, kw, pt, pl), "conv_up2_wgrad: bad geometry");
     SubMap m;
@@ -1672,6 +1758,7 @@ int conv_up2_wgrad_launch(int B, int Hl, int Wl, int Cin, int Cout, int kh, int 
     p.n_items = items * p.splits;
     p.ldw = slots * Cin;
     p.split_stride = 4LL * Cout * p.ldw;
+    p.hwio = hwio; p.hwio_c = Cout; p.hwio_rows = Cout;
     if (p.splits > 1) {
         OTGAN_REQUIRE(ws && ws_bytes >= (size_t)p.splits * p.split_stride * sizeof(float), "conv_up2_wgrad: workspace too small");
         p.out = reinterpret_cast<float*>(ws);
@@ -1709,10 +1796,10 @@ int conv_plan_describe(int op, int B, int H, int W, int Cin, int Cout, int kh, i
     switch (op) {
     case 0: rc = conv_fprop_launch(B, H, W, Cin, Cout, kh, kw, s, pt, pl, H / s, W / s, dummy, dummy, nullptr, dummy, big_ws, big, nullptr); break;
     case 1: rc = conv_dgrad_launch(B, H, W, Cin, Cout, kh, kw, s, pt, pl, H / s, W / s, dummy, dummy, dummy, big_ws, big, nullptr); break;
-    case 2: rc = conv_wgrad_launch(B, H, W, Cin, Cout, kh, kw, s, pt, pl, H / s, W / s, dummy, dummy, dummy, big_ws, big, nullptr); break;
+    case 2: rc = conv_wgrad_launch(B, H, W, Cin, Cout, kh, kw, s, pt, pl, H / s, W / s, dummy, dummy, dummy, big_ws, big, nullptr, 0); break;
     case 3: rc = conv_up2_fprop_launch(B, H, W, Cin, Cout, kh, kw, pt, pl, dummy, dummy, nullptr, dummy, big_ws, big, nullptr); break;
     case 4: rc = conv_up2_dgrad_launch(B, H, W, Cin, Cout, kh, kw, pt, pl, dummy, dummy, dummy, big_ws, big, nullptr); break;
-    case 5: rc = conv_up2_wgrad_launch(B, H, W, Cin, Cout, kh, kw, pt, pl, dummy, dummy, dummy, big_ws, big, nullptr); break;
+    case 5: rc = conv_up2_wgrad_launch(B, H, W, Cin, Cout, kh, kw, pt, pl, dummy, dummy, dummy, big_ws, big, nullptr, 0); break;
     default: set_error("conv_plan_describe: unknown op %d", op);
     }
     t_capture = nullptr;

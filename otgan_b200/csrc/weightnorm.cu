@@ -137,6 +137,115 @@ wn_bwd_apply_kernel(int K, int C, int KS, const float* __restrict__ V, const flo
     }
 }
 
+// ---- streaming forms (round 2): float4 along the contiguous output-channel axis, no shared-memory transposes except the one
+// the OHWI layout itself needs.
+// partial[ks][c] = sum over the K-slice of A[k][c] * B[k][c]   (A == B: squared norms; A = dW (HWIO), B = V: the weight-norm dot)
+__global__ void __launch_bounds__(256)
+wn_coldot4_kernel(int K, int C4, int rows_per_slice, const float4* __restrict__ A, const float4* __restrict__ B, float4* __restrict__ partial)
+{
+    __shared__ float4 red[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c4 = blockIdx.x * 32 + tx;
+    const int kbeg = blockIdx.y * rows_per_slice;
+    int kend = kbeg + rows_per_slice;
+    kend = kend > K ? K : kend;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < C4)
+        for (int k = kbeg + ty; k < kend; k += 8) {
+            const float4 a = A[(size_t)k * C4 + c4], b = B[(size_t)k * C4 + c4];
+            s.x = fmaf(a.x, b.x, s.x); s.y = fmaf(a.y, b.y, s.y); s.z = fmaf(a.z, b.z, s.z); s.w = fmaf(a.w, b.w, s.w);
+        }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c4 < C4) {
+#pragma unroll
+        for (int r = 1; r < 8; ++r) { const float4 v = red[r][tx]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+        partial[(size_t)blockIdx.y * C4 + c4] = s;
+    }
+}
+
+// Forward apply, 64 x 64 tiles: Wt[c][k] = V[k][c] * g[c] * inv[c] (OHWI, through a shared-memory transpose, float4 on both sides)
+// and, when ihwo != null, ihwo[(ci * T + t)][c] = V[(t * cin + ci)][c] * g[c] * inv[c] (the dgrad operand: a scaled row
+// permutation of V, written straight from the loaded tile -- no second transpose pass).  K % 4 == 0, C % 4 == 0.
+__global__ void __launch_bounds__(256)
+wn_fwd_apply64_kernel(int K, int C, int KS, int T, const float* __restrict__ V, const float* __restrict__ g,
+                      const float* __restrict__ partial, float* __restrict__ Wt, float* __restrict__ ihwo, float* __restrict__ inv)
+{
+    __shared__ float tile[64][65];
+    __shared__ float scale[64];
+    const int c0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+    if (threadIdx.x < 64) {
+        const int c = c0 + threadIdx.x;
+        float t = 0.f;
+        if (c < C) for (int s = 0; s < KS; ++s) t += partial[(size_t)s * C + c];
+        const float r = rsqrtf(fmaxf(t, 1e-12f));
+        scale[threadIdx.x] = (c < C) ? g[c] * r : 0.f;
+        if (blockIdx.y == 0 && c < C) inv[c] = r;
+    }
+    __syncthreads();
+    const int cin = K / T;
+    const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;       // 16 float4 columns x 16 rows per pass
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int kk = ly + 16 * r, k = k0 + kk, c = c0 + 4 * lx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < K && c < C) {
+            v = *reinterpret_cast<const float4*>(V + (size_t)k * C + c);
+            v.x *= scale[4 * lx]; v.y *= scale[4 * lx + 1]; v.z *= scale[4 * lx + 2]; v.w *= scale[4 * lx + 3];
+            if (ihwo) {
+                const int t = k / cin, ci = k - t * cin;
+                *reinterpret_cast<float4*>(ihwo + ((size_t)ci * T + t) * C + c) = v;
+            }
+        }
+        tile[kk][4 * lx] = v.x; tile[kk][4 * lx + 1] = v.y; tile[kk][4 * lx + 2] = v.z; tile[kk][4 * lx + 3] = v.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int cc = ly + 16 * r, c = c0 + cc, k = k0 + 4 * lx;
+        if (c < C && k < K)
+            *reinterpret_cast<float4*>(Wt + (size_t)c * K + k) =
+                make_float4(tile[4 * lx][cc], tile[4 * lx + 1][cc], tile[4 * lx + 2][cc], tile[4 * lx + 3][cc]);
+    }
+}
+
+// Backward apply on an HWIO gradient: dV[k][c] = s_c (dW[k][c] - V[k][c] q_c), dg[c] = dot_c inv_c; pure streaming (float4 along c).
+__global__ void __launch_bounds__(256)
+wn_bwd_apply_hwio_kernel(int K, int C4, int KS, int rows_per_block, const float4* __restrict__ V, const float* __restrict__ g,
+                         const float* __restrict__ inv, const float* __restrict__ partial, const float4* __restrict__ dW,
+                         float4* __restrict__ dV, float* __restrict__ dg)
+{
+    __shared__ float4 s_c[32], q_c[32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c4 = blockIdx.x * 32 + tx, C = 4 * C4;
+    if (ty == 0) {
+        float dot[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {0.f, 0.f, 0.f, 0.f}, qc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c4 < C4) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = 4 * c4 + e;
+                for (int s = 0; s < KS; ++s) dot[e] += partial[(size_t)s * C + c];
+                const float r = inv[c];
+                sc[e] = g[c] * r;
+                qc[e] = r * r * dot[e];
+                if (blockIdx.y == 0) dg[c] = dot[e] * r;
+            }
+        }
+        s_c[tx] = make_float4(sc[0], sc[1], sc[2], sc[3]);
+        q_c[tx] = make_float4(qc[0], qc[1], qc[2], qc[3]);
+    }
+    __syncthreads();
+    if (c4 >= C4) return;
+    const float4 s = s_c[tx], q = q_c[tx];
+    const int kbeg = blockIdx.y * rows_per_block;
+    int kend = kbeg + rows_per_block;
+    kend = kend > K ? K : kend;
+    for (int k = kbeg + ty; k < kend; k += 8) {
+        const float4 d = dW[(size_t)k * C4 + c4], v = V[(size_t)k * C4 + c4];
+        dV[(size_t)k * C4 + c4] = make_float4(s.x * (d.x - v.x * q.x), s.y * (d.y - v.y * q.y), s.z * (d.z - v.z * q.z), s.w * (d.w - v.w * q.w));
+    }
+}
+
 int plan_slices(int K, int C, int* rows_per_slice)
 {
     const int col_blocks = ceil_div(C, TS);
@@ -189,6 +298,39 @@ int weightnorm_bwd_launch(int K, int C, const float* V, const float* g, const fl
                           float* dg, void* ws, cudaStream_t stream)
 {
     return weightnorm_bwd_ex_launch(K, C, V, g, inv, nullptr, 0, 0, 0, dWt, dV, dg, ws, stream);
+}
+
+// W = g V / ||V|| as OHWI (+ the IHWO dgrad operand in the same pass); K = T * cin rows, K % 4 == 0, C % 4 == 0
+int weightnorm_fwd2_launch(int K, int C, int T, const float* V, const float* g, float* Wt, float* ihwo, float* inv, void* ws, cudaStream_t stream)
+{
+    int rps;
+    const int KS = plan_slices(K, C, &rps);
+    float* partial = reinterpret_cast<float*>(ws);
+    wn_coldot4_kernel<<<dim3(ceil_div(C / 4, 32), KS), 256, 0, stream>>>(K, C / 4, rps, reinterpret_cast<const float4*>(V),
+                                                                       reinterpret_cast<const float4*>(V), reinterpret_cast<float4*>(partial));
+    OTGAN_CHECK_LAUNCH("wn_coldot4_kernel");
+    wn_fwd_apply64_kernel<<<dim3(ceil_div(C, 64), ceil_div(K, 64)), 256, 0, stream>>>(K, C, KS, T, V, g, partial, Wt, ihwo, inv);
+    OTGAN_CHECK_LAUNCH("wn_fwd_apply64_kernel");
+    return OTGAN_OK;
+}
+
+// dW given in HWIO layout ([K][C], the layout of V): no transposes at all
+int weightnorm_bwd_hwio_launch(int K, int C, const float* V, const float* g, const float* inv, const float* dW, float* dV, float* dg,
+                               void* ws, cudaStream_t stream)
+{
+    int rps;
+    const int KS = plan_slices(K, C, &rps);
+    float* partial = reinterpret_cast<float*>(ws);
+    wn_coldot4_kernel<<<dim3(ceil_div(C / 4, 32), KS), 256, 0, stream>>>(K, C / 4, rps, reinterpret_cast<const float4*>(dW),
+                                                                       reinterpret_cast<const float4*>(V), reinterpret_cast<float4*>(partial));
+    OTGAN_CHECK_LAUNCH("wn_coldot4_kernel");
+    int rows_per_block = ceil_div(K, ceil_div(8 * kNumSMs, ceil_div(C / 4, 32)));
+    rows_per_block = rows_per_block < 8 ? 8 : rows_per_block;
+    wn_bwd_apply_hwio_kernel<<<dim3(ceil_div(C / 4, 32), ceil_div(K, rows_per_block)), 256, 0, stream>>>(
+        K, C / 4, KS, rows_per_block, reinterpret_cast<const float4*>(V), g, inv, partial, reinterpret_cast<const float4*>(dW),
+        reinterpret_cast<float4*>(dV), dg);
+    OTGAN_CHECK_LAUNCH("wn_bwd_apply_hwio_kernel");
+    return OTGAN_OK;
 }
 
 }  // namespace otgan

@@ -158,12 +158,17 @@ class VariableStore:
                     ent = self.wcache[scope] = (wt, inv, wt_t)
                 wt, inv, wt_t = ent
                 ws = _wn_workspace(self.device, lib.otgan_workspace_bytes_weightnorm(K, C) // 4)
-                rc = lib.otgan_weightnorm_fwd_f32(K, C, V.data_ptr(), g.data_ptr(), wt.data_ptr(), inv.data_ptr(), ws.data_ptr(),
-                                                  ws.numel() * 4, stream)
-                _lib.check(rc, "otgan_weightnorm_fwd_f32")
-                if wt_t is not None:
-                    rc = lib.otgan_ohwi_to_ihwo_f32(C, shape[0] * shape[1], shape[2], wt.data_ptr(), wt_t.data_ptr(), stream)
-                    _lib.check(rc, "otgan_ohwi_to_ihwo_f32")
+                if wt_t is not None and K % 4 == 0 and C % 4 == 0:      # W and the IHWO dgrad operand from one pass over V
+                    rc = lib.otgan_weightnorm_fwd2_f32(K, C, shape[0] * shape[1], V.data_ptr(), g.data_ptr(), wt.data_ptr(), wt_t.data_ptr(),
+                                                       inv.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream)
+                    _lib.check(rc, "otgan_weightnorm_fwd2_f32")
+                else:
+                    rc = lib.otgan_weightnorm_fwd_f32(K, C, V.data_ptr(), g.data_ptr(), wt.data_ptr(), inv.data_ptr(), ws.data_ptr(),
+                                                      ws.numel() * 4, stream)
+                    _lib.check(rc, "otgan_weightnorm_fwd_f32")
+                    if wt_t is not None:
+                        rc = lib.otgan_ohwi_to_ihwo_f32(C, shape[0] * shape[1], shape[2], wt.data_ptr(), wt_t.data_ptr(), stream)
+                        _lib.check(rc, "otgan_ohwi_to_ihwo_f32")
         self.cache_version = self.version
 
     def cached_weight(self, scope):
@@ -346,6 +351,7 @@ def _conv2d_nhwc(x, W, stride, pad, bias=None):
 CONV_BACKEND = "tcgen05"      # "tcgen05": this library's implicit-GEMM kernels where they tile the shape; "cudnn": library rung only
 UPSAMPLE_FUSION = True        # nn.upsample2x / nn.glu(upsample=True) hand the following conv2d an un-materialised Upsampled2x
 CONV_NARROW = True            # route the two 3-channel layers through _ConvNarrow (False: cuDNN, for A/B timing)
+WN_FUSION = True              # weight norm fused into the tcgen05 convolution nodes (_ConvTCWN / _ConvUp2TCWN: HWIO gradient pipeline)
 DENSE_BLOCK_FUSION = True     # nn.dense_block runs DenseNet's blocks on the dense-block kernels (False: the literal list code)
 _conv_ws = {}
 _wn_ws = {}
@@ -1123,6 +1129,178 @@ def dense_block(x, layers_per_block, filters_per_layer, pre_activation="crelu", 
     z = _DenseBlock.apply(len(x), layers_per_block, *tensors)
     return Crelu8Tensor(z, [int(t.shape[3]) for t in x] + [16] * layers_per_block)
 
+
+class LazyWN:
+    """W = g * V / ||V|| not yet materialised: the tcgen05 convolution paths fuse the weight norm with the convolution
+    (_ConvTCWN / _ConvUp2TCWN: the whole parameter-space pipeline stays in the variable's HWIO layout, one transpose per layer
+    and step); every other consumer calls .materialize() and gets the TransposedWeight of the stand-alone weight-norm kernels."""
+
+    def __init__(self, V, g, cached=None):
+        self.V, self.g, self.vshape, self.cached = V, g, tuple(V.shape), cached      # cached: (wt, wt_ihwo) of the weight cache
+
+    def materialize(self):
+        if self.cached is not None:
+            return TransposedWeight(self.cached[0], self.vshape, self.cached[1])
+        return TransposedWeight(_WeightNorm.apply(self.V, self.g), self.vshape)
+
+
+def _wn_fwd2(lib, V, g, taps, want_ihwo, stream):
+    """otgan_weightnorm_fwd2_f32: (wt [C, K], wt_ihwo [Cin, taps * C] or None, inv [C])."""
+    C = V.shape[-1]
+    K = V.numel() // C
+    wt = torch.empty((C, K), device=V.device, dtype=torch.float32)
+    inv = torch.empty((C,), device=V.device, dtype=torch.float32)
+    ihwo = torch.empty((K // taps, taps * C), device=V.device, dtype=torch.float32) if want_ihwo else None
+    ws = _wn_workspace(V.device, lib.otgan_workspace_bytes_weightnorm(K, C) // 4)
+    rc = lib.otgan_weightnorm_fwd2_f32(K, C, taps, V.data_ptr(), g.data_ptr(), wt.data_ptr(), ihwo.data_ptr() if want_ihwo else None,
+                                       inv.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream)
+    _lib.check(rc, "otgan_weightnorm_fwd2_f32")
+    return wt, ihwo, inv
+
+
+def _wn_bwd_hwio(lib, V, g, inv, dw_hwio, stream):
+    C = V.shape[-1]
+    K = V.numel() // C
+    dV, dg = torch.empty_like(V), torch.empty_like(g)
+    ws = _wn_workspace(V.device, lib.otgan_workspace_bytes_weightnorm(K, C) // 4)
+    rc = lib.otgan_weightnorm_bwd_hwio_f32(K, C, V.data_ptr(), g.data_ptr(), inv.data_ptr(), dw_hwio.data_ptr(), dV.data_ptr(), dg.data_ptr(),
+                                           ws.data_ptr(), ws.numel() * 4, stream)
+    _lib.check(rc, "otgan_weightnorm_bwd_hwio_f32")
+    return dV, dg
+
+
+class _ConvTCWN(torch.autograd.Function):
+    """Weight norm (utils/nn.py:176-180) + tf.nn.conv2d 'SAME' + bias_add as ONE autograd node on the tcgen05 kernels.
+    Forward: V -> W (OHWI) and the IHWO dgrad operand in one pass; backward: wgrad writes the filter gradient in V's own HWIO
+    layout and the weight-norm backward streams it -- no gradient transposes.  cached = (wt, wt_ihwo) skips the weight norm
+    (calls that build no parameter gradients, VariableStore.refresh_weight_cache)."""
+
+    @staticmethod
+    def forward(ctx, x, V, g, bias, geom, cached):
+        lib = _lib.load()
+        kh, kw, s, pt, pl = geom
+        stream = torch.cuda.current_stream().cuda_stream
+        B, H, W, cin = x.shape
+        cout = V.shape[-1]
+        x = x.contiguous()
+        if cached is not None:
+            wt, ihwo, inv = cached[0], cached[1], None
+            Vc = gc = None
+        else:
+            Vc, gc = V.contiguous(), g.contiguous()
+            wt, ihwo, inv = _wn_fwd2(lib, Vc, gc, kh * kw, ctx.needs_input_grad[0], stream)
+        if bias is not None and bias.data_ptr() % 16:
+            bias = bias.clone()
+        y = torch.empty((B, H // s, W // s, cout), device=x.device, dtype=torch.float32)
+        ws = _workspace(x.device, lib.otgan_workspace_bytes_conv_gemm(B, H // s, W // s, cout))
+        rc = lib.otgan_conv2d_fprop_tf32(B, H, W, cin, cout, kh, kw, s, pt, pl, x.data_ptr(), wt.data_ptr(),
+                                         bias.data_ptr() if bias is not None else None, y.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream)
+        _lib.check(rc, "otgan_conv2d_fprop_tf32")
+        ctx.geom, ctx.has_bias, ctx.cout = geom, bias is not None, cout
+        ctx.wt, ctx.ihwo = wt, ihwo
+        ctx.save_for_backward(x, Vc, gc, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, V, g, inv = ctx.saved_tensors
+        kh, kw, s, pt, pl = ctx.geom
+        B, H, W, cin = x.shape
+        cout = ctx.cout
+        dy = dy.contiguous()
+        stream = torch.cuda.current_stream().cuda_stream
+        dx = dV = dg = db = None
+        if ctx.needs_input_grad[0]:
+            wt_t = ctx.ihwo
+            if wt_t is None:
+                wt_t = torch.empty((cin, kh * kw * cout), device=x.device, dtype=torch.float32)
+                _lib.check(lib.otgan_ohwi_to_ihwo_f32(cout, kh * kw, cin, ctx.wt.data_ptr(), wt_t.data_ptr(), stream), "otgan_ohwi_to_ihwo_f32")
+            dx = torch.empty_like(x)
+            ws = _workspace(x.device, lib.otgan_workspace_bytes_conv_gemm(B, H, W, cin))
+            rc = lib.otgan_conv2d_dgrad_tf32(B, H, W, cin, cout, kh, kw, s, pt, pl, dy.data_ptr(), wt_t.data_ptr(), dx.data_ptr(),
+                                             ws.data_ptr(), ws.numel() * 4, stream)
+            _lib.check(rc, "otgan_conv2d_dgrad_tf32")
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            ws = _workspace(x.device, lib.otgan_workspace_bytes_conv_wgrad(B, H, W, cin, cout, kh, kw, s))
+            dw = torch.empty((kh * kw * cin, cout), device=x.device, dtype=torch.float32)               # HWIO: dV's layout
+            rc = lib.otgan_conv2d_wgrad_hwio_tf32(B, H, W, cin, cout, kh, kw, s, pt, pl, dy.data_ptr(), x.data_ptr(), dw.data_ptr(),
+                                                  ws.data_ptr(), ws.numel() * 4, stream)
+            _lib.check(rc, "otgan_conv2d_wgrad_hwio_tf32")
+            dV, dg = _wn_bwd_hwio(lib, V, g, inv, dw, stream)
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            P = dy.numel() // cout
+            ws = _workspace(x.device, lib.otgan_workspace_bytes_colsum(P, cout))
+            db = torch.empty((cout,), device=x.device, dtype=torch.float32)
+            _lib.check(lib.otgan_colsum_f32(P, cout, dy.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream), "otgan_colsum_f32")
+        return dx, dV, dg, db, None, None
+
+
+class _ConvUp2TCWN(torch.autograd.Function):
+    """Weight norm + (2x nearest-neighbour upsample -> conv 'SAME') + bias as one node (generator, models/dcgan.py:37-46):
+    V -> W -> 4 pre-summed sub-filters forward; backward in V's layout: sub-filter dgrad operand from W_ihwo, wgrad and the chain
+    rule of the pre-sum on HWIO gradients, streaming weight-norm backward."""
+
+    @staticmethod
+    def forward(ctx, x_low, V, g, bias, geom):
+        lib = _lib.load()
+        kh, kw, pt, pl = geom
+        stream = torch.cuda.current_stream().cuda_stream
+        B, H, W, cin = x_low.shape
+        cout = V.shape[-1]
+        n1 = lib.otgan_up2_subtaps(kh, pt)
+        slots = n1 * n1
+        x_low, Vc, gc = x_low.contiguous(), V.contiguous(), g.contiguous()
+        wt, ihwo, inv = _wn_fwd2(lib, Vc, gc, kh * kw, ctx.needs_input_grad[0], stream)
+        if bias is not None and bias.data_ptr() % 16:
+            bias = bias.clone()
+        w_sub = torch.empty((4, cout, slots * cin), device=x_low.device, dtype=torch.float32)
+        _lib.check(lib.otgan_up2_weight_presum_f32(cout, kh, kw, cin, pt, pl, wt.data_ptr(), w_sub.data_ptr(), stream), "otgan_up2_weight_presum_f32")
+        y = torch.empty((B, 2 * H, 2 * W, cout), device=x_low.device, dtype=torch.float32)
+        ws = _workspace(x_low.device, lib.otgan_workspace_bytes_conv_gemm(B, 2 * H, 2 * W, cout))
+        rc = lib.otgan_conv2d_up2_fprop_tf32(B, H, W, cin, cout, kh, kw, pt, pl, x_low.data_ptr(), w_sub.data_ptr(),
+                                             bias.data_ptr() if bias is not None else None, y.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream)
+        _lib.check(rc, "otgan_conv2d_up2_fprop_tf32")
+        ctx.geom, ctx.has_bias, ctx.cout, ctx.slots, ctx.ihwo = geom, bias is not None, cout, slots, ihwo
+        ctx.save_for_backward(x_low, Vc, gc, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x_low, V, g, inv = ctx.saved_tensors
+        kh, kw, pt, pl = ctx.geom
+        B, H, W, cin = x_low.shape
+        cout, slots = ctx.cout, ctx.slots
+        dy = dy.contiguous()
+        stream = torch.cuda.current_stream().cuda_stream
+        dx = dV = dg = db = None
+        if ctx.needs_input_grad[0]:
+            w_sub_t = torch.empty((4, cin, slots * cout), device=dy.device, dtype=torch.float32)
+            _lib.check(lib.otgan_up2_weight_presum_ihwo_f32(cout, kh, kw, cin, pt, pl, ctx.ihwo.data_ptr(), w_sub_t.data_ptr(), stream),
+                       "otgan_up2_weight_presum_ihwo_f32")
+            dx = torch.empty_like(x_low)
+            ws = _workspace(dy.device, lib.otgan_workspace_bytes_conv_gemm(B, H, W, cin))
+            rc = lib.otgan_conv2d_up2_dgrad_tf32(B, H, W, cin, cout, kh, kw, pt, pl, dy.data_ptr(), w_sub_t.data_ptr(), dx.data_ptr(),
+                                                 ws.data_ptr(), ws.numel() * 4, stream)
+            _lib.check(rc, "otgan_conv2d_up2_dgrad_tf32")
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            ws = _workspace(dy.device, lib.otgan_workspace_bytes_conv_up2_wgrad(B, H, W, cin, cout, kh, kw, pt, pl))
+            dw_sub = torch.empty((4, slots * cin, cout), device=dy.device, dtype=torch.float32)
+            rc = lib.otgan_conv2d_up2_wgrad_hwio_tf32(B, H, W, cin, cout, kh, kw, pt, pl, dy.data_ptr(), x_low.data_ptr(), dw_sub.data_ptr(),
+                                                      ws.data_ptr(), ws.numel() * 4, stream)
+            _lib.check(rc, "otgan_conv2d_up2_wgrad_hwio_tf32")
+            dw = torch.empty((kh * kw * cin, cout), device=dy.device, dtype=torch.float32)
+            _lib.check(lib.otgan_up2_weight_unsum_hwio_f32(cout, kh, kw, cin, pt, pl, dw_sub.data_ptr(), dw.data_ptr(), stream),
+                       "otgan_up2_weight_unsum_hwio_f32")
+            dV, dg = _wn_bwd_hwio(lib, V, g, inv, dw, stream)
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            P = dy.numel() // cout
+            ws = _workspace(dy.device, lib.otgan_workspace_bytes_colsum(P, cout))
+            db = torch.empty((cout,), device=dy.device, dtype=torch.float32)
+            _lib.check(lib.otgan_colsum_f32(P, cout, dy.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream), "otgan_colsum_f32")
+        return dx, dV, dg, db, None
+
 # ------------------------------------------------------------------------------------------------ get_params
 def get_params(layer_name, x=None, init=False, ema=None, use_W=True, use_g=True, use_b=True, f=None, weight_norm=True,
                init_scale=1.0, filter_size=None, num_units=None, pre_activation=None, raw=False):
@@ -1165,7 +1343,9 @@ def get_params(layer_name, x=None, init=False, ema=None, use_W=True, use_g=True,
     if use_W:
         V = store.get(scope + "/V", ema_src)
         cached = store.cached_weight(scope) if (weight_norm and use_g and ema is None and store.frozen) else None
-        if cached is not None:
+        if weight_norm and use_g and V.is_cuda and store.frozen and V.dim() == 4 and WN_FUSION and CONV_BACKEND == "tcgen05":
+            params["W"] = LazyWN(V, g, cached)                                                        # :176-180 fused into the convolution
+        elif cached is not None:
             params["W"] = TransposedWeight(cached[0], V.shape, cached[1])                             # reuse (no param grads)
         elif weight_norm and use_g and V.is_cuda and store.frozen:
             params["W"] = TransposedWeight(_WeightNorm.apply(V, g), V.shape)                          # :176-180 fused
@@ -1192,11 +1372,29 @@ def _conv2d(x, W, stride=(1, 1), pad="SAME", dilate=1, pre_activation=None, upsa
     if isinstance(x, Crelu8Tensor):
         raise TypeError("a Crelu8Tensor is consumed by nn.conv2d(..., pre_activation='crelu') on the GPU path only")
     if isinstance(x, Upsampled2x):
-        if (pre_activation is None and not upsample and isinstance(W, TransposedWeight) and CONV_BACKEND == "tcgen05"
+        if (pre_activation is None and not upsample and isinstance(W, (TransposedWeight, LazyWN)) and CONV_BACKEND == "tcgen05"
                 and conv_up2_supported(tuple(x.low.shape), W.vshape[3], W.vshape[0], W.vshape[1], stride, pad)):
             kh, kw = W.vshape[0], W.vshape[1]
-            return _ConvUp2TC.apply(x.low, W.wt, bias, (kh, kw, (kh - 1) // 2, (kw - 1) // 2))
+            geom_up = (kh, kw, (kh - 1) // 2, (kw - 1) // 2)
+            if isinstance(W, LazyWN) and W.cached is None and W.vshape[3] % 4 == 0 and (kh * kw * W.vshape[2]) % 4 == 0:
+                return _ConvUp2TCWN.apply(x.low, W.V, W.g, bias, geom_up)
+            if isinstance(W, LazyWN):
+                W = W.materialize()
+            return _ConvUp2TC.apply(x.low, W.wt, bias, geom_up)
         x = x.materialize()
+    if isinstance(W, LazyWN):
+        xs_ = _as_list(x)
+        x0 = xs_[0]
+        fused_ok = (len(xs_) == 1 and not isinstance(x0, Upsampled2x) and x0.is_cuda and x0.dtype == torch.float32 and x0.dim() == 4
+                    and dilate == 1 and not upsample and pre_activation in (None, "crelu") and CONV_BACKEND == "tcgen05")
+        if fused_ok:
+            kh, kw, cin, cout = W.vshape
+            B, H, Wd, C = x0.shape
+            if conv_tc_supported((B, H, Wd, cin), cout, kh, kw, stride, pad):
+                z = x0.contiguous() if pre_activation is None else _CreluPad.apply(x0.contiguous(), (0, 0, 0, 0))
+                geom = (kh, kw, stride[0], same_padding(H, kh, stride[0])[0], same_padding(Wd, kw, stride[1])[0])
+                return _ConvTCWN.apply(z, W.V, W.g, bias, geom, W.cached)
+        W = W.materialize()
     xl = _as_list(x)
     xl = [xi.materialize() if isinstance(xi, Upsampled2x) else xi for xi in xl]
     if dilate != 1:

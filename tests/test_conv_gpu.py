@@ -157,6 +157,7 @@ def test_dcgan_networks_every_conv_call_checked_against_float64():
         return res
 
     nn._ConvTC.forward, nn._ConvTC.backward = staticmethod(fwd), staticmethod(bwd)
+    nn.WN_FUSION = False                               # record the stand-alone convolution nodes (the fused nodes: test_wn_fusion_*)
     try:
         discriminator.reset(); generator.reset()
         torch.manual_seed(3)
@@ -175,6 +176,7 @@ def test_dcgan_networks_every_conv_call_checked_against_float64():
         torch.autograd.grad([f2], [generator.flat], [gy])
     finally:
         nn._ConvTC.forward, nn._ConvTC.backward = staticmethod(orig_fwd), staticmethod(orig_bwd)
+        nn.WN_FUSION = True
     assert len(calls) == 3 + 3                         # critic c1-c3 on the real images, critic c1-c3 on the generated images
                                                        # (the generator's layers run on _ConvUp2TC / _ConvNarrow, tested separately)
     n_dx = n_dw = 0
@@ -329,20 +331,20 @@ def test_generator_uses_the_fused_upsample_path():
         generator(init=True, device=dev, batch_size=16)
         u = torch.rand(16, 100, device=dev) * 2 - 1
         calls = []
-        orig = nn._ConvUp2TC.forward
+        orig = nn._ConvUp2TCWN.forward                # the weight-norm-fused node (nn.WN_FUSION, default)
 
         def fwd(ctx, *a):
             calls.append(a[0].shape)
             return orig(ctx, *a)
 
-        nn._ConvUp2TC.forward = staticmethod(fwd)
+        nn._ConvUp2TCWN.forward = staticmethod(fwd)
         try:
             img = generator(batch_size=16, u=u)
             nn.UPSAMPLE_FUSION = False
             ref = generator(batch_size=16, u=u)
         finally:
             nn.UPSAMPLE_FUSION = True
-            nn._ConvUp2TC.forward = staticmethod(orig)
+            nn._ConvUp2TCWN.forward = staticmethod(orig)
     assert [tuple(c) for c in calls] == [(16, 4, 4, 1024), (16, 8, 8, 512), (16, 16, 16, 256)]
     assert float((img - ref).abs().max() / ref.abs().max()) <= 5e-3
     generator.reset()
@@ -437,3 +439,44 @@ def test_256_row_tile_variant_matches_the_128_row_kernel():
     finally:
         lib.otgan_conv_set_option(0, 1)
         lib.otgan_conv_set_option(2, 500)
+
+
+@pytest.mark.parametrize("which", ["discriminator", "generator"])
+def test_wn_fusion_matches_the_unfused_nodes(which):
+    """The weight-norm-fused convolution nodes (_ConvTCWN / _ConvUp2TCWN: W and the IHWO dgrad operand from one pass over V,
+    filter gradients written in V's HWIO layout, streaming weight-norm backward) against the stand-alone nodes
+    (_WeightNorm -> _ConvTC / _ConvUp2TC).  Same tcgen05 kernels for the three convolution passes, so only the fp32 summation
+    order of the weight-norm reductions differs: 2e-5 of the largest gradient entry."""
+    from otgan_b200.models import dcgan
+    from otgan_b200.utils import nn
+    dev = torch.device("cuda", 0)
+    tpl = getattr(dcgan, which)
+    tpl.reset()
+    torch.manual_seed(4)
+    B = 16
+    with torch.no_grad():
+        if which == "discriminator":
+            tpl(torch.zeros(B, 32, 32, 3, device=dev) + 0.1, init=True)
+        else:
+            tpl(B, init=True, device=dev)
+    with torch.no_grad():
+        for n, p in tpl.named_parameters():
+            if n.endswith("/g"):
+                p.mul_(0.5 + torch.rand_like(p))
+    x = (torch.rand(B, 32, 32, 3, device=dev) * 2 - 1).requires_grad_(True)
+    u = torch.rand(B, 100, device=dev) * 2 - 1
+    outs = {}
+    try:
+        for fused in (True, False):
+            nn.WN_FUSION = fused
+            y = tpl(x) if which == "discriminator" else tpl(B, u=u)
+            gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(9)).to(dev)
+            grads = torch.autograd.grad([y], [tpl.flat] + ([x] if which == "discriminator" else []), grad_outputs=[gy])
+            outs[fused] = (y.detach(), [g.detach() for g in grads])
+    finally:
+        nn.WN_FUSION = True
+    (y1, g1), (y0, g0) = outs[True], outs[False]
+    assert float((y1 - y0).abs().max() / y0.abs().max()) < 1e-5
+    for a, b in zip(g1, g0):
+        assert float((a - b).abs().max() / b.abs().max()) < 2e-5
+    tpl.reset()
