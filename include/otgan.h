@@ -310,18 +310,21 @@ OTGAN_API int otgan_weightnorm_bwd_ex_f32(int K, int C, const float* V, const fl
 /* ---- DenseNet dense block (models/densenet.py:10-15, 56-61: `block`) ---------------------------------------------------------------
  * x = [e_0 .. e_{n_base-1}] (base elements, base_ch[i] channels each, multiples of 8); L times: x.append(conv3x3(crelu(x), 16)).
  * Z [B,H,W,Ctot], Ctot = otgan_dense_channels = 2 (sum base_ch + 16 L): the crelu8-activated list, element after element.  The
- * caller fills the base slots (otgan_crelu8_fwd_f32); fprop runs the L layers, each reading the channel prefix of Z and writing
- * its own slot from the convolution's epilogue.  wf_host[r]: W_r as [16][9][cin_r], cin_r = 2 (sum base_ch + 16 r), input channels
- * in Z order (otgan_weightnorm_fwd_ex_f32 with the otgan_crelu8_perm_host permutation); bias_host[r]: [16] or NULL.
+ * caller fills the base slots (otgan_crelu8_fwd_f32); fprop runs the L layers in "contribution" form: launch j convolves slot j of Z
+ * with the filters of ALL later layers (N = 16 (L - j) columns of the pre-activation accumulator S [B,H,W,16L], scratch) and writes
+ * the layer that is complete at that point into slot j + 1 from its epilogue.
+ * wf_all [16L][9][Ctot]: wf_all[16 r + co][t][ci] = W_r[co][t][ci] with the input channels in Z order, ZERO for ci >= cin_r =
+ * 2 (sum base_ch + 16 r) (otgan_weightnorm_fwd_ex_f32 with the otgan_crelu8_perm_host permutation and strides ldtap = Ctot,
+ * ldrow = 9 Ctot into a zeroed buffer); bias_all [16L] or NULL.
  * bgrad: dZ = gradient w.r.t. Z from the block's consumer; writes dY [B,H,W,16L] (gradients of the L pre-activations),
  * dbase_host[i] [B,H,W,base_ch[i]], dW_all [16L][9][Ctot] (row block r valid for ci < cin_r) and db_all [16L] (either may be NULL).
- * WB [Ctot][9][16L] = otgan_dense_build_wb_f32(wf_host): the weight operand of the backward "gather" convolutions. */
+ * WB [Ctot][9][16L] = otgan_dense_build_wb_f32(wf_all): the weight operand of the backward "gather" convolutions. */
 typedef struct { int B, H, W, n_base, base_ch[4], L, growth; } otgan_dense_geom_t;
 OTGAN_API int otgan_dense_channels(const otgan_dense_geom_t* geom);
 OTGAN_API size_t otgan_dense_wb_floats(const otgan_dense_geom_t* geom);
-OTGAN_API int otgan_dense_build_wb_f32(const otgan_dense_geom_t* geom, const float* const* wf_host, float* WB, void* stream);
-OTGAN_API int otgan_dense_block_fprop_tf32(const otgan_dense_geom_t* geom, const float* const* wf_host,
-                                           const float* const* bias_host, float* Z, void* stream);
+OTGAN_API int otgan_dense_build_wb_f32(const otgan_dense_geom_t* geom, const float* wf_all, float* WB, void* stream);
+OTGAN_API int otgan_dense_block_fprop_tf32(const otgan_dense_geom_t* geom, const float* wf_all, const float* bias_all, float* Z,
+                                           float* S, void* stream);
 OTGAN_API size_t otgan_workspace_bytes_dense_bgrad(const otgan_dense_geom_t* geom);
 OTGAN_API int otgan_dense_block_bgrad_tf32(const otgan_dense_geom_t* geom, const float* Z, const float* dZ, const float* WB,
                                            float* dY, float* const* dbase_host, float* dW_all, float* db_all, void* ws,

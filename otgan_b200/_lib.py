@@ -100,7 +100,7 @@ SIGNATURES = {
     "otgan_dense_channels": (_i, [_gp]),
     "otgan_dense_wb_floats": (_sz, [_gp]),
     "otgan_dense_build_wb_f32": (_i, [_gp, _vp, _vp, _vp]),
-    "otgan_dense_block_fprop_tf32": (_i, [_gp, _vp, _vp, _vp, _vp]),
+    "otgan_dense_block_fprop_tf32": (_i, [_gp, _vp, _vp, _vp, _vp, _vp]),
     "otgan_workspace_bytes_dense_bgrad": (_sz, [_gp]),
     "otgan_dense_block_bgrad_tf32": (_i, [_gp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

@@ -61,8 +61,8 @@ int crelu8_fwd_launch(long long P, int C, const float* x, int ldx, float* z, int
 int crelu8_bwd_launch(long long P, int C, const float* z, int ldz, const float* dz, int lddz, float* dx, int lddx, cudaStream_t stream);
 int dense_channels(const otgan_dense_geom_t* g);
 size_t dense_wb_floats(const otgan_dense_geom_t* g);
-int dense_build_wb_launch(const otgan_dense_geom_t* g, const float* const* wf, float* WB, cudaStream_t stream);
-int dense_block_fprop_launch(const otgan_dense_geom_t* g, const float* const* wf, const float* const* bias, float* Z, cudaStream_t stream);
+int dense_build_wb_launch(const otgan_dense_geom_t* g, const float* wf_all, float* WB, cudaStream_t stream);
+int dense_block_fprop_launch(const otgan_dense_geom_t* g, const float* wf_all, const float* bias_all, float* Z, float* S, cudaStream_t stream);
 size_t dense_bgrad_workspace_bytes(const otgan_dense_geom_t* g);
 int dense_block_bgrad_launch(const otgan_dense_geom_t* g, const float* Z, const float* dZ, const float* WB, float* dY,
                              float* const* dbase, float* dW_all, float* db_all, void* ws, size_t ws_bytes, cudaStream_t stream);
@@ -679,14 +679,14 @@ int otgan_dense_channels(const otgan_dense_geom_t* geom)
     return c;
 }
 size_t otgan_dense_wb_floats(const otgan_dense_geom_t* geom) { return dense_wb_floats(geom); }
-int otgan_dense_build_wb_f32(const otgan_dense_geom_t* geom, const float* const* wf_host, float* WB, void* stream)
+int otgan_dense_build_wb_f32(const otgan_dense_geom_t* geom, const float* wf_all, float* WB, void* stream)
 {
-    return dense_build_wb_launch(geom, wf_host, WB, (cudaStream_t)stream);
+    return dense_build_wb_launch(geom, wf_all, WB, (cudaStream_t)stream);
 }
-int otgan_dense_block_fprop_tf32(const otgan_dense_geom_t* geom, const float* const* wf_host, const float* const* bias_host, float* Z,
+int otgan_dense_block_fprop_tf32(const otgan_dense_geom_t* geom, const float* wf_all, const float* bias_all, float* Z, float* S,
                                  void* stream)
 {
-    return dense_block_fprop_launch(geom, wf_host, bias_host, Z, (cudaStream_t)stream);
+    return dense_block_fprop_launch(geom, wf_all, bias_all, Z, S, (cudaStream_t)stream);
 }
 size_t otgan_workspace_bytes_dense_bgrad(const otgan_dense_geom_t* geom) { return dense_bgrad_workspace_bytes(geom); }
 int otgan_dense_block_bgrad_tf32(const otgan_dense_geom_t* geom, const float* Z, const float* dZ, const float* WB, float* dY,

@@ -5,7 +5,7 @@
 namespace otgan {
 
 // Epilogues of the generic mode ("crelu8" slot order: see conv_tc.cu).
-enum { EPI_PLAIN = 0, EPI_CRELU8 = 1, EPI_CRELU8_BWD = 2 };
+enum { EPI_PLAIN = 0, EPI_CRELU8 = 1, EPI_CRELU8_BWD = 2, EPI_DENSE_FWD = 3 };
 
 // One generic fprop / dgrad launch.  Any channel counts (multiples of 4), any batch, power-of-two spatial extents; operands
 // may be channel SLICES of wider NHWC buffers (pixel strides lda / ldo); the weight operand is a K-slice / row-slice of a 3-D
@@ -18,6 +18,8 @@ struct ConvEx {
     const float* w; int w_K, w_taps, w_rows; long long w_ldtap, w_ldrow; int k0, row0;
     const float* bias;
     int epi_mode; const float* e_add; const float* e_z; int e_ld;
+    int accumulate;              // EPI_DENSE_FWD: add the previous contents of `out` (read-modify-write of the pre-activation buffer)
+    float* e_out2;               // EPI_DENSE_FWD: the first 16 columns (the layer that just completed) go here as crelu8 (pixel stride e_ld)
 };
 int conv_fprop_ex_launch(const ConvEx& c, cudaStream_t stream);
 int conv_dgrad_ex_launch(const ConvEx& c, cudaStream_t stream);

@@ -95,6 +95,8 @@ struct GemmParams {
     const float* e_add;                       // EPI_CRELU8_BWD: g = acc + e_add (may be null), sign pattern from e_z; both are
     const float* e_z;                         //   [.., 2 * N_out] slices addressed with the strides below
     long long esW, esH, esN;
+    int accumulate;                           // EPI_DENSE_FWD: v += previous contents of out (pre-activation accumulator S)
+    float* e_out2;                            // EPI_DENSE_FWD: crelu8 of the first 16 columns goes here (strides es*), the rest to out
 };
 
 // Epilogues of the generic mode.  CReLU slot layout ("crelu8"): channel c of a tensor with C channels is stored as
@@ -149,6 +151,42 @@ __device__ __forceinline__ void epilogue_generic(const GemmParams& p, uint32_t t
                     *reinterpret_cast<float4*>(o + 16 * q + 12) = make_float4(neg[4], neg[5], neg[6], neg[7]);
                 }
             }
+        } else if (p.epi_mode == EPI_DENSE_FWD) {
+            // DenseNet forward in "contribution" form: this launch adds the contribution of one input slot to the pre-activations
+            // of ALL later layers (columns); the first 16 columns belong to the layer that is now complete: they leave as crelu8
+            // into its slot of the feature buffer, the others go back to the accumulator S.
+            float* o = orow + col0;
+            if (p.accumulate) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    if (col0 + j < lim) {
+                        const float4 a = *reinterpret_cast<const float4*>(o + j);
+                        v[j] = __float_as_uint(__uint_as_float(v[j]) + a.x); v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + a.y);
+                        v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + a.z); v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + a.w);
+                    }
+            }
+            int jbeg = 0;
+            if (col0 == 0) {
+                float* z2 = p.e_out2 + epix;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    float pos[8], neg[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float x = __uint_as_float(v[8 * q + i]);
+                        pos[i] = fmaxf(x, 0.f);
+                        neg[i] = fmaxf(-x, 0.f);
+                    }
+                    *reinterpret_cast<float4*>(z2 + 16 * q) = make_float4(pos[0], pos[1], pos[2], pos[3]);
+                    *reinterpret_cast<float4*>(z2 + 16 * q + 4) = make_float4(pos[4], pos[5], pos[6], pos[7]);
+                    *reinterpret_cast<float4*>(z2 + 16 * q + 8) = make_float4(neg[0], neg[1], neg[2], neg[3]);
+                    *reinterpret_cast<float4*>(z2 + 16 * q + 12) = make_float4(neg[4], neg[5], neg[6], neg[7]);
+                }
+                jbeg = 16;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                if (j >= jbeg && col0 + j < lim) *reinterpret_cast<uint4*>(o + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         } else {    // EPI_CRELU8_BWD: 32 accumulator columns (gradient of a crelu8 slot) -> 16 gradients of the pre-activation
             float* o = orow + (col0 >> 1);
             const float* z = p.e_z + epix + col0;
@@ -1283,6 +1321,7 @@ static bool ex_common(GemmParams& p, const ConvEx& c, int TN)
     p.n_tiles = (c.N + p.n_inst - 1) / p.n_inst;
     p.bias = c.bias;
     p.epi_mode = c.epi_mode; p.e_add = c.e_add; p.e_z = c.e_z;
+    p.accumulate = c.accumulate; p.e_out2 = c.e_out2;
     (void)TN;
     return make_weight_map_3d(&p.bmap, c.w, c.w_K, c.w_taps, c.w_rows, c.w_ldtap, c.w_ldrow, p.n_inst);
 }
@@ -1295,6 +1334,7 @@ static bool ex_args_ok(const ConvEx& c)
     if (!aligned16(c.a) || !aligned16(c.out) || !aligned16(c.w)) return false;
     if (c.epi_mode == EPI_CRELU8 && (c.N & 7)) return false;
     if (c.epi_mode == EPI_CRELU8_BWD && ((c.N & 15) || c.stride != 1 || !c.e_z || (c.e_ld & 3))) return false;
+    if (c.epi_mode == EPI_DENSE_FWD && ((c.N & 15) || c.stride != 1 || !c.e_out2 || (c.e_ld & 3) || !aligned16(c.e_out2))) return false;
     return true;
 }
 

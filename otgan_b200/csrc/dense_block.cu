@@ -11,6 +11,15 @@
 // every filter is permuted accordingly when W = g V / ||V|| is built (weightnorm.cu `perm`), so the variables keep the
 // reference's HWIO layout and names.
 //
+// Forward, "contribution" form.  A 16-filter layer is a poor tensor-core shape: with N = 16 the MMA is bound by reading the
+// 128-pixel activation operand from shared memory (4 KB per K = 8 step, 32 cycles) while the tensor pipe needs 8.  So the
+// forward pass is re-associated: as soon as slot j of Z exists, ONE convolution adds its contribution to the pre-activations of
+// ALL later layers -- K = the slot's channels, N = 16 (L - j) columns of an accumulator S [B, H, W, 16 L] (read-modify-write in
+// the epilogue) -- and the first 16 of those columns, which are complete at that point, leave the same epilogue as crelu8 into
+// slot j + 1.  Same products, same sums (per layer the contributions are added slot by slot instead of tap by tap), 3.9x fewer
+// tensor-pipe cycles; launch 0 (the base slots, K = 2 c0) also carries the biases.  Weights for this form: WF_all [16 L][9][Ctot],
+// WF_all[16 q + co][t][ci] = W_q[co][t][ci] (0 for ci >= cin_q) -- the layout of dW_all -- read as a K-slice / row-slice.
+//
 // Backward (what tf.gradients emits for the list graph), per block, with dZ = gradient w.r.t. Z from the consumer:
 //     for r = L-1 .. 0:   g      = dZ[slot r+1] + sum_{q > r} conv_T( dy_q, W_q[:, slot r+1] )        "gather" form: ONE convolution with
 //                         dy_r   = crelu'(g)                                                            K = 16 (L-1-r) per tap, N = 32, the
@@ -71,19 +80,23 @@ crelu8_bwd_kernel(long long P, int C8, const float* __restrict__ z, int ldz, con
     }
 }
 
-// WB[ci][t][G q + co] = wf_q[co][t][ci] for ci < cin_q, else 0.   grid = (Ctot, taps), block = G * L threads (<= 1024)
-struct WbParams {
-    const float* wf[32];
-    int cin[32];
-    int L, G, taps, Ctot;
-};
-__global__ void dense_wb_kernel(const __grid_constant__ WbParams p, float* __restrict__ WB)
+// WB[ci][t][k] = WF_all[k][t][ci]  (k = 16 q + co; the zeros of WF_all -- layer q does not see channel ci -- carry over);
+// 32 x 32 tiles through shared memory, one tap per blockIdx.z
+__global__ void __launch_bounds__(256)
+dense_wb_kernel(int KY, int taps, int Ctot, const float* __restrict__ WF, float* __restrict__ WB)
 {
-    const int ci = blockIdx.x, t = blockIdx.y, k = threadIdx.x;
-    const int q = k / p.G, co = k - q * p.G;
-    float v = 0.f;
-    if (ci < p.cin[q]) v = p.wf[q][((size_t)co * p.taps + t) * p.cin[q] + ci];
-    WB[((size_t)ci * p.taps + t) * (p.G * p.L) + k] = v;
+    __shared__ float tile[32][33];
+    const int t = blockIdx.z, ci0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int k = k0 + i, ci = ci0 + tx;
+        tile[i][tx] = (k < KY && ci < Ctot) ? WF[((size_t)k * taps + t) * Ctot + ci] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int ci = ci0 + i, k = k0 + tx;
+        if (ci < Ctot && k < KY) WB[((size_t)ci * taps + t) * KY + k] = tile[tx][i];
+    }
 }
 
 inline unsigned ew_blocks(long long n)
@@ -140,34 +153,33 @@ size_t dense_wb_floats(const otgan_dense_geom_t* g)
     return geom_ok(g, q) ? (size_t)q.ctot() * 9 * q.G * q.L : 0;
 }
 
-int dense_build_wb_launch(const otgan_dense_geom_t* g, const float* const* wf, float* WB, cudaStream_t stream)
+int dense_build_wb_launch(const otgan_dense_geom_t* g, const float* wf_all, float* WB, cudaStream_t stream)
 {
     Geom q;
-    OTGAN_REQUIRE(geom_ok(g, q) && wf && WB, "dense_build_wb: bad geometry / null pointer");
-    WbParams p;
-    memset(&p, 0, sizeof(p));
-    p.L = q.L; p.G = q.G; p.taps = 9; p.Ctot = q.ctot();
-    for (int r = 0; r < q.L; ++r) { OTGAN_REQUIRE(wf[r], "dense_build_wb: null weight %d", r); p.wf[r] = wf[r]; p.cin[r] = q.cin(r); }
-    dense_wb_kernel<<<dim3(p.Ctot, 9), q.G * q.L, 0, stream>>>(p, WB);
+    OTGAN_REQUIRE(geom_ok(g, q) && wf_all && WB, "dense_build_wb: bad geometry / null pointer");
+    const int KY = q.G * q.L, Ctot = q.ctot();
+    dense_wb_kernel<<<dim3(ceil_div(Ctot, 32), ceil_div(KY, 32), 9), 256, 0, stream>>>(KY, 9, Ctot, wf_all, WB);
     OTGAN_CHECK_LAUNCH("dense_wb_kernel");
     return OTGAN_OK;
 }
 
-// Z base slots must already hold crelu8(e_0 ...) (crelu8_fwd_launch per base element).  wf[r]: [16][9][cin_r] in Z channel order.
-int dense_block_fprop_launch(const otgan_dense_geom_t* g, const float* const* wf, const float* const* bias, float* Z, cudaStream_t stream)
+// Z base slots must already hold crelu8(e_0 ...) (crelu8_fwd_launch per base element).  wf_all: [16L][9][Ctot] in Z channel order
+// (zero where a layer does not see a channel), bias_all: [16L] or null, S: scratch [B,H,W,16L] (the pre-activation accumulator).
+int dense_block_fprop_launch(const otgan_dense_geom_t* g, const float* wf_all, const float* bias_all, float* Z, float* S, cudaStream_t stream)
 {
     Geom q;
-    OTGAN_REQUIRE(geom_ok(g, q) && wf && Z, "dense_block_fprop: bad geometry / null pointer");
-    const int Ctot = q.ctot();
-    for (int r = 0; r < q.L; ++r) {
+    OTGAN_REQUIRE(geom_ok(g, q) && wf_all && Z && S, "dense_block_fprop: bad geometry / null pointer");
+    const int Ctot = q.ctot(), KY = q.G * q.L;
+    for (int j = 0; j < q.L; ++j) {
         ConvEx c;
         memset(&c, 0, sizeof(c));
         c.B = q.B; c.H = q.H; c.W = q.W; c.kh = 3; c.kw = 3; c.stride = 1; c.pt = 1; c.pl = 1;
-        c.a = Z; c.Ka = q.cin(r); c.lda = Ctot;
-        c.out = Z + q.cin(r); c.N = q.G; c.ldo = Ctot;                    // the slot of e_{r+1} starts right after the prefix
-        c.w = wf[r]; c.w_K = q.cin(r); c.w_taps = 9; c.w_rows = q.G; c.w_ldtap = q.cin(r); c.w_ldrow = 9LL * q.cin(r);
-        c.bias = bias ? bias[r] : nullptr;
-        c.epi_mode = EPI_CRELU8;
+        const int k0 = j == 0 ? 0 : q.cin(j - 1);                      // input slot j: channels [k0, cin(j))
+        c.a = Z + k0; c.Ka = q.cin(j) - k0; c.lda = Ctot;
+        c.out = S + q.G * j; c.N = q.G * (q.L - j); c.ldo = KY;
+        c.w = wf_all; c.w_K = Ctot; c.w_taps = 9; c.w_rows = KY; c.w_ldtap = Ctot; c.w_ldrow = 9LL * Ctot; c.k0 = k0; c.row0 = q.G * j;
+        c.bias = (j == 0 && bias_all) ? bias_all : nullptr;
+        c.epi_mode = EPI_DENSE_FWD; c.accumulate = j > 0; c.e_out2 = Z + q.cin(j); c.e_ld = Ctot;
         const int rc = conv_fprop_ex_launch(c, stream);
         if (rc != OTGAN_OK) return rc;
     }

@@ -1037,25 +1037,26 @@ class _DenseBlock(torch.autograd.Function):
             _lib.check(lib.otgan_crelu8_fwd_f32(P, c, t.data_ptr(), c, Z.data_ptr() + 4 * 2 * off, ctot, stream), "otgan_crelu8_fwd_f32")
             off += c
         c0 = off
-        wfs, invs = [], []
+        # W_r = g V / ||V|| of all layers into ONE tensor [16L][9][Ctot] (input channels in crelu8 order, zero past cin_r)
+        wf_all = torch.zeros((16 * L, 9, ctot), device=dev, dtype=torch.float32)
+        invs = []
         for r in range(L):
             cin = 2 * (c0 + 16 * r)
             K = 9 * cin
             V, g = Vs[r].contiguous(), gs[r].contiguous()
-            wf = torch.empty((16, K), device=dev, dtype=torch.float32)
             inv = torch.empty((16,), device=dev, dtype=torch.float32)
             perm = crelu8_perm(base_ch + [16] * r, 9, dev)
             ws = _wn_workspace(dev, lib.otgan_workspace_bytes_weightnorm(K, 16) // 4)
-            rc = lib.otgan_weightnorm_fwd_ex_f32(K, 16, V.data_ptr(), g.data_ptr(), perm.data_ptr(), 0, 0, 0, wf.data_ptr(), inv.data_ptr(),
-                                                 ws.data_ptr(), ws.numel() * 4, stream)
+            rc = lib.otgan_weightnorm_fwd_ex_f32(K, 16, V.data_ptr(), g.data_ptr(), perm.data_ptr(), cin, ctot, 9 * ctot,
+                                                 wf_all.data_ptr() + 4 * 16 * r * 9 * ctot, inv.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream)
             _lib.check(rc, "otgan_weightnorm_fwd_ex_f32")
-            wfs.append(wf); invs.append(inv)
-        bias = [b.contiguous() for b in bs]
-        rc = lib.otgan_dense_block_fprop_tf32(ctypes.byref(geom), _lib.ptr_array([w.data_ptr() for w in wfs]),
-                                              _lib.ptr_array([b.data_ptr() for b in bias]), Z.data_ptr(), stream)
+            invs.append(inv)
+        bias_all = torch.cat([b.reshape(-1) for b in bs])
+        S = torch.empty((B, H, W, 16 * L), device=dev, dtype=torch.float32)
+        rc = lib.otgan_dense_block_fprop_tf32(ctypes.byref(geom), wf_all.data_ptr(), bias_all.data_ptr(), Z.data_ptr(), S.data_ptr(), stream)
         _lib.check(rc, "otgan_dense_block_fprop_tf32")
         ctx.geom, ctx.base_ch, ctx.L, ctx.n_base, ctx.ctot = geom, base_ch, L, n_base, ctot
-        ctx.wfs, ctx.invs = wfs, invs
+        ctx.wf_all, ctx.invs = wf_all, invs
         ctx.save_for_backward(Z, *[t.contiguous() for t in Vs], *[t.contiguous() for t in gs])
         return Z
 
@@ -1071,8 +1072,7 @@ class _DenseBlock(torch.autograd.Function):
         stream = torch.cuda.current_stream().cuda_stream
         dZ = dZ.contiguous()
         WB = torch.empty((lib.otgan_dense_wb_floats(ctypes.byref(geom)),), device=dev, dtype=torch.float32)
-        _lib.check(lib.otgan_dense_build_wb_f32(ctypes.byref(geom), _lib.ptr_array([w.data_ptr() for w in ctx.wfs]), WB.data_ptr(), stream),
-                   "otgan_dense_build_wb_f32")
+        _lib.check(lib.otgan_dense_build_wb_f32(ctypes.byref(geom), ctx.wf_all.data_ptr(), WB.data_ptr(), stream), "otgan_dense_build_wb_f32")
         dY = torch.empty((B, H, W, 16 * L), device=dev, dtype=torch.float32)
         dbase = [torch.empty((B, H, W, c), device=dev, dtype=torch.float32) for c in base_ch]
         need_w = any(ctx.needs_input_grad[2 + n_base + 3 * r + j] for r in range(L) for j in range(3))

@@ -166,8 +166,12 @@ def test_dense_block_forward_backward_bit_exact(lib, B, H, W, base, L):
     for x, c in zip(xs, base):
         _lib.check(lib.otgan_crelu8_fwd_f32(P, c, x.data_ptr(), c, Z.data_ptr() + 8 * off, ctot, st()), "crelu8_fwd")
         off += c
-    rc = lib.otgan_dense_block_fprop_tf32(ctypes.byref(geom), _lib.ptr_array([w.data_ptr() for w in wfs]),
-                                          _lib.ptr_array([b.data_ptr() for b in bs]), Z.data_ptr(), st())
+    wf_all = torch.zeros((G * L, 9, ctot), device="cuda")
+    for r in range(L):
+        wf_all[G * r:G * r + G, :, :2 * (c0 + G * r)] = wfs[r]
+    bias_all = torch.cat(bs)
+    S = torch.full((B, H, W, G * L), float("nan"), device="cuda")
+    rc = lib.otgan_dense_block_fprop_tf32(ctypes.byref(geom), wf_all.data_ptr(), bias_all.data_ptr(), Z.data_ptr(), S.data_ptr(), st())
     _lib.check(rc, "dense_block_fprop")
     # float64 reference in the same (crelu8) channel order
     xd = [x.double().requires_grad_(True) for x in xs]
@@ -183,7 +187,7 @@ def test_dense_block_forward_backward_bit_exact(lib, B, H, W, base, L):
     dZ = ints((B, H, W, ctot), -2, 2, 60)
     zr.backward(dZ.double())
     WB = torch.empty(lib.otgan_dense_wb_floats(ctypes.byref(geom)), device="cuda")
-    _lib.check(lib.otgan_dense_build_wb_f32(ctypes.byref(geom), _lib.ptr_array([w.data_ptr() for w in wfs]), WB.data_ptr(), st()), "build_wb")
+    _lib.check(lib.otgan_dense_build_wb_f32(ctypes.byref(geom), wf_all.data_ptr(), WB.data_ptr(), st()), "build_wb")
     dY = torch.full((B, H, W, G * L), float("nan"), device="cuda")
     dbase = [torch.full((B, H, W, c), float("nan"), device="cuda") for c in base]
     dW = torch.full((G * L, 9, ctot), float("nan"), device="cuda")
