@@ -351,6 +351,7 @@ def _conv2d_nhwc(x, W, stride, pad, bias=None):
 CONV_BACKEND = "tcgen05"      # "tcgen05": this library's implicit-GEMM kernels where they tile the shape; "cudnn": library rung only
 UPSAMPLE_FUSION = True        # nn.upsample2x / nn.glu(upsample=True) hand the following conv2d an un-materialised Upsampled2x
 CONV_NARROW = True            # route the two 3-channel layers through _ConvNarrow (False: cuDNN, for A/B timing)
+DENSE_ON_TCGEN05 = True       # nn.dense as a 1x1 convolution on the generic tcgen05 kernels (False: cuBLAS through F.linear)
 WN_FUSION = True              # weight norm fused into the tcgen05 convolution nodes (_ConvTCWN / _ConvUp2TCWN: HWIO gradient pipeline)
 DENSE_BLOCK_FUSION = True     # nn.dense_block runs DenseNet's blocks on the dense-block kernels (False: the literal list code)
 _conv_ws = {}
@@ -1363,6 +1364,12 @@ def get_params(layer_name, x=None, init=False, ema=None, use_W=True, use_g=True,
 def _dense(x, W, pre_activation=None):
     x = apply_pre_activation(x, pre_activation, 1)
     if isinstance(W, TransposedWeight):
+        if (CONV_BACKEND == "tcgen05" and DENSE_ON_TCGEN05 and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
+                and x.shape[1] % 4 == 0 and W.wt.shape[0] % 4 == 0):
+            # tf.matmul(x, W) (utils/nn.py:208-209) as a 1x1 convolution of a [B, 1, 1, K] image on the generic tcgen05 kernels:
+            # W.wt [units, K] is exactly the OHWI filter matrix; the filter gradient is the same kernels' wgrad
+            B, K = x.shape
+            return _ConvGen.apply(x.contiguous().view(B, 1, 1, K), W.wt, None, (1, 1, 1, 0, 0)).view(B, W.wt.shape[0])
         return F.linear(x, W.wt)
     return x @ W                                                                                      # :208-209
 

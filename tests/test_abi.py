@@ -102,3 +102,33 @@ def test_product_path_has_no_cpu_fallback():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, fn)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, fn
+
+
+def test_crelu8_permutation_and_dense_geometry_host_side():
+    """Host-only entry points of the DenseNet path (no GPU needed): the crelu8 <-> reference channel permutation
+    (utils/nn.py:198-200 orders a CReLU'd LIST as [x0, -x0, x1, -x1, ...]) and the dense-block geometry queries."""
+    import ctypes
+    import numpy as np
+    from otgan_b200 import _lib
+    lib = _lib.load()
+    elems, taps = [32, 16, 16, 8], 3
+    c2 = 2 * sum(elems)
+    buf = (ctypes.c_int * (taps * c2))()
+    assert lib.otgan_crelu8_perm_host(len(elems), (ctypes.c_int * len(elems))(*elems), taps, buf, taps * c2) == taps * c2
+    perm = np.array(list(buf))
+    assert sorted(perm.tolist()) == list(range(taps * c2))                       # a permutation, tap by tap
+    xs = [np.random.RandomState(i).randn(c) for i, c in enumerate(elems)]
+    ref = np.maximum(np.concatenate([t for x in xs for t in (x, -x)]), 0)        # the reference's order
+    mine = np.concatenate([np.concatenate([np.maximum(x.reshape(-1, 8), 0), np.maximum(-x.reshape(-1, 8), 0)], 1).reshape(-1) for x in xs])
+    for t in range(taps):
+        assert np.array_equal(mine, ref[perm[t * c2:(t + 1) * c2] - t * c2])
+    assert lib.otgan_crelu8_perm_host(1, (ctypes.c_int * 1)(12), 1, buf, 24) < 0          # 12 channels: not a multiple of 8
+    assert lib.otgan_crelu8_perm_host(len(elems), (ctypes.c_int * len(elems))(*elems), taps, buf, 10) < 0   # buffer too small
+    g = _lib.DenseGeom()
+    g.B, g.H, g.W, g.n_base, g.L, g.growth = 4, 8, 8, 2, 16, 16
+    g.base_ch[0], g.base_ch[1] = 144, 16
+    assert lib.otgan_dense_channels(ctypes.byref(g)) == 2 * (160 + 256)
+    assert lib.otgan_dense_wb_floats(ctypes.byref(g)) == 2 * (160 + 256) * 9 * 256
+    assert lib.otgan_workspace_bytes_dense_bgrad(ctypes.byref(g)) > 0
+    g.growth = 12
+    assert lib.otgan_dense_channels(ctypes.byref(g)) < 0

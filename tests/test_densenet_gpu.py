@@ -284,3 +284,35 @@ def test_densenet_step_launches_no_library_convolution():
     finally:
         F.conv2d = orig
     assert calls == [], "library convolutions were called for input shapes %s" % (calls[:5],)
+
+
+def test_dense_layer_on_the_generic_kernels_matches_cublas():
+    """nn.dense (utils/nn.py:315-325; the generator's 100 -> 32768 layer) as a 1x1 convolution on the generic tcgen05 kernels:
+    forward and the V / g / b gradients against the cuBLAS path (F.linear, TF32 off)."""
+    from otgan_b200.models import dcgan
+    from otgan_b200.utils import nn
+    dev = torch.device("cuda")
+    dcgan.generator.reset()
+    torch.manual_seed(5)
+    with torch.no_grad():
+        dcgan.generator(8, init=True, device=dev)
+    u = torch.rand(8, 100, device=dev) * 2 - 1
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    outs = {}
+    try:
+        for flag in (True, False):
+            nn.DENSE_ON_TCGEN05 = flag
+            y = dcgan.generator(8, u=u)
+            gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(2)).to(dev)
+            (g,) = torch.autograd.grad([y], [dcgan.generator.flat], [gy])
+            n_dense = sum(p.numel() for n, p in dcgan.generator.named_parameters() if n.startswith("generator/dense_0/"))
+            outs[flag] = (y.detach(), g.detach()[:n_dense])
+    finally:
+        nn.DENSE_ON_TCGEN05 = True
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    (y1, g1), (y0, g0) = outs[True], outs[False]
+    assert float((y1 - y0).abs().max() / y0.abs().max()) < 5e-3
+    rel = float((g1 - g0).norm() / g0.norm())
+    assert rel < 2e-2, rel
+    dcgan.generator.reset()
