@@ -112,6 +112,11 @@ OTGAN_API int otgan_matched_two_batch_f32(int h, int D, const float* P, const fl
 /* Fused form: Ga = f_aa - f_ab, Gb = f_bb - f_ba written directly (train.py:111,125-126). */
 OTGAN_API int otgan_grad_features_f32(int h, int D, const float* P, const float* A, const float* B, int ld,
                             float* Ga, float* Gb, int ldo, void* ws, size_t ws_bytes, int impl, void* stream);
+/* Same for the rows [row_lo, row_hi) of Ga / Gb only (what one data-parallel rank back-propagates: its own towers, train.py:72-85):
+ * computes the half-blocks that intersect the range and leaves the other rows untouched. */
+OTGAN_API int otgan_grad_features_rows_f32(int h, int D, const float* P, const float* A, const float* B, int ld, float* Ga,
+                                           float* Gb, int ldo, int row_lo, int row_hi, void* ws, size_t ws_bytes, int impl,
+                                           void* stream);
 /* Single-batch matched features: P = [P_aa, P_bb, P_ab] ([n, n] each), A, B: [n, D].  utils/matching.py:131-134. */
 OTGAN_API int otgan_matched_single_batch_f32(int n, int D, const float* P, const float* A, const float* B, int ld,
                                    float* f_aa, float* f_bb, float* f_ab, float* f_ba, int ldo, void* ws,

@@ -48,6 +48,7 @@ SIGNATURES = {
     "otgan_plan_apply_f32": (_i, [ctypes.POINTER(Plan), _i, _i, _vp, _vp, _i, _vp, _i, _vp, _sz, _i, _vp]),
     "otgan_matched_two_batch_f32": (_i, [_i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _i, _vp]),
     "otgan_grad_features_f32": (_i, [_i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _sz, _i, _vp]),
+    "otgan_grad_features_rows_f32": (_i, [_i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _sz, _i, _vp]),
     "otgan_matched_single_batch_f32": (_i, [_i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _i, _vp]),
     "otgan_workspace_bytes_distance": (_sz, [_i, _i]),
     "otgan_calc_distance_f32": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _sz, _vp]),

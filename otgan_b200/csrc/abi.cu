@@ -259,6 +259,32 @@ int otgan_grad_features_f32(int h, int D, const float* P, const float* A, const 
     return otgan_plan_apply_f32(&p, h, D, P, F, ld, out, ldo, ws, ws_bytes, impl, stream);
 }
 
+// Same, restricted to the rows [row_lo, row_hi) of Ga and Gb (a data-parallel rank back-propagates only its own towers' rows):
+// only the half-blocks that intersect the range are computed, the other rows of Ga / Gb are left untouched.
+int otgan_grad_features_rows_f32(int h, int D, const float* P, const float* A, const float* B, int ld, float* Ga, float* Gb,
+                                 int ldo, int row_lo, int row_hi, void* ws, size_t ws_bytes, int impl, void* stream)
+{
+    OTGAN_REQUIRE(P && A && B && Ga && Gb, "grad_features_rows: null pointer");
+    OTGAN_REQUIRE(h >= 1 && D >= 1 && row_lo >= 0 && row_hi <= 2 * h && row_lo < row_hi, "grad_features_rows: bad shape / row range");
+    const bool lo_half = row_lo < h, hi_half = row_hi > h;
+    otgan_plan_t p;
+    memset(&p, 0, sizeof(p));
+    const size_t hl = (size_t)h * ld, ho = (size_t)h * ldo;
+    const float* F[4] = {A, A + hl, B, B + hl};
+    float* out[4];
+    int n = 0;
+    if (lo_half) {
+        add_term(&p, n, 0, 0, 1, 1.f); add_term(&p, n, 2, 0, 2, -.5f); add_term(&p, n, 3, 0, 3, -.5f); out[n++] = Ga;        // Ga[A1 rows]
+        add_term(&p, n, 1, 1, 3, 1.f); add_term(&p, n, 2, 1, 0, -.5f); add_term(&p, n, 4, 1, 1, -.5f); out[n++] = Gb;        // Gb[B1 rows]
+    }
+    if (hi_half) {
+        add_term(&p, n, 0, 1, 0, 1.f); add_term(&p, n, 4, 0, 2, -.5f); add_term(&p, n, 5, 0, 3, -.5f); out[n++] = Ga + ho;   // Ga[A2 rows]
+        add_term(&p, n, 1, 0, 2, 1.f); add_term(&p, n, 3, 1, 0, -.5f); add_term(&p, n, 5, 1, 1, -.5f); out[n++] = Gb + ho;   // Gb[B2 rows]
+    }
+    p.n_out = n;
+    return otgan_plan_apply_f32(&p, h, D, P, F, ld, out, ldo, ws, ws_bytes, impl, stream);
+}
+
 // sources: 0 = A, 1 = B;  plans: 0 = aa, 1 = bb, 2 = ab      (utils/matching.py:131-134)
 int otgan_matched_single_batch_f32(int n, int D, const float* P, const float* A, const float* B, int ld, float* f_aa,
                                    float* f_bb, float* f_ab, float* f_ba, int ldo, void* ws, size_t ws_bytes, int impl,

@@ -105,6 +105,7 @@ class Trainer:
             self.gen_optimizer = opt(generator, lr=args.learning_rate_gen, mom1=0.5)
             self.disc_optimizer = opt(discriminator, lr=-args.learning_rate_disc, mom1=0.5)
         self.sync = {'disc': GradSync(discriminator, world), 'gen': GradSync(generator, world)}
+        self.match_all_rows = False                        # parity checks: compute grad_ys for every row on every rank
         self.step_counter = 0
         self.gather_buf = None
         self.graphs = None                                 # set by enable_cuda_graphs()
@@ -113,8 +114,8 @@ class Trainer:
     def _gather_features(self, f_gen, f_dat):
         return gather_features(f_gen, f_dat, self.world)
 
-    def _match(self, A, B):
-        """A (fake) / B (real): [N, D] features of ALL towers -> (Ga, Gb, [dist, entropy])."""
+    def _match(self, A, B, rows=None):
+        """A (fake) / B (real): [N, D] features of ALL towers -> (Ga, Gb, [dist, entropy]); rows: the row range this rank needs."""
         a = self.args
         G = a.nr_gpu
         fa, fb = list(torch.chunk(A, G, 0)), list(torch.chunk(B, G, 0))
@@ -127,7 +128,7 @@ class Trainer:
             Ga = torch.cat([x - y for x, y in zip(m[0], m[2])], 0)                               # train.py:111
             Gb = torch.cat([x - y for x, y in zip(m[1], m[3])], 0)                               # train.py:126
             return Ga, Gb, torch.stack([d, m[4].to(d.dtype)])
-        ga, gb, stats = matching.matching_step(fa, fb, a.sinkhorn_lambda, a.nr_sinkhorn_iter)
+        ga, gb, stats = matching.matching_step(fa, fb, a.sinkhorn_lambda, a.nr_sinkhorn_iter, rows=rows)
         return torch.cat(ga, 0), torch.cat(gb, 0), stats
 
     def step(self, x_real, u=None, apply_update=True):
@@ -162,8 +163,8 @@ class Trainer:
             with nn.frozen_params():                      # tf.gradients(xs=gen_params): no critic filter gradients
                 f_gen = disc(x_gen, **self.model_opts)
         A, B = self._gather_features(f_gen, f_dat)
-        Ga, Gb, stats = self._match(A.detach(), B.detach())
         lo, hi = local_rows(self.rank, bs)
+        Ga, Gb, stats = self._match(A.detach(), B.detach(), rows=(lo, hi) if (self.world > 1 and not self.match_all_rows) else None)
         ga, gb = Ga[lo:hi], Gb[lo:hi]                                                            # this rank's towers
         self.last_grad_ys = (Ga, Gb)
         if train_disc:
@@ -402,6 +403,7 @@ def parity_check(world, rank, device, n_total=64, backends=(("cudnn", 1e-3), ("t
                     w, r = (world, rank) if mode == "multi" else (1, 0)
                     tr = Trainer(build_parser().parse_args(argv), device, r, w)                  # same seed -> identical parameters
                     tr.step_counter = 0 if step_kind == "disc" else 1
+                    tr.match_all_rows = True
                     bs = tr.bs_local
                     lo = r * bs
                     kind, stats = tr.step(x_all[lo:lo + bs], u=u_all[lo:lo + bs], apply_update=False)

@@ -201,11 +201,12 @@ def calc_distance(features_a, features_b, matched_features):
     return out[0]
 
 
-def matching_step(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, impl=_lib.IMPL_AUTO):
+def matching_step(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, impl=_lib.IMPL_AUTO, rows=None):
     """Fused form of train.py:96-128 for the two-batch matching: returns (grad_a list, grad_b list, stats) where
     grad_a[i] = f_aa[i] - f_ab[i] (grad_ys of the fake features, train.py:111), grad_b[i] = f_bb[i] - f_ba[i]
     (grad_ys of the real features, train.py:126) and stats is a 2-element CUDA tensor [distance, entropy]
-    (calc_distance via the <P,C> identity; utils/matching.py:61)."""
+    (calc_distance via the <P,C> identity; utils/matching.py:61).  rows = (lo, hi): only these rows of grad_a / grad_b are
+    needed (a data-parallel rank's own towers) -- the half-blocks outside the range are skipped and their rows left undefined."""
     lib = _lib.load()
     A, B, h, P, ent, pc = _two_batch_plans(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, impl=impl)
     ngpu = len(features_a)
@@ -213,8 +214,12 @@ def matching_step(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, imp
     Ga = torch.empty((N, D), device=A.device, dtype=torch.float32)
     Gb = torch.empty((N, D), device=A.device, dtype=torch.float32)
     ws, ws_bytes = _plan_ws(A.device, h)
-    rc = lib.otgan_grad_features_f32(h, D, P.data_ptr(), A.data_ptr(), B.data_ptr(), A.stride(0), Ga.data_ptr(),
-                                     Gb.data_ptr(), D, ws.data_ptr(), ws_bytes, impl, _stream())
+    if rows is None:
+        rc = lib.otgan_grad_features_f32(h, D, P.data_ptr(), A.data_ptr(), B.data_ptr(), A.stride(0), Ga.data_ptr(),
+                                         Gb.data_ptr(), D, ws.data_ptr(), ws_bytes, impl, _stream())
+    else:
+        rc = lib.otgan_grad_features_rows_f32(h, D, P.data_ptr(), A.data_ptr(), B.data_ptr(), A.stride(0), Ga.data_ptr(),
+                                              Gb.data_ptr(), D, int(rows[0]), int(rows[1]), ws.data_ptr(), ws_bytes, impl, _stream())
     _lib.check(rc, "otgan_grad_features_f32")
     stats = torch.empty((2,), device=A.device, dtype=torch.float32)
     rc = lib.otgan_distance_from_pc_f32(pc.data_ptr(), ent.data_ptr(), N, stats.data_ptr(), _stream())
