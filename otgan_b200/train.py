@@ -295,8 +295,11 @@ class GradSync:
     stream (layers finish last-to-first; each slice starts travelling as soon as its layer is done).  Works the same
     eagerly and under CUDA-graph capture (the side stream forks from and joins into the capturing stream)."""
 
-    def __init__(self, template, world):
+    def __init__(self, template, world, overlap=None):
         self.tpl, self.world = template, world
+        # OTGAN_GRAD_SYNC=overlap|single: per-layer all-reduces on a side stream while the backward pass runs, or ONE all-reduce of
+        # the flat gradient after it (A/B switch; the measured default is recorded in DESIGN.md section 6)
+        self.overlap = (os.environ.get("OTGAN_GRAD_SYNC", "single") == "overlap") if overlap is None else bool(overlap)
         st = template.store
         self.flat_grad = torch.zeros_like(st.flat.detach())
         self.side = torch.cuda.Stream(device=st.flat.device) if world > 1 else None
@@ -325,7 +328,7 @@ class GradSync:
                 dst.copy_(g.reshape(-1))
             scope = self.var_layer[i]
             pending[scope] -= 1
-            if pending[scope] == 0 and self.world > 1:
+            if pending[scope] == 0 and self.world > 1 and self.overlap:
                 lo, hi, _ = self.layers[scope]
                 self.side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(self.side):
@@ -345,14 +348,17 @@ class GradSync:
                 if g is None:
                     _, _, off, n = st.specs[i]
                     self.flat_grad[off:off + n].zero_()
-            if self.world > 1:
+            if self.world > 1 and self.overlap:
                 self.side.wait_stream(main)
                 with torch.cuda.stream(self.side):
                     for k in missing:
                         lo, hi, _ = self.layers[k]
                         dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM)
         if self.world > 1:
-            main.wait_stream(self.side)
+            if self.overlap:
+                main.wait_stream(self.side)
+            else:
+                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
         del done_events
         return self.flat_grad
 
