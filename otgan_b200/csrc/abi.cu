@@ -42,7 +42,7 @@ bool plan_apply_tc_supported(const otgan_plan_t* plan, int h, int D, const float
                              float* const* out, int ldo);
 size_t plan_apply_tc_workspace_bytes(int n_out, int h);
 int plan_apply_tc_launch(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F, int ldf,
-                         float* const* out, int ldo, void* ws, size_t ws_bytes, cudaStream_t stream);
+                         float* const* out, int ldo, void* ws, size_t ws_bytes, cudaStream_t stream, int row_lo, int row_hi);
 size_t distance_workspace_bytes(int n, int D);
 int distance_launch(int n, int D, const float* A, const float* B, const float* f_aa, const float* f_bb,
                     const float* f_ab, int ld, float scale, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
@@ -185,8 +185,19 @@ int otgan_sinkhorn_f32(int nblk, int rows, int cols, int T, float lam, const flo
 size_t otgan_workspace_bytes_plan(void) { return plan_apply_tc_workspace_bytes(OTGAN_MAX_OUTPUTS, 128); }
 size_t otgan_workspace_bytes_plan_h(int h) { return plan_apply_tc_workspace_bytes(OTGAN_MAX_OUTPUTS, h); }
 
+static int plan_apply_rows(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F_host, int ldf,
+                           float* const* out_host, int ldo, void* ws, size_t ws_bytes, int impl, void* stream, int row_lo, int row_hi);
+
 int otgan_plan_apply_f32(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F_host, int ldf,
                          float* const* out_host, int ldo, void* ws, size_t ws_bytes, int impl, void* stream)
+{
+    return plan_apply_rows(plan, h, D, P, F_host, ldf, out_host, ldo, ws, ws_bytes, impl, stream, 0, 0);
+}
+
+// row_hi <= 0: all rows; otherwise the tensor-core kernel computes only the 128-row tiles of every output that intersect
+// [row_lo, row_hi) (the SIMT rung computes everything)
+static int plan_apply_rows(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F_host, int ldf,
+                           float* const* out_host, int ldo, void* ws, size_t ws_bytes, int impl, void* stream, int row_lo, int row_hi)
 {
     OTGAN_REQUIRE(plan && P && F_host && out_host, "plan_apply: null pointer");
     OTGAN_REQUIRE(plan->n_out >= 1 && plan->n_out <= OTGAN_MAX_OUTPUTS, "plan_apply: n_out=%d", plan->n_out);
@@ -208,7 +219,7 @@ int otgan_plan_apply_f32(const otgan_plan_t* plan, int h, int D, const float* P,
         return OTGAN_EUNSUPPORTED;
     }
     if (tc_ok && impl != OTGAN_IMPL_SIMT)
-        return plan_apply_tc_launch(plan, h, D, P, F_host, ldf, out_host, ldo, ws, ws_bytes, (cudaStream_t)stream);
+        return plan_apply_tc_launch(plan, h, D, P, F_host, ldf, out_host, ldo, ws, ws_bytes, (cudaStream_t)stream, row_lo, row_hi);
     return plan_apply_simt_launch(plan, h, D, P, F_host, ldf, out_host, ldo, (cudaStream_t)stream);
 }
 
@@ -282,7 +293,11 @@ int otgan_grad_features_rows_f32(int h, int D, const float* P, const float* A, c
         add_term(&p, n, 1, 0, 2, 1.f); add_term(&p, n, 3, 1, 0, -.5f); add_term(&p, n, 5, 1, 1, -.5f); out[n++] = Gb + ho;   // Gb[B2 rows]
     }
     p.n_out = n;
-    return otgan_plan_apply_f32(&p, h, D, P, F, ld, out, ldo, ws, ws_bytes, impl, stream);
+    // inside the selected half-blocks only the 128-row tiles that hold rows of the range (the range lies in ONE half for a
+    // data-parallel rank; a range that spans both halves computes both halves completely)
+    int t_lo = 0, t_hi = 0;
+    if (lo_half != hi_half) { t_lo = lo_half ? row_lo : row_lo - h; t_hi = lo_half ? row_hi : row_hi - h; }
+    return plan_apply_rows(&p, h, D, P, F, ld, out, ldo, ws, ws_bytes, impl, stream, t_lo, t_hi);
 }
 
 // sources: 0 = A, 1 = B;  plans: 0 = aa, 1 = bb, 2 = ab      (utils/matching.py:131-134)

@@ -41,7 +41,7 @@ struct Params {
     CUtensorMap map_f[OTGAN_MAX_OUTPUTS];        // sources [h, D]
     otgan_plan_t plan;
     float* out[OTGAN_MAX_OUTPUTS];
-    int h, hp, row_tiles, D, ldo, n_col_tiles, n_items, kchunks, box_bytes;
+    int h, hp, row_tiles, rt_lo, D, ldo, n_col_tiles, n_items, kchunks, box_bytes;   // row_tiles = tiles walked, starting at tile rt_lo
 };
 
 // Aop[(o*3 + t)*128 + i][k] = coef * op(P)[i][k] (zero padded), split into hi / lo TF32 planes
@@ -114,7 +114,7 @@ plan_apply_tc_kernel(const __grid_constant__ Params p)
         if (lane == 0) {
             int c = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const int rt = item % p.row_tiles, oc = item / p.row_tiles;
+                const int rt = p.rt_lo + item % p.row_tiles, oc = item / p.row_tiles;
                 const int o = oc / p.n_col_tiles, d0 = (oc % p.n_col_tiles) * TN_;
                 for (int t = 0; t < p.plan.nterms[o]; ++t) {
                     const CUtensorMap* mf = &p.map_f[p.plan.src[o][t]];
@@ -200,7 +200,7 @@ plan_apply_tc_kernel(const __grid_constant__ Params p)
         const int m = quad * 32 + lane;
         int n = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
-            const int rt = item % p.row_tiles, oc = item / p.row_tiles;
+            const int rt = p.rt_lo + item % p.row_tiles, oc = item / p.row_tiles;
             const int o = oc / p.n_col_tiles, d0 = (oc % p.n_col_tiles) * TN_, b = n & 1;
             const int row = rt * TM_ + m;
             mbar_wait(tfull_bar(b), ((uint32_t)(n >> 1)) & 1u);
@@ -252,7 +252,7 @@ size_t plan_apply_tc_workspace_bytes(int n_out, int h)
 }
 
 int plan_apply_tc_launch(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F, int ldf,
-                         float* const* out, int ldo, void* ws, size_t ws_bytes, cudaStream_t stream)
+                         float* const* out, int ldo, void* ws, size_t ws_bytes, cudaStream_t stream, int row_lo, int row_hi)
 {
     OTGAN_REQUIRE(ws && ws_bytes >= plan_apply_tc_workspace_bytes(plan->n_out, h), "plan_apply(tcgen05): workspace too small");
     const int hp = ceil_div(h, TM_) * TM_;
@@ -279,7 +279,10 @@ int plan_apply_tc_launch(const otgan_plan_t* plan, int h, int D, const float* P,
     for (int s = 0; s < OTGAN_MAX_OUTPUTS; ++s)
         if (used[s] && !make_tensor_map_2d(&p.map_f[s], F[s], h, D, ldf, box_rows, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
             return OTGAN_EUNSUPPORTED;
-    p.h = h; p.hp = hp; p.row_tiles = hp / TM_; p.D = D; p.ldo = ldo;
+    // rows [row_lo, row_hi) of every output group only (row_hi <= 0: all rows): whole 128-row tiles that intersect the range
+    if (row_hi <= 0) { row_lo = 0; row_hi = h; }
+    p.rt_lo = row_lo / TM_;
+    p.h = h; p.hp = hp; p.row_tiles = ceil_div(row_hi, TM_) - p.rt_lo; p.D = D; p.ldo = ldo;
     p.n_col_tiles = ceil_div(D, TN_);
     p.n_items = plan->n_out * p.n_col_tiles * p.row_tiles;
     p.kchunks = ceil_div(h, BK);

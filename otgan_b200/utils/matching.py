@@ -118,9 +118,38 @@ def sinkhorn(L, lam, nr_iter, want_plan=True, impl=_lib.IMPL_AUTO, want_stats=Fa
     return P, ent, pc
 
 
+def sharded_cost_blocks(A, B, h, lam, rows, rank, world, cost_kind=_lib.COST_COSINE, impl=_lib.IMPL_AUTO):
+    """The six cost blocks with the ROWS sharded over the data-parallel ranks -- the reference's own partition
+    (utils/matching.py:29-39: tower i computes `1 - features_a[i] . batch^T`, i.e. the row slab of its own rows) followed by its
+    `tf.concat(dist, 0)` (:41-43) as ONE all-gather of the [3, rows, h] slabs (O(h^2) bytes).  A, B: the gathered [2h, D]
+    embeddings; rows = (lo, hi): this rank's rows.  Ranks of the first half own rows of a1 (blocks a1a2, a1b1, a1b2), ranks of the
+    second half rows of a2 and b2 (blocks a2b1, a2b2, b2b1): three slabs per rank, perfectly balanced.  Every rank ends up with
+    the same bits in L [6, h, h]."""
+    import torch.distributed as dist
+    lo, hi = rows
+    bs = hi - lo
+    if world % 2 or (world // 2) * bs != h:
+        raise ValueError("sharded cost blocks need an even number of ranks that tile both halves of the batch")
+    a2, b1, b2 = A[h:], B[:h], B[h:]
+    if lo < h:
+        xa = A[lo:hi]
+        Lloc = cost_blocks([xa, xa, xa], [a2, b1, b2], lam, cost_kind, None, impl)            # rows of blocks 0, 2, 3
+    else:
+        xa, xb = A[lo:hi], B[lo:hi]
+        Lloc = cost_blocks([xa, xa, xb], [b1, b2, b1], lam, cost_kind, None, impl)            # rows of blocks 4, 5, 1
+    buf = torch.empty((world, 3, bs, h), device=A.device, dtype=torch.float32)
+    dist.all_gather_into_tensor(buf, Lloc)
+    halves = buf.view(2, world // 2, 3, bs, h).permute(0, 2, 1, 3, 4).reshape(2, 3, h, h)
+    L = torch.empty((6, h, h), device=A.device, dtype=torch.float32)
+    L[[0, 2, 3]] = halves[0]
+    L[[4, 5, 1]] = halves[1]
+    return L
+
+
 def _two_batch_plans(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, cost_kind=_lib.COST_COSINE,
-                     impl=_lib.IMPL_AUTO):
-    """Cost blocks + Sinkhorn of utils/matching.py:11-61.  Returns (A, B, h, P[6,h,h], ent[6], pc[6])."""
+                     impl=_lib.IMPL_AUTO, shard=None):
+    """Cost blocks + Sinkhorn of utils/matching.py:11-61.  Returns (A, B, h, P[6,h,h], ent[6], pc[6]).
+    shard = (rows, rank, world): compute only this rank's row slabs of the cost blocks and all-gather them."""
     _check_features(features_a, features_b)
     ngpu = len(features_a)
     if ngpu % 2 != 0:
@@ -128,6 +157,10 @@ def _two_batch_plans(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, 
     A, B = _gather(features_a), _gather(features_b)
     h = A.shape[0] // 2
     a1, a2, b1, b2 = A[:h], A[h:], B[:h], B[h:]
+    if shard is not None:
+        L = sharded_cost_blocks(A, B, h, sinkhorn_lambda, shard[0], shard[1], shard[2], cost_kind, impl)
+        P, ent, pc = sinkhorn(L, sinkhorn_lambda, nr_sinkhorn_iter, True, impl)
+        return A, B, h, P, ent, pc
     # block order of utils/matching.py:41-43: a1a2, b2b1, a1b1, a1b2, a2b1, a2b2
     L = cost_blocks([a1, b2, a1, a1, a2, a2], [a2, b1, b1, b2, b1, b2], sinkhorn_lambda, cost_kind, None, impl)
     P, ent, pc = sinkhorn(L, sinkhorn_lambda, nr_sinkhorn_iter, True, impl)
@@ -201,14 +234,16 @@ def calc_distance(features_a, features_b, matched_features):
     return out[0]
 
 
-def matching_step(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, impl=_lib.IMPL_AUTO, rows=None):
+def matching_step(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, impl=_lib.IMPL_AUTO, rows=None, shard=None):
     """Fused form of train.py:96-128 for the two-batch matching: returns (grad_a list, grad_b list, stats) where
     grad_a[i] = f_aa[i] - f_ab[i] (grad_ys of the fake features, train.py:111), grad_b[i] = f_bb[i] - f_ba[i]
     (grad_ys of the real features, train.py:126) and stats is a 2-element CUDA tensor [distance, entropy]
     (calc_distance via the <P,C> identity; utils/matching.py:61).  rows = (lo, hi): only these rows of grad_a / grad_b are
-    needed (a data-parallel rank's own towers) -- the half-blocks outside the range are skipped and their rows left undefined."""
+    needed (a data-parallel rank's own towers) -- the half-blocks / row tiles outside the range are skipped and their rows left
+    undefined.  shard = (rank, world): additionally shard the cost blocks' rows over the ranks (sharded_cost_blocks)."""
     lib = _lib.load()
-    A, B, h, P, ent, pc = _two_batch_plans(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, impl=impl)
+    A, B, h, P, ent, pc = _two_batch_plans(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, impl=impl,
+                                           shard=(rows, shard[0], shard[1]) if (shard is not None and rows is not None) else None)
     ngpu = len(features_a)
     N, D = A.shape
     Ga = torch.empty((N, D), device=A.device, dtype=torch.float32)

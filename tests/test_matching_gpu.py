@@ -451,3 +451,43 @@ def test_sinkhorn_any_size(M, rows, cols, T):
     p, e, _ = mo.sinkhorn(C32[0], 50.0, T, np.float64)
     assert relerr(P[0], p) < TOL_P and abs(float(ent[0]) - e) <= TOL_ENT * abs(e)
     assert abs(float(pc[0]) - np.sum(p * C32[0])) < 2e-5 * rows
+
+
+def test_row_restricted_feature_gradients_are_bitwise_the_full_ones(M):
+    """otgan_grad_features_rows_f32 (what one data-parallel rank computes): the rows of the requested range equal the full
+    computation bit for bit (same tiles, same order), for ranges inside one half and at h = 256 inside one row tile."""
+    from otgan_b200 import _lib
+    lib = _lib.load()
+    for h, D, lo, hi in ((128, 4096, 32, 64), (128, 4096, 160, 192), (256, 2048, 128, 192), (256, 2048, 320, 384), (64, 512, 0, 128)):
+        rng = np.random.RandomState(h + lo)
+        P = rng.rand(6, h, h)
+        P /= P.sum(axis=2, keepdims=True)
+        Pd = dev(P.astype(np.float32))
+        Ad, Bd = dev(rng.rand(2 * h, D).astype(np.float32)), dev(rng.rand(2 * h, D).astype(np.float32))
+        ws, wsb = M._plan_ws(Ad.device, h)
+        s = torch.cuda.current_stream().cuda_stream
+        Ga, Gb = torch.empty(2 * h, D, device="cuda"), torch.empty(2 * h, D, device="cuda")
+        _lib.check(lib.otgan_grad_features_f32(h, D, Pd.data_ptr(), Ad.data_ptr(), Bd.data_ptr(), D, Ga.data_ptr(), Gb.data_ptr(), D,
+                                               ws.data_ptr(), wsb, 0, s), "grad_features")
+        Ra, Rb = torch.full((2 * h, D), float("nan"), device="cuda"), torch.full((2 * h, D), float("nan"), device="cuda")
+        _lib.check(lib.otgan_grad_features_rows_f32(h, D, Pd.data_ptr(), Ad.data_ptr(), Bd.data_ptr(), D, Ra.data_ptr(), Rb.data_ptr(), D,
+                                                    lo, hi, ws.data_ptr(), wsb, 0, s), "grad_features_rows")
+        assert torch.equal(Ra[lo:hi], Ga[lo:hi]) and torch.equal(Rb[lo:hi], Gb[lo:hi]), (h, lo, hi)
+
+
+def test_cost_row_slabs_match_the_full_blocks(M):
+    """The per-rank row slabs of partition "S" ([rows, h] against the full column batch) against the full h x h blocks."""
+    h, D, bs = 256, 4096, 64
+    A, B = mo.synth_embeddings(2 * h, D, 1, "clustered", sigma=1.0), mo.synth_embeddings(2 * h, D, 2, "clustered", sigma=1.0)
+    Ad, Bd = dev(A), dev(B)
+    a1, a2, b1, b2 = Ad[:h], Ad[h:], Bd[:h], Bd[h:]
+    full = M.cost_blocks([a1, b2, a1, a1, a2, a2], [a2, b1, b1, b2, b1, b2], 500.0)
+    for lo in (0, 128, 192):
+        xa = Ad[lo:lo + bs]
+        slab = M.cost_blocks([xa, xa, xa], [a2, b1, b2], 500.0)
+        for k, blk in enumerate((0, 2, 3)):
+            assert float((slab[k] - full[blk, lo:lo + bs]).abs().max()) / 500.0 < 1e-6
+    xa, xb = Ad[h + 64:h + 128], Bd[h + 64:h + 128]
+    slab = M.cost_blocks([xa, xa, xb], [b1, b2, b1], 500.0)
+    for k, blk in enumerate((4, 5, 1)):
+        assert float((slab[k] - full[blk, 64:128]).abs().max()) / 500.0 < 1e-6
