@@ -141,8 +141,9 @@ def sharded_cost_blocks(A, B, h, lam, rows, rank, world, cost_kind=_lib.COST_COS
     dist.all_gather_into_tensor(buf, Lloc)
     halves = buf.view(2, world // 2, 3, bs, h).permute(0, 2, 1, 3, 4).reshape(2, 3, h, h)
     L = torch.empty((6, h, h), device=A.device, dtype=torch.float32)
-    L[[0, 2, 3]] = halves[0]
-    L[[4, 5, 1]] = halves[1]
+    for src, blocks in ((halves[0], (0, 2, 3)), (halves[1], (4, 5, 1))):      # plain copies: capturable in a CUDA graph
+        for k, blk in enumerate(blocks):
+            L[blk].copy_(src[k])
     return L
 
 
