@@ -486,6 +486,67 @@ def measure_tf32_peak(torch, n=8192, reps=8):
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
+DENSE_BLOCKS = {  # DenseNet dense blocks (models/densenet.py): (H, W, base element channels); L = 16 layers of 16 filters each
+    "critic block 1": (32, 32, [32]), "critic block 2": (16, 16, [144]), "critic block 3": (8, 8, [200]),
+    "generator block 1": (8, 8, [16, 16]), "generator block 2": (16, 16, [144, 16]), "generator block 3": (32, 32, [208, 16])}
+
+
+def densenet_benchmark(torch, batch_critic, batch_gen, iters=3):
+    """Live times of the dense-block kernels (csrc/dense_block.cu) at the cfg4 shapes: forward (16 contribution-form launches) and
+    backward (15 gather dgrads + base dgrads + ONE wgrad GEMM + bias column sums) per block.  gflop = algorithmic FLOPs of the 16
+    3x3 convolutions (2 * pixels * 9 * 16 * sum_r cin_r) -- the same for forward, for the input gradients and for the filter
+    gradients; the backward executes more (the batched wgrad also fills the causally-masked half of dW_all)."""
+    import ctypes
+    from otgan_b200 import _lib
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    out = {}
+    for name, (H, W, base) in DENSE_BLOCKS.items():
+        B = batch_critic if name.startswith("critic") else batch_gen
+        L, G = 16, 16
+        geom = _lib.DenseGeom()
+        geom.B, geom.H, geom.W, geom.n_base, geom.L, geom.growth = B, H, W, len(base), L, G
+        for i, c in enumerate(base):
+            geom.base_ch[i] = c
+        c0 = sum(base)
+        ctot = lib.otgan_dense_channels(ctypes.byref(geom))
+        Z = torch.rand(B, H, W, ctot, device="cuda")
+        S = torch.empty(B, H, W, G * L, device="cuda")
+        wf = torch.randn(G * L, 9, ctot, device="cuda") * 0.02
+        bias = torch.randn(G * L, device="cuda") * 0.1
+        dZ = torch.randn(B, H, W, ctot, device="cuda")
+        WB = torch.empty(lib.otgan_dense_wb_floats(ctypes.byref(geom)), device="cuda")
+        dY = torch.empty(B, H, W, G * L, device="cuda")
+        dbase = [torch.empty(B, H, W, c, device="cuda") for c in base]
+        dW = torch.empty(G * L, 9, ctot, device="cuda")
+        db = torch.empty(G * L, device="cuda")
+        ws = torch.empty(lib.otgan_workspace_bytes_dense_bgrad(ctypes.byref(geom)) // 4 + 64, device="cuda")
+        _lib.check(lib.otgan_dense_build_wb_f32(ctypes.byref(geom), wf.data_ptr(), WB.data_ptr(), st), "build_wb")
+        ops = {"fprop": lambda: lib.otgan_dense_block_fprop_tf32(ctypes.byref(geom), wf.data_ptr(), bias.data_ptr(), Z.data_ptr(), S.data_ptr(), st),
+               "bgrad": lambda: lib.otgan_dense_block_bgrad_tf32(ctypes.byref(geom), Z.data_ptr(), dZ.data_ptr(), WB.data_ptr(), dY.data_ptr(),
+                                                                 _lib.ptr_array([t.data_ptr() for t in dbase]), dW.data_ptr(), db.data_ptr(),
+                                                                 ws.data_ptr(), ws.numel() * 4, st)}
+        flops = 2.0 * B * H * W * 9 * G * sum(2 * (c0 + G * r) for r in range(L))
+        row = {"shape": [B, H, W, base, L], "channels": ctot, "gflop": flops / 1e9}
+        for op, fn in ops.items():
+            for _ in range(2):
+                _lib.check(fn(), op)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            nf = 1.0 if op == "fprop" else 2.0           # backward = input gradients + filter gradients
+            row[op] = {"ms": ms, "tflops_algorithmic": nf * flops / ms / 1e9}
+        out[name] = row
+        del Z, S, wf, dZ, WB, dY, dbase, dW, ws
+        torch.cuda.empty_cache()
+    return out
+
+
 def conv_roofline(conv, tf32_peak=None):
     """Roofline object of the step's dominant kernel, conv_gemm_tc_kernel<256> (fprop / dgrad; 49% of the step in the ncu
     launch list profiles/r01_p_train_launches.txt), on the launch that was also captured with ncu --set full."""
@@ -608,7 +669,7 @@ def run_ours(args):
             res = conv_benchmark(torch)
             print(json.dumps({"conv_layers": res, "roofline": conv_roofline(res)}))
         return
-    match_res, roof, conv_res = (None, None, None)
+    match_res, roof, conv_res, dense_res = (None, None, None, None)
     if rank == 0 and not args.step_only:
         match_res, match_roof = matching_benchmark(torch, devv, 100, 5)
         if args.n_total:                           # diagnostics run at another N: keep the matching roofline only
@@ -617,6 +678,8 @@ def run_ours(args):
             conv_res = conv_benchmark(torch)
             roof = conv_roofline(conv_res, measure_tf32_peak(torch))
             match_res["roofline_matching"] = match_roof
+            # cfg4 per-rank shapes: the critic sees 2 * 256 / max(world, 1) images, the generator 256 / world
+            dense_res = densenet_benchmark(torch, 2 * N_TOTAL // world, N_TOTAL // world)
     barrier()
 
     # ---- the training step (all ranks): towers = 2 per rank, N_TOTAL images in total
@@ -743,7 +806,7 @@ def run_ours(args):
             "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "tf32-conv/f32", "data": "synthetic", "config": workload_config(world, args.workload),
             "sinkhorn_iters_per_sec": match_res["sinkhorn_iters_per_sec"] if match_res else None,
-            "roofline": roof, "conv_layers": conv_res, "matching": match_res,
+            "roofline": roof, "conv_layers": conv_res, "densenet_blocks": dense_res, "matching": match_res,
             "e2e": {"value": N_TOTAL / (ms_e2e / args.steps * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "cuda_graphs": graphs_on,
