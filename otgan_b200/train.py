@@ -95,16 +95,21 @@ class Trainer:
         opt = {'adam': nn.adam_updates, 'adamax': nn.adamax_updates, 'nesterov': nn.nesterov_updates}.get(args.optimizer)
         if opt is None:
             raise ValueError('unsupported optimizer')                                            # :151
+        self.sync = {'disc': GradSync(discriminator, world), 'gen': GradSync(generator, world)}
+        self.sharded_opt = args.optimizer == 'adam' and self.sync['gen'].sharded
+        if not self.sharded_opt:
+            for sy in self.sync.values():
+                sy.sharded = False
+        shard = (rank, world) if self.sharded_opt else None
         if args.optimizer == 'adam':
-            self.gen_optimizer = opt(generator, lr=args.learning_rate_gen, mom1=0.5, mom2=0.999, ema=self.ema)
-            self.disc_optimizer = opt(discriminator, lr=-args.learning_rate_disc, mom1=0.5, mom2=0.999)
+            self.gen_optimizer = opt(generator, lr=args.learning_rate_gen, mom1=0.5, mom2=0.999, ema=self.ema, shard=shard)
+            self.disc_optimizer = opt(discriminator, lr=-args.learning_rate_disc, mom1=0.5, mom2=0.999, shard=shard)
         elif args.optimizer == 'adamax':
             self.gen_optimizer = opt(generator, lr=args.learning_rate_gen, mom1=0.5, mom2=0.999)
             self.disc_optimizer = opt(discriminator, lr=-args.learning_rate_disc, mom1=0.5, mom2=0.999)
         else:
             self.gen_optimizer = opt(generator, lr=args.learning_rate_gen, mom1=0.5)
             self.disc_optimizer = opt(discriminator, lr=-args.learning_rate_disc, mom1=0.5)
-        self.sync = {'disc': GradSync(discriminator, world), 'gen': GradSync(generator, world)}
         self.match_all_rows = False                        # parity checks: compute grad_ys for every row on every rank
         self.step_counter = 0
         self.gather_buf = None
@@ -157,6 +162,8 @@ class Trainer:
         bs = self.bs_local
         if train_disc:
             with torch.no_grad():
+                if a.train_disc_against_ema:
+                    self.sync_ema()
                 x_gen = gen(ema=self.ema, u=u, **self.model_opts) if a.train_disc_against_ema else gen(u=u, **self.model_opts)
             feats = disc(torch.cat([x_gen, x_real], 0), **self.model_opts)                       # fake rows, then real rows
             f_gen, f_dat = feats[:bs], feats[bs:]
@@ -175,14 +182,30 @@ class Trainer:
             grad = self.sync['disc'].backward([feats], [torch.cat([ga, gb], 0)])                 # :122-128 + :134-139 (sum, not mean)
             if apply_update:
                 self.disc_optimizer.run(grad, lr=-a.learning_rate_disc, hyper_dev=hyper_dev)     # :143,215
+                if self.sharded_opt:
+                    self.sync['disc'].gather_params(self.rank)
                 if a.optimizer == 'adam':
                     disc.store.refresh_weight_cache()      # W of the updated critic, reused by the generator steps that follow
         else:
             grad = self.sync['gen'].backward([f_gen], [ga])                                      # :111-112 + :134-139
             if apply_update:
                 self.gen_optimizer.run(grad, lr=a.learning_rate_gen, hyper_dev=hyper_dev)        # :142,222 (+ EMA :223)
+                if self.sharded_opt:
+                    self.sync['gen'].gather_params(self.rank)
+        if self.sharded_opt and not apply_update:          # parity checks read the FULL summed gradient
+            full = torch.empty_like(self.sync[kind].flat_grad)
+            dist.all_gather_into_tensor(full, grad)
+            grad = full
         self.last_grad = grad
         return stats
+
+    def sync_ema(self):
+        """With the sharded optimiser every rank updates only its slice of the generator's EMA shadow (train.py:63-64, 223): gather
+        the slices before the shadow is read (sampling from the EMA generator, --train_disc_against_ema, checkpoints)."""
+        if self.sharded_opt:
+            sh = self.ema.shadow
+            n = sh.numel() // self.world
+            dist.all_gather_into_tensor(sh, sh[self.rank * n:(self.rank + 1) * n].clone())
 
     # ---- CUDA graphs: one captured critic step and one captured generator step, replayed with refreshed inputs ----------
     def enable_cuda_graphs(self, warmup=3):
@@ -282,6 +305,7 @@ class Trainer:
     def sample_tiles(self, path, path_ema=None, n=100):
         """train.py:233-243: PNG tile of generated samples (and of the EMA generator's samples)."""
         from .utils import plotting
+        self.sync_ema()
         with torch.no_grad():
             x = self.generator(**self.model_opts)
             plotting.save_tile_img(plotting.img_tile(x[:n].cpu().numpy(), aspect_ratio=1.0, border_color=1.0, stretch=False), path)
@@ -301,9 +325,13 @@ class GradSync:
 
     def __init__(self, template, world, overlap=None):
         self.tpl, self.world = template, world
-        # OTGAN_GRAD_SYNC=overlap|single: per-layer all-reduces on a side stream while the backward pass runs, or ONE all-reduce of
-        # the flat gradient after it (A/B switch; the measured default is recorded in DESIGN.md section 6)
-        self.overlap = (os.environ.get("OTGAN_GRAD_SYNC", "single") == "overlap") if overlap is None else bool(overlap)
+        # OTGAN_GRAD_SYNC = sharded (default) | single | overlap: reduce-scatter + sharded Adam + all-gather of the parameters
+        # (ZeRO-1), ONE all-reduce of the flat gradient after the backward pass, or per-layer all-reduces on a side stream while it
+        # runs (A/B switches; measurements in DESIGN.md section 6)
+        mode = os.environ.get("OTGAN_GRAD_SYNC", "sharded")
+        self.overlap = (mode == "overlap") if overlap is None else bool(overlap)
+        self.sharded = (mode == "sharded") and world > 1 and not self.overlap
+        self.grad_shard = None
         st = template.store
         self.flat_grad = torch.zeros_like(st.flat.detach())
         self.side = torch.cuda.Stream(device=st.flat.device) if world > 1 else None
@@ -361,10 +389,23 @@ class GradSync:
         if self.world > 1:
             if self.overlap:
                 main.wait_stream(self.side)
+            elif self.sharded:                             # ZeRO-1: every rank receives the SUM of its own 1/world slice only
+                n = self.flat_grad.numel() // self.world
+                if self.grad_shard is None:
+                    self.grad_shard = torch.empty(n, device=self.flat_grad.device, dtype=torch.float32)
+                dist.reduce_scatter_tensor(self.grad_shard, self.flat_grad, op=dist.ReduceOp.SUM)
+                del done_events
+                return self.grad_shard
             else:
                 dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
         del done_events
         return self.flat_grad
+
+    def gather_params(self, rank):
+        """After the sharded optimiser step: all-gather the updated parameter slices (in place in the flat buffer)."""
+        flat = self.tpl.store.flat.detach()
+        n = flat.numel() // self.world
+        dist.all_gather_into_tensor(flat, flat[rank * n:(rank + 1) * n].clone())
 
 
 def gather_features(f_gen, f_dat, world):

@@ -97,7 +97,7 @@ class VariableStore:
 
     def pack(self):
         total = sum(s[3] for s in self.specs)
-        pad = (-total) % 4                      # keep the flat buffers float4-sized for the fused optimiser kernel
+        pad = (-total) % 64                     # float4-sized for the fused optimiser kernel AND divisible into <= 16 equal float4 shards (sharded Adam)
         flat = torch.zeros(total + pad, device=self.device, dtype=torch.float32)
         for name, shape, off, n in self.specs:
             flat[off:off + n] = self.pending[name].reshape(-1)
@@ -1517,14 +1517,26 @@ def _flat_of(params):
     return params.flat if isinstance(params, Template) else params
 
 
-def adam_updates(params, cost_or_grads=None, lr=0.001, mom1=0.9, mom2=0.999, ema=None):
+def adam_updates(params, cost_or_grads=None, lr=0.001, mom1=0.9, mom2=0.999, ema=None, shard=None):
     """utils/nn.py:50-73 on the flat variable buffer, as ONE fused CUDA kernel (otgan_adam_ema_f32):
         v = mom1 v + (1-mom1) g ; v_hat = v / (1 - mom1^t) ; mg = mom2 mg + (1-mom2) g^2 ; mg_hat = mg / (1 - mom2^t)
         p = p - lr * v_hat / sqrt(mg_hat + 1e-8)        (epsilon INSIDE the root, t starts at 1)
     and, when `ema` is given, shadow = decay*shadow + (1-decay)*p in the same pass (train.py:64,223).
-    Returns an object whose .run(grads_flat, lr=None) applies one step (lr may be negative: the critic ascends, train.py:143)."""
+    Returns an object whose .run(grads_flat, lr=None) applies one step (lr may be negative: the critic ascends, train.py:143).
+    shard = (rank, world): optimiser state sharded over the data-parallel ranks (ZeRO-1): this rank keeps the Adam moments of, and
+    updates, only its 1/world slice of the flat buffer; .run then expects the REDUCE-SCATTERED gradient slice and the caller
+    all-gathers the updated parameters (train.GradSync / Trainer): same NVLink volume as the all-reduce it replaces, the 7-pass Adam
+    + EMA kernel at 1/world of the parameters.  The EMA shadow is updated on the own slice only (Trainer.sync_ema gathers it)."""
     flat = _flat_of(params)
-    state = {"t": 1, "mg": torch.zeros_like(flat), "v": torch.zeros_like(flat) if mom1 > 0 else None}
+    lo, hi = 0, flat.numel()
+    if shard is not None:
+        rank, world = shard
+        assert flat.numel() % (4 * world) == 0, "flat parameter buffer must split into float4-sized shards"
+        n = flat.numel() // world
+        lo, hi = rank * n, (rank + 1) * n
+    nloc = hi - lo
+    state = {"t": 1, "mg": torch.zeros(nloc, device=flat.device), "v": torch.zeros(nloc, device=flat.device) if mom1 > 0 else None,
+             "range": (lo, hi)}
     default_lr = lr
 
     def hyper(lr=None):
@@ -1544,11 +1556,13 @@ def adam_updates(params, cost_or_grads=None, lr=0.001, mom1=0.9, mom2=0.999, ema
             ema.attach(params)
         stream = torch.cuda.current_stream().cuda_stream
         v_ptr = state["v"].data_ptr() if state["v"] is not None else None
-        e_ptr = ema.shadow.data_ptr() if ema is not None else None
+        e_ptr = (ema.shadow.data_ptr() + 4 * lo) if ema is not None else None
         decay = float(ema.decay) if ema is not None else 0.0
+        p_ptr = flat.data_ptr() + 4 * lo
+        assert g.numel() == nloc, "adam_updates: gradient size does not match the (sharded) parameter range"
         if hyper_dev is not None:                           # scalars come from device memory; t is advanced by hyper()
             with torch.no_grad():
-                rc = lib.otgan_adam_ema_dev_f32(flat.numel(), flat.data_ptr(), g.data_ptr(), v_ptr, state["mg"].data_ptr(), e_ptr,
+                rc = lib.otgan_adam_ema_dev_f32(nloc, p_ptr, g.data_ptr(), v_ptr, state["mg"].data_ptr(), e_ptr,
                                                 hyper_dev.data_ptr(), float(mom1), float(mom2), decay, stream)
             _lib.check(rc, "otgan_adam_ema_dev_f32")
             return
@@ -1556,7 +1570,7 @@ def adam_updates(params, cost_or_grads=None, lr=0.001, mom1=0.9, mom2=0.999, ema
         c1 = (1.0 - mom1 ** t) if mom1 > 0 else 1.0        # bias-correction denominators (utils/nn.py:63,68)
         c2 = 1.0 - mom2 ** t
         with torch.no_grad():
-            rc = lib.otgan_adam_ema_f32(flat.numel(), flat.data_ptr(), g.data_ptr(), v_ptr, state["mg"].data_ptr(), e_ptr,
+            rc = lib.otgan_adam_ema_f32(nloc, p_ptr, g.data_ptr(), v_ptr, state["mg"].data_ptr(), e_ptr,
                                         float(step_lr), float(mom1), float(mom2), float(c1), float(c2), decay, stream)
         _lib.check(rc, "otgan_adam_ema_f32")
         state["t"] = t + 1
