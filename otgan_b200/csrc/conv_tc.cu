@@ -344,17 +344,36 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
                 out = p.tail_ws + ((size_t)tail * p.tail_splits + sp) * (size_t)(TM * TN) + (size_t)r * TN;
                 bias = nullptr;
             }
-            mbar_wait(tfull_bar(b), ((uint32_t)(n >> 1)) & 1u);
-            tcgen05_fence_after();
             if (p.generic) {
                 if constexpr (TN != 16) {
                     const bool row_ok = (w0 + rw < p.m_w) && (h0 + rh < p.m_h) && (n0 + rn < p.m_b);
                     const long long epix = (long long)(n0 + rn) * p.esN + (long long)(h0 + rh) * p.esH + (long long)(w0 + rw) * p.esW;
                     float* orow = p.out + p.cls_out_off[cls] + (long long)(n0 + rn) * p.osN + (long long)(h0 + rh) * p.osH +
                                   (long long)(w0 + rw) * p.osW;
+                    // The read-modify-write epilogues (dense-block forward accumulator, crelu8 backward inputs) are latency-bound on
+                    // short tiles: pull this row's operands towards L2 / L1 while the tile's MMAs are still running.
+                    if (row_ok) {
+                        int lim = (nt + 1) * p.n_inst;
+                        lim = lim > p.n_valid ? p.n_valid : lim;
+                        if (p.epi_mode == EPI_DENSE_FWD && p.accumulate) {
+                            for (int c = nt * p.n_inst; c < lim; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(orow + c));
+                        } else if (p.epi_mode == EPI_CRELU8_BWD) {
+                            for (int c = nt * p.n_inst; c < lim; c += 32) {
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.e_z + epix + c));
+                                if (p.e_add) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.e_add + epix + c));
+                            }
+                        }
+                    }
+                    mbar_wait(tfull_bar(b), ((uint32_t)(n >> 1)) & 1u);
+                    tcgen05_fence_after();
                     epilogue_generic<TN>(p, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TN), nt, orow, epix, row_ok);
+                } else {
+                    mbar_wait(tfull_bar(b), ((uint32_t)(n >> 1)) & 1u);
+                    tcgen05_fence_after();
                 }
             } else if constexpr (TN == 16) {
+                mbar_wait(tfull_bar(b), ((uint32_t)(n >> 1)) & 1u);
+                tcgen05_fence_after();
                 // narrow outputs (the generator's 3-channel image, the critic's image gradient): only n_valid columns exist;
                 // the weight box has n_valid rows, the other accumulator columns hold garbage and are never stored
                 uint32_t v[16];
@@ -364,6 +383,8 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
                 for (int j = 0; j < 16; ++j)
                     if (j < p.n_valid) out[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + j) : 0.f);
             } else {
+            mbar_wait(tfull_bar(b), ((uint32_t)(n >> 1)) & 1u);
+            tcgen05_fence_after();
 #pragma unroll 1
             for (int cc = 0; cc < TN / 32; ++cc) {
                 uint32_t v[32];
