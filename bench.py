@@ -712,6 +712,14 @@ def run_ours(args):
         stats_host = torch.empty(2).pin_memory()
         x_dev = torch.empty((bs, 32, 32, 3), device=devv)
 
+        def e2e_input(i):
+            """The public API takes the step's images as a tensor: under CUDA graphs Trainer.step copies them straight from the
+            pinned HOST buffer into the graph's input (one H2D copy); eagerly they are uploaded first (also one H2D copy)."""
+            if tr.graphs is not None:
+                return host_imgs[i % 8]
+            x_dev.copy_(host_imgs[i % 8], non_blocking=True)
+            return x_dev
+
         def measure():
             sampler = ClockSampler(local)
             sampler.start()
@@ -728,14 +736,12 @@ def run_ours(args):
             t_dev = e0.elapsed_time(e1)
             # ---- end to end: pinned host images -> H2D -> step -> D2H of [distance, entropy], every step
             for i in range(2):
-                x_dev.copy_(host_imgs[i % 8], non_blocking=True)
-                stats_host.copy_(tr.step(x_dev)[1], non_blocking=True)
+                stats_host.copy_(tr.step(e2e_input(i))[1], non_blocking=True)
             barrier()
             e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e2.record(stream)
             for i in range(args.steps):
-                x_dev.copy_(host_imgs[i % 8], non_blocking=True)
-                stats_host.copy_(tr.step(x_dev)[1], non_blocking=True)
+                stats_host.copy_(tr.step(e2e_input(i))[1], non_blocking=True)
                 stream.synchronize()                   # the host reads (distance, entropy) every step, like sess.run
             e3.record(stream)
             barrier()
