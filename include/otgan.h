@@ -41,11 +41,7 @@ enum {
 };
 
 /* implementation selectors (for A/B parity tests and benchmarking; AUTO picks the fastest valid one) */
-enum { OTGAN_IMPL_AUTO = 0, OTGAN_IMPL_SIMT = 1, OTGAN_IMPL_TCGEN05 = 2,
-       /* cost blocks only: the fp16-split tensor-core kernel (csrc/cost_h.cu).  NOT a free choice like the others: the caller asserts
-        * that every input element satisfies |x| < 4 (rows with L2 norm <= 1, i.e. the critic head's output, models/dcgan.py:16-19);
-        * larger values overflow the fp16 operand planes (inf/NaN in L, never silently wrong finite numbers). */
-       OTGAN_IMPL_TCGEN05_UNIT = 3 };
+enum { OTGAN_IMPL_AUTO = 0, OTGAN_IMPL_SIMT = 1, OTGAN_IMPL_TCGEN05 = 2 };
 
 #define OTGAN_MAX_BLOCKS 8   /* two-batch matching uses 6 blocks, single-batch 3 */
 #define OTGAN_MAX_TERMS 3

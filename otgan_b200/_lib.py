@@ -11,7 +11,6 @@ OTGAN_MAX_TERMS = 3
 OTGAN_MAX_OUTPUTS = 8
 COST_COSINE, COST_EUCLID_MEAN = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
-IMPL_TCGEN05_UNIT = 3      # cost blocks only: fp16-split tensor-core kernel, the caller asserts |x| < 4 (unit-norm rows)
 
 _vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
 

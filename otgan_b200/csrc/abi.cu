@@ -24,10 +24,6 @@ int cost_simt_launch(int nblk, int rows, int cols, int D, const float* const* X,
                      cudaStream_t stream);
 bool cost_tc_supported(int nblk, int rows, int cols, int D, const float* const* X, const float* const* Y, int ldx, int ldy);
 size_t cost_tc_workspace_bytes(int nblk, int rows, int cols, int D);
-bool cost_h_supported(int nblk, int rows, int cols, int D, const float* const* X, const float* const* Y, int ldx, int ldy);
-size_t cost_h_workspace_bytes(int nblk, int rows, int cols, int D);
-int cost_h_launch(int nblk, int rows, int cols, int D, const float* const* X, const float* const* Y, int ldx, int ldy,
-                  int cost_kind, const float* diag, float lam, float* L, void* ws, size_t ws_bytes, cudaStream_t stream);
 int cost_tc_launch(int nblk, int rows, int cols, int D, const float* const* X, const float* const* Y, int ldx,
                    int ldy, int cost_kind, const float* diag, float lam, float* L, void* ws, size_t ws_bytes,
                    cudaStream_t stream);
@@ -45,11 +41,6 @@ int plan_apply_simt_launch(const otgan_plan_t* plan, int h, int D, const float* 
 bool plan_apply_tc_supported(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F, int ldf,
                              float* const* out, int ldo);
 size_t plan_apply_tc_workspace_bytes(int n_out, int h);
-bool plan_apply_h_supported(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F, int ldf,
-                            float* const* out, int ldo);
-size_t plan_apply_h_workspace_bytes(int n_out, int h);
-int plan_apply_h_launch(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F, int ldf,
-                        float* const* out, int ldo, void* ws, size_t ws_bytes, cudaStream_t stream, int row_lo, int row_hi);
 int plan_apply_tc_launch(const otgan_plan_t* plan, int h, int D, const float* P, const float* const* F, int ldf,
                          float* const* out, int ldo, void* ws, size_t ws_bytes, cudaStream_t stream, int row_lo, int row_hi);
 size_t distance_workspace_bytes(int n, int D);
@@ -134,8 +125,7 @@ size_t otgan_workspace_bytes_cost(int nblk, int rows, int cols, int D, int impl)
     (void)impl;
     if (nblk < 1 || nblk > OTGAN_MAX_BLOCKS || rows < 1 || cols < 1 || D < 1) return 0;
     const size_t a = cost_simt_workspace_bytes(nblk, rows, cols, D), b = cost_tc_workspace_bytes(nblk, rows, cols, D);
-    const size_t c = cost_h_workspace_bytes(nblk, rows, cols, D);
-    return a > b ? (a > c ? a : c) : (b > c ? b : c);     // one size fits every implementation the call may select
+    return a > b ? a : b;     // one size fits every implementation the call may select
 }
 
 int otgan_cost_blocks_f32(int nblk, int rows, int cols, int D, const float* const* X_host, const float* const* Y_host,
@@ -148,18 +138,7 @@ int otgan_cost_blocks_f32(int nblk, int rows, int cols, int D, const float* cons
     OTGAN_REQUIRE(cost_kind == OTGAN_COST_COSINE || cost_kind == OTGAN_COST_EUCLID_MEAN, "cost: unknown cost_kind %d", cost_kind);
     OTGAN_REQUIRE(X_host && Y_host && L && ws, "cost: null pointer");
     for (int k = 0; k < nblk; ++k) OTGAN_REQUIRE(X_host[k] && Y_host[k], "cost: null block pointer %d", k);
-    OTGAN_REQUIRE(impl == OTGAN_IMPL_AUTO || impl == OTGAN_IMPL_SIMT || impl == OTGAN_IMPL_TCGEN05 || impl == OTGAN_IMPL_TCGEN05_UNIT,
-                  "cost: unknown impl %d", impl);
-    if (impl == OTGAN_IMPL_TCGEN05_UNIT) {
-        // the caller vouches for |x| < 4 (unit-norm rows); short contractions keep the exact-fp32 kernel like AUTO does
-        if (D < 2048)
-            return cost_simt_launch(nblk, rows, cols, D, X_host, Y_host, ldx, ldy, cost_kind, diag_add_host, lam, L, ws, ws_bytes, (cudaStream_t)stream);
-        if (!cost_h_supported(nblk, rows, cols, D, X_host, Y_host, ldx, ldy)) {
-            set_error("cost: the fp16-split tcgen05 path needs 16-byte aligned rows (ld %% 4 == 0, D %% 4 == 0) and D >= 32");
-            return OTGAN_EUNSUPPORTED;
-        }
-        return cost_h_launch(nblk, rows, cols, D, X_host, Y_host, ldx, ldy, cost_kind, diag_add_host, lam, L, ws, ws_bytes, (cudaStream_t)stream);
-    }
+    OTGAN_REQUIRE(impl == OTGAN_IMPL_AUTO || impl == OTGAN_IMPL_SIMT || impl == OTGAN_IMPL_TCGEN05, "cost: unknown impl %d", impl);
     const bool tc_ok = cost_tc_supported(nblk, rows, cols, D, X_host, Y_host, ldx, ldy);
     if (impl == OTGAN_IMPL_TCGEN05 && !tc_ok) {
         set_error("cost: tcgen05 path needs 16-byte aligned rows (ld %% 4 == 0) and D >= 32");
@@ -232,15 +211,7 @@ static int plan_apply_rows(const otgan_plan_t* plan, int h, int D, const float* 
                           "plan_apply: bad source");
         }
     }
-    OTGAN_REQUIRE(impl == OTGAN_IMPL_AUTO || impl == OTGAN_IMPL_SIMT || impl == OTGAN_IMPL_TCGEN05 || impl == OTGAN_IMPL_TCGEN05_UNIT,
-                  "plan_apply: unknown impl %d", impl);
-    if (impl == OTGAN_IMPL_TCGEN05_UNIT) {
-        // the caller vouches for |F| < 4 (unit-norm rows) and a plan P (entries in [0, 1]); the fp16 planes need half the TF32 workspace
-        if (ws != nullptr && ws_bytes >= plan_apply_h_workspace_bytes(plan->n_out, h) && D >= 2048 &&
-            plan_apply_h_supported(plan, h, D, P, F_host, ldf, out_host, ldo))
-            return plan_apply_h_launch(plan, h, D, P, F_host, ldf, out_host, ldo, ws, ws_bytes, (cudaStream_t)stream, row_lo, row_hi);
-        impl = OTGAN_IMPL_AUTO;                       // short rows / unaligned outputs: the general kernels
-    }
+    OTGAN_REQUIRE(impl == OTGAN_IMPL_AUTO || impl == OTGAN_IMPL_SIMT || impl == OTGAN_IMPL_TCGEN05, "plan_apply: unknown impl %d", impl);
     const bool tc_ok = ws != nullptr && ws_bytes >= plan_apply_tc_workspace_bytes(plan->n_out, h) &&
                        plan_apply_tc_supported(plan, h, D, P, F_host, ldf, out_host, ldo);
     if (impl == OTGAN_IMPL_TCGEN05 && !tc_ok) {

@@ -9,7 +9,7 @@
 // box of tile (ti, tj) starts at row 128 ti / 128 tj of the same tensor maps, ragged edges are zero-filled.  Tiles that share
 // an embedding slab run concurrently on the same K range, so HBM sees every element once (the rest hits in L2).
 //
-// Accuracy.  (1) Operands: x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi); D += Ahi*Blo + Alo*Bhi + Ahi*Bhi
+// Accuracy.  (1) Operands: x = hi + lo with hi = rna_tf32(x), lo = x - hi (tc_common.cuh: split_tf32); D += Ahi*Blo + Alo*Bhi + Ahi*Bhi
 // reproduces the fp32 product to 2^-22 (measured 2e-9 on the headline shape; a single TF32 pass is 1e-5 and would be
 // amplified 500x by lambda).  (2) Accumulation: the tensor-core accumulator TRUNCATES (measured on B200: a K=32768 chain
 // of positive products comes out biased by -3e-6 relative).  The TMEM accumulator is therefore restarted every K = 32 and
@@ -154,16 +154,21 @@ cost_tc_kernel(const __grid_constant__ Params p)
             mbar_wait(full_bar(s), (uint32_t)(c / STAGES) & 1u);
             float4* hi = reinterpret_cast<float4*>(smem_gen + s * STAGE_BYTES);
             float4* lo = reinterpret_cast<float4*>(smem_gen + s * STAGE_BYTES + 2 * TILE_BYTES);
-            const int n4 = ntiles * (TILE_BYTES / 16);
-#pragma unroll 4
-            for (int i = st; i < n4; i += NUM_SPLIT_THREADS) {
-                const float4 x = hi[i];
-                uint4 h, l;
-                h.x = cvt_rna_tf32(x.x); h.y = cvt_rna_tf32(x.y); h.z = cvt_rna_tf32(x.z); h.w = cvt_rna_tf32(x.w);
-                l.x = cvt_rna_tf32(x.x - __uint_as_float(h.x)); l.y = cvt_rna_tf32(x.y - __uint_as_float(h.y));
-                l.z = cvt_rna_tf32(x.z - __uint_as_float(h.z)); l.w = cvt_rna_tf32(x.w - __uint_as_float(h.w));
-                reinterpret_cast<uint4*>(hi)[i] = h;
-                reinterpret_cast<uint4*>(lo)[i] = l;
+            // all loads of the chunk first (8 per tile and thread: one round trip to shared memory instead of a dependent
+            // load -> split -> store chain per float4), then the splits and the stores
+            const int nit = ntiles * (TILE_BYTES / 16 / NUM_SPLIT_THREADS);        // 8 or 16
+            float4 x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < nit) x[j] = hi[st + j * NUM_SPLIT_THREADS];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (j < nit) {
+                    uint4 h, l;
+                    split_tf32(x[j].x, h.x, l.x); split_tf32(x[j].y, h.y, l.y); split_tf32(x[j].z, h.z, l.z); split_tf32(x[j].w, h.w, l.w);
+                    reinterpret_cast<uint4*>(hi)[st + j * NUM_SPLIT_THREADS] = h;
+                    reinterpret_cast<uint4*>(lo)[st + j * NUM_SPLIT_THREADS] = l;
+                }
             }
             fence_proxy_async_smem();                           // generic-proxy writes -> visible to the tensor core
             mbar_arrive(ready_bar(s));

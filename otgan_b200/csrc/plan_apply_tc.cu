@@ -180,15 +180,15 @@ plan_apply_tc_kernel(const __grid_constant__ Params p)
                 mbar_wait(full_bar(s), ((uint32_t)(c / STAGES)) & 1u);
                 float4* hi = reinterpret_cast<float4*>(smem_gen + s * STAGE_BYTES + 2 * A_TILE);
                 float4* lo = reinterpret_cast<float4*>(smem_gen + s * STAGE_BYTES + 2 * A_TILE + B_TILE);
+                float4 x[B_TILE / 16 / NUM_SPLIT_THREADS];                  // all 8 loads first, then the splits and the stores
 #pragma unroll
-                for (int i = st_id; i < B_TILE / 16; i += NUM_SPLIT_THREADS) {
-                    const float4 x = hi[i];
+                for (int j = 0; j < B_TILE / 16 / NUM_SPLIT_THREADS; ++j) x[j] = hi[st_id + j * NUM_SPLIT_THREADS];
+#pragma unroll
+                for (int j = 0; j < B_TILE / 16 / NUM_SPLIT_THREADS; ++j) {
                     uint4 hh, ll;
-                    hh.x = cvt_rna_tf32(x.x); hh.y = cvt_rna_tf32(x.y); hh.z = cvt_rna_tf32(x.z); hh.w = cvt_rna_tf32(x.w);
-                    ll.x = cvt_rna_tf32(x.x - __uint_as_float(hh.x)); ll.y = cvt_rna_tf32(x.y - __uint_as_float(hh.y));
-                    ll.z = cvt_rna_tf32(x.z - __uint_as_float(hh.z)); ll.w = cvt_rna_tf32(x.w - __uint_as_float(hh.w));
-                    reinterpret_cast<uint4*>(hi)[i] = hh;
-                    reinterpret_cast<uint4*>(lo)[i] = ll;
+                    split_tf32(x[j].x, hh.x, ll.x); split_tf32(x[j].y, hh.y, ll.y); split_tf32(x[j].z, hh.z, ll.z); split_tf32(x[j].w, hh.w, ll.w);
+                    reinterpret_cast<uint4*>(hi)[st_id + j * NUM_SPLIT_THREADS] = hh;
+                    reinterpret_cast<uint4*>(lo)[st_id + j * NUM_SPLIT_THREADS] = ll;
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(ready_bar(s));

@@ -156,6 +156,16 @@ __device__ __forceinline__ uint32_t cvt_rna_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+// x = hi + lo for the 3xTF32 operand split: hi = x rounded to TF32 (nearest, ties away: add half an ulp of the 10-bit mantissa and
+// clear the 13 low bits), lo = x - hi exactly, handed to the tensor core as it is (the MMA reads only its TF32 bits: a truncation
+// of a remainder that is symmetric around zero, i.e. unbiased, 2^-21 of x at worst).  3 instructions per element.  On sm_100a
+// cvt.rna.tf32.f32 is not a single instruction: it compiles to VIADD + FSETP + SEL + LOP3 (the inf/NaN guard), and rounding lo as
+// well made the split 9 instructions per element -- the ncu source page showed the four split warps of cost_tc.cu busy ~100% of the
+// kernel (580 instructions per K-chunk each) while the tensor pipe idled at 36%.  Finite inputs only.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
 #endif  // __CUDACC__
 
 // ---------------------------------------------------------------------------------------------------- host side

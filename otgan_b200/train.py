@@ -137,8 +137,7 @@ class Trainer:
         # slab is a fraction of ONE tensor-core tile, so replicating the 66 us cost stage is cheaper than the extra collective
         shard = (self.rank, self.world) if (rows is not None and A.shape[0] // 2 > 128 and self.world % 2 == 0
                                             and os.environ.get("OTGAN_SHARD_COST", "1") == "1") else None
-        ga, gb, stats = matching.matching_step(fa, fb, a.sinkhorn_lambda, a.nr_sinkhorn_iter, rows=rows, shard=shard,
-                                               unit_rows=True)      # critic features are L2-normalised rows (models/*.py)
+        ga, gb, stats = matching.matching_step(fa, fb, a.sinkhorn_lambda, a.nr_sinkhorn_iter, rows=rows, shard=shard)
         return torch.cat(ga, 0), torch.cat(gb, 0), stats
 
     def step(self, x_real, u=None, apply_update=True):

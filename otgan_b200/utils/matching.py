@@ -118,13 +118,6 @@ def sinkhorn(L, lam, nr_iter, want_plan=True, impl=_lib.IMPL_AUTO, want_stats=Fa
     return P, ent, pc
 
 
-def _cost_impl(impl, unit_rows):
-    """unit_rows: the caller asserts that every feature row has L2 norm <= 1 (the critic head's output, models/dcgan.py:16-19):
-    AUTO then selects the fp16-split tensor-core cost and plan-apply kernels (csrc/cost_h.cu, csrc/plan_apply_h.cu), whose
-    operand planes hold |x| < 4 only."""
-    return _lib.IMPL_TCGEN05_UNIT if (unit_rows and impl == _lib.IMPL_AUTO) else impl
-
-
 def sharded_cost_blocks(A, B, h, lam, rows, rank, world, cost_kind=_lib.COST_COSINE, impl=_lib.IMPL_AUTO):
     """The six cost blocks with the ROWS sharded over the data-parallel ranks -- the reference's own partition
     (utils/matching.py:29-39: tower i computes `1 - features_a[i] . batch^T`, i.e. the row slab of its own rows) followed by its
@@ -155,7 +148,7 @@ def sharded_cost_blocks(A, B, h, lam, rows, rank, world, cost_kind=_lib.COST_COS
 
 
 def _two_batch_plans(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, cost_kind=_lib.COST_COSINE,
-                     impl=_lib.IMPL_AUTO, shard=None, unit_rows=False):
+                     impl=_lib.IMPL_AUTO, shard=None):
     """Cost blocks + Sinkhorn of utils/matching.py:11-61.  Returns (A, B, h, P[6,h,h], ent[6], pc[6]).
     shard = (rows, rank, world): compute only this rank's row slabs of the cost blocks and all-gather them."""
     _check_features(features_a, features_b)
@@ -166,11 +159,11 @@ def _two_batch_plans(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, 
     h = A.shape[0] // 2
     a1, a2, b1, b2 = A[:h], A[h:], B[:h], B[h:]
     if shard is not None:
-        L = sharded_cost_blocks(A, B, h, sinkhorn_lambda, shard[0], shard[1], shard[2], cost_kind, _cost_impl(impl, unit_rows))
+        L = sharded_cost_blocks(A, B, h, sinkhorn_lambda, shard[0], shard[1], shard[2], cost_kind, impl)
         P, ent, pc = sinkhorn(L, sinkhorn_lambda, nr_sinkhorn_iter, True, impl)
         return A, B, h, P, ent, pc
     # block order of utils/matching.py:41-43: a1a2, b2b1, a1b1, a1b2, a2b1, a2b2
-    L = cost_blocks([a1, b2, a1, a1, a2, a2], [a2, b1, b1, b2, b1, b2], sinkhorn_lambda, cost_kind, None, _cost_impl(impl, unit_rows))
+    L = cost_blocks([a1, b2, a1, a1, a2, a2], [a2, b1, b1, b2, b1, b2], sinkhorn_lambda, cost_kind, None, impl)
     P, ent, pc = sinkhorn(L, sinkhorn_lambda, nr_sinkhorn_iter, True, impl)
     return A, B, h, P, ent, pc
 
@@ -182,17 +175,17 @@ def get_matched_features_random(features_a, features_b):
     return features_a_a, features_b_b, features_b, features_a, torch.zeros((), device=features_a[0].device)
 
 
-def get_matched_features(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, impl=_lib.IMPL_AUTO, unit_rows=False):
-    """utils/matching.py:11-85.  unit_rows (addition): see _cost_impl."""
+def get_matched_features(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, impl=_lib.IMPL_AUTO):
+    """utils/matching.py:11-85."""
     lib = _lib.load()
-    A, B, h, P, ent, _pc = _two_batch_plans(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, impl=impl, unit_rows=unit_rows)
+    A, B, h, P, ent, _pc = _two_batch_plans(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, impl=impl)
     ngpu = len(features_a)
     N, D = A.shape
     outs = [torch.empty((N, D), device=A.device, dtype=torch.float32) for _ in range(4)]
     ws, ws_bytes = _plan_ws(A.device, h)
     rc = lib.otgan_matched_two_batch_f32(h, D, P.data_ptr(), A.data_ptr(), B.data_ptr(), A.stride(0),
                                          outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(),
-                                         D, ws.data_ptr(), ws_bytes, _cost_impl(impl, unit_rows), _stream())
+                                         D, ws.data_ptr(), ws_bytes, impl, _stream())
     _lib.check(rc, "otgan_matched_two_batch_f32")
     entropy = ent.sum() / 6.0       # sum(entropy)/len(entropy), utils/matching.py:61
     f_aa, f_bb, f_ab, f_ba = (list(torch.chunk(o, ngpu, dim=0)) for o in outs)
@@ -242,19 +235,16 @@ def calc_distance(features_a, features_b, matched_features):
     return out[0]
 
 
-def matching_step(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, impl=_lib.IMPL_AUTO, rows=None, shard=None,
-                  unit_rows=False):
+def matching_step(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, impl=_lib.IMPL_AUTO, rows=None, shard=None):
     """Fused form of train.py:96-128 for the two-batch matching: returns (grad_a list, grad_b list, stats) where
     grad_a[i] = f_aa[i] - f_ab[i] (grad_ys of the fake features, train.py:111), grad_b[i] = f_bb[i] - f_ba[i]
     (grad_ys of the real features, train.py:126) and stats is a 2-element CUDA tensor [distance, entropy]
     (calc_distance via the <P,C> identity; utils/matching.py:61).  rows = (lo, hi): only these rows of grad_a / grad_b are
     needed (a data-parallel rank's own towers) -- the half-blocks / row tiles outside the range are skipped and their rows left
-    undefined.  shard = (rank, world): additionally shard the cost blocks' rows over the ranks (sharded_cost_blocks).
-    unit_rows: the features are L2-normalised rows (the critic head's output): selects the fp16-split cost kernel (_cost_impl)."""
+    undefined.  shard = (rank, world): additionally shard the cost blocks' rows over the ranks (sharded_cost_blocks)."""
     lib = _lib.load()
     A, B, h, P, ent, pc = _two_batch_plans(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, impl=impl,
-                                           shard=(rows, shard[0], shard[1]) if (shard is not None and rows is not None) else None,
-                                           unit_rows=unit_rows)
+                                           shard=(rows, shard[0], shard[1]) if (shard is not None and rows is not None) else None)
     ngpu = len(features_a)
     N, D = A.shape
     Ga = torch.empty((N, D), device=A.device, dtype=torch.float32)
@@ -262,11 +252,10 @@ def matching_step(features_a, features_b, sinkhorn_lambda, nr_sinkhorn_iter, imp
     ws, ws_bytes = _plan_ws(A.device, h)
     if rows is None:
         rc = lib.otgan_grad_features_f32(h, D, P.data_ptr(), A.data_ptr(), B.data_ptr(), A.stride(0), Ga.data_ptr(),
-                                         Gb.data_ptr(), D, ws.data_ptr(), ws_bytes, _cost_impl(impl, unit_rows), _stream())
+                                         Gb.data_ptr(), D, ws.data_ptr(), ws_bytes, impl, _stream())
     else:
         rc = lib.otgan_grad_features_rows_f32(h, D, P.data_ptr(), A.data_ptr(), B.data_ptr(), A.stride(0), Ga.data_ptr(),
-                                              Gb.data_ptr(), D, int(rows[0]), int(rows[1]), ws.data_ptr(), ws_bytes,
-                                              _cost_impl(impl, unit_rows), _stream())
+                                              Gb.data_ptr(), D, int(rows[0]), int(rows[1]), ws.data_ptr(), ws_bytes, impl, _stream())
     _lib.check(rc, "otgan_grad_features_f32")
     stats = torch.empty((2,), device=A.device, dtype=torch.float32)
     rc = lib.otgan_distance_from_pc_f32(pc.data_ptr(), ent.data_ptr(), N, stats.data_ptr(), _stream())

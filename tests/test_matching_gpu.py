@@ -95,30 +95,29 @@ def test_cost_blocks_kernel(M, rows, cols, D, kind):
 
 
 @pytest.mark.parametrize("h,D", [(128, 32768), (128, 7296), (64, 32768), (128, 4096), (96, 2052), (256, 8192), (200, 2304), (128, 131072)])
-def test_cost_blocks_fp16_split_unit_rows(M, h, D):
-    """The fp16-split tensor-core cost kernel (csrc/cost_h.cu; IMPL_TCGEN05_UNIT: inputs are L2-normalised rows) on the six-block
-    two-batch pattern: same gate as the 3xTF32 kernel against the fp64 oracle, ragged tiles (h = 96, 200), a K tail that is not
-    a multiple of the 64-element stage (D = 2052, 7296 = 114 stages), and cfg5's D = 131072.  Also the single-batch X == Y case
-    (diagonal tiles load one operand)."""
+def test_cost_blocks_tcgen05_unit_rows_sweep(M, h, D):
+    """The 3xTF32 tensor-core cost kernel on L2-normalised rows (what the critic head emits) in the six-block two-batch pattern:
+    ragged tiles (h = 96, 200), K tails that are not a multiple of the 32-element chunk (D = 2052), cfg4's D = 7296 and cfg5's
+    D = 131072 against the fp64 oracle.  Also the single-batch X == Y case (diagonal tiles load one operand, +999 diagonal)."""
     from otgan_b200 import _lib
     A, B = mo.synth_embeddings(2 * h, D, 1, "clustered", sigma=1.0), mo.synth_embeddings(2 * h, D, 2, "clustered", sigma=1.0)
     Ad, Bd = dev(A), dev(B)
     a1, a2, b1, b2 = Ad[:h], Ad[h:], Bd[:h], Bd[h:]
     X, Y = [a1, b2, a1, a1, a2, a2], [a2, b1, b1, b2, b1, b2]
     lam = 500.0
-    Lh = M.cost_blocks(X, Y, lam, 0, None, _lib.IMPL_TCGEN05_UNIT)
+    Lh = M.cost_blocks(X, Y, lam, 0, None, _lib.IMPL_TCGEN05)
     torch.cuda.synchronize()
     A64, B64 = A.astype(np.float64), B.astype(np.float64)
     xs = [A64[:h], B64[h:], A64[:h], A64[:h], A64[h:], A64[h:]]
     ys = [A64[h:], B64[:h], B64[:h], B64[h:], B64[:h], B64[h:]]
     for k in range(6):
-        assert relerr(Lh[k] / -lam, mo.cosine_cost(xs[k], ys[k])) < TOL_C, ("fp16-split vs fp64", k)
+        assert relerr(Lh[k] / -lam, mo.cosine_cost(xs[k], ys[k])) < TOL_C, ("tcgen05 vs fp64", k)
     if h <= 128 and D <= 8192:
-        Ls = M.cost_blocks([Ad, Bd, Ad], [Ad, Bd, Bd], lam, 0, [999.0, 999.0, 0.0], _lib.IMPL_TCGEN05_UNIT)
+        Ls = M.cost_blocks([Ad, Bd, Ad], [Ad, Bd, Bd], lam, 0, [999.0, 999.0, 0.0], _lib.IMPL_TCGEN05)
         torch.cuda.synchronize()
         for k, (x, y, dg) in enumerate(((A64, A64, 999.0), (B64, B64, 999.0), (A64, B64, 0.0))):
             C = mo.cosine_cost(x, y) + dg * np.eye(2 * h)
-            assert relerr(Ls[k] / -lam, C) < TOL_C, ("fp16-split single-batch vs fp64", k)
+            assert relerr(Ls[k] / -lam, C) < TOL_C, ("tcgen05 single-batch vs fp64", k)
 
 
 @pytest.mark.parametrize("h,D,kind", [(128, 32768, 0), (128, 7296, 0), (64, 32768, 0), (128, 4096, 0), (96, 1000, 0),
@@ -317,10 +316,10 @@ def test_plan_apply_kernels(M, h, D, impl):
 
 
 @pytest.mark.parametrize("h,D", [(128, 32768), (128, 7296), (64, 4096), (96, 2052), (256, 8192), (200, 2304)])
-def test_plan_apply_fp16_split_unit_rows(M, h, D):
-    """The fp16-split tensor-core plan-apply kernel (csrc/plan_apply_h.cu; IMPL_TCGEN05_UNIT: L2-normalised feature rows, P a
-    plan): matched features and the fused grad_ys against fp64, same gate as the 3xTF32 kernel; ragged h and D tails; and the
-    row-range form (one rank's towers) against the full result, bit for bit."""
+def test_plan_apply_tcgen05_plan_like_inputs(M, h, D):
+    """The tensor-core plan-apply kernel on the inputs the train loop gives it (L2-normalised non-negative feature rows, peaked
+    plans): matched features and the fused grad_ys against fp64; ragged h and D tails; and the row-range form (one rank's
+    towers) against the full result, bit for bit."""
     from otgan_b200 import _lib
     lib = _lib.load()
     ws, ws_bytes = M._plan_ws(torch.device("cuda", 0), h)
@@ -334,7 +333,7 @@ def test_plan_apply_fp16_split_unit_rows(M, h, D):
     s = torch.cuda.current_stream().cuda_stream
     rc = lib.otgan_matched_two_batch_f32(h, D, Pd.data_ptr(), Ad.data_ptr(), Bd.data_ptr(), D, outs[0].data_ptr(),
                                          outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(), D, ws.data_ptr(),
-                                         ws_bytes, _lib.IMPL_TCGEN05_UNIT, s)
+                                         ws_bytes, _lib.IMPL_TCGEN05, s)
     assert rc == 0, lib.otgan_last_error()
     ref = mo._combine_two_batch(list(P64), A64[:h], A64[h:], B64[:h], B64[h:])
     # all-positive products and an accumulator that truncates (cost_tc.cu, note 2): the chain of 3 terms x h / 16 MMAs per
@@ -344,7 +343,7 @@ def test_plan_apply_fp16_split_unit_rows(M, h, D):
         assert relerr(o, r) < tol
     Ga, Gb = torch.empty(2 * h, D, device="cuda"), torch.empty(2 * h, D, device="cuda")
     rc = lib.otgan_grad_features_f32(h, D, Pd.data_ptr(), Ad.data_ptr(), Bd.data_ptr(), D, Ga.data_ptr(), Gb.data_ptr(), D,
-                                     ws.data_ptr(), ws_bytes, _lib.IMPL_TCGEN05_UNIT, s)
+                                     ws.data_ptr(), ws_bytes, _lib.IMPL_TCGEN05, s)
     assert rc == 0, lib.otgan_last_error()
     ra, rb = mo.fused_grad_features(list(P64), A64[:h], A64[h:], B64[:h], B64[h:])
     scale = max(np.abs(ref[0]).max(), np.abs(ref[2]).max())          # grad_ys = f_aa - f_ab: gate relative to the features' scale
@@ -353,14 +352,14 @@ def test_plan_apply_fp16_split_unit_rows(M, h, D):
         lo, hi = h // 2, h + h // 2
         Ga2, Gb2 = torch.zeros_like(Ga), torch.zeros_like(Gb)
         rc = lib.otgan_grad_features_rows_f32(h, D, Pd.data_ptr(), Ad.data_ptr(), Bd.data_ptr(), D, Ga2.data_ptr(), Gb2.data_ptr(), D,
-                                              lo, hi, ws.data_ptr(), ws_bytes, _lib.IMPL_TCGEN05_UNIT, s)
+                                              lo, hi, ws.data_ptr(), ws_bytes, _lib.IMPL_TCGEN05, s)
         assert rc == 0, lib.otgan_last_error()
         assert torch.equal(Ga2[lo:hi], Ga[lo:hi]) and torch.equal(Gb2[lo:hi], Gb[lo:hi])
 
 
-def test_matching_step_unit_rows_matches_general_path(M):
-    """matching_step(unit_rows=True) (what the train loop calls: fp16-split cost + plan-apply kernels) against the general 3xTF32
-    path and the fp64 oracle at the headline size."""
+def test_matching_step_headline_vs_oracle(M):
+    """matching_step (what the train loop calls: fused grad_ys + distance / entropy from <P,C>) against the fp64 oracle at the
+    headline size."""
     N, D, G, lam, T = 256, 32768, 2, 500.0, 100
     A, B = mo.synth_embeddings(N, D, 1, "clustered", sigma=1.0), mo.synth_embeddings(N, D, 2, "clustered", sigma=1.0)
     fa, fb = list(np.split(A, G)), list(np.split(B, G))
@@ -369,14 +368,13 @@ def test_matching_step_unit_rows_matches_general_path(M):
     ref32 = mo.get_matched_features(fa, fb, lam, T, dtype=np.float32)
     tol = tol_f(ref[:4], ref32[:4], c_fp32_two_batch(A, B, lam, T))
     scale = np.abs(np.concatenate(ref[0])).max()
-    for unit in (True, False):
-        ga, gb, stats = M.matching_step(towers(A, G), towers(B, G), lam, T, unit_rows=unit)
-        torch.cuda.synchronize()
-        ea = np.abs(torch.cat(ga).cpu().double().numpy() - np.concatenate(rga)).max() / scale
-        eb = np.abs(torch.cat(gb).cpu().double().numpy() - np.concatenate(rgb)).max() / scale
-        assert ea < tol and eb < tol, (unit, ea, eb, tol)
-        assert abs(float(stats[0]) - mo.calc_distance(fa, fb, ref)) < TOL_DIST
-        assert abs(float(stats[1]) - ref[4]) < TOL_ENT * abs(ref[4])
+    ga, gb, stats = M.matching_step(towers(A, G), towers(B, G), lam, T)
+    torch.cuda.synchronize()
+    ea = np.abs(torch.cat(ga).cpu().double().numpy() - np.concatenate(rga)).max() / scale
+    eb = np.abs(torch.cat(gb).cpu().double().numpy() - np.concatenate(rgb)).max() / scale
+    assert ea < tol and eb < tol, (ea, eb, tol)
+    assert abs(float(stats[0]) - mo.calc_distance(fa, fb, ref)) < TOL_DIST
+    assert abs(float(stats[1]) - ref[4]) < TOL_ENT * abs(ref[4])
 
 
 # ----------------------------------------------------------------------------------------------- API level
