@@ -869,33 +869,34 @@ struct SubMap {
     int kh, kw, n1h, n1w;
     int dmin_h[2], dmin_w[2];          // first low-res offset of parity 0 / 1
     int idx_h[2][8], idx_w[2][8];      // idx[a][k] = floor((a + k - pad) / 2) - dmin[a]  in [0, n1)
+    // idx is non-decreasing in k, so the taps that fold onto one sub-row / sub-column are CONSECUTIVE: [lo, hi)
+    unsigned char h_lo[2][8], h_hi[2][8], w_lo[2][8], w_hi[2][8];
 };
 
 // w_sub[cls = 2a+b][co][(ri * n1w + ci) * Cin + c] = sum_{kh: idx_h[a][kh] == ri} sum_{kw: idx_w[b][kw] == ci} w[co][(kh * KW + kw) * Cin + c]
-// One thread per float4 of channels (Cin % 4 == 0): streams the filter once (read w, write 1.44x as much).
+// One CTA per (filter co, parity class): it walks the class's slots and, per slot, only the 1-4 taps that fold onto it; threads =
+// float4s of input channels.  The four classes of a filter are neighbouring CTAs, so the filter row (kh*kw*Cin floats) comes from
+// HBM once and from L2 three times.  (Round 1 ran one flat index over all outputs: four 64-bit div/mods and a scan over all kh x kw
+// taps per float4 made it instruction-bound at 2.5 TB/s.)
 __global__ void __launch_bounds__(256)
 up2_presum_kernel(SubMap m, int Cout, int Cin, const float* __restrict__ w, float* __restrict__ w_sub)
 {
     const int slots = m.n1h * m.n1w, C4 = Cin >> 2;
-    const size_t total = (size_t)4 * Cout * slots * C4;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(i % C4);
-        size_t r = i / C4;
-        const int slot = (int)(r % slots); r /= slots;
-        const int co = (int)(r % Cout);
-        const int cls = (int)(r / Cout);
-        const int a = cls >> 1, b = cls & 1, ri = slot / m.n1w, ci = slot % m.n1w;
-        const float4* wrow = reinterpret_cast<const float4*>(w + (size_t)co * m.kh * m.kw * Cin) + c4;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int kh = 0; kh < m.kh; ++kh) {
-            if (m.idx_h[a][kh] != ri) continue;
-            for (int kw = 0; kw < m.kw; ++kw) {
-                if (m.idx_w[b][kw] != ci) continue;
-                const float4 v = __ldg(wrow + (size_t)(kh * m.kw + kw) * C4);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            }
+    const int co = blockIdx.x >> 2, cls = blockIdx.x & 3, a = cls >> 1, b = cls & 1;
+    const float4* wrow = reinterpret_cast<const float4*>(w + (size_t)co * m.kh * m.kw * Cin);
+    float4* orow = reinterpret_cast<float4*>(w_sub) + ((size_t)cls * Cout + co) * slots * C4;
+    for (int slot = 0; slot < slots; ++slot) {
+        const int ri = slot / m.n1w, ci = slot - ri * m.n1w;
+        const int h0 = m.h_lo[a][ri], h1 = m.h_hi[a][ri], w0 = m.w_lo[b][ci], w1 = m.w_hi[b][ci];
+        for (int c4 = threadIdx.x; c4 < C4; c4 += blockDim.x) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int kh = h0; kh < h1; ++kh)
+                for (int kw = w0; kw < w1; ++kw) {
+                    const float4 v = __ldg(wrow + (size_t)(kh * m.kw + kw) * C4 + c4);
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+            orow[(size_t)slot * C4 + c4] = acc;
         }
-        reinterpret_cast<float4*>(w_sub)[i] = acc;
     }
 }
 
@@ -928,54 +929,54 @@ up2_unsum_kernel(SubMap m, int Cout, int Cin, const float* __restrict__ dw_sub, 
 // The same two maps in the layouts whose contiguous axis is the OUTPUT channel (float4 along co):
 //   w_sub_t[cls][ci][slot][co] = sum_{taps t in (cls, slot)} w_ihwo[ci][t][co]      (the dgrad operand of the fused-upsample layers,
 //                                                                                  built from the IHWO filter in one pass)
+// One CTA per (input channel ci, parity class), like up2_presum_kernel.
 __global__ void __launch_bounds__(256)
 up2_presum_ihwo_kernel(SubMap m, int Cout, int Cin, const float* __restrict__ w_ihwo, float* __restrict__ w_sub_t)
 {
     const int slots = m.n1h * m.n1w, C4 = Cout >> 2, taps = m.kh * m.kw;
-    const size_t total = (size_t)4 * Cin * slots * C4;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(i % C4);
-        size_t r = i / C4;
-        const int slot = (int)(r % slots); r /= slots;
-        const int ci = (int)(r % Cin);
-        const int cls = (int)(r / Cin);
-        const int a = cls >> 1, b = cls & 1, ri = slot / m.n1w, cj = slot % m.n1w;
-        const float4* src = reinterpret_cast<const float4*>(w_ihwo + (size_t)ci * taps * Cout) + c4;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int kh = 0; kh < m.kh; ++kh) {
-            if (m.idx_h[a][kh] != ri) continue;
-            for (int kw = 0; kw < m.kw; ++kw) {
-                if (m.idx_w[b][kw] != cj) continue;
-                const float4 v = __ldg(src + (size_t)(kh * m.kw + kw) * C4);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            }
+    const int ci = blockIdx.x >> 2, cls = blockIdx.x & 3, a = cls >> 1, b = cls & 1;
+    const float4* src = reinterpret_cast<const float4*>(w_ihwo + (size_t)ci * taps * Cout);
+    float4* orow = reinterpret_cast<float4*>(w_sub_t) + ((size_t)cls * Cin + ci) * slots * C4;
+    for (int slot = 0; slot < slots; ++slot) {
+        const int ri = slot / m.n1w, cj = slot - ri * m.n1w;
+        const int h0 = m.h_lo[a][ri], h1 = m.h_hi[a][ri], w0 = m.w_lo[b][cj], w1 = m.w_hi[b][cj];
+        for (int c4 = threadIdx.x; c4 < C4; c4 += blockDim.x) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int kh = h0; kh < h1; ++kh)
+                for (int kw = w0; kw < w1; ++kw) {
+                    const float4 v = __ldg(src + (size_t)(kh * m.kw + kw) * C4 + c4);
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+            orow[(size_t)slot * C4 + c4] = acc;
         }
-        reinterpret_cast<float4*>(w_sub_t)[i] = acc;
     }
 }
 //   dw_hwio[t][ci][co] = sum_{a, b} dw_sub_hwio[2a+b][slot(a, b, t)][ci][co]          (chain rule of the pre-sum on HWIO gradients)
+// One CTA per (tap, input channel) row of the gradient; threads = float4s of output channels.
 __global__ void __launch_bounds__(256)
 up2_unsum_hwio_kernel(SubMap m, int Cout, int Cin, const float* __restrict__ dw_sub, float* __restrict__ dw)
 {
-    const int slots = m.n1h * m.n1w, taps = m.kh * m.kw, C4 = Cout >> 2;
-    const size_t total = (size_t)taps * Cin * C4;
+    const int slots = m.n1h * m.n1w, C4 = Cout >> 2;
+    const int t = blockIdx.x / Cin, ci = blockIdx.x - t * Cin;
+    const int kh = t / m.kw, kw = t - kh * m.kw;
     const float4* src = reinterpret_cast<const float4*>(dw_sub);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(i % C4);
-        size_t r = i / C4;
-        const int ci = (int)(r % Cin);
-        const int t = (int)(r / Cin);
-        const int kh = t / m.kw, kw = t % m.kw;
+    const float4* rows[4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int slot = m.idx_h[a][kh] * m.n1w + m.idx_w[b][kw];
+            rows[2 * a + b] = src + (((size_t)(2 * a + b) * slots + slot) * Cin + ci) * C4;
+        }
+    float4* orow = reinterpret_cast<float4*>(dw) + (size_t)blockIdx.x * C4;
+    for (int c4 = threadIdx.x; c4 < C4; c4 += blockDim.x) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const int slot = m.idx_h[a][kh] * m.n1w + m.idx_w[b][kw];
-                const float4 v = __ldg(src + (((size_t)(2 * a + b) * slots + slot) * Cin + ci) * C4 + c4);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            }
-        reinterpret_cast<float4*>(dw)[i] = acc;
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = __ldg(rows[q] + c4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        orow[c4] = acc;
     }
 }
 
@@ -1626,6 +1627,13 @@ bool make_submap(SubMap& m, int kh, int kw, int pt, int pl)
     }
     if (n1[0][0] != n1[0][1] || n1[1][0] != n1[1][1]) return false;     // both parities must see the same number of sub-taps
     m.n1h = n1[0][0]; m.n1w = n1[1][0];
+    for (int a = 0; a < 2; ++a) {
+        for (int r = 0; r < 8; ++r) { m.h_lo[a][r] = m.h_hi[a][r] = m.w_lo[a][r] = m.w_hi[a][r] = 0; }
+        for (int k = kh - 1; k >= 0; --k) m.h_lo[a][m.idx_h[a][k]] = (unsigned char)k;
+        for (int k = 0; k < kh; ++k) m.h_hi[a][m.idx_h[a][k]] = (unsigned char)(k + 1);
+        for (int k = kw - 1; k >= 0; --k) m.w_lo[a][m.idx_w[a][k]] = (unsigned char)k;
+        for (int k = 0; k < kw; ++k) m.w_hi[a][m.idx_w[a][k]] = (unsigned char)(k + 1);
+    }
     return 4 * m.n1h * m.n1w <= MAX_TAPS;
 }
 
@@ -1653,7 +1661,7 @@ int up2_presum_launch(int Cout, int kh, int kw, int Cin, int pt, int pl, const f
     SubMap m;
     if (!make_submap(m, kh, kw, pt, pl)) { set_error("up2_presum: unsupported filter geometry %dx%d pad %d,%d", kh, kw, pt, pl); return OTGAN_EUNSUPPORTED; }
     OTGAN_REQUIRE(Cin % 4 == 0 && aligned16(w) && aligned16(w_sub), "up2_presum: Cin must be a multiple of 4, buffers 16-byte aligned");
-    up2_presum_kernel<<<ew_grid((size_t)4 * Cout * m.n1h * m.n1w * (Cin / 4)), 256, 0, stream>>>(m, Cout, Cin, w, w_sub);
+    up2_presum_kernel<<<4 * Cout, (Cin / 4) < 256 ? ((Cin / 4 + 31) / 32) * 32 : 256, 0, stream>>>(m, Cout, Cin, w, w_sub);
     OTGAN_CHECK_LAUNCH("up2_presum_kernel");
     return OTGAN_OK;
 }
@@ -1673,7 +1681,7 @@ int up2_presum_ihwo_launch(int Cout, int kh, int kw, int Cin, int pt, int pl, co
     SubMap m;
     if (!make_submap(m, kh, kw, pt, pl)) { set_error("up2_presum_ihwo: unsupported filter geometry %dx%d pad %d,%d", kh, kw, pt, pl); return OTGAN_EUNSUPPORTED; }
     OTGAN_REQUIRE(Cout % 4 == 0 && aligned16(w_ihwo) && aligned16(w_sub_t), "up2_presum_ihwo: Cout must be a multiple of 4, buffers 16-byte aligned");
-    up2_presum_ihwo_kernel<<<ew_grid((size_t)4 * Cin * m.n1h * m.n1w * (Cout / 4)), 256, 0, stream>>>(m, Cout, Cin, w_ihwo, w_sub_t);
+    up2_presum_ihwo_kernel<<<4 * Cin, (Cout / 4) < 256 ? ((Cout / 4 + 31) / 32) * 32 : 256, 0, stream>>>(m, Cout, Cin, w_ihwo, w_sub_t);
     OTGAN_CHECK_LAUNCH("up2_presum_ihwo_kernel");
     return OTGAN_OK;
 }
@@ -1683,7 +1691,7 @@ int up2_unsum_hwio_launch(int Cout, int kh, int kw, int Cin, int pt, int pl, con
     SubMap m;
     if (!make_submap(m, kh, kw, pt, pl)) { set_error("up2_unsum_hwio: unsupported filter geometry %dx%d pad %d,%d", kh, kw, pt, pl); return OTGAN_EUNSUPPORTED; }
     OTGAN_REQUIRE(Cout % 4 == 0 && aligned16(dw_sub) && aligned16(dw), "up2_unsum_hwio: Cout must be a multiple of 4, buffers 16-byte aligned");
-    up2_unsum_hwio_kernel<<<ew_grid((size_t)kh * kw * Cin * (Cout / 4)), 256, 0, stream>>>(m, Cout, Cin, dw_sub, dw);
+    up2_unsum_hwio_kernel<<<kh * kw * Cin, (Cout / 4) < 256 ? ((Cout / 4 + 31) / 32) * 32 : 256, 0, stream>>>(m, Cout, Cin, dw_sub, dw);
     OTGAN_CHECK_LAUNCH("up2_unsum_hwio_kernel");
     return OTGAN_OK;
 }

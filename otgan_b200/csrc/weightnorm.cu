@@ -257,6 +257,20 @@ int plan_slices(int K, int C, int* rows_per_slice)
     return ceil_div(K, rps);
 }
 
+// K-slices of the float4 streaming kernels: their column blocks are 128 floats wide (32 float4), so the tiled plan above (32-float
+// blocks) gave the 1024-channel layers a grid of 8 x 18 = 144 CTAs -- one per SM, one or two loads in flight per thread, 1.3 TB/s.
+// Eight CTAs per SM's worth of slices (at most the 64 partial rows the workspace and the apply kernels are sized for).
+int plan_slices4(int K, int C, int* rows_per_slice)
+{
+    const int col_blocks = ceil_div(C / 4, 32);
+    int KS = (8 * kNumSMs) / (col_blocks > 0 ? col_blocks : 1);
+    KS = KS < 1 ? 1 : (KS > 64 ? 64 : KS);
+    int rps = ceil_div(K, KS);
+    rps = ceil_div(rps, 8) * 8;                   // whole 8-row passes of a CTA per slice
+    *rows_per_slice = rps;
+    return ceil_div(K, rps);
+}
+
 }  // namespace
 
 size_t weightnorm_workspace_bytes(int K, int C) { (void)K; return (size_t)64 * C * sizeof(float); }
@@ -264,8 +278,12 @@ size_t weightnorm_workspace_bytes(int K, int C) { (void)K; return (size_t)64 * C
 int weightnorm_fwd_ex_launch(int K, int C, const float* V, const float* g, const int* perm, int cin, long long ldtap, long long ldrow,
                              float* Wt, float* inv, void* ws, cudaStream_t stream)
 {
+    // The squared-norm pass takes the K-slices of the streaming form whenever that form could have been used (same slices, same
+    // summation order => bit-identical 1/||V|| from the fused and the stand-alone nodes; the tensor cores read W as TF32 by
+    // truncation, so a last-bit difference of a filter's scale moves a few of its weights by 2^-10 and, through ReLU sign flips,
+    // single gradient entries by percents: tests/test_conv_gpu.py::test_wn_fusion_matches_the_unfused_nodes compares the two)
     int rps;
-    const int KS = plan_slices(K, C, &rps);
+    const int KS = (perm == nullptr && (K & 3) == 0 && (C & 3) == 0) ? plan_slices4(K, C, &rps) : plan_slices(K, C, &rps);
     float* partial = reinterpret_cast<float*>(ws);
     const WtAddr wa{cin, ldrow, ldtap};
     wn_col_partial_kernel<0><<<dim3(ceil_div(C, TS), KS), 256, 0, stream>>>(K, C, rps, V, nullptr, partial, perm, wa);
@@ -304,7 +322,7 @@ int weightnorm_bwd_launch(int K, int C, const float* V, const float* g, const fl
 int weightnorm_fwd2_launch(int K, int C, int T, const float* V, const float* g, float* Wt, float* ihwo, float* inv, void* ws, cudaStream_t stream)
 {
     int rps;
-    const int KS = plan_slices(K, C, &rps);
+    const int KS = plan_slices4(K, C, &rps);
     float* partial = reinterpret_cast<float*>(ws);
     wn_coldot4_kernel<<<dim3(ceil_div(C / 4, 32), KS), 256, 0, stream>>>(K, C / 4, rps, reinterpret_cast<const float4*>(V),
                                                                        reinterpret_cast<const float4*>(V), reinterpret_cast<float4*>(partial));
@@ -319,7 +337,7 @@ int weightnorm_bwd_hwio_launch(int K, int C, const float* V, const float* g, con
                                void* ws, cudaStream_t stream)
 {
     int rps;
-    const int KS = plan_slices(K, C, &rps);
+    const int KS = plan_slices4(K, C, &rps);
     float* partial = reinterpret_cast<float*>(ws);
     wn_coldot4_kernel<<<dim3(ceil_div(C / 4, 32), KS), 256, 0, stream>>>(K, C / 4, rps, reinterpret_cast<const float4*>(dW),
                                                                        reinterpret_cast<const float4*>(V), reinterpret_cast<float4*>(partial));
