@@ -26,11 +26,13 @@
 // memory traffic per half-step is 16 KB (a 1x32 tiling needs 64 KB and is crossbar-bound; 8x8 needs a 4th shuffle stage).  L0 stays in
 // shared memory, plain and transposed, for the slow path and the epilogue.
 //
-// Code size matters as much as arithmetic here: the slow path and the epilogue run once or twice per launch, COLD.  Written
-// on the register tiles (fully unrolled: 64 double-precision exponentials per thread, three call sites) they were 12 000
-// instructions = 190 KB of straight-line code, and the ncu source page showed half of the kernel's 140 us at T = 100 in
-// instruction-fetch stalls of code executed once.  They are therefore ROLLED loops over rows (one warp per row, four rows in
-// flight, results through the KX staging tile, then 32 LDS.128 into the two register copies), one call site each: ~10x less code.
+// The slow path and the epilogue are ROLLED loops over rows (one warp per row, four rows in flight, results through the KX staging
+// tile, then 32 LDS.128 into the two register copies), one call site each.  Written on the register tiles (fully unrolled, three
+// call sites) they were 12 000 SASS instructions of straight-line code executed once or twice per launch; rolling them did not
+// change the kernel time by itself (the fp64 arithmetic was the cost, see above) but is what made the error-free fp32 form -- ~35
+// operations per element -- affordable in code size (4 800 instructions in total).  The epilogue needs no exponential at all:
+// P_ij = u'_i K_ij v_j with u' from one more row half-step on the register copy of K.
+// Phase clocks: tools/sinkhorn_phases.cu compiles this file with OTGAN_SINKHORN_CLOCKS.
 #include "common.cuh"
 #include <math.h>
 #include <stddef.h>
