@@ -104,7 +104,7 @@ def workload_config(world, workload):
            "conv_backend": "libotgan tcgen05 implicit-GEMM kernels (fprop / dgrad / wgrad, TF32 operands, fp32 accumulation) for every "
                            "convolution of the step; the generator's resize_nearest_neighbor + 5x5 convolution pairs run as the fused "
                            "sub-pixel form (4 parity classes x 3x3 pre-summed sub-filters on the low-resolution input: same algebra, "
-                           "9 instead of 25 taps); the 100-wide dense layer is a cuBLAS call",
+                           "9 instead of 25 taps); the 100-wide dense layer runs on them as a 1x1 convolution",
            "precision": "fp32 storage everywhere; matching kernels are fp32-exact (3xTF32 operands + fp32 register accumulation); "
                         "convolutions read the fp32 tensors as TF32 on the tensor cores (the math class of cuDNN's default fp32 convolution)",
            "l2_policy": "per-step working set (activations + 72 M parameters + Adam state, > 1 GB) exceeds the 126 MB L2; the "
@@ -762,22 +762,46 @@ def run_ours(args):
             barrier()
             n_launch = _lib.launch_count() + tr.replayed_launches      # eager launches + kernels inside replayed graphs
             t_dev = e0.elapsed_time(e1)
-            # ---- end to end: pinned host images -> H2D -> step -> D2H of [distance, entropy], every step
-            for i in range(2):
-                stats_host.copy_(tr.step(e2e_input(i))[1], non_blocking=True)
+            # ---- end to end through the public API, the way otgan_b200.train.main drives it: pinned host images -> Trainer.stage
+            # (H2D on a copy stream) -> Trainer.step -> Trainer.fetch_async (D2H of [distance, entropy]) -> host read, EVERY step.
+            # Software-pipelined: the upload of step k+1 and the host's read of step k-1 happen while step k computes.
+            def e2e_pipelined(nsteps):
+                staged = tr.stage(host_imgs[0])
+                pending = None
+                for i in range(nsteps):
+                    _, st = tr.step(staged)
+                    staged = tr.stage(host_imgs[(i + 1) % 8])
+                    hnd = tr.fetch_async(st)
+                    if pending is not None:
+                        pending.result()               # the host reads (distance, entropy) of the previous step
+                    pending = hnd
+                return pending.result()
+
+            e2e_pipelined(2)
             barrier()
             e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e2.record(stream)
-            for i in range(args.steps):
-                stats_host.copy_(tr.step(e2e_input(i))[1], non_blocking=True)
-                stream.synchronize()                   # the host reads (distance, entropy) every step, like sess.run
+            e2e_pipelined(args.steps)
             e3.record(stream)
             barrier()
             t_e2e = e2.elapsed_time(e3)
+            # ---- the same with sess.run semantics (upload, step, read back, block -- every step): what the pipelining buys
+            for i in range(2):
+                stats_host.copy_(tr.step(e2e_input(i))[1], non_blocking=True)
+            barrier()
+            e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e4.record(stream)
+            for i in range(args.steps):
+                stats_host.copy_(tr.step(e2e_input(i))[1], non_blocking=True)
+                stream.synchronize()                   # the host reads (distance, entropy) every step, like sess.run
+            e5.record(stream)
+            barrier()
+            measure.t_blocking = e4.elapsed_time(e5)
             sampler.stop_flag = True
             sampler.join()
             return t_dev, t_e2e, n_launch, sampler
 
+        measure.t_blocking = 0.0
         ms_total, ms_e2e, launches, sampler = measure()
         bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
         remeasured = False
@@ -788,6 +812,7 @@ def run_ours(args):
             ms_total, ms_e2e, launches, sampler = measure()
             remeasured = True
         h2d, d2h = bs * 32 * 32 * 3 * 4 * world, 8
+        ms_blocking = measure.t_blocking
     else:
         sampler = ClockSampler(local)
         sampler.start()
@@ -796,6 +821,7 @@ def run_ours(args):
         sampler.join()
         ms_total = (res2["ms_per_step"] * args.steps) if rank == 0 else 0.0
         ms_e2e, launches, h2d, d2h = ms_total, int(res2["gpu_launches_per_step"] * args.steps) if rank == 0 else 0, 0, 0
+        ms_blocking = 0.0
         remeasured = False
 
     t = torch.tensor([ms_total, ms_e2e], device=devv, dtype=torch.float64)
@@ -842,7 +868,10 @@ def run_ours(args):
             "sinkhorn_iters_per_sec": match_res["sinkhorn_iters_per_sec"] if match_res else None,
             "roofline": roof, "conv_layers": conv_res, "densenet_blocks": dense_res, "matching": match_res,
             "e2e": {"value": N_TOTAL / (ms_e2e / args.steps * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                    "api": "Trainer.stage (H2D of the next step's pinned host images on a copy stream) -> Trainer.step -> Trainer.fetch_async "
+                           "(D2H of [distance, entropy]) -> host read of every step's result one step behind the GPU: the loop of otgan_b200.train.main",
+                    "blocking_ms_per_step": ms_blocking / args.steps if ms_blocking else None},
             "gpu_launches": launches, "cuda_graphs": graphs_on,
             "clocks": dict(sampler.result(), remeasured_after_slowdown=remeasured),
             "configs": configs, "mgpu_parity": parity,

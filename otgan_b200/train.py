@@ -58,6 +58,17 @@ def build_parser():
     return parser
 
 
+class _Fetched:
+    """Handle of Trainer.fetch_async: .result() -> [distance, entropy] once the device-to-host copy has completed."""
+
+    def __init__(self, buf, event):
+        self.buf, self.event = buf, event
+
+    def result(self):
+        self.event.synchronize()
+        return self.buf.tolist()
+
+
 class Trainer:
     """One data-parallel rank of the OT-GAN step.  `step(x_real_local)` is one sess.run of train.py:214-226."""
 
@@ -115,6 +126,8 @@ class Trainer:
         self.gather_buf = None
         self.graphs = None                                 # set by enable_cuda_graphs()
         self.replayed_launches = 0                         # libotgan kernels executed through graph replays
+        self._stage = None                                 # stage(): double-buffered upload of the NEXT step's images
+        self._fetch = None                                 # fetch_async(): double-buffered pinned read-back of [distance, entropy]
 
     def _gather_features(self, f_gen, f_dat):
         return gather_features(f_gen, f_dat, self.world)
@@ -147,11 +160,61 @@ class Trainer:
         a = self.args
         train_disc = self.step_counter % (a.nr_gen_per_disc + 1) == 0                            # :214
         kind = 'disc' if train_disc else 'gen'
+        slot = self._staged_slot(x_real)
+        if slot is not None:                               # images uploaded by stage(): wait for that copy, not for the host
+            torch.cuda.current_stream().wait_event(self._stage['ready'][slot])
         if self.graphs is not None and apply_update:
-            return kind, self._replay(kind, x_real, u)
-        stats = self._step_body(kind, x_real, u, apply_update)
-        self.step_counter += 1
+            stats = self._replay(kind, x_real, u)
+        else:
+            stats = self._step_body(kind, x_real, u, apply_update)
+            self.step_counter += 1
+        if slot is not None:                               # the staging buffer may be refilled once this step has consumed it
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._stage['consumed'][slot] = ev
         return kind, stats
+
+    # ---- input / output pipelining around step(): the upload of step k+1 and the read-back of step k run while the GPU computes ----
+    def stage(self, x_host):
+        """Start uploading the images of a LATER step (pinned host tensor or numpy-backed CPU tensor, [bs_local, S, S, 3]) on a
+        copy stream and return the device tensor to hand to step().  Called right after step(k) has been enqueued, the H2D copy
+        of step k+1 overlaps step k's kernels; step() makes its own stream wait for the copy.  Two buffers alternate."""
+        if self._stage is None:
+            shape = (self.bs_local, self.image_size, self.image_size, 3)
+            self._stage = {'bufs': [torch.empty(shape, device=self.device) for _ in range(2)], 'ready': [torch.cuda.Event(), torch.cuda.Event()],
+                           'consumed': [None, None], 'stream': torch.cuda.Stream(device=self.device), 'next': 0}
+        st = self._stage
+        i = st['next']
+        st['next'] ^= 1
+        cs = st['stream']
+        if st['consumed'][i] is not None:
+            cs.wait_event(st['consumed'][i])               # the step that last read this buffer
+        with torch.cuda.stream(cs):
+            st['bufs'][i].copy_(x_host, non_blocking=True)
+            st['ready'][i].record(cs)
+        return st['bufs'][i]
+
+    def _staged_slot(self, x):
+        if self._stage is None or not isinstance(x, torch.Tensor):
+            return None
+        for i, b in enumerate(self._stage['bufs']):
+            if x is b:
+                return i
+        return None
+
+    def fetch_async(self, stats):
+        """Queue the read-back of a step's [distance, entropy] into pinned host memory and return a handle whose .result() gives the
+        two floats (blocking only until THAT copy has landed).  Reading step k's handle after step k+1 has been enqueued keeps the
+        GPU busy across the host's read (the reference's sess.run blocks on every step)."""
+        if self._fetch is None:
+            self._fetch = {'bufs': [torch.empty(2).pin_memory() for _ in range(2)], 'next': 0}
+        f = self._fetch
+        i = f['next']
+        f['next'] ^= 1
+        f['bufs'][i].copy_(stats, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        return _Fetched(f['bufs'][i], ev)
 
     def _step_body(self, kind, x_real, u, apply_update=True, hyper_dev=None):
         """One sess.run of train.py:214-226 as a pure stream of kernel launches (no host synchronisation): this is also
@@ -552,21 +615,37 @@ def main(argv=None):
         inds = np.random.RandomState(args.seed + epoch).permutation(trainx.shape[0])             # :200 (same on every rank)
         trainx = trainx[inds]
         dist_gen, dist_disc, entropy = [], [], []
-        for t in range(nr_batches_train_per_gpu):
+        def batch(t):                                                                            # :209-211
             xs = []
-            for i in range(trainer.towers_local):                                               # :209-211
+            for i in range(trainer.towers_local):
                 tower = rank * trainer.towers_local + i
                 td = t + tower * nr_batches_train_per_gpu
                 xs.append(maybe_flip(trainx[td * args.batch_size:(td + 1) * args.batch_size], rng))
-            x = torch.from_numpy(np.concatenate(xs, 0)).to(device, non_blocking=True)
-            kind, stats = trainer.step(x)
-            s = stats.tolist()                                                                   # the sess.run fetch
+            return torch.from_numpy(np.concatenate(xs, 0)).pin_memory()
+
+        def log(kind, s):                                                                        # the sess.run fetch
             (dist_disc if kind == 'disc' else dist_gen).append(s[0])
             entropy.append(s[1])
-            if rank == 0 and args.log_every and trainer.step_counter % args.log_every == 0:
-                print('step %d (%s): distance %.6f entropy %.6f' % (trainer.step_counter, kind, s[0], s[1]))
+
+        # software pipeline: while step t computes, the images of step t+1 are uploaded and the statistics of step t-1 are read
+        pending = None
+        x = trainer.stage(batch(0)) if nr_batches_train_per_gpu > 0 else None
+        for t in range(nr_batches_train_per_gpu):
+            kind, stats = trainer.step(x)
+            if t + 1 < nr_batches_train_per_gpu:
+                x = trainer.stage(batch(t + 1))
+            h = (kind, trainer.fetch_async(stats), trainer.step_counter)
+            if pending is not None:
+                log(pending[0], pending[1].result())
+                if rank == 0 and args.log_every and pending[2] % args.log_every == 0:
+                    print('step %d (%s): distance %.6f entropy %.6f' % (pending[2], pending[0], dist_disc[-1] if pending[0] == 'disc' else dist_gen[-1], entropy[-1]))
+            pending = h
             if args.max_steps and trainer.step_counter >= args.max_steps:
                 break
+        if pending is not None:
+            log(pending[0], pending[1].result())
+            if rank == 0 and args.log_every and pending[2] % args.log_every == 0:
+                print('step %d (%s): distance %.6f entropy %.6f' % (pending[2], pending[0], dist_disc[-1] if pending[0] == 'disc' else dist_gen[-1], entropy[-1]))
         if rank == 0:                                                                            # :231
             print("Iteration %d, time = %ds, train distance before gen = %.6f, train distance before disc = %.6f, avg matching entropy = %.6f"
                   % (epoch, time.time() - begin, np.mean(dist_gen) if dist_gen else float('nan'),

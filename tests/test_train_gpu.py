@@ -195,6 +195,42 @@ def test_cuda_graph_replay_matches_eager_steps():
     assert all(e <= 1e-3 for e in errs.values()), errs
 
 
+@pytest.mark.parametrize("graphs", [False, True])
+def test_stage_and_fetch_pipeline_matches_plain_steps(graphs):
+    """Trainer.stage (upload of the NEXT step's pinned host images on a copy stream) + Trainer.fetch_async (read-back of
+    [distance, entropy] one step behind the GPU) -- the loop of train.main -- give exactly the statistics and parameters of
+    plain step(device_tensor) calls, eagerly and under CUDA graphs."""
+    from otgan_b200 import train as T
+    args = T.build_parser().parse_args(["--synthetic", "--nr_gpu", "2", "--batch_size", "8", "--nr_sinkhorn_iter", "20"])
+    gcpu = torch.Generator().manual_seed(5)
+    xs_host = [(torch.rand(16, 32, 32, 3, generator=gcpu) * 2 - 1).pin_memory() for _ in range(7)]
+    us = [(torch.rand(16, 100, generator=gcpu) * 2 - 1).cuda() for _ in range(7)]
+    out = {}
+    for mode in ("plain", "pipelined"):
+        tr = T.Trainer(args, torch.device("cuda", 0))
+        if graphs:
+            tr.enable_cuda_graphs()
+        stats = []
+        if mode == "plain":
+            for x, u in zip(xs_host, us):
+                stats.append(tr.step(x.cuda(), u=u)[1].tolist())
+        else:
+            pending, x = None, tr.stage(xs_host[0])
+            for i, u in enumerate(us):
+                _, s = tr.step(x, u=u)
+                if i + 1 < len(us):
+                    x = tr.stage(xs_host[i + 1])
+                h = tr.fetch_async(s)
+                if pending is not None:
+                    stats.append(pending.result())
+                pending = h
+            stats.append(pending.result())
+        torch.cuda.synchronize()
+        out[mode] = (torch.tensor(stats), tr.generator.flat.detach().clone(), tr.discriminator.flat.detach().clone())
+    for a, b in zip(out["plain"], out["pipelined"]):
+        assert torch.equal(a, b)
+
+
 def test_critic_weight_cache_matches_recomputed_weights():
     """Generator steps reuse the critic's W = g V/||V|| (and its IHWO copy) computed once after the critic update: the
     features / input gradient through the cached weights equal those through freshly normalised weights, and an
