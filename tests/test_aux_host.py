@@ -96,3 +96,31 @@ def test_reference_style_variable_dump_loads_and_reproduces_the_reference_featur
     assert np.abs(f - g["features"]).max() / np.abs(g["features"]).max() < 2e-5
     assert np.abs(img - g["image"]).max() < 2e-5
     dcgan.discriminator.reset(); dcgan.generator.reset()
+
+
+def test_inception_score_hook_arithmetic_and_contract():
+    """utils/inception.py:43-52: the split / KL / exp arithmetic against a direct restatement, the reference's input checks, and
+    the loud failure without a classifier."""
+    import numpy as np
+    import pytest
+    from otgan_b200.utils import inception
+    rng = np.random.RandomState(0)
+    imgs = [rng.randint(0, 256, size=(32, 32, 3)).astype(np.float64) for _ in range(250)]
+    W = rng.randn(3 * 32 * 32, 7) * 1e-3
+
+    def predict(batch):
+        z = batch.reshape(len(batch), -1) @ W
+        z = np.exp(z - z.max(1, keepdims=True))
+        return z / z.sum(1, keepdims=True)
+
+    mean, std = inception.get_inception_score(imgs, splits=5, predict_fn=predict)
+    preds = np.concatenate([predict(np.stack(imgs[i:i + 100]).astype(np.float32)) for i in range(0, 250, 100)])
+    ref = []
+    for part in np.array_split(preds, 5):
+        py = part.mean(0, keepdims=True)
+        ref.append(np.exp(np.mean(np.sum(part * (np.log(part) - np.log(py)), 1))))
+    assert abs(mean - np.mean(ref)) < 1e-12 and abs(std - np.std(ref)) < 1e-12 and 1.0 <= mean <= 7.0
+    with pytest.raises(RuntimeError):
+        inception.get_inception_score(imgs)
+    with pytest.raises(AssertionError):
+        inception.get_inception_score([im / 255.0 for im in imgs], predict_fn=predict)      # reference check: values in [0, 255]
