@@ -192,6 +192,14 @@ OTGAN_API size_t otgan_workspace_bytes_conv_gemm(int B, int H, int W, int C);
 OTGAN_API int otgan_conv2d_fprop_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top,
                                       int pad_left, const float* x, const float* w_ohwi, const float* bias, float* y,
                                       void* ws, size_t ws_bytes, void* stream);
+/* Same convolution with the NEXT layer's CReLU pre-activation (utils/nn.py:198-200 on one tensor: relu(concat([y, -y], 3))) written by
+ * the epilogue: z [B, H/s, W/s, 2 Cout] = [relu(conv + bias) | relu(-(conv + bias))].  Cout % 128 == 0; the launch is never split over
+ * the filter taps (use it when the output has at least one 128-pixel x TN tile per SM).  models/dcgan.py:10-13. */
+OTGAN_API int otgan_conv2d_fprop_crelu_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top,
+                                            int pad_left, const float* x, const float* w_ohwi, const float* bias, float* z,
+                                            void* stream);
+/* Backward of that CReLU from the ACTIVATED tensor: dy [P, C] = (z_pos > 0 ? dz_pos : 0) - (z_neg > 0 ? dz_neg : 0), z / dz: [P, 2C]. */
+OTGAN_API int otgan_crelu_bwd_from_activated_f32(long long P, int C, const float* z, const float* dz, float* dy, void* stream);
 OTGAN_API int otgan_conv2d_dgrad_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top,
                                       int pad_left, const float* dy, const float* w_ihwo, float* dx, void* ws,
                                       size_t ws_bytes, void* stream);

@@ -66,6 +66,8 @@ SIGNATURES = {
     "otgan_glu_up_bwd_f32": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "otgan_workspace_bytes_conv_gemm": (_sz, [_i, _i, _i, _i]),
     "otgan_conv2d_fprop_tf32": (_i, [_i] * 10 + [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "otgan_conv2d_fprop_crelu_tf32": (_i, [_i] * 10 + [_vp, _vp, _vp, _vp, _vp]),
+    "otgan_crelu_bwd_from_activated_f32": (_i, [ctypes.c_longlong, _i, _vp, _vp, _vp, _vp]),
     "otgan_conv2d_dgrad_tf32": (_i, [_i] * 10 + [_vp, _vp, _vp, _vp, _sz, _vp]),
     "otgan_workspace_bytes_conv_wgrad": (_sz, [_i] * 8),
     "otgan_conv2d_wgrad_tf32": (_i, [_i] * 10 + [_vp, _vp, _vp, _vp, _sz, _vp]),

@@ -72,13 +72,14 @@ int weightnorm_bwd_launch(int K, int C, const float* V, const float* g, const fl
                           float* dg, void* ws, cudaStream_t stream);
 
 int crelu_pad_fwd_launch(int B, int H, int W, int C, int pt, int pl, int pb, int pr, const float* x, float* z, cudaStream_t stream);
+int crelu_bwd_z_launch(size_t P, int C, const float* z, const float* dz, float* dy, cudaStream_t stream);
 int crelu_pad_bwd_launch(int B, int H, int W, int C, int pt, int pl, int pb, int pr, const float* x, const float* dz, float* dx,
                          cudaStream_t stream);
 int glu_up_fwd_launch(int B, int H, int W, int C, int up, const float* y, float* out, cudaStream_t stream);
 int glu_up_bwd_launch(int B, int H, int W, int C, int up, const float* y, const float* dout, float* dy, cudaStream_t stream);
 size_t conv_gemm_workspace_bytes(int B, int H, int W, int C);
 int conv_fprop_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo,
-                      const float* x, const float* w, const float* bias, float* y, void* ws, size_t ws_bytes, cudaStream_t stream);
+                      const float* x, const float* w, const float* bias, float* y, void* ws, size_t ws_bytes, cudaStream_t stream, int crelu);
 int conv_dgrad_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo,
                       const float* dy, const float* wt, float* dx, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t conv_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int kh, int kw);
@@ -432,7 +433,24 @@ int otgan_conv2d_fprop_tf32(int B, int H, int W, int Cin, int Cout, int kh, int 
     OTGAN_REQUIRE(aligned16(x) && aligned16(w_ohwi) && aligned16(y) && (!bias || aligned16(bias)) && (!ws || aligned16(ws)),
                   "conv2d_fprop: buffers must be 16-byte aligned");
     return conv_fprop_launch(B, H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, H / stride, W / stride, x, w_ohwi, bias, y,
-                             ws, ws_bytes, (cudaStream_t)stream);
+                             ws, ws_bytes, (cudaStream_t)stream, 0);
+}
+
+int otgan_conv2d_fprop_crelu_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top, int pad_left,
+                                  const float* x, const float* w_ohwi, const float* bias, float* z, void* stream)
+{
+    OTGAN_REQUIRE(x && w_ohwi && z, "conv2d_fprop_crelu: null pointer");
+    OTGAN_REQUIRE(stride == 1 || stride == 2, "conv2d_fprop_crelu: stride %d not in {1, 2}", stride);
+    OTGAN_REQUIRE(aligned16(x) && aligned16(w_ohwi) && aligned16(z) && (!bias || aligned16(bias)), "conv2d_fprop_crelu: buffers must be 16-byte aligned");
+    return conv_fprop_launch(B, H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, H / stride, W / stride, x, w_ohwi, bias, z,
+                             nullptr, 0, (cudaStream_t)stream, 1);
+}
+
+int otgan_crelu_bwd_from_activated_f32(long long P, int C, const float* z, const float* dz, float* dy, void* stream)
+{
+    OTGAN_REQUIRE(P >= 1 && C >= 4 && C % 4 == 0 && z && dz && dy, "crelu_bwd_from_activated: bad arguments (C must be a multiple of 4)");
+    OTGAN_REQUIRE(aligned16(z) && aligned16(dz) && aligned16(dy), "crelu_bwd_from_activated: buffers must be 16-byte aligned");
+    return crelu_bwd_z_launch((size_t)P, C, z, dz, dy, (cudaStream_t)stream);
 }
 
 int otgan_conv2d_dgrad_tf32(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad_top, int pad_left,

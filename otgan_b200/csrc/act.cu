@@ -84,6 +84,26 @@ crelu_pad_bwd_kernel(size_t n4, int H, int W, int C, int pt, int pl, int Hp, int
     }
 }
 
+// dy[px][c] = (z[px][c] > 0 ? dz[px][c] : 0) - (z[px][C + c] > 0 ? dz[px][C + c] : 0): the CReLU backward taken from the ACTIVATED tensor
+// z = [relu(y) | relu(-y)] (z_pos > 0 <=> y > 0, z_neg > 0 <=> y < 0; relu'(0) = 0 on both sides like the pre-activation form)
+__global__ void __launch_bounds__(256)
+crelu_bwd_z_kernel(size_t n4, int C4, const float* __restrict__ z, const float* __restrict__ dz, float* __restrict__ dy)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t px = i / (unsigned)C4;
+        const unsigned c4 = (unsigned)(i - px * (unsigned)C4);
+        const size_t off = (px * 2 * (size_t)C4 + c4) * 4;
+        const float4 zp = ld4(z + off), zn = ld4(z + off + 4 * (size_t)C4);
+        const float4 gp = ld4(dz + off), gn = ld4(dz + off + 4 * (size_t)C4);
+        float4 o;
+        o.x = (zp.x > 0.f ? gp.x : 0.f) - (zn.x > 0.f ? gn.x : 0.f);
+        o.y = (zp.y > 0.f ? gp.y : 0.f) - (zn.y > 0.f ? gn.y : 0.f);
+        o.z = (zp.z > 0.f ? gp.z : 0.f) - (zn.z > 0.f ? gn.z : 0.f);
+        o.w = (zp.w > 0.f ? gp.w : 0.f) - (zn.w > 0.f ? gn.w : 0.f);
+        st4(dy + i * 4, o);
+    }
+}
+
 __device__ __forceinline__ float sigmoidf_(float t) { return 1.f / (1.f + __expf(-t)); }
 
 // y: [B,H,W,2C] -> out: [B,UP*H,UP*W,C]
@@ -168,6 +188,14 @@ int crelu_pad_bwd_launch(int B, int H, int W, int C, int pt, int pl, int pb, int
     const size_t n4 = (size_t)B * H * W * C / 4;
     crelu_pad_bwd_kernel<<<grid_for(n4), 256, 0, stream>>>(n4, H, W, C, pt, pl, Hp, Wp, x, dz, dx);
     OTGAN_CHECK_LAUNCH("crelu_pad_bwd_kernel");
+    return OTGAN_OK;
+}
+
+int crelu_bwd_z_launch(size_t P, int C, const float* z, const float* dz, float* dy, cudaStream_t stream)
+{
+    const size_t n4 = P * (size_t)C / 4;
+    crelu_bwd_z_kernel<<<grid_for(n4), 256, 0, stream>>>(n4, C / 4, z, dz, dy);
+    OTGAN_CHECK_LAUNCH("crelu_bwd_z_kernel");
     return OTGAN_OK;
 }
 

@@ -87,6 +87,7 @@ struct GemmParams {
     // shape outside the DCGAN family.  The weight operand is a 3-D tensor [K, taps, rows] so that TMA zero-fills both the K
     // tail of a tap and the rows past N; the accumulator N is a run-time multiple of 16 (n_inst <= TN); rows / columns outside
     // the tensor are masked in the epilogue.
+    int crelu_half;                           // fused CReLU output of the plain fprop epilogue: 0 = off, else Cout -- row = [relu(y) (Cout) | relu(-y) (Cout)]
     int generic;
     int b_k0;                                 // K coordinate of the first weight column used (a K-slice of a wider weight tensor)
     int n_inst;                               // UMMA N of this launch (= the N tile stride: tile nt covers columns [nt * n_inst, ..))
@@ -400,9 +401,20 @@ conv_gemm_tc_kernel(const __grid_constant__ GemmParams p)
                         v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + bb.w);
                     }
                 }
+                if (p.crelu_half) {
+                    // CReLU of the next layer (utils/nn.py:198-200 on one tensor: concat([y, -y], 3) then relu) leaves this epilogue
+                    // directly: relu(y) into channels [0, Cout), relu(-y) into [Cout, 2 Cout) of a 2 Cout-wide row
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]), a2 = __uint_as_float(v[j + 2]), a3 = __uint_as_float(v[j + 3]);
+                        *reinterpret_cast<float4*>(out + cc * 32 + j) = make_float4(fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f));
+                        *reinterpret_cast<float4*>(out + p.crelu_half + cc * 32 + j) = make_float4(fmaxf(-a0, 0.f), fmaxf(-a1, 0.f), fmaxf(-a2, 0.f), fmaxf(-a3, 0.f));
+                    }
+                } else {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<uint4*>(out + cc * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
             }
             }
             tcgen05_fence_before();
@@ -1118,7 +1130,7 @@ int run_gemm(GemmParams& p, int TN, size_t out_numel, float* out, void* ws, size
         min_taps = T < min_taps ? T : min_taps;
     }
     const int tiles = p.m_tiles * p.n_tiles * p.n_cls;
-    p.splits = ((out_numel % 4) || p.generic) ? 1 : gemm_splits(tiles, min_taps);   // generic: slices / fused epilogues are not split
+    p.splits = ((out_numel % 4) || p.generic || p.crelu_half) ? 1 : gemm_splits(tiles, min_taps);   // generic: slices / fused epilogues are not split
     if (p.splits > 1 && (!ws || ws_bytes < (size_t)p.splits * out_numel * sizeof(float))) p.splits = 1;   // no room: unsplit
     p.split_stride = (long long)out_numel;
     p.out = p.splits > 1 ? reinterpret_cast<float*>(ws) : out;
@@ -1127,7 +1139,7 @@ int run_gemm(GemmParams& p, int TN, size_t out_numel, float* out, void* ws, size
     p.tail_ws = nullptr;
     // 256 x 256 tiles (two sub-tiles share the weight tile) when the launch keeps >= 0.75 waves of them and a tile is long
     // enough to amortise the un-overlapped epilogue
-    if (g_use_gemm2 && !p.generic && p.splits == 1 && TN == 256 && (p.m_tiles & 1) == 0 && tiles / 2 >= (kNumSMs * 3) / 4 && min_taps * p.kchunks >= g_gemm2_min_chunks) {
+    if (g_use_gemm2 && !p.generic && !p.crelu_half && p.splits == 1 && TN == 256 && (p.m_tiles & 1) == 0 && tiles / 2 >= (kNumSMs * 3) / 4 && min_taps * p.kchunks >= g_gemm2_min_chunks) {
         p.n_items = tiles / 2;
         if (capturing()) { t_capture->kind = 1; t_capture->TN = 256; t_capture->gemm = p; return OTGAN_OK; }
         OTGAN_SET_MAX_SMEM((conv_gemm2_tc_kernel), G2_SMEM_BYTES);
@@ -1137,7 +1149,7 @@ int run_gemm(GemmParams& p, int TN, size_t out_numel, float* out, void* ws, size
         return OTGAN_OK;
     }
     int n_tail = 0;
-    if (g_tail_split && !p.generic && p.splits == 1 && TN >= 128 && ws) {   // cut the last, partial wave of tiles along the taps
+    if (g_tail_split && !p.generic && !p.crelu_half && p.splits == 1 && TN >= 128 && ws) {   // cut the last, partial wave of tiles along the taps
         n_tail = tiles % kNumSMs;
         const int S = tail_splits_for(n_tail, min_taps);
         if (S > 1 && ws_bytes >= (size_t)n_tail * S * TM * TN * sizeof(float)) {
@@ -1236,8 +1248,10 @@ size_t conv_gemm_workspace_bytes(int B, int H, int W, int C)
     return r ? (size_t)r * 8 * TM * TN * sizeof(float) + 256 : 256;
 }
 
+// crelu != 0: y is [B, Ho, Wo, 2 Cout] = relu(concat([conv + bias, -(conv + bias)], 3)) (the plain epilogue's fused CReLU; Cout % 128 == 0,
+// never split over the filter taps: the caller keeps it for launches with at least one tile per SM)
 int conv_fprop_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, int s, int pt, int pl, int Ho, int Wo,
-                      const float* x, const float* w, const float* bias, float* y, void* ws, size_t ws_bytes, cudaStream_t stream)
+                      const float* x, const float* w, const float* bias, float* y, void* ws, size_t ws_bytes, cudaStream_t stream, int crelu)
 {
     OTGAN_REQUIRE(conv_dims_ok(B, H, W, Cin, Cout, kh, kw, s, pt, pl, Ho, Wo), "conv_fprop: unsupported geometry");
     GemmParams p;
@@ -1270,7 +1284,12 @@ int conv_fprop_launch(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
     p.m_tiles = p.tiles_w * p.tiles_h * (B / p.bn);
     p.n_tiles = Cout < TN ? 1 : Cout / TN;
     p.kchunks = Cin / BK;
-    p.osW = Cout; p.osH = (long long)Wo * Cout; p.osN = (long long)Ho * Wo * Cout;
+    const long long ldo = crelu ? 2LL * Cout : Cout;
+    if (crelu) {
+        OTGAN_REQUIRE(TN >= 128, "conv_fprop: the fused CReLU output needs Cout %% 128 == 0");
+        p.crelu_half = Cout;
+    }
+    p.osW = ldo; p.osH = (long long)Wo * ldo; p.osN = (long long)Ho * Wo * ldo;
     p.bias = bias;
     return run_gemm(p, TN, (size_t)B * Ho * Wo * Cout, y, ws, ws_bytes, stream);
 }
@@ -1863,7 +1882,7 @@ int conv_plan_describe(int op, int B, int H, int W, int Cin, int Cout, int kh, i
     t_capture = &cap_state;
     int rc = OTGAN_EINVAL;
     switch (op) {
-    case 0: rc = conv_fprop_launch(B, H, W, Cin, Cout, kh, kw, s, pt, pl, H / s, W / s, dummy, dummy, nullptr, dummy, big_ws, big, nullptr); break;
+    case 0: rc = conv_fprop_launch(B, H, W, Cin, Cout, kh, kw, s, pt, pl, H / s, W / s, dummy, dummy, nullptr, dummy, big_ws, big, nullptr, 0); break;
     case 1: rc = conv_dgrad_launch(B, H, W, Cin, Cout, kh, kw, s, pt, pl, H / s, W / s, dummy, dummy, dummy, big_ws, big, nullptr); break;
     case 2: rc = conv_wgrad_launch(B, H, W, Cin, Cout, kh, kw, s, pt, pl, H / s, W / s, dummy, dummy, dummy, big_ws, big, nullptr, 0); break;
     case 3: rc = conv_up2_fprop_launch(B, H, W, Cin, Cout, kh, kw, pt, pl, dummy, dummy, nullptr, dummy, big_ws, big, nullptr); break;

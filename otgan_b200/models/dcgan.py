@@ -20,9 +20,12 @@ from ..utils.nn import arg_scope
 # //// discriminator ////
 def disc_spec(x, init=False, nonlinearity='crelu', ema=None, **kwargs):
     with arg_scope([nn.conv2d, nn.dense], counters={}, init=init, weight_norm=True, ema=ema):
-        x = nn.conv2d(x, 128, filter_size=[5, 5], pre_activation=None)
-        x = nn.conv2d(x, 256, filter_size=[5, 5], pre_activation=nonlinearity, stride=[2, 2])
-        x = nn.conv2d(x, 512, filter_size=[5, 5], pre_activation=nonlinearity, stride=[2, 2])
+        # crelu_out: the CReLU that the NEXT layer applies to its input (pre_activation) is written by THIS layer's convolution
+        # epilogue on the tcgen05 path (nn.CreluOut); same values, one pass over the activations less per layer
+        fuse = nonlinearity == 'crelu'
+        x = nn.conv2d(x, 128, filter_size=[5, 5], pre_activation=None, crelu_out=fuse)
+        x = nn.conv2d(x, 256, filter_size=[5, 5], pre_activation=nonlinearity, stride=[2, 2], crelu_out=fuse)
+        x = nn.conv2d(x, 512, filter_size=[5, 5], pre_activation=nonlinearity, stride=[2, 2], crelu_out=fuse)
         x = nn.conv2d(x, 1024, filter_size=[5, 5], pre_activation=nonlinearity, stride=[2, 2])
 
         # :16-19  concat([relu(x), relu(-x)], 3) -> reshape [B, -1] (NHWC order) -> x / sqrt(sum(x^2)) (no epsilon)

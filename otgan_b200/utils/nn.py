@@ -508,7 +508,7 @@ class _ConvNarrow(torch.autograd.Function):
         return out
 
     @staticmethod
-    def forward(ctx, x, wt, bias, geom):
+    def forward(ctx, x, wt, bias, geom, crelu=False):
         lib = _lib.load()
         kh, kw, s, pt, pl = geom
         B, H, W, cin = x.shape
@@ -518,8 +518,15 @@ class _ConvNarrow(torch.autograd.Function):
         if bias is not None and bias.data_ptr() % 16:
             bias = bias.clone()
         stream = torch.cuda.current_stream().cuda_stream
-        y = torch.empty((B, H, W, cout), device=x.device, dtype=torch.float32)
-        if cin <= 16:                                      # critic conv2d_0: image and filter zero-padded to 32 channels
+        ctx.crelu = bool(crelu)
+        y = torch.empty((B, H, W, 2 * cout if crelu else cout), device=x.device, dtype=torch.float32)
+        if cin <= 16 and crelu:                            # critic conv2d_0 with the next layer's CReLU written by the epilogue
+            xk = _pad_channels(x, 32)
+            wk = _pad_channels(wt.view(cout, taps, cin), 32).reshape(cout, -1)
+            rc = lib.otgan_conv2d_fprop_crelu_tf32(B, H, W, 32, cout, kh, kw, 1, pt, pl, xk.data_ptr(), wk.data_ptr(),
+                                                   bias.data_ptr() if bias is not None else None, y.data_ptr(), stream)
+            _lib.check(rc, "otgan_conv2d_fprop_crelu_tf32")
+        elif cin <= 16:                                    # critic conv2d_0: image and filter zero-padded to 32 channels
             xk = _pad_channels(x, 32)
             wk = _pad_channels(wt.view(cout, taps, cin), 32).reshape(cout, -1)
             ws = _workspace(x.device, lib.otgan_workspace_bytes_conv_gemm(B, H, W, cout))
@@ -534,20 +541,26 @@ class _ConvNarrow(torch.autograd.Function):
             rc = lib.otgan_col2im_narrow_f32(B, H, W, cout, kh, kw, pt, pl, 0, z.data_ptr(), 128,
                                              bias.data_ptr() if bias is not None else None, y.data_ptr(), stream)
             _lib.check(rc, "otgan_col2im_narrow_f32")
-        ctx.save_for_backward(x, wt)
+        if crelu:
+            assert cin <= 16, "the fused CReLU output exists for the narrow-INPUT layer only"
+            ctx.save_for_backward(x, wt, y)
+        else:
+            ctx.save_for_backward(x, wt)
         ctx.geom, ctx.has_bias = geom, bias is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
         lib = _lib.load()
-        x, wt = ctx.saved_tensors
+        x, wt = ctx.saved_tensors[:2]
         kh, kw, s, pt, pl = ctx.geom
         B, H, W, cin = x.shape
         cout = wt.shape[0]
         taps = kh * kw
         dy = dy.contiguous()
         stream = torch.cuda.current_stream().cuda_stream
+        if ctx.crelu:                                      # gradient of z = crelu(y) -> gradient of y
+            dy = _crelu_bwd_from_z(lib, ctx.saved_tensors[2], dy, stream)
         dx = dwt = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
@@ -584,7 +597,7 @@ class _ConvNarrow(torch.autograd.Function):
                 _lib.check(lib.otgan_colsum_f32(P, cout, dy.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream), "otgan_colsum_f32")
             else:
                 db = dy.reshape(-1, cout).sum(0)
-        return dx, dwt, db, None
+        return dx, dwt, db, None, None
 
 
 class Upsampled2x:
@@ -625,6 +638,53 @@ def upsample2x(x, lazy=True):
     if lazy and UPSAMPLE_FUSION and CONV_BACKEND == "tcgen05" and x.is_cuda and x.dtype == torch.float32:
         return Upsampled2x(x.contiguous())
     return resize_nearest_neighbor(x, [2 * x.shape[1], 2 * x.shape[2]])
+
+
+class CreluOut:
+    """The CReLU-activated output of a convolution, relu(concat([y, -y], 3)) (utils/nn.py:198-200 on one tensor), produced by
+    nn.conv2d(..., crelu_out=True): `z` is the [B, H, W, 2C] tensor, `shape` reports the RAW [B, H, W, C] like the tensor the
+    reference passes between the layers.  The next nn.conv2d(..., pre_activation='crelu') consumes `z` as it is.  On the tcgen05
+    path the producing convolution writes z from its epilogue (otgan_conv2d_fprop_crelu_tf32): the separate CReLU pass -- a read
+    of y and a write of 2x its size per critic layer -- disappears."""
+
+    def __init__(self, z):
+        self.z = z
+
+    @property
+    def shape(self):
+        B, H, W, C2 = self.z.shape
+        return torch.Size((B, H, W, C2 // 2))
+
+    @property
+    def is_cuda(self):
+        return self.z.is_cuda
+
+    @property
+    def dtype(self):
+        return self.z.dtype
+
+    @property
+    def device(self):
+        return self.z.device
+
+    def dim(self):
+        return 4
+
+
+def _crelu_fusable(B, Ho, Wo, cout):
+    """The fused CReLU epilogue is never split over the filter taps: use it when the launch has a tile per SM anyway."""
+    if cout % 128:
+        return False
+    tn = 256 if cout % 256 == 0 else 128
+    return (B * Ho * Wo // 128) * (cout // tn) >= 148
+
+
+def _crelu_bwd_from_z(lib, z, dz, stream):
+    B, H, W, C2 = z.shape
+    dy = torch.empty((B, H, W, C2 // 2), device=z.device, dtype=torch.float32)
+    _lib.check(lib.otgan_crelu_bwd_from_activated_f32(B * H * W, C2 // 2, z.data_ptr(), dz.data_ptr(), dy.data_ptr(), stream),
+               "otgan_crelu_bwd_from_activated_f32")
+    return dy
 
 
 def conv_up2_supported(lowshape, cout, kh, kw, stride, pad):
@@ -1177,13 +1237,14 @@ class _ConvTCWN(torch.autograd.Function):
     (calls that build no parameter gradients, VariableStore.refresh_weight_cache)."""
 
     @staticmethod
-    def forward(ctx, x, V, g, bias, geom, cached):
+    def forward(ctx, x, V, g, bias, geom, cached, crelu=False):
         lib = _lib.load()
         kh, kw, s, pt, pl = geom
         stream = torch.cuda.current_stream().cuda_stream
         B, H, W, cin = x.shape
         cout = V.shape[-1]
         x = x.contiguous()
+        ctx.crelu = bool(crelu)
         if cached is not None:
             wt, ihwo, inv = cached[0], cached[1], None
             Vc = gc = None
@@ -1192,25 +1253,36 @@ class _ConvTCWN(torch.autograd.Function):
             wt, ihwo, inv = _wn_fwd2(lib, Vc, gc, kh * kw, ctx.needs_input_grad[0], stream)
         if bias is not None and bias.data_ptr() % 16:
             bias = bias.clone()
-        y = torch.empty((B, H // s, W // s, cout), device=x.device, dtype=torch.float32)
-        ws = _workspace(x.device, lib.otgan_workspace_bytes_conv_gemm(B, H // s, W // s, cout))
-        rc = lib.otgan_conv2d_fprop_tf32(B, H, W, cin, cout, kh, kw, s, pt, pl, x.data_ptr(), wt.data_ptr(),
-                                         bias.data_ptr() if bias is not None else None, y.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream)
-        _lib.check(rc, "otgan_conv2d_fprop_tf32")
+        if crelu:                                          # z = relu(concat([y, -y], 3)) straight from the convolution's epilogue
+            y = torch.empty((B, H // s, W // s, 2 * cout), device=x.device, dtype=torch.float32)
+            rc = lib.otgan_conv2d_fprop_crelu_tf32(B, H, W, cin, cout, kh, kw, s, pt, pl, x.data_ptr(), wt.data_ptr(),
+                                                   bias.data_ptr() if bias is not None else None, y.data_ptr(), stream)
+            _lib.check(rc, "otgan_conv2d_fprop_crelu_tf32")
+        else:
+            y = torch.empty((B, H // s, W // s, cout), device=x.device, dtype=torch.float32)
+            ws = _workspace(x.device, lib.otgan_workspace_bytes_conv_gemm(B, H // s, W // s, cout))
+            rc = lib.otgan_conv2d_fprop_tf32(B, H, W, cin, cout, kh, kw, s, pt, pl, x.data_ptr(), wt.data_ptr(),
+                                             bias.data_ptr() if bias is not None else None, y.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream)
+            _lib.check(rc, "otgan_conv2d_fprop_tf32")
         ctx.geom, ctx.has_bias, ctx.cout = geom, bias is not None, cout
         ctx.wt, ctx.ihwo = wt, ihwo
-        ctx.save_for_backward(x, Vc, gc, inv)
+        if crelu:
+            ctx.save_for_backward(x, Vc, gc, inv, y)
+        else:
+            ctx.save_for_backward(x, Vc, gc, inv)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         lib = _lib.load()
-        x, V, g, inv = ctx.saved_tensors
+        x, V, g, inv = ctx.saved_tensors[:4]
         kh, kw, s, pt, pl = ctx.geom
         B, H, W, cin = x.shape
         cout = ctx.cout
         dy = dy.contiguous()
         stream = torch.cuda.current_stream().cuda_stream
+        if ctx.crelu:                                      # gradient of z = crelu(y) -> gradient of y
+            dy = _crelu_bwd_from_z(lib, ctx.saved_tensors[4], dy, stream)
         dx = dV = dg = db = None
         if ctx.needs_input_grad[0]:
             wt_t = ctx.ihwo
@@ -1234,7 +1306,7 @@ class _ConvTCWN(torch.autograd.Function):
             ws = _workspace(x.device, lib.otgan_workspace_bytes_colsum(P, cout))
             db = torch.empty((cout,), device=x.device, dtype=torch.float32)
             _lib.check(lib.otgan_colsum_f32(P, cout, dy.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream), "otgan_colsum_f32")
-        return dx, dV, dg, db, None, None
+        return dx, dV, dg, db, None, None, None
 
 
 class _ConvUp2TCWN(torch.autograd.Function):
@@ -1374,10 +1446,46 @@ def _dense(x, W, pre_activation=None):
     return x @ W                                                                                      # :208-209
 
 
-def _conv2d(x, W, stride=(1, 1), pad="SAME", dilate=1, pre_activation=None, upsample=False, bias=None):
-    """utils/nn.py:234-275 (__list_conv2d): optional NN-upsample of the concatenated list, pre-activation, conv."""
+def _conv2d_fused_crelu(x, W, stride, pad, dilate, pre_activation, upsample, bias):
+    """z = crelu(conv(x) + b) from the convolution's own epilogue, or None when this call has no such form."""
+    if (CONV_BACKEND != "tcgen05" or upsample or dilate != 1 or pre_activation is not None or isinstance(x, (list, tuple, Upsampled2x))
+            or not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4)):
+        return None
+    kh, kw, cin, cout = W.vshape if isinstance(W, (LazyWN, TransposedWeight)) else (0, 0, 0, 0)
+    if not kh:
+        return None
+    B, H, Wd, _ = x.shape
+    s = stride[0]
+    if stride[0] != stride[1] or H % s or Wd % s or not _crelu_fusable(B, H // s, Wd // s, cout):
+        return None
+    geom = (kh, kw, s, same_padding(H, kh, s)[0], same_padding(Wd, kw, s)[0])
+    if isinstance(W, LazyWN) and conv_tc_supported((B, H, Wd, cin), cout, kh, kw, stride, pad):
+        return _ConvTCWN.apply(x.contiguous(), W.V, W.g, bias, geom, W.cached, True)
+    if CONV_NARROW and cin <= 16 and conv_narrow_supported((B, H, Wd, cin), cout, kh, kw, stride, pad):
+        Wm = W.materialize() if isinstance(W, LazyWN) else W
+        return _ConvNarrow.apply(x.contiguous(), Wm.wt, bias, geom, True)
+    return None
+
+
+def _conv2d(x, W, stride=(1, 1), pad="SAME", dilate=1, pre_activation=None, upsample=False, bias=None, crelu_out=False):
+    """utils/nn.py:234-275 (__list_conv2d): optional NN-upsample of the concatenated list, pre-activation, conv.
+    crelu_out: return CreluOut(relu(concat([y, -y], 3))) -- the next layer's CReLU -- instead of y (fused into the epilogue of the
+    tcgen05 convolution where the launch has a tile per SM; the literal ops otherwise)."""
     if isinstance(x, Crelu8Tensor):
         raise TypeError("a Crelu8Tensor is consumed by nn.conv2d(..., pre_activation='crelu') on the GPU path only")
+    if isinstance(x, CreluOut):                            # already activated by the producing layer
+        if pre_activation != "crelu" or upsample:
+            raise ValueError("a CreluOut input needs pre_activation='crelu' (it IS the activated tensor)")
+        x, pre_activation = x.z, None
+    if crelu_out:
+        y = _conv2d_fused_crelu(x, W, stride, pad, dilate, pre_activation, upsample, bias)
+        if y is None:                                      # no fused form for this call: convolution, then the CReLU pass
+            y = _conv2d(x, W, stride, pad, dilate, pre_activation, upsample, bias)
+            if y.is_cuda and y.dtype == torch.float32 and y.dim() == 4 and y.shape[3] % 4 == 0:
+                y = _CreluPad.apply(y.contiguous(), (0, 0, 0, 0))
+            else:
+                y = torch.relu(torch.cat([y, -y], 3))
+        return CreluOut(y)
     if isinstance(x, Upsampled2x):
         if (pre_activation is None and not upsample and isinstance(W, (TransposedWeight, LazyWN)) and CONV_BACKEND == "tcgen05"
                 and conv_up2_supported(tuple(x.low.shape), W.vshape[3], W.vshape[0], W.vshape[1], stride, pad)):
@@ -1488,8 +1596,8 @@ def dense(x, num_units, pre_activation="celu", init_scale=1.0, counters={}, init
 @add_arg_scope
 def conv2d(x, num_filters, pre_activation="celu", filter_size=[3, 3], stride=[1, 1], pad="SAME", dilate=1,
            upsample=False, init_scale=1.0, counters={}, init=False, ema=None, weight_norm=True, use_b=True, use_g=True,
-           **kwargs):
-    """utils/nn.py:328-338"""
+           crelu_out=False, **kwargs):
+    """utils/nn.py:328-338.  crelu_out (addition): hand the NEXT layer's CReLU to this convolution -- returns a CreluOut."""
     layer_name = get_name("conv2d", counters)
     if isinstance(x, Crelu8Tensor):
         if not (pre_activation == "crelu" and weight_norm and use_g and not upsample and dilate == 1 and not init):
@@ -1501,7 +1609,8 @@ def conv2d(x, num_filters, pre_activation="celu", filter_size=[3, 3], stride=[1,
                         init_scale=init_scale, filter_size=list(filter_size), num_units=num_filters,
                         pre_activation=pre_activation)
     # tf.nn.bias_add (:337) rides in the convolution's epilogue instead of a separate pass over the activations
-    return _conv2d(x, params["W"], stride, pad, dilate, pre_activation, upsample, bias=params["b"] if use_b else None)
+    return _conv2d(x, params["W"], stride, pad, dilate, pre_activation, upsample, bias=params["b"] if use_b else None,
+                   crelu_out=crelu_out and not init)
 
 
 # ------------------------------------------------------------------------------------------------ optimisers
