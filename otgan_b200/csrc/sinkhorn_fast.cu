@@ -5,10 +5,12 @@
 // memory) and a SCALING part (u_i, v_j):   exp(log_a)_ij = K_ij * u_i * v_j,   K_ij = exp(L0_ij - f_i - g_j).
 //   fast half-step:  u_i = 1 / sum_j K_ij v_j        (a 128x128 mat-vec: FMAs only, no exp/log)
 //   slow half-step:  absorb (f -= log u, g -= log v), r_i = max-subtracted LSE of (L0 - f - g), f += r, K rebuilt
-// A half-step takes the fast path unless some u_i (v_j) leaves [2^-40, 2^40] (checked every step, CTA-uniform via a
+// A half-step takes the fast path unless some u_i (v_j) leaves [2^-51, 2^51] (checked every step, CTA-uniform via a
 // shared-memory flag read after the step's barrier); then the same half-step is redone on the slow path from the last good state.  The first row step is
-// always slow.  Exact algebra, fp32 rounding of the same class as the log-domain form (entries of K that underflow at an
-// absorption are < 2^-126 and can regain at most 2^80, i.e. stay < 2^-46 of a row sum).
+// always slow.  Exact algebra, fp32 rounding of the same class as the log-domain form: K keeps its entries down to the smallest
+// DENORMAL (2^-149; FMAs take denormal operands at full rate), so what a rebuild flushes or quantises is < 2^-149 absolutely and
+// can regain at most 2^102 before the next rebuild, i.e. stays < 2^-47 of a row sum.  (Round 2a flushed at 2^-126 and
+// allowed [2^-40, 2^40]: the wider window saves about one 6 us rebuild in four.)
 // Precision of the absorbed potentials.  With lambda = 500 they reach ~350, where one fp32 ulp is 3e-5, and exp(L0 - f - g) is
 // a difference of such numbers: in plain fp32 that rounding went straight into P (measured 2.9e-5 on a peaked h = 32 problem, 8x
 // the log-domain kernel).  Round 2 first took the difference in double -- accurate (P error 1.3e-7) but the fp64 pipe of this
@@ -56,7 +58,7 @@ constexpr float LN2 = 0.6931471805599453f;
 constexpr float CH = 1.44269502162933349609375f, CL = 1.925963033500011e-08f;   // log2(e) = CH + CL (fp32 pair)
 constexpr float MAGIC = 12582912.f;                 // 1.5 * 2^23: (x + MAGIC) - MAGIC = rint(x) for |x| < 2^22
 constexpr int MAGIC_BITS = 0x4B400000;
-constexpr float S_LO = 9.094947017729282e-13f /* 2^-40 */, S_HI = 1099511627776.f /* 2^40 */;
+constexpr float S_LO = 4.440892098500626e-16f /* 2^-51 */, S_HI = 2251799813685248.f /* 2^51 */;
 
 struct Smem {
     float L0[H * LDS_];        // L0[r][c] = -lambda*C (natural-log units, exactly the caller's fp32), -inf outside [rows, cols)
@@ -138,7 +140,9 @@ __device__ __forceinline__ void exponent_pair(float l, float ph, float pl, float
     t_lo = __fadd_rn(__fsub_rn(__fsub_rn(tl, pl), ql), __fadd_rn(e1, e2));
 }
 // 2^(t_hi + t_lo - shift) for an integer shift >= rint(t_hi): n = rint(t_hi), fraction = (t_hi - n) + t_lo in [-0.5, 0.5] exactly
-// representable, ex2 of the fraction, the integer part through the exponent field; results below 2^-125 flush to zero.
+// representable, ex2 of the fraction, the integer part through the exponent field.  Results below 2^-126 come out as DENORMALS
+// (second factor 2^-64 through a multiply, which rounds correctly) and only values below 2^-149 flush to zero: the 23 extra binades
+// are what lets the scalings range over [2^-51, 2^51] between two rebuilds (see the header).
 // ex_out = n - shift (for the entropy term), fr_out = the fraction.
 __device__ __forceinline__ float exp2_pair(float t_hi, float t_lo, int shift, int& ex_out, float& fr_out)
 {
@@ -149,7 +153,10 @@ __device__ __forceinline__ float exp2_pair(float t_hi, float t_lo, int shift, in
     const float k = ex2_approx(fr);
     ex_out = ex;
     fr_out = fr;
-    return (ex < -125) ? 0.f : __int_as_float(__float_as_int(k) + (ex << 23));
+    if (ex < -150) return 0.f;
+    const bool low = ex < -100;
+    const float r = __int_as_float(__float_as_int(k) + ((low ? ex + 64 : ex) << 23));
+    return low ? __fmul_rn(r, 5.421010862427522e-20f /* 2^-64 */) : r;
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -421,8 +428,9 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
                     const float k = Kr[i][4 * m + e];
                     p[e] = (k * xs[e]) * up[i];
                     if (p[e] > 0.f) {
-                        const int b = __float_as_int(k);
-                        const float ek = __int_as_float(MAGIC_BITS + ((b >> 23) - 127)) - MAGIC;        // exponent of K as a float, no I2F
+                        const bool tiny = k < 1.0e-30f;                                                  // denormal K: normalise before taking its exponent
+                        const int b = __float_as_int(tiny ? k * 18446744073709551616.f /* 2^64 */ : k);
+                        const float ek = __int_as_float(MAGIC_BITS + ((b >> 23) - (tiny ? 191 : 127))) - MAGIC;   // exponent of K as a float, no I2F
                         const float mk = lg2_approx(__int_as_float((b & 0x007FFFFF) | 0x3F800000));
                         entI = fmaf(p[e], ek + (vis[e] + lui[i]), entI);
                         entF = fmaf(p[e], mk + (vfs[e] + luf[i]), entF);
