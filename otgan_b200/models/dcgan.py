@@ -44,8 +44,9 @@ def gen_spec(batch_size, init=False, nonlinearity='crelu', ema=None, u=None, ima
         u = torch.rand((batch_size, 100), device=device) * 2.0 - 1.0            # tf.random_uniform(-1, 1)  :30
     with arg_scope([nn.conv2d, nn.dense], counters={}, init=init, weight_norm=True, ema=ema):
         x = nn.dense(u, 2 * s0 * s0 * 1024, pre_activation=None)
-        x, l = torch.chunk(x, 2, 1)
-        x = x * torch.sigmoid(l)                                                # gated linear unit  :35-36
+        # x, l = split(x, 2, 1); x *= sigmoid(l)  (gated linear unit, :35-36) -- the same split as nn.glu's channel split on a
+        # [B, 1, 1, 2F] view: one fused kernel forward / backward on the GPU path
+        x = nn.glu(x.reshape(batch_size, 1, 1, 2 * s0 * s0 * 1024))
         x = x.reshape(batch_size, s0, s0, 1024)
         x = nn.upsample2x(x)              # tf.image.resize_nearest_neighbor(x, [8, 8])  :37-38 (fused into the next conv2d)
         x = nn.conv2d(x, 2 * 512, filter_size=[5, 5], pre_activation=None)

@@ -1433,7 +1433,8 @@ def get_params(layer_name, x=None, init=False, ema=None, use_W=True, use_g=True,
 
 
 # ------------------------------------------------------------------------------------------------ layers
-def _dense(x, W, pre_activation=None):
+def _dense(x, W, pre_activation=None, bias=None):
+    """tf.matmul(x, W) (+ bias when given: the caller's `x + b` rides in the GEMM epilogue on the tcgen05 path)."""
     x = apply_pre_activation(x, pre_activation, 1)
     if isinstance(W, TransposedWeight):
         if (CONV_BACKEND == "tcgen05" and DENSE_ON_TCGEN05 and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
@@ -1441,9 +1442,11 @@ def _dense(x, W, pre_activation=None):
             # tf.matmul(x, W) (utils/nn.py:208-209) as a 1x1 convolution of a [B, 1, 1, K] image on the generic tcgen05 kernels:
             # W.wt [units, K] is exactly the OHWI filter matrix; the filter gradient is the same kernels' wgrad
             B, K = x.shape
-            return _ConvGen.apply(x.contiguous().view(B, 1, 1, K), W.wt, None, (1, 1, 1, 0, 0)).view(B, W.wt.shape[0])
-        return F.linear(x, W.wt)
-    return x @ W                                                                                      # :208-209
+            return _ConvGen.apply(x.contiguous().view(B, 1, 1, K), W.wt, bias, (1, 1, 1, 0, 0)).view(B, W.wt.shape[0])
+        y = F.linear(x, W.wt)
+        return y if bias is None else y + bias
+    y = x @ W                                                                                         # :208-209
+    return y if bias is None else y + bias
 
 
 def _conv2d_fused_crelu(x, W, stride, pad, dilate, pre_activation, upsample, bias):
@@ -1587,10 +1590,7 @@ def dense(x, num_units, pre_activation="celu", init_scale=1.0, counters={}, init
     f = lambda x, W: _dense(x, W, pre_activation)
     params = get_params(layer_name, x, init, ema, use_W=True, use_g=use_g, use_b=use_b, f=f, weight_norm=weight_norm,
                         init_scale=init_scale, num_units=num_units, pre_activation=pre_activation)
-    x = f(x, params["W"])
-    if use_b:
-        x = x + params["b"]
-    return x
+    return _dense(x, params["W"], pre_activation, bias=params["b"] if use_b else None)      # x @ W + b  (:322-324)
 
 
 @add_arg_scope
