@@ -11,13 +11,16 @@ blocks -> Sinkhorn -> feature gradients + distance/entropy), backward, summed to
 images/sec = N / step time.  At N GPUs the 256 images are split over the ranks (strong scaling): one all-gather of the
 [2*256/N, D] embedding slab, replicated cost+Sinkhorn, each rank back-propagates its own rows, gradient all-reduce(sum).
 
-`value` feeds the step from device-resident images; `e2e` goes through the public API (otgan_b200.train.Trainer.step)
-with pinned HOST image buffers (H2D inside the timed region) and reads [distance, entropy] back every step.
-`matching` is the matching hot path alone (this library's kernels only) with kernel-only times (back-to-back launches,
-no host gaps); `roofline` is the step's dominant kernel against MEASURED_PEAKS.json, with a cuBLAS TF32 GEMM measured in
-the same run as the honest ceiling of a TF32 kernel.  `configs` carries the other BASELINE.json configurations that fit
-the launch (cfg2 / cfg3 at 1 GPU, cfg4 = DenseNet at 4 GPUs, cfg5 = 64 x 64 / N = 512 at 8 GPUs) and, for N > 1, a
-weak-scaling line (256 images per rank); `mgpu_parity` is the multi-rank parity check (otgan_b200.train.parity_check).
+`value` feeds the step from device-resident images; `e2e` goes through the public API the way otgan_b200.train.main drives
+it: Trainer.stage (H2D of pinned HOST images on a copy stream) -> Trainer.step -> Trainer.fetch_async (D2H of [distance,
+entropy]) -> host read of every step's result, software-pipelined (upload of step k+1 and read of step k-1 while step k
+computes); `e2e.blocking_ms_per_step` is the same with sess.run semantics (upload, step, read, block -- every step).
+`matching` is the matching hot path alone (this library's kernels only): kernel times and the 6-launch step are timed
+through CUDA-graph replays (the per-call host work is as long as the kernels); `roofline` is the step's dominant kernel
+against MEASURED_PEAKS.json, with a cuBLAS TF32 GEMM measured in the same run as the honest ceiling of a TF32 kernel.
+`configs` carries the other BASELINE.json configurations that fit the launch (cfg2 / cfg3 at 1 GPU, cfg4 = DenseNet at
+4 GPUs, cfg5 = 64 x 64 / N = 512 at 8 GPUs) and, for N > 1, a weak-scaling line (128 images per rank); `mgpu_parity` is
+the multi-rank parity check (otgan_b200.train.parity_check).
 `cpu_baseline` / `--impl reference`: the reference algorithm on the host cores at the SAME N = 256 -- torch-CPU conv
 stacks + oracle/torch_oracle.py (one torch-CPU op per TensorFlow op of utils/matching.py), the C+OpenMP oracle's matching
 phase reported beside it (TensorFlow 1.x is not installable here: kind = "port").

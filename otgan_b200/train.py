@@ -151,7 +151,7 @@ class Trainer:
         shard = (self.rank, self.world) if (rows is not None and A.shape[0] // 2 > 128 and self.world % 2 == 0
                                             and os.environ.get("OTGAN_SHARD_COST", "1") == "1") else None
         ga, gb, stats = matching.matching_step(fa, fb, a.sinkhorn_lambda, a.nr_sinkhorn_iter, rows=rows, shard=shard)
-        return torch.cat(ga, 0), torch.cat(gb, 0), stats
+        return matching._gather(ga), matching._gather(gb), stats      # the tower chunks of one [N, D] buffer: a view, no copy
 
     def step(self, x_real, u=None, apply_update=True):
         """x_real: this rank's [bs_local, 32, 32, 3] real images in [-1, 1].  Returns ('disc'|'gen', stats[2] tensor).
