@@ -354,6 +354,8 @@ CONV_NARROW = True            # route the two 3-channel layers through _ConvNarr
 DENSE_ON_TCGEN05 = True       # nn.dense as a 1x1 convolution on the generic tcgen05 kernels (False: cuBLAS through F.linear)
 WN_FUSION = True              # weight norm fused into the tcgen05 convolution nodes (_ConvTCWN / _ConvUp2TCWN: HWIO gradient pipeline)
 DENSE_BLOCK_FUSION = True     # nn.dense_block runs DenseNet's blocks on the dense-block kernels (False: the literal list code)
+CRELU_FUSION = True           # nn.conv2d(crelu_out=True) writes the CReLU from the convolution's epilogue (False: separate pass, for A/B tests)
+CRELU_FUSION_MIN_TILES = 148  # ... for launches with at least this many output tiles (the fused epilogue is never split over the taps)
 _conv_ws = {}
 _wn_ws = {}
 _retired_ws = []              # outgrown scratch buffers stay alive: a captured CUDA graph may still hold their addresses
@@ -673,10 +675,10 @@ class CreluOut:
 
 def _crelu_fusable(B, Ho, Wo, cout):
     """The fused CReLU epilogue is never split over the filter taps: use it when the launch has a tile per SM anyway."""
-    if cout % 128:
+    if cout % 128 or not CRELU_FUSION:
         return False
     tn = 256 if cout % 256 == 0 else 128
-    return (B * Ho * Wo // 128) * (cout // tn) >= 148
+    return (B * Ho * Wo // 128) * (cout // tn) >= CRELU_FUSION_MIN_TILES
 
 
 def _crelu_bwd_from_z(lib, z, dz, stream):

@@ -480,3 +480,78 @@ def test_wn_fusion_matches_the_unfused_nodes(which):
     for a, b in zip(g1, g0):
         assert float((a - b).abs().max() / b.abs().max()) < 2e-5
     tpl.reset()
+
+
+@pytest.mark.parametrize("shape", [(8, 8, 8, 128, 128, 5, 1), (2, 32, 32, 256, 256, 5, 2), (8, 8, 8, 256, 512, 5, 2), (4, 16, 16, 128, 256, 3, 1),
+                                   (80, 16, 16, 128, 256, 5, 1), (32, 32, 32, 32, 128, 5, 1)])
+def test_fprop_with_fused_crelu_output_exact(shape):
+    """otgan_conv2d_fprop_crelu_tf32: z = [relu(conv + b) | relu(-(conv + b))] written by the convolution's epilogue, bit for bit
+    against float64 on integer inputs (incl. a launch with a tail wave and the 32-channel padded form of the critic's first
+    layer); and otgan_crelu_bwd_from_activated_f32 against the CReLU backward taken from the pre-activation."""
+    from otgan_b200 import _lib
+    lib = _lib.load()
+    B, H, W, Cin, Cout, k, s = shape
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randint(-2, 3, (B, H, W, Cin), device="cuda", generator=g).float()
+    w = torch.randint(-2, 3, (Cout, k, k, Cin), device="cuda", generator=g).float()
+    b = torch.randint(-4, 5, (Cout,), device="cuda", generator=g).float()
+    pt, pl = _same_pad(H, k, s)[0], _same_pad(W, k, s)[0]
+    z = torch.full((B, H // s, W // s, 2 * Cout), float("nan"), device="cuda")
+    rc = lib.otgan_conv2d_fprop_crelu_tf32(B, H, W, Cin, Cout, k, k, s, pt, pl, x.data_ptr(), w.reshape(Cout, -1).contiguous().data_ptr(),
+                                           b.data_ptr(), z.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.otgan_last_error()
+    y = _ref_conv(x.double(), w.double(), b.double(), k, s)
+    zr = torch.relu(torch.cat([y, -y], 3))
+    assert torch.equal(z.double(), zr)
+    dz = torch.randint(-3, 4, z.shape, device="cuda", generator=g).float()
+    dy = torch.empty((B, H // s, W // s, Cout), device="cuda")
+    rc = lib.otgan_crelu_bwd_from_activated_f32(B * (H // s) * (W // s), Cout, z.data_ptr(), dz.data_ptr(), dy.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.otgan_last_error()
+    dyr = torch.where(y > 0, dz[..., :Cout].double(), torch.zeros_like(y)) - torch.where(y < 0, dz[..., Cout:].double(), torch.zeros_like(y))
+    assert torch.equal(dy.double(), dyr)
+
+
+def test_critic_with_fused_crelu_matches_the_separate_pass():
+    """models/dcgan.py critic with nn.conv2d(crelu_out=True) taking the fused epilogue on every layer against the same network with
+    the separate CReLU pass.  Batch 128: every forward launch has enough tiles that neither form is split over the filter taps,
+    so both run the same kernels on the same operands in the same summation order -- features and gradients must agree to the
+    last bit (a 16-image batch does not: the unfused launches are then split, and last-bit differences of an activation flip
+    TF32-truncated operands of the next layer by 2^-10: 1.8e-4 on the features, ~1 % on the gradients)."""
+    from otgan_b200.models import dcgan
+    from otgan_b200.utils import nn
+    from otgan_b200 import _lib
+    dev = torch.device("cuda", 0)
+    tpl = dcgan.discriminator
+    tpl.reset()
+    torch.manual_seed(3)
+    B = 128
+    with torch.no_grad():
+        tpl(torch.zeros(16, 32, 32, 3, device=dev) + 0.1, init=True)
+        for n, p in tpl.named_parameters():
+            if n.endswith("/g"):
+                p.mul_(0.5 + torch.rand_like(p))
+            if n.endswith("/b"):
+                p.add_(0.1 * torch.randn_like(p))
+    x = (torch.rand(B, 32, 32, 3, device=dev) * 2 - 1).requires_grad_(True)
+    outs, launches = {}, {}
+    prev = (nn.CRELU_FUSION, nn.CRELU_FUSION_MIN_TILES)
+    try:
+        for fused in (True, False):
+            nn.CRELU_FUSION, nn.CRELU_FUSION_MIN_TILES = fused, 1
+            _lib.reset_launch_count()
+            y = tpl(x)
+            gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(9)).to(dev)
+            grads = torch.autograd.grad([y], [tpl.flat, x], grad_outputs=[gy])
+            torch.cuda.synchronize()
+            launches[fused] = _lib.launch_count()
+            outs[fused] = (y.detach(), [g.detach() for g in grads])
+    finally:
+        nn.CRELU_FUSION, nn.CRELU_FUSION_MIN_TILES = prev
+    (y1, g1), (y0, g0) = outs[True], outs[False]
+    # three CReLU passes folded into the producing convolutions (and their launches are never split over the filter taps: no split-reduce)
+    assert launches[True] <= launches[False] - 3, launches
+    assert torch.equal(y1, y0)
+    for a, b in zip(g1, g0):
+        assert torch.equal(a, b)
+    tpl.reset()
