@@ -23,6 +23,8 @@ def main():
     a1, a2, b1, b2 = A[:32], A[32:], B[:32], B[32:]
     L = M.cost_blocks([a1, b2, a1, a1, a2, a2], [a2, b1, b1, b2, b1, b2], 500.0, 0, None, _lib.IMPL_TCGEN05)
     P, ent, pc = M.sinkhorn(L, 500.0, 10)
+    L2 = (torch.rand(2, 128, 128, device="cuda") * -600.0).contiguous()    # full-size blocks with a wide cost range: slow steps of both kinds
+    M.sinkhorn(L2, 500.0, 30)
     ws, wsb = M._plan_ws(A.device, 32)
     Ga, Gb = torch.empty_like(A), torch.empty_like(B)
     _lib.check(lib.otgan_grad_features_f32(32, 256, P.data_ptr(), A.data_ptr(), B.data_ptr(), 256, Ga.data_ptr(), Gb.data_ptr(), 256,
@@ -33,6 +35,8 @@ def main():
     w = torch.randn(Co, 25 * Ci, device="cuda") * 0.05
     y = torch.empty(Bn, H, W, Co, device="cuda")
     _lib.check(lib.otgan_conv2d_fprop_tf32(Bn, H, W, Ci, Co, 5, 5, 1, 2, 2, x.data_ptr(), w.data_ptr(), None, y.data_ptr(), None, 0, st), "fprop")
+    zc = torch.empty(Bn, H, W, 2 * Co, device="cuda")                      # the fused CReLU epilogue of the plain fprop kernel
+    _lib.check(lib.otgan_conv2d_fprop_crelu_tf32(Bn, H, W, Ci, Co, 5, 5, 1, 2, 2, x.data_ptr(), w.data_ptr(), None, zc.data_ptr(), st), "fprop_crelu")
     wt = torch.empty(Ci, 25 * Co, device="cuda")
     _lib.check(lib.otgan_ohwi_to_ihwo_f32(Co, 25, Ci, w.data_ptr(), wt.data_ptr(), st), "ihwo")
     dx = torch.empty_like(x)
