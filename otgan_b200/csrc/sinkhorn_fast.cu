@@ -128,10 +128,15 @@ __device__ __forceinline__ void log2_split(float x, float& ipart, float& fpart)
 }
 // exponent t = l * log2(e) - (ph + pl) - (qh + ql) of one matrix entry as (t_hi, t_lo): t_hi is the EXACT fp32 sum chain's head,
 // t_lo collects every rounding error and the low words (|t_lo| << 1).  l must be finite.
-__device__ __forceinline__ void exponent_pair(float l, float ph, float pl, float qh, float ql, float& t_hi, float& t_lo)
+__device__ __forceinline__ void exponent_pair(float l, float ph, float pl, float qh, float ql, float& t_hi, float& t_lo, bool zero_potentials = false)
 {
     const float th = __fmul_rn(l, CH);
     const float tl = __fmaf_rn(l, CL, __fmaf_rn(l, CH, -th));
+    if (zero_potentials) {                                         // the very first rebuild (f = g = 0): nothing to subtract
+        t_hi = th;
+        t_lo = tl;
+        return;
+    }
     const float s1 = __fsub_rn(th, ph), b1 = __fsub_rn(s1, th);
     const float e1 = __fsub_rn(__fsub_rn(th, __fsub_rn(s1, b1)), __fadd_rn(ph, b1));
     const float s2 = __fsub_rn(s1, qh), b2 = __fsub_rn(s2, s1);
@@ -224,7 +229,7 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
     // ---- slow path, rolled: one warp per LINE of M (a row of L0, or a row of L0T = a column), lane = 4 consecutive entries, four
     // lines in flight.  Entry exponent t = M[line][o] * log2(e) - p_line - q_o as an fp32 pair (exponent_pair); the line maximum of
     // the heads (rounded to an integer: the shift), K = 2^(t - shift), the line sum, KX[line][:] = K / sum, p_line += shift + log2(sum).
-    auto rebuild = [&](const float* __restrict__ M, float* ph, float* pl, const float* qh, const float* ql, int nvalid) {
+    auto rebuild = [&](const float* __restrict__ M, float* ph, float* pl, const float* qh, const float* ql, int nvalid, bool first) {
         float qhv[4], qlv[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) { qhv[e] = qh[4 * lane + e]; qlv[e] = ql[4 * lane + e]; }
@@ -242,7 +247,7 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const bool live = lv[e] > -3.0e38f;                   // -inf marks entries outside [rows, cols)
-                    exponent_pair(live ? lv[e] : 0.f, p_h, p_l, qhv[e], qlv[e], thi[a][e], tlo[a][e]);
+                    exponent_pair(live ? lv[e] : 0.f, p_h, p_l, qhv[e], qlv[e], thi[a][e], tlo[a][e], first);
                     if (!(live && thi[a][e] > -4.0e6f)) thi[a][e] = -INFINITY;   // also: beyond the range of the integer split (K = 0 anyway)
                     mx[a] = fmaxf(mx[a], thi[a][e]);
                 }
@@ -311,7 +316,7 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
     };
     // absorb: f -= log2 u, g -= log2 v; afterwards u = v = 1 in the current buffers.  Then the half-step itself in the log domain:
     // row:    f_i += LSE_j(L0 - f - g), K rebuilt row-normalised;   column: g_j += LSE_i(L0 - f - g), K rebuilt column-normalised
-    auto slow_step = [&](bool row_step) {
+    auto slow_step = [&](bool row_step, bool first) {
         if (tid < H) {
             float ip, fp, h = sm.fh[tid], l = sm.fl[tid];
             log2_split(sm.u[ub][tid], ip, fp);
@@ -325,7 +330,7 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
             sm.v[vb][tid] = 1.f;
         }
         __syncthreads();
-        if (row_step) rebuild(sm.L0, sm.fh, sm.fl, sm.gh, sm.gl, rows); else rebuild(sm.L0T, sm.gh, sm.gl, sm.fh, sm.fl, cols);
+        if (row_step) rebuild(sm.L0, sm.fh, sm.fl, sm.gh, sm.gl, rows, first); else rebuild(sm.L0T, sm.gh, sm.gl, sm.fh, sm.fl, cols, false);
         if (row_step) load_tiles(Kr, Kc); else load_tiles(Kc, Kr);
         ++n_slow;
     };
@@ -377,7 +382,7 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
 #ifdef OTGAN_SINKHORN_CLOCKS
             const long long t0 = clock64();
 #endif
-            slow_step(row_step);
+            slow_step(row_step, hs == 0);
             SK_CLK_ADD(5, t0);
         }
         if (hs == 0) SK_CLK(2);
@@ -427,15 +432,14 @@ sinkhorn_fast_kernel(const float* __restrict__ L0g, float* __restrict__ P, float
                 for (int e = 0; e < 4; ++e) {
                     const float k = Kr[i][4 * m + e];
                     p[e] = (k * xs[e]) * up[i];
-                    if (p[e] > 0.f) {
-                        const bool tiny = k < 1.0e-30f;                                                  // denormal K: normalise before taking its exponent
-                        const int b = __float_as_int(tiny ? k * 18446744073709551616.f /* 2^64 */ : k);
-                        const float ek = __int_as_float(MAGIC_BITS + ((b >> 23) - (tiny ? 191 : 127))) - MAGIC;   // exponent of K as a float, no I2F
-                        const float mk = lg2_approx(__int_as_float((b & 0x007FFFFF) | 0x3F800000));
-                        entI = fmaf(p[e], ek + (vis[e] + lui[i]), entI);
-                        entF = fmaf(p[e], mk + (vfs[e] + luf[i]), entF);
-                        pcs = fmaf(p[e], ls[e], pcs);
-                    }
+                    // branch-free: an entry with p = 0 (K = 0, masked row / column) adds exactly 0 -- every factor below is finite
+                    const bool tiny = k < 1.0e-30f;                                                      // denormal K: normalise before taking its exponent
+                    const int b = __float_as_int(tiny ? k * 18446744073709551616.f /* 2^64 */ : k);
+                    const float ek = __int_as_float(MAGIC_BITS + ((b >> 23) - (tiny ? 191 : 127))) - MAGIC;       // exponent of K as a float, no I2F
+                    const float mk = lg2_approx(__int_as_float((b & 0x007FFFFF) | 0x3F800000));
+                    entI = fmaf(p[e], ek + (vis[e] + lui[i]), entI);
+                    entF = fmaf(p[e], mk + (vfs[e] + luf[i]), entF);
+                    pcs = fmaf(p[e], p[e] > 0.f ? ls[e] : 0.f, pcs);                                      // L0 is -inf outside [rows, cols)
                 }
                 if (P && r < rows && c < cols) {
                     float* dst = P + boff + (size_t)r * cols + c;
