@@ -33,6 +33,9 @@ int sinkhorn_reg_max_side();
 int sinkhorn_fast_launch(int nblk, int rows, int cols, int T, float lam, const float* L0, float* P, float* entropy,
                          float* pc, int* slow_steps, cudaStream_t stream);
 int sinkhorn_stream_max_side();
+int sinkhorn_cluster_max_side();
+int sinkhorn_cluster_launch(int nblk, int rows, int cols, int T, float lam, const float* L0, float* P, float* entropy,
+                            float* pc, cudaStream_t stream);
 int sinkhorn_stream_launch(int nblk, int rows, int cols, int T, float lam, const float* L0, float* P, float* entropy,
                            float* pc, cudaStream_t stream);
 int distance_from_pc_launch(const float* pc, const float* entropy, int n_total, float* out, cudaStream_t stream);
@@ -167,6 +170,11 @@ int otgan_sinkhorn_ex_f32(int nblk, int rows, int cols, int T, float lam, const 
         if (impl == OTGAN_IMPL_SIMT)   // literal log-domain kernel (every half-step is a max-subtracted LSE)
             return sinkhorn_reg_launch(nblk, rows, cols, T, lam, L0, P, entropy, pc, (cudaStream_t)stream);
         return sinkhorn_fast_launch(nblk, rows, cols, T, lam, L0, P, entropy, pc, slow_steps, (cudaStream_t)stream);
+    }
+    if (impl == OTGAN_IMPL_AUTO && rows <= sinkhorn_cluster_max_side() && cols <= sinkhorn_cluster_max_side()) {
+        // 128 < side <= 512: one 8-CTA cluster per block, persistent over T (SIMT keeps the one-launch-per-half-step rung)
+        if (slow_steps) OTGAN_CUDA(cudaMemsetAsync(slow_steps, 0, sizeof(int) * nblk, (cudaStream_t)stream));
+        return sinkhorn_cluster_launch(nblk, rows, cols, T, lam, L0, P, entropy, pc, (cudaStream_t)stream);
     }
     if (rows <= sinkhorn_stream_max_side() && cols <= sinkhorn_stream_max_side()) {
         OTGAN_REQUIRE(P != nullptr, "sinkhorn: blocks larger than %d need the P buffer as working storage", sinkhorn_reg_max_side());

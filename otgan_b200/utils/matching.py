@@ -104,8 +104,11 @@ def sinkhorn(L, lam, nr_iter, want_plan=True, impl=_lib.IMPL_AUTO, want_stats=Fa
     lib = _lib.load()
     nblk, rows, cols = L.shape
     assert L.is_cuda and L.dtype == torch.float32 and L.is_contiguous()
-    # results are fresh tensors owned by the caller; blocks larger than one SM need P as working storage
-    P = torch.empty((nblk, rows, cols), device=L.device, dtype=torch.float32) if (want_plan or max(rows, cols) > 128) else None
+    # results are fresh tensors owned by the caller; the streaming rung (side > 512, or side > 128 with IMPL_SIMT) needs P as
+    # working storage, the register-resident kernels (one CTA up to 128, one 8-CTA cluster up to 512) do not
+    side = max(rows, cols)
+    streaming = side > 512 or (side > 128 and impl != _lib.IMPL_AUTO)
+    P = torch.empty((nblk, rows, cols), device=L.device, dtype=torch.float32) if (want_plan or streaming) else None
     ent = torch.empty((nblk,), device=L.device, dtype=torch.float32)
     pc = torch.empty((nblk,), device=L.device, dtype=torch.float32)
     slow = torch.zeros((nblk,), device=L.device, dtype=torch.int32) if want_stats else None

@@ -223,16 +223,20 @@ def test_sinkhorn_fast_path_is_taken(M):
     assert (slow >= 1).all() and (slow <= 40).all(), slow           # 200 half-steps in total
 
 
+@pytest.mark.parametrize("impl", [0, 1])      # 0 = AUTO (8-CTA cluster kernel up to side 512), 1 = SIMT (streaming kernels)
 @pytest.mark.parametrize("nblk,rows,cols,lam,T", [(3, 256, 256, 500.0, 100), (2, 200, 150, 500.0, 20), (1, 1024, 1024, 500.0, 10),
-                                                  (2, 129, 300, 100.0, 5), (1, 256, 256, 500.0, 0)])
-def test_sinkhorn_large_blocks(M, nblk, rows, cols, lam, T):
-    """Blocks larger than one SM (single-batch N = 256, 64x64-image configs): streaming log-domain kernels."""
+                                                  (2, 129, 300, 100.0, 5), (1, 256, 256, 500.0, 0), (6, 256, 256, 500.0, 100),
+                                                  (2, 512, 512, 500.0, 100), (2, 100, 130, 500.0, 30), (1, 511, 257, 500.0, 7),
+                                                  (3, 130, 129, 50.0, 1)])
+def test_sinkhorn_large_blocks(M, nblk, rows, cols, lam, T, impl):
+    """Blocks larger than one SM (single-batch N = 256, 64x64-image configs): the persistent cluster kernel (one 8-CTA cluster per
+    block, slabs of rows in registers, column partials through distributed shared memory) and the streaming log-domain kernels."""
     D = 128
     C = np.stack([mo.cosine_cost(mo.synth_embeddings(rows, D, 70 + k, "clustered", sigma=1.0).astype(np.float64),
                                  mo.synth_embeddings(cols, D, 80 + k, "clustered", sigma=1.0).astype(np.float64))
                   for k in range(nblk)])
     L0 = dev((-lam * C).astype(np.float32))
-    P, ent, pc = M.sinkhorn(L0, lam, T)
+    P, ent, pc = M.sinkhorn(L0, lam, T, True, impl)
     torch.cuda.synchronize()
     C32 = L0.cpu().double().numpy() / -lam
     for k in range(nblk):
@@ -240,6 +244,10 @@ def test_sinkhorn_large_blocks(M, nblk, rows, cols, lam, T):
         assert relerr(P[k], p) < TOL_P
         assert abs(float(ent[k]) - e) <= TOL_ENT * max(abs(e), 1e-3)
         assert abs(float(pc[k]) - np.sum(p * C32[k])) < 2e-5 * rows
+    if impl == 0 and max(rows, cols) <= 512:
+        # the cluster kernel keeps the block in registers: the plan is optional, the statistics do not depend on it
+        P2, ent2, pc2 = M.sinkhorn(L0, lam, T, False, impl)
+        assert P2 is None and torch.equal(ent2, ent) and torch.equal(pc2, pc)
 
 
 def test_single_batch_at_headline_size(M):
