@@ -69,9 +69,10 @@ OTGAN_API int otgan_cost_blocks_f32(int nblk, int rows, int cols, int D,
  * For each block k: log_a = L0[k]; T x { log_a -= logsumexp(log_a, axis=1); log_a -= logsumexp(log_a, axis=0) };
  * P[k] = softmax(log_a, axis=-1); entropy[k] = mean_i( -sum_j P log_softmax(log_a) ); pc[k] = sum_ij P * (-L0/lam).
  * Replaces utils/matching.py:46-57 (== :113-125, toy_example/matching_cpu.py:51-62).  One persistent kernel: the block
- * stays in registers/shared memory for all T iterations.  P, entropy, pc may each be NULL.  rows, cols <= 128 use the
- * single-CTA kernel; larger blocks (<= 1024) stream the L2-resident block with one kernel per half-step and need P
- * (it is the working storage). */
+ * stays in registers/shared memory for all T iterations.  P, entropy, pc may each be NULL.  rows, cols <= 128: one CTA per
+ * block; <= 512: one 8-CTA thread-block cluster per block (row slabs in registers, column reductions through distributed
+ * shared memory); larger blocks (any size), or 128 < side with OTGAN_IMPL_SIMT, stream the L2-resident block with one
+ * kernel per half-step and need P (it is the working storage). */
 OTGAN_API int otgan_sinkhorn_f32(int nblk, int rows, int cols, int T, float lam,
                        const float* L0 /* [nblk, rows, cols] */, float* P /* [nblk, rows, cols] */,
                        float* entropy /* [nblk] */, float* pc /* [nblk] */, int impl, void* stream);

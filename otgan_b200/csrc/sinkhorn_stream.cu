@@ -1,5 +1,5 @@
-// sinkhorn_stream.cu -- Sinkhorn for blocks that do not fit one SM (rows or cols > 128: the single-batch variant at
-// N = 256, utils/matching.py:88-136, and 64x64-image configs with h = 256+).
+// sinkhorn_stream.cu -- Sinkhorn for blocks that fit neither one SM nor one cluster (side > 512; sides in (128, 512] are
+// sinkhorn_cluster.cu's, this rung remains their OTGAN_IMPL_SIMT comparison path).
 //
 // Literal log-domain iteration of utils/matching.py:50-57 with the block held in global memory (it stays L2-resident:
 // 6 x 1024^2 fp32 = 24 MB << 126 MB L2): one kernel per half-step,

@@ -25,6 +25,9 @@ def main():
     P, ent, pc = M.sinkhorn(L, 500.0, 10)
     L2 = (torch.rand(2, 128, 128, device="cuda") * -600.0).contiguous()    # full-size blocks with a wide cost range: slow steps of both kinds
     M.sinkhorn(L2, 500.0, 30)
+    L3 = (torch.rand(2, 256, 200, device="cuda") * -600.0).contiguous()    # sinkhorn_cluster_kernel: DSMEM pushes + mbarrier exchange
+    M.sinkhorn(L3, 500.0, 6)
+    M.sinkhorn((torch.rand(1, 300, 512, device="cuda") * -600.0).contiguous(), 500.0, 4)
     ws, wsb = M._plan_ws(A.device, 32)
     Ga, Gb = torch.empty_like(A), torch.empty_like(B)
     _lib.check(lib.otgan_grad_features_f32(32, 256, P.data_ptr(), A.data_ptr(), B.data_ptr(), 256, Ga.data_ptr(), Gb.data_ptr(), 256,
