@@ -406,6 +406,31 @@ def matching_benchmark(torch, devv, steps, warmup):
             "note": "fp32-exact 3xTF32: three tcgen05 passes per algorithmic flop, operands at TF32 rate (= bf16/2)"}
     kernels["cost"]["kernel"] = "cost_tc_kernel + cost_finalize_kernel (3xTF32)"
     kernels["grad"]["kernel"] = "plan_prep_kernel + plan_apply_tc_kernel (3xTF32)"
+    # Blocks larger than one SM (cfg5: h = 256; weak scaling at 8 GPUs: h = 512): the 8-CTA cluster kernel (AUTO) beside the
+    # one-launch-per-half-step rung (SIMT), each as ONE graph replay of 4 calls on synthetic cost blocks.
+    large = {}
+    for hl in (256, 512):
+        Ll = (torch.rand((6, hl, hl), device=devv) * -600.0).contiguous()
+        for name, impl in (("cluster_us", _lib.IMPL_AUTO), ("stream_us", _lib.IMPL_SIMT)):
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                M.sinkhorn(Ll, lam, T, True, impl)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for i in range(4):
+                    M.sinkhorn(Ll, lam, T, True, impl)
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            large.setdefault("6x%dx%d_T%d" % (hl, hl, T), {})[name] = e0.elapsed_time(e1) / 4 * 1e3
+            del g
+    kernels["sinkhorn"]["large_blocks"] = large
     res = {"ms_per_step": ms, "images_per_sec": N / (ms * 1e-3), "sinkhorn_iters_per_sec": T / (kernel_ms["sinkhorn"] * 1e-3),
            "kernels": kernels, "gpu_launches_per_step": launches / steps}
     del dev_sets

@@ -1,7 +1,7 @@
 """One small launch of every tcgen05 / mbarrier kernel of libotgan.so, for `compute-sanitizer --tool racecheck` (and memcheck):
 
-    compute-sanitizer --tool racecheck python tools/racecheck.py
-Shapes are the smallest that still take the tensor-core paths (the sanitizer slows kernels ~100x)."""
+    compute-sanitizer --tool racecheck python tools/racecheck.py [--cluster-only]
+`--cluster-only`: just the 8-CTA cluster Sinkhorn kernel (distributed-shared-memory pushes + mbarrier exchange).  Shapes are the smallest that still take the tensor-core paths (the sanitizer slows kernels ~100x)."""
 import ctypes
 import os
 import sys
@@ -13,10 +13,21 @@ from otgan_b200 import _lib  # noqa: E402
 from otgan_b200.utils import matching as M  # noqa: E402
 
 
+def cluster_sinkhorn():
+    L3 = (torch.rand(2, 256, 200, device="cuda") * -600.0).contiguous()    # sinkhorn_cluster_kernel: DSMEM pushes + mbarrier exchange
+    M.sinkhorn(L3, 500.0, 6)
+    M.sinkhorn((torch.rand(1, 300, 512, device="cuda") * -600.0).contiguous(), 500.0, 4)
+
+
 def main():
     lib = _lib.load()
     st = torch.cuda.current_stream().cuda_stream
     torch.manual_seed(0)
+    if "--cluster-only" in sys.argv:
+        cluster_sinkhorn()
+        torch.cuda.synchronize()
+        print("racecheck driver: cluster launches completed")
+        return
     # cost_tc_kernel (forced) + cost_finalize, sinkhorn_fast_kernel, plan_apply_tc_kernel + plan_prep
     A = torch.nn.functional.normalize(torch.rand(64, 256, device="cuda"), dim=1)
     B = torch.nn.functional.normalize(torch.rand(64, 256, device="cuda"), dim=1)
@@ -25,9 +36,7 @@ def main():
     P, ent, pc = M.sinkhorn(L, 500.0, 10)
     L2 = (torch.rand(2, 128, 128, device="cuda") * -600.0).contiguous()    # full-size blocks with a wide cost range: slow steps of both kinds
     M.sinkhorn(L2, 500.0, 30)
-    L3 = (torch.rand(2, 256, 200, device="cuda") * -600.0).contiguous()    # sinkhorn_cluster_kernel: DSMEM pushes + mbarrier exchange
-    M.sinkhorn(L3, 500.0, 6)
-    M.sinkhorn((torch.rand(1, 300, 512, device="cuda") * -600.0).contiguous(), 500.0, 4)
+    cluster_sinkhorn()
     ws, wsb = M._plan_ws(A.device, 32)
     Ga, Gb = torch.empty_like(A), torch.empty_like(B)
     _lib.check(lib.otgan_grad_features_f32(32, 256, P.data_ptr(), A.data_ptr(), B.data_ptr(), 256, Ga.data_ptr(), Gb.data_ptr(), 256,
