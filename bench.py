@@ -16,7 +16,8 @@ it: Trainer.stage (H2D of pinned HOST images on a copy stream) -> Trainer.step -
 entropy]) -> host read of every step's result, software-pipelined (upload of step k+1 and read of step k-1 while step k
 computes); `e2e.blocking_ms_per_step` is the same with sess.run semantics (upload, step, read, block -- every step).
 `matching` is the matching hot path alone (this library's kernels only): kernel times and the 6-launch step are timed
-through CUDA-graph replays (the per-call host work is as long as the kernels); `roofline` is the step's dominant kernel
+through CUDA-graph replays (the per-call host work is as long as the kernels), `matching.kernels.sinkhorn.large_blocks` times
+six 256 x 256 / 512 x 512 blocks on the cluster kernel beside the streaming rung; `roofline` is the step's dominant kernel
 against MEASURED_PEAKS.json, with a cuBLAS TF32 GEMM measured in the same run as the honest ceiling of a TF32 kernel.
 `configs` carries the other BASELINE.json configurations that fit the launch (cfg2 / cfg3 at 1 GPU, cfg4 = DenseNet at
 4 GPUs, cfg5 = 64 x 64 / N = 512 at 8 GPUs) and, for N > 1, a weak-scaling line (128 images per rank); `mgpu_parity` is
