@@ -50,7 +50,9 @@ def main():
             print("cost (%s): %s" % (name, e))
     L32 = np.stack([(-lam * d).astype(np.float32) for d in dists])
     P64 = [mo.sinkhorn(L32[k].astype(np.float64) / -lam, lam, T, np.float64)[0] for k in range(6)]
-    for name, impl in (("scaling-form", 0), ("log-domain", 1)):
+    auto_name = "scaling-form, one CTA per block" if h <= 128 else "log-domain, one 8-CTA cluster per block" if h <= 512 else "log-domain, streaming"
+    simt_name = "log-domain, one CTA per block" if h <= 128 else "log-domain, streaming"
+    for name, impl in ((auto_name, 0), (simt_name, 1)):
         P, ent, pc = M.sinkhorn(dev(L32), lam, T, True, impl)
         print("sinkhorn (%s): max |dP| / max P = %.3e" % (name, max(rel(P[k], P64[k]) for k in range(6))))
     P32 = np.stack([p.astype(np.float32) for p in plans])
