@@ -60,7 +60,7 @@ def main():
     ref = mo._combine_two_batch([p.astype(np.float64) for p in P32], A[:h].astype(np.float64), A[h:].astype(np.float64),
                                 B[:h].astype(np.float64), B[h:].astype(np.float64))
     lib = _lib.load()
-    ws, ws_bytes = M._plan_ws(Ad.device)
+    ws, ws_bytes = M._plan_ws(Ad.device, h)
     for name, impl in (("tcgen05", 2), ("simt", 1)):
         outs = [torch.empty(N, D, device="cuda") for _ in range(4)]
         rc = lib.otgan_matched_two_batch_f32(h, D, Pd.data_ptr(), Ad.data_ptr(), Bd.data_ptr(), D, outs[0].data_ptr(), outs[1].data_ptr(),
