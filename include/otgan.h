@@ -72,7 +72,8 @@ OTGAN_API int otgan_cost_blocks_f32(int nblk, int rows, int cols, int D,
  * stays in registers/shared memory for all T iterations.  P, entropy, pc may each be NULL.  rows, cols <= 128: one CTA per
  * block; <= 512: one 8-CTA thread-block cluster per block (row slabs in registers, column reductions through distributed
  * shared memory); larger blocks (any size), or 128 < side with OTGAN_IMPL_SIMT, stream the L2-resident block with one
- * kernel per half-step and need P (it is the working storage). */
+ * kernel per half-step and need P (it is the working storage).  L0 and P are float-aligned and, when cols % 4 == 0, share their
+ * offset within 16 bytes (both 16-byte aligned in practice): rows move as float4 when L0's block addresses allow it. */
 OTGAN_API int otgan_sinkhorn_f32(int nblk, int rows, int cols, int T, float lam,
                        const float* L0 /* [nblk, rows, cols] */, float* P /* [nblk, rows, cols] */,
                        float* entropy /* [nblk] */, float* pc /* [nblk] */, int impl, void* stream);

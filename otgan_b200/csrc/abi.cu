@@ -164,6 +164,10 @@ int otgan_sinkhorn_ex_f32(int nblk, int rows, int cols, int T, float lam, const 
     OTGAN_REQUIRE(nblk >= 1 && nblk <= 65535, "sinkhorn: nblk=%d", nblk);
     OTGAN_REQUIRE(rows >= 1 && cols >= 1 && T >= 0, "sinkhorn: bad shape rows=%d cols=%d T=%d", rows, cols, T);
     OTGAN_REQUIRE(L0 != nullptr, "sinkhorn: null L0");
+    // the kernels decide per block, from L0's address, whether rows can move as float4; P follows the same decision
+    OTGAN_REQUIRE((reinterpret_cast<uintptr_t>(L0) & 3u) == 0 && (reinterpret_cast<uintptr_t>(P) & 3u) == 0 &&
+                      ((cols & 3) != 0 || P == nullptr || ((reinterpret_cast<uintptr_t>(P) ^ reinterpret_cast<uintptr_t>(L0)) & 15u) == 0),
+                  "sinkhorn: L0 and P must be float-aligned and (cols %% 4 == 0) share their offset within 16 bytes");
     OTGAN_REQUIRE(lam != 0.f || pc == nullptr, "sinkhorn: lam=0 with pc requested");
     OTGAN_REQUIRE(impl == OTGAN_IMPL_AUTO || impl == OTGAN_IMPL_SIMT, "sinkhorn: impl %d not available", impl);
     if (rows <= sinkhorn_reg_max_side() && cols <= sinkhorn_reg_max_side()) {

@@ -68,6 +68,9 @@ def test_invalid_arguments_are_rejected_before_launch(lib):
     assert lib.otgan_sinkhorn_f32(1, 0, 4, 1, 1.0, 16, null, null, null, 0, null) == -1
     assert lib.otgan_sinkhorn_f32(1, 4, 4, -1, 1.0, 16, null, null, null, 0, null) == -1
     assert lib.otgan_sinkhorn_f32(1, 4, 4, 1, 1.0, null, null, null, null, 0, null) == -1
+    assert lib.otgan_sinkhorn_f32(1, 4, 4, 1, 1.0, 16, 36, null, null, 0, null) == -1                      # P is 4 bytes off L0's 16-byte phase
+    assert b"16 bytes" in lib.otgan_last_error()
+    assert lib.otgan_sinkhorn_f32(1, 4, 4, 1, 1.0, 18, null, null, null, 0, null) == -1                    # L0 not float-aligned
     assert lib.otgan_grad_features_f32(4, 4, null, null, null, 4, null, null, 4, null, 0, 0, null) == -1
     assert lib.otgan_calc_distance_f32(4, 8, 16, 16, 16, 16, 16, 4, 1.0, 16, 16, 1 << 20, null) == -1     # ld < D
     assert lib.otgan_distance_from_pc_f32(null, null, 4, null, null) == -1
