@@ -10,7 +10,6 @@ Extension (not in the reference, whose shapes are hard-wired to 32 x 32: train.p
 2 * (S/8)^2 * 1024 units) and emits [B, S, S, 3]; the critic is fully convolutional, so a [B, S, S, 3] input gives
 (S/8)^2 * 2048 features (131 072 at S = 64).  S = 32 is exactly the reference.
 """
-import numpy as np
 import torch
 
 from ..utils import nn

@@ -2,7 +2,6 @@
 
     compute-sanitizer --tool racecheck python tools/racecheck.py [--cluster-only]
 `--cluster-only`: just the 8-CTA cluster Sinkhorn kernel (distributed-shared-memory pushes + mbarrier exchange).  Shapes are the smallest that still take the tensor-core paths (the sanitizer slows kernels ~100x)."""
-import ctypes
 import os
 import sys
 
